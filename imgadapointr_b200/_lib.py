@@ -1,0 +1,95 @@
+"""ctypes binding of libiapt_b200.so (C ABI: include/iapt_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, an exception is raised.  PyTorch is used only
+for device memory (outputs and workspaces come from its caching allocator) and for the current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libiapt_b200.so")
+ABI_VERSION = 1
+
+_lib = None
+
+_c_int = ctypes.c_int
+_c_void_p = ctypes.c_void_p
+_c_size_t = ctypes.c_size_t
+_c_float = ctypes.c_float
+
+# name -> (restype, argtypes); mirrors include/iapt_b200.h one to one (tests/test_abi.py checks the header against it)
+SIGNATURES = {
+    "iapt_abi_version": (_c_int, []),
+    "iapt_error_string": (ctypes.c_char_p, [_c_int]),
+    "iapt_launch_count": (ctypes.c_ulonglong, []),
+    "iapt_chamfer_forward_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "iapt_chamfer_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
+                                      _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "iapt_chamfer_backward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
+                                       _c_int, _c_void_p, _c_void_p, _c_void_p]),
+    "iapt_chamfer_reduce": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
+    "iapt_fscore_counts": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p]),
+    "iapt_fps_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "iapt_fps": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "iapt_gather": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
+    "iapt_gather_grad": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
+    "iapt_gather_xyz": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
+    "iapt_knn": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
+}
+
+
+class IaptError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA library (once).  Raises if it has not been built: there is no CPU / eager fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IaptError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C imgadapointr_b200/csrc`). imgadapointr_b200 has no fallback path.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if handle.iapt_abi_version() != ABI_VERSION:
+            raise IaptError(f"ABI mismatch: library {handle.iapt_abi_version()} != binding {ABI_VERSION}")
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = lib().iapt_error_string(code)
+        raise IaptError(f"{what} failed ({code}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(lib().iapt_launch_count())
+
+
+def require_cuda_f32(t: torch.Tensor, name: str, ndim: int) -> None:
+    """The checks the reference leaves to data_ptr<float>() / CHECK_* macros, made explicit."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise IaptError(f"{name} must be a CUDA tensor (imgadapointr_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise IaptError(f"{name} must be float32, got {t.dtype}")
+    if t.dim() != ndim:
+        raise IaptError(f"{name} must have {ndim} dims, got shape {tuple(t.shape)}")
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,94 @@
+"""Drop-in for the reference's pybind module ``chamfer`` (extensions/chamfer_dist/chamfer_cuda.cpp:36-39).
+
+``forward(xyz1, xyz2) -> [dist1, dist2, idx1, idx2]`` and
+``backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2) -> [grad_xyz1, grad_xyz2]``
+with the reference's shapes and dtypes (dist float32, idx int32), computed by libiapt_b200.so on the current
+stream of the inputs' device.  Differences, all deliberate:
+  * inputs are validated (CUDA, float32, [B,n,3]) and made contiguous instead of silently reading garbage;
+  * CUDA errors raise instead of being printf()ed (chamfer.cu:166-169);
+  * the current torch stream is used instead of the legacy default stream (chamfer.cu:159).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _prep(xyz1, xyz2):
+    _lib.require_cuda_f32(xyz1, "xyz1", 3)
+    _lib.require_cuda_f32(xyz2, "xyz2", 3)
+    if xyz1.size(2) != 3 or xyz2.size(2) != 3:
+        raise _lib.IaptError("xyz1 / xyz2 must be [B, n, 3]")
+    if xyz1.size(0) != xyz2.size(0):
+        raise _lib.IaptError("xyz1 and xyz2 must have the same batch size")
+    if xyz1.device != xyz2.device:
+        raise _lib.IaptError("xyz1 and xyz2 must be on the same device")
+    return xyz1.contiguous(), xyz2.contiguous()
+
+
+def forward(xyz1: torch.Tensor, xyz2: torch.Tensor):
+    xyz1, xyz2 = _prep(xyz1.detach(), xyz2.detach())
+    B, N, _ = xyz1.shape
+    M = xyz2.size(1)
+    dev = xyz1.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        dist1 = torch.empty((B, N), dtype=torch.float32, device=dev)
+        dist2 = torch.empty((B, M), dtype=torch.float32, device=dev)
+        idx1 = torch.empty((B, N), dtype=torch.int32, device=dev)
+        idx2 = torch.empty((B, M), dtype=torch.int32, device=dev)
+        ws_bytes = int(L.iapt_chamfer_forward_workspace_bytes(B, N, M))
+        ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev)
+        _lib.check(
+            L.iapt_chamfer_forward(_lib.ptr(xyz1), _lib.ptr(xyz2), B, N, M, _lib.ptr(dist1), _lib.ptr(dist2),
+                                   _lib.ptr(idx1), _lib.ptr(idx2), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)),
+            "iapt_chamfer_forward")
+    return [dist1, dist2, idx1, idx2]
+
+
+def backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
+    xyz1, xyz2 = _prep(xyz1.detach(), xyz2.detach())
+    B, N, _ = xyz1.shape
+    M = xyz2.size(1)
+    dev = xyz1.device
+    if idx1.dtype != torch.int32 or idx2.dtype != torch.int32:
+        raise _lib.IaptError("idx1 / idx2 must be int32 (as returned by forward)")
+    idx1, idx2 = idx1.contiguous(), idx2.contiguous()
+    g1 = grad_dist1.to(torch.float32).contiguous()  # autograd may hand over expanded / strided grads
+    g2 = grad_dist2.to(torch.float32).contiguous()
+    if tuple(g1.shape) != (B, N) or tuple(g2.shape) != (B, M) or tuple(idx1.shape) != (B, N) or tuple(idx2.shape) != (B, M):
+        raise _lib.IaptError("backward: shape mismatch between xyz, idx and grad_dist")
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        gx1 = torch.empty_like(xyz1)
+        gx2 = torch.empty_like(xyz2)
+        _lib.check(
+            L.iapt_chamfer_backward(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(idx1), _lib.ptr(idx2), _lib.ptr(g1),
+                                    _lib.ptr(g2), B, N, M, _lib.ptr(gx1), _lib.ptr(gx2), _lib.stream_ptr(dev)),
+            "iapt_chamfer_backward")
+    return [gx1, gx2]
+
+
+def reduce_sums(dist1: torch.Tensor, dist2: torch.Tensor) -> torch.Tensor:
+    """[B,4] per-cloud {sum d1, sum d2, sum sqrt d1, sum sqrt d2} in one launch (iapt_chamfer_reduce)."""
+    B, N = dist1.shape
+    M = dist2.size(1)
+    dev = dist1.device
+    with torch.cuda.device(dev):
+        sums = torch.empty((B, 4), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().iapt_chamfer_reduce(_lib.ptr(dist1), _lib.ptr(dist2), B, N, M, _lib.ptr(sums),
+                                                  _lib.stream_ptr(dev)), "iapt_chamfer_reduce")
+    return sums
+
+
+def fscore_counts(dist1: torch.Tensor, dist2: torch.Tensor, th: float) -> torch.Tensor:
+    """[B,2] int32 {#sqrt(dist1)<th, #sqrt(dist2)<th} (iapt_fscore_counts)."""
+    B, N = dist1.shape
+    M = dist2.size(1)
+    dev = dist1.device
+    with torch.cuda.device(dev):
+        counts = torch.empty((B, 2), dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().iapt_fscore_counts(_lib.ptr(dist1), _lib.ptr(dist2), B, N, M, float(th),
+                                                 _lib.ptr(counts), _lib.stream_ptr(dev)), "iapt_fscore_counts")
+    return counts

@@ -1,0 +1,163 @@
+// c_api.cu - the extern "C" surface declared in include/iapt_b200.h: argument validation + launch.
+#include <atomic>
+#include <cstdio>
+
+#include "../../include/iapt_b200.h"
+#include "common.cuh"
+
+namespace iapt {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+size_t chamfer_forward_workspace_bytes(int B, int N, int M);
+int chamfer_forward_launch(const float*, const float*, int, int, int, float*, float*, int32_t*, int32_t*, void*,
+                           cudaStream_t);
+int chamfer_backward_launch(const float*, const float*, const int32_t*, const int32_t*, const float*, const float*, int,
+                            int, int, float*, float*, cudaStream_t);
+int chamfer_metrics_launch(const float*, const float*, int, int, int, float, float*, int32_t*, cudaStream_t);
+size_t fps_workspace_bytes(int B, int N, int npoint);
+int fps_launch(const float*, int, int, int, int, int32_t*, void*, cudaStream_t);
+int gather_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
+int gather_xyz_launch(const float*, const int32_t*, int, int, int, float*, cudaStream_t);
+int gather_grad_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
+int knn_launch(const float*, const float*, int, int, int, int, int64_t*, float*, cudaStream_t);
+}  // namespace iapt
+
+using namespace iapt;
+
+#define IAPT_REQUIRE(cond) \
+  do {                     \
+    if (!(cond)) return IAPT_EINVAL; \
+  } while (0)
+
+extern "C" {
+
+int iapt_abi_version(void) { return IAPT_ABI_VERSION; }
+
+const char* iapt_error_string(int code) {
+  switch (code) {
+    case 0: return "success";
+    case IAPT_EINVAL: return "iapt: invalid argument (null pointer or bad size)";
+    case IAPT_EWORKSPACE: return "iapt: workspace too small (see *_workspace_bytes)";
+    case IAPT_EUNSUPPORTED: return "iapt: unsupported configuration";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "iapt: unknown error";
+  }
+}
+
+unsigned long long iapt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t iapt_chamfer_forward_workspace_bytes(int B, int N, int M) {
+  if (B <= 0 || N <= 0 || M <= 0) return 0;
+  return chamfer_forward_workspace_bytes(B, N, M);
+}
+
+int iapt_chamfer_forward(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1, float* dist2,
+                         int32_t* idx1, int32_t* idx2, void* workspace, size_t workspace_bytes,
+                         iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && N >= 0 && M >= 0);
+  IAPT_REQUIRE((dist1 == nullptr) == (idx1 == nullptr) && (dist2 == nullptr) == (idx2 == nullptr));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) return 0;
+  if (N == 0 || M == 0) {  // reference: torch::zeros outputs, kernel writes nothing (chamfer.cu:152-157)
+    cudaError_t e = cudaSuccess;
+    if (dist1 && N > 0) {
+      e = cudaMemsetAsync(dist1, 0, sizeof(float) * (size_t)B * N, st);
+      if (e == cudaSuccess) e = cudaMemsetAsync(idx1, 0, sizeof(int32_t) * (size_t)B * N, st);
+    }
+    if (e == cudaSuccess && dist2 && M > 0) {
+      e = cudaMemsetAsync(dist2, 0, sizeof(float) * (size_t)B * M, st);
+      if (e == cudaSuccess) e = cudaMemsetAsync(idx2, 0, sizeof(int32_t) * (size_t)B * M, st);
+    }
+    return (int)e;
+  }
+  IAPT_REQUIRE(xyz1 && xyz2 && workspace);
+  IAPT_REQUIRE((long long)B * N < (1LL << 31) && (long long)B * M < (1LL << 31));
+  if (workspace_bytes < chamfer_forward_workspace_bytes(B, N, M)) return IAPT_EWORKSPACE;
+  return chamfer_forward_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, workspace, st);
+}
+
+int iapt_chamfer_backward(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
+                          const float* grad_dist1, const float* grad_dist2, int B, int N, int M, float* grad_xyz1,
+                          float* grad_xyz2, iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && N >= 0 && M >= 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) return 0;
+  if (N == 0 || M == 0) {
+    cudaError_t e = cudaSuccess;
+    if (N > 0 && grad_xyz1) e = cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * 3 * (size_t)B * N, st);
+    if (e == cudaSuccess && M > 0 && grad_xyz2) e = cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * 3 * (size_t)B * M, st);
+    return (int)e;
+  }
+  IAPT_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && grad_xyz1 && grad_xyz2);
+  return chamfer_backward_launch(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2, B, N, M, grad_xyz1, grad_xyz2, st);
+}
+
+int iapt_chamfer_reduce(const float* dist1, const float* dist2, int B, int N, int M, float* sums,
+                        iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && N >= 0 && M >= 0);
+  if (B == 0) return 0;
+  IAPT_REQUIRE(dist1 && dist2 && sums);
+  return chamfer_metrics_launch(dist1, dist2, B, N, M, 0.f, sums, nullptr, (cudaStream_t)stream);
+}
+
+int iapt_fscore_counts(const float* dist1, const float* dist2, int B, int N, int M, float th, int32_t* counts,
+                       iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && N >= 0 && M >= 0);
+  if (B == 0) return 0;
+  IAPT_REQUIRE(dist1 && dist2 && counts);
+  return chamfer_metrics_launch(dist1, dist2, B, N, M, th, nullptr, counts, (cudaStream_t)stream);
+}
+
+size_t iapt_fps_workspace_bytes(int B, int N, int npoint) {
+  if (B <= 0 || N <= 0) return 0;
+  return fps_workspace_bytes(B, N, npoint);
+}
+
+int iapt_fps(const float* xyz, int B, int N, int npoint, int flags, int32_t* idx, void* workspace,
+             size_t workspace_bytes, iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && N >= 1 && npoint >= 0);
+  if (B == 0 || npoint == 0) return 0;
+  IAPT_REQUIRE(xyz && idx);
+  const size_t need = fps_workspace_bytes(B, N, npoint);
+  if (need > 0 && (workspace == nullptr || workspace_bytes < need)) return IAPT_EWORKSPACE;
+  return fps_launch(xyz, B, N, npoint, flags, idx, workspace, (cudaStream_t)stream);
+}
+
+int iapt_gather(const float* features, const int32_t* idx, int B, int C, int N, int npoint, float* out,
+                iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && C >= 0 && N >= 1 && npoint >= 0);
+  if (B == 0 || C == 0 || npoint == 0) return 0;
+  IAPT_REQUIRE(features && idx && out);
+  return gather_launch(features, idx, B, C, N, npoint, out, (cudaStream_t)stream);
+}
+
+int iapt_gather_grad(const float* grad_out, const int32_t* idx, int B, int C, int N, int npoint, float* grad_features,
+                     iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && C >= 0 && N >= 1 && npoint >= 0);
+  if (B == 0 || C == 0) return 0;
+  IAPT_REQUIRE(grad_features);
+  if (npoint == 0) return (int)cudaMemsetAsync(grad_features, 0, sizeof(float) * (size_t)B * C * N, (cudaStream_t)stream);
+  IAPT_REQUIRE(grad_out && idx);
+  IAPT_REQUIRE(B <= 65535);
+  return gather_grad_launch(grad_out, idx, B, C, N, npoint, grad_features, (cudaStream_t)stream);
+}
+
+int iapt_gather_xyz(const float* xyz, const int32_t* idx, int B, int N, int npoint, float* out,
+                    iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && N >= 1 && npoint >= 0);
+  if (B == 0 || npoint == 0) return 0;
+  IAPT_REQUIRE(xyz && idx && out);
+  return gather_xyz_launch(xyz, idx, B, N, npoint, out, (cudaStream_t)stream);
+}
+
+int iapt_knn(const float* ref, const float* query, int B, int R, int Q, int k, int64_t* idx, float* dist,
+             iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && R >= 1 && Q >= 0 && k >= 1);
+  if (k > IAPT_KNN_MAX_K) return IAPT_EUNSUPPORTED;
+  IAPT_REQUIRE(k <= R);
+  if (B == 0 || Q == 0) return 0;
+  IAPT_REQUIRE(ref && query && idx);
+  return knn_launch(ref, query, B, R, Q, k, idx, dist, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+// chamfer_bwd.cu - deterministic, floating-point-atomics-free Chamfer backward for sm_100a.
+//
+// Replaces chamfer_dist_grad_kernel x2 (reference extensions/chamfer_dist/chamfer.cu:173-201, launched :215-222),
+// which scatters with 6 float atomicAdd per point from only 4096 threads (grid (1,16), block 256) and therefore
+// sums in a run-dependent order.
+//
+// Owner-computes formulation.  For output point j of cloud side X (other side Y):
+//     grad_X[j] = 2 gX[j] (x_j - y_{idxX[j]})                      "own" term   (chamfer.cu:193-195)
+//               - sum_{k : idxY[k] == j} 2 gY[k] (y_k - x_j)       fan-in term  (chamfer.cu:196-198, roles swapped)
+// A warp owns kBins consecutive output points, keeps their fan-in accumulators in shared memory, and scans the
+// other side's index array idxY[b, :] in ascending k (coalesced 128 B loads; hits are rare: kBins / N per key).
+// Lanes that hit the same bin in one step are serialised in lane order, so every accumulator receives its
+// contributions in ascending k: the result is bit-reproducible and independent of the launch geometry.
+// Cost: each key is read N / kBins times from L2 - ~1 % of the forward search's work - and worst-case fan-in
+// (all keys in one bin) degrades to a sequential sum inside one warp, never to atomics.
+#include "common.cuh"
+
+namespace iapt {
+
+constexpr int kBwdThreads = 256;
+constexpr int kBwdWarps = kBwdThreads / 32;
+constexpr int kBins = 256;  // output points per warp
+
+struct BwdParams {
+  const float* xyz[2];     // [B, n[s], 3]
+  const int32_t* idx[2];   // [B, n[s]]   idx[s][j] indexes into side 1-s
+  const float* gdist[2];   // [B, n[s]]   (may be null = zeros)
+  float* grad[2];          // [B, n[s], 3]
+  int n[2];
+  int B;
+  int blocks_per_cloud[2];  // ceil(n[s] / kBins)
+  long long warps_side0;    // B * blocks_per_cloud[0]
+  long long total_warps;
+};
+
+__global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
+  __shared__ float acc[kBwdWarps][kBins * 3];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * kBwdWarps + warp;
+  if (gw >= p.total_warps) return;  // whole warp exits together; no block-level sync below
+
+  int side;
+  long long w = gw;
+  if (w < p.warps_side0) {
+    side = 0;
+  } else {
+    side = 1;
+    w -= p.warps_side0;
+  }
+  const int other = side ^ 1;
+  const int bpc = p.blocks_per_cloud[side];
+  const int b = (int)(w / bpc);
+  const int j0 = (int)(w - (long long)b * bpc) * kBins;
+  const int nX = p.n[side], nY = p.n[other];
+  const float* __restrict__ X = p.xyz[side] + (size_t)b * nX * 3;
+  const float* __restrict__ Y = p.xyz[other] + (size_t)b * nY * 3;
+  const int32_t* __restrict__ idxX = p.idx[side] + (size_t)b * nX;
+  const int32_t* __restrict__ idxY = p.idx[other] + (size_t)b * nY;
+  const float* __restrict__ gX = p.gdist[side] ? p.gdist[side] + (size_t)b * nX : nullptr;
+  const float* __restrict__ gY = p.gdist[other] ? p.gdist[other] + (size_t)b * nY : nullptr;
+  float* __restrict__ out = p.grad[side] + (size_t)b * nX * 3;
+  float* a = acc[warp];
+
+  for (int i = lane; i < kBins * 3; i += 32) a[i] = 0.f;
+  __syncwarp();
+
+  if (gY != nullptr) {
+    // ---- scan the other side's nearest-neighbour indices, 128 keys per step, ascending k ---------------------
+    for (int k0 = 0; k0 < nY; k0 += 128) {
+      int key[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = k0 + e * 32 + lane;
+        key[e] = (k < nY) ? __ldg(idxY + k) : -1;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned bin = (unsigned)(key[e] - j0);
+        const bool hit = (key[e] >= 0) && (bin < (unsigned)kBins) && ((int)bin + j0 < nX);
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask == 0u) continue;  // warp-uniform
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        unsigned rank = 0;
+        if (hit) {
+          const int k = k0 + e * 32 + lane;
+          const int j = j0 + (int)bin;
+          const float g = __fmul_rn(__ldg(gY + k), 2.f);
+          cx = __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 0), __ldg(X + 3 * (size_t)j + 0)));
+          cy = __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 1), __ldg(X + 3 * (size_t)j + 1)));
+          cz = __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 2), __ldg(X + 3 * (size_t)j + 2)));
+          const unsigned peers = __match_any_sync(mask, bin);
+          rank = __popc(peers & ((1u << lane) - 1u));
+        }
+        // lanes with the same bin take turns in lane (= ascending k) order
+        for (unsigned r = 0;; ++r) {
+          if (hit && rank == r) {
+            a[bin * 3 + 0] = __fadd_rn(a[bin * 3 + 0], cx);
+            a[bin * 3 + 1] = __fadd_rn(a[bin * 3 + 1], cy);
+            a[bin * 3 + 2] = __fadd_rn(a[bin * 3 + 2], cz);
+          }
+          __syncwarp();
+          if (!__any_sync(0xffffffffu, hit && rank > r)) break;
+        }
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- own term and write-out ------------------------------------------------------------------------------
+  for (int i = lane; i < kBins; i += 32) {
+    const int j = j0 + i;
+    if (j >= nX) break;
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (gX != nullptr) {
+      const int j2 = __ldg(idxX + j);
+      const float g = __fmul_rn(__ldg(gX + j), 2.f);
+      ox = __fmul_rn(g, __fsub_rn(__ldg(X + 3 * (size_t)j + 0), __ldg(Y + 3 * (size_t)j2 + 0)));
+      oy = __fmul_rn(g, __fsub_rn(__ldg(X + 3 * (size_t)j + 1), __ldg(Y + 3 * (size_t)j2 + 1)));
+      oz = __fmul_rn(g, __fsub_rn(__ldg(X + 3 * (size_t)j + 2), __ldg(Y + 3 * (size_t)j2 + 2)));
+    }
+    out[3 * (size_t)j + 0] = __fsub_rn(ox, a[i * 3 + 0]);
+    out[3 * (size_t)j + 1] = __fsub_rn(oy, a[i * 3 + 1]);
+    out[3 * (size_t)j + 2] = __fsub_rn(oz, a[i * 3 + 2]);
+  }
+}
+
+int chamfer_backward_launch(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
+                            const float* grad_dist1, const float* grad_dist2, int B, int N, int M, float* grad_xyz1,
+                            float* grad_xyz2, cudaStream_t stream) {
+  BwdParams p;
+  p.xyz[0] = xyz1;
+  p.xyz[1] = xyz2;
+  p.idx[0] = idx1;
+  p.idx[1] = idx2;
+  p.gdist[0] = grad_dist1;
+  p.gdist[1] = grad_dist2;
+  p.grad[0] = grad_xyz1;
+  p.grad[1] = grad_xyz2;
+  p.n[0] = N;
+  p.n[1] = M;
+  p.B = B;
+  p.blocks_per_cloud[0] = (N + kBins - 1) / kBins;
+  p.blocks_per_cloud[1] = (M + kBins - 1) / kBins;
+  p.warps_side0 = (long long)B * p.blocks_per_cloud[0];
+  p.total_warps = p.warps_side0 + (long long)B * p.blocks_per_cloud[1];
+  const long long blocks = (p.total_warps + kBwdWarps - 1) / kBwdWarps;
+  chamfer_bwd_kernel<<<(unsigned)blocks, kBwdThreads, 0, stream>>>(p);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace iapt

@@ -1,0 +1,107 @@
+// common.cuh - shared device helpers for the sm_100a geometry kernels.
+//
+// One squared-distance formula is used EVERYWHERE (search, index resolution, kNN, FPS):
+//     d = fma(dz,dz, fma(dx,dx, dy*dy)),   dx,dy,dz = b - a   (sign is irrelevant after squaring)
+// which is what nvcc 12.9 emits for the reference's `x2*x2 + y2*y2 + z2*z2` (extensions/chamfer_dist/chamfer.cu:42-45).
+// It is spelled with explicit round-to-nearest intrinsics / PTX so no compiler contraction can change it, and the
+// packed f32x2 form (two independent IEEE lanes) is bit-identical to the scalar form.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef __CUDA_ARCH__
+#define IAPT_HOST 1
+#endif
+
+namespace iapt {
+
+typedef unsigned long long u64;
+
+// Host-side launch bookkeeping (c_api.cu).
+void count_launch(int n = 1);
+
+// Padding sentinel for out-of-range points.  (1e18)^2 * 3 = 3e36 < FLT_MAX, so no Inf/NaN is ever produced,
+// and any real distance (|coords| < 1e15) is smaller than a distance to a sentinel.
+__device__ __host__ constexpr float kPadCoord() { return 1.0e18f; }
+
+__device__ __forceinline__ float sqdist(float ax, float ay, float az, float bx, float by, float bz) {
+  float dx = __fsub_rn(bx, ax);
+  float dy = __fsub_rn(by, ay);
+  float dz = __fsub_rn(bz, az);
+  float t = __fmul_rn(dy, dy);
+  t = __fmaf_rn(dx, dx, t);
+  t = __fmaf_rn(dz, dz, t);
+  return t;
+}
+
+// ---- packed f32x2 (Blackwell FADD2 / FMUL2 / FFMA2): one issue slot for two FP32 lanes --------------------
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// Two squared distances at once: lanes (lo,hi) of a* are two points, b* holds one point duplicated in both lanes.
+__device__ __forceinline__ u64 sqdist2(u64 ax, u64 ay, u64 az, u64 bx, u64 by, u64 bz) {
+  u64 dx = sub2(bx, ax);
+  u64 dy = sub2(by, ay);
+  u64 dz = sub2(bz, az);
+  u64 t = mul2(dy, dy);
+  t = fma2(dx, dx, t);
+  t = fma2(dz, dz, t);
+  return t;
+}
+
+// 3-input min (FMNMX3 on sm_100): one ALU-pipe slot folds two candidates into a running minimum.
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// Warp-wide reductions in ONE instruction (REDUX).  Distances are >= +0 so their bit patterns order like uints.
+__device__ __forceinline__ unsigned redux_min_u32(unsigned v) {
+  unsigned r;
+  asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ unsigned redux_max_u32(unsigned v) {
+  unsigned r;
+  asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ int redux_max_s32(int v) {
+  int r;
+  asm volatile("redux.sync.max.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ int redux_min_s32(int v) {
+  int r;
+  asm volatile("redux.sync.min.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+}
+
+// (distance bits, coarse id) packed so that an unsigned 64-bit min is the lexicographic (distance, id) min -
+// i.e. the lowest id among equal distances, which is how the lowest-index tie rule survives the atomics.
+__device__ __forceinline__ u64 pack_key(float d, unsigned id) { return ((u64)__float_as_uint(d) << 32) | (u64)id; }
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+}  // namespace iapt

@@ -1,0 +1,300 @@
+// fps.cu - furthest point sampling and index gathers for sm_100a.
+//
+// Replaces pointnet2_ops' furthest_point_sampling_kernel / gather_points_kernel / gather_points_grad_kernel
+// (third-party pointnet2_ops_lib, NOT vendored in the reference; call sites utils/misc.py:37-38,
+// models/base_blocks.py:550-558).  Upstream: one block per cloud, running-min array `temp` in GLOBAL memory,
+// a 9-level shared-memory tree reduction with a __syncthreads per level per round.
+//
+// Here: one CTA per cloud; the cloud AND the running minimum live in registers (or shared memory for big
+// clouds); each of the npoint-1 dependent rounds costs ONE __syncthreads: warp argmax via two REDUX
+// instructions (max of the value bits, then min index among the lanes holding it), one shared-memory slot per
+// warp (double-buffered by round parity), and every warp redundantly folds the <= 32 slots with two more REDUX.
+// Tie rule: LOWEST index among equal maxima (documented in include/iapt_b200.h and DESIGN.md).
+#include "common.cuh"
+
+namespace iapt {
+
+constexpr int kFpsMaxSmemPoints = 18432;  // 12 B per point SoA -> 216 KB
+
+struct FpsSlots {
+  int val[2][32];
+  int idx[2][32];
+};
+
+// kRegs: points cached in registers (N <= kT * kPPT); otherwise re-read from shared memory each round.
+template <int kT, int kPPT, bool kRegs>
+__global__ void __launch_bounds__(kT) fps_kernel(const float* __restrict__ xyz, int N, int npoint, int flags,
+                                                 int32_t* __restrict__ idx_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FpsSlots* slots = reinterpret_cast<FpsSlots*>(smem_raw);
+  float* sx = reinterpret_cast<float*>(smem_raw + sizeof(FpsSlots));
+  float* sy = sx + N;
+  float* sz = sy + N;
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  constexpr int kNW = kT / 32;
+  const float* __restrict__ P = xyz + (size_t)b * N * 3;
+  int32_t* __restrict__ out = idx_out + (size_t)b * npoint;
+
+  // coalesced fill of the SoA copy
+  for (int i = tid; i < N * 3; i += kT) {
+    const float v = __ldg(P + i);
+    const int k = i / 3, c = i - 3 * k;
+    (c == 0 ? sx : (c == 1 ? sy : sz))[k] = v;
+  }
+  __syncthreads();
+
+  float px[kRegs ? kPPT : 1], py[kRegs ? kPPT : 1], pz[kRegs ? kPPT : 1];
+  float tmp[kPPT];  // running min distance; -1 marks a point that can never be selected
+#pragma unroll
+  for (int i = 0; i < kPPT; ++i) {
+    const int k = tid + i * kT;
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool ok = k < N;
+    if (ok) {
+      x = sx[k];
+      y = sy[k];
+      z = sz[k];
+      if (flags & 1) {
+        // upstream: `if (mag <= 1e-3) continue;` - float magnitude against the DOUBLE literal
+        const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+        ok = !((double)mag <= 1e-3);
+      }
+    }
+    if (kRegs) {
+      px[i] = x;
+      py[i] = y;
+      pz[i] = z;
+    }
+    tmp[i] = ok ? 1e10f : -1.f;
+  }
+
+  int old = 0;
+  if (tid == 0) out[0] = 0;
+
+  for (int j = 1; j < npoint; ++j) {
+    const float ox = sx[old], oy = sy[old], oz = sz[old];
+    float best = -1.f;
+    int besti = 0;
+#pragma unroll
+    for (int i = 0; i < kPPT; ++i) {
+      const int k = tid + i * kT;
+      float x, y, z;
+      if (kRegs) {
+        x = px[i];
+        y = py[i];
+        z = pz[i];
+      } else {
+        const int kk = k < N ? k : 0;
+        x = sx[kk];
+        y = sy[kk];
+        z = sz[kk];
+      }
+      const float d = sqdist(ox, oy, oz, x, y, z);
+      const float t = fminf(tmp[i], d);  // stays -1 for ineligible points (d >= 0)
+      tmp[i] = t;
+      if (t > best) {  // ascending k inside a thread + strict '>' keeps the thread's lowest index
+        best = t;
+        besti = k;
+      }
+    }
+    // warp argmax: value bits order like signed ints (-1.f is negative, distances are >= +0)
+    const int vb = __float_as_int(best);
+    const int vmax = redux_max_s32(vb);
+    const int imin = redux_min_s32(vb == vmax ? besti : 0x7fffffff);
+    const int par = j & 1;
+    if (lane == 0) {
+      slots->val[par][warp] = vmax;
+      slots->idx[par][warp] = imin;
+    }
+    __syncthreads();
+    int v = (lane < kNW) ? slots->val[par][lane] : (int)0x80000000;
+    int ii = (lane < kNW) ? slots->idx[par][lane] : 0x7fffffff;
+    const int gmax = redux_max_s32(v);
+    old = redux_min_s32(v == gmax ? ii : 0x7fffffff);
+    if (tid == 0) out[j] = old;
+  }
+}
+
+// Generic fallback for clouds too large for shared memory: points from global (L2), running min in a workspace.
+__global__ void __launch_bounds__(1024) fps_generic_kernel(const float* __restrict__ xyz, int N, int npoint, int flags,
+                                                           float* __restrict__ temp_all,
+                                                           int32_t* __restrict__ idx_out) {
+  __shared__ FpsSlots slots;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* __restrict__ P = xyz + (size_t)b * N * 3;
+  float* __restrict__ temp = temp_all + (size_t)b * N;
+  int32_t* __restrict__ out = idx_out + (size_t)b * npoint;
+  for (int k = tid; k < N; k += 1024) {
+    bool ok = true;
+    if (flags & 1) {
+      const float x = P[3 * (size_t)k], y = P[3 * (size_t)k + 1], z = P[3 * (size_t)k + 2];
+      const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+      ok = !((double)mag <= 1e-3);
+    }
+    temp[k] = ok ? 1e10f : -1.f;
+  }
+  int old = 0;
+  if (tid == 0) out[0] = 0;
+  __syncthreads();
+  for (int j = 1; j < npoint; ++j) {
+    const float ox = P[3 * (size_t)old], oy = P[3 * (size_t)old + 1], oz = P[3 * (size_t)old + 2];
+    float best = -1.f;
+    int besti = 0;
+    for (int k = tid; k < N; k += 1024) {
+      const float d = sqdist(ox, oy, oz, P[3 * (size_t)k], P[3 * (size_t)k + 1], P[3 * (size_t)k + 2]);
+      const float t = fminf(temp[k], d);
+      temp[k] = t;
+      if (t > best) {
+        best = t;
+        besti = k;
+      }
+    }
+    const int vb = __float_as_int(best);
+    const int vmax = redux_max_s32(vb);
+    const int imin = redux_min_s32(vb == vmax ? besti : 0x7fffffff);
+    const int par = j & 1;
+    if (lane == 0) {
+      slots.val[par][warp] = vmax;
+      slots.idx[par][warp] = imin;
+    }
+    __syncthreads();
+    const int v = slots.val[par][lane];
+    const int ii = slots.idx[par][lane];
+    const int gmax = redux_max_s32(v);
+    old = redux_min_s32(v == gmax ? ii : 0x7fffffff);
+    if (tid == 0) out[j] = old;
+  }
+}
+
+size_t fps_workspace_bytes(int B, int N, int /*npoint*/) {
+  return N > kFpsMaxSmemPoints ? sizeof(float) * (size_t)B * N : 0;
+}
+
+template <int kT, int kPPT, bool kRegs>
+static int fps_launch_t(const float* xyz, int B, int N, int npoint, int flags, int32_t* idx, cudaStream_t stream) {
+  const size_t smem = sizeof(FpsSlots) + sizeof(float) * 3 * (size_t)N;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(fps_kernel<kT, kPPT, kRegs>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
+  }
+  fps_kernel<kT, kPPT, kRegs><<<B, kT, smem, stream>>>(xyz, N, npoint, flags, idx);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int fps_launch(const float* xyz, int B, int N, int npoint, int flags, int32_t* idx, void* workspace,
+               cudaStream_t stream) {
+  if (N <= 128) return fps_launch_t<128, 1, true>(xyz, B, N, npoint, flags, idx, stream);
+  if (N <= 256) return fps_launch_t<256, 1, true>(xyz, B, N, npoint, flags, idx, stream);
+  if (N <= 512) return fps_launch_t<256, 2, true>(xyz, B, N, npoint, flags, idx, stream);
+  if (N <= 1024) return fps_launch_t<512, 2, true>(xyz, B, N, npoint, flags, idx, stream);
+  if (N <= 2048) return fps_launch_t<512, 4, true>(xyz, B, N, npoint, flags, idx, stream);
+  if (N <= 4096) return fps_launch_t<512, 8, true>(xyz, B, N, npoint, flags, idx, stream);
+  if (N <= 8192) return fps_launch_t<1024, 8, true>(xyz, B, N, npoint, flags, idx, stream);
+  if (N <= kFpsMaxSmemPoints) return fps_launch_t<1024, 18, false>(xyz, B, N, npoint, flags, idx, stream);
+  fps_generic_kernel<<<B, 1024, 0, stream>>>(xyz, N, npoint, flags, static_cast<float*>(workspace), idx);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ---- gathers -----------------------------------------------------------------------------------------------
+// out[b,c,j] = features[b,c,idx[b,j]]
+__global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx,
+                                                     int C, int N, int m, float* __restrict__ out, long long total) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(t % m);
+    const long long bc = t / m;
+    const int b = (int)(bc / C);
+    out[t] = __ldg(feat + bc * N + __ldg(idx + (size_t)b * m + j));
+  }
+}
+
+// out[b,j,:] = xyz[b,idx[b,j],:]   (utils.misc.fps without the transposes)
+__global__ void __launch_bounds__(256) gather_xyz_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
+                                                         int N, int m, float* __restrict__ out, long long total) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % 3);
+    const long long bj = t / 3;
+    const int b = (int)(bj / m);
+    out[t] = __ldg(xyz + ((size_t)b * N + __ldg(idx + bj)) * 3 + c);
+  }
+}
+
+// grad_features[b,c,n] = sum_{j asc : idx[b,j]==n} grad_out[b,c,j].  Owner-computes (one thread per (b,n)),
+// deterministic, every output written exactly once.  idx[b,:] is staged in shared memory.
+__global__ void __launch_bounds__(256) gather_grad_kernel(const float* __restrict__ gout, const int32_t* __restrict__ idx,
+                                                          int C, int N, int m, float* __restrict__ gfeat) {
+  extern __shared__ int sidx[];
+  const int b = blockIdx.y;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) sidx[j] = __ldg(idx + (size_t)b * m + j);
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int first[4];
+  int cnt = 0;
+  for (int j = 0; j < m; ++j) {
+    if (sidx[j] == n) {
+      if (cnt < 4) first[cnt] = j;
+      ++cnt;
+    }
+  }
+  for (int c = 0; c < C; ++c) {
+    const float* g = gout + ((size_t)b * C + c) * m;
+    float v = 0.f;
+    if (cnt <= 4) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < cnt) v = __fadd_rn(v, __ldg(g + first[q]));
+    } else {
+      for (int j = 0; j < m; ++j)
+        if (sidx[j] == n) v = __fadd_rn(v, __ldg(g + j));
+    }
+    gfeat[((size_t)b * C + c) * N + n] = v;
+  }
+}
+
+static inline int grid_for(long long total, int threads) {
+  long long g = (total + threads - 1) / threads;
+  if (g > 148LL * 32) g = 148LL * 32;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int gather_launch(const float* feat, const int32_t* idx, int B, int C, int N, int m, float* out, cudaStream_t stream) {
+  const long long total = (long long)B * C * m;
+  gather_kernel<<<grid_for(total, 256), 256, 0, stream>>>(feat, idx, C, N, m, out, total);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int gather_xyz_launch(const float* xyz, const int32_t* idx, int B, int N, int m, float* out, cudaStream_t stream) {
+  const long long total = (long long)B * m * 3;
+  gather_xyz_kernel<<<grid_for(total, 256), 256, 0, stream>>>(xyz, idx, N, m, out, total);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int gather_grad_launch(const float* gout, const int32_t* idx, int B, int C, int N, int m, float* gfeat,
+                       cudaStream_t stream) {
+  dim3 grid((N + 255) / 256, B);
+  const size_t smem = sizeof(int) * (size_t)m;
+  if (smem > 48 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(gather_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      configured = true;
+    }
+  }
+  gather_grad_kernel<<<grid, 256, smem, stream>>>(gout, idx, C, N, m, gfeat);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace iapt

@@ -1,0 +1,51 @@
+"""Register the B200 implementations under the module names the reference imports.
+
+After ``imgadapointr_b200.dropin.install()``:
+    import chamfer                                  -> imgadapointr_b200.chamfer
+    from pointnet2_ops import pointnet2_utils       -> imgadapointr_b200.pointnet2_ops.pointnet2_utils
+    from extensions.chamfer_dist import ...         -> imgadapointr_b200.extensions.chamfer_dist   (optional)
+and ``patch_reference_modules()`` swaps ``knn_point`` / ``fps`` / ``Metrics`` inside already-imported reference modules
+(models.Transformer_utils, models.base_blocks, utils.misc, utils.metrics, ...), which is needed because the reference
+star-imports ``knn_point`` into every model module (models/base_blocks.py:9, models/external/AdaPoinTr.py:14).
+"""
+from __future__ import annotations
+
+import sys
+
+
+def install(override_extensions: bool = True) -> None:
+    from . import chamfer, pointnet2_ops
+    from .extensions import chamfer_dist
+    from .pointnet2_ops import pointnet2_utils
+
+    sys.modules["chamfer"] = chamfer
+    sys.modules["pointnet2_ops"] = pointnet2_ops
+    sys.modules["pointnet2_ops.pointnet2_utils"] = pointnet2_utils
+    if override_extensions:
+        sys.modules["extensions.chamfer_dist"] = chamfer_dist
+        ext = sys.modules.get("extensions")
+        if ext is not None:
+            setattr(ext, "chamfer_dist", chamfer_dist)
+
+
+def patch_reference_modules() -> list:
+    """Replace knn_point / fps / Metrics in every loaded reference module that holds them. Returns what was patched."""
+    from .models import Transformer_utils as tu
+    from .utils import metrics as m
+    from .utils import misc
+
+    patched = []
+    for name, mod in list(sys.modules.items()):
+        if mod is None or name.startswith("imgadapointr_b200"):
+            continue
+        root = name.split(".")[0]
+        if root not in ("models", "utils", "tools", "extensions", "datasets"):
+            continue
+        for attr, new in (("knn_point", tu.knn_point), ("fps", misc.fps), ("Metrics", m.Metrics)):
+            old = getattr(mod, attr, None)
+            if old is not None and old is not new and callable(old):
+                if attr == "fps" and not name.endswith("misc") and getattr(old, "__module__", "") != "utils.misc":
+                    continue
+                setattr(mod, attr, new)
+                patched.append(f"{name}.{attr}")
+    return patched

@@ -1,0 +1,232 @@
+"""Drop-in for the reference's ``utils/metrics.py`` (``Metrics``, :15-165) on the B200 path.
+
+``Metrics.get(pred, gt, require_emd=False) -> [F-Score, CDL1, CDL2, EMDistance]`` keeps the reference's item list,
+scaling (x1000) and ``ignore_zeros=True`` behaviour, but F-Score, CD-L1 and CD-L2 all come from ONE
+nearest-neighbour search (the reference runs 2 Chamfer searches plus two open3d KD-tree passes on the CPU,
+utils/metrics.py:67-109):
+  * F-Score@th: precision = mean(sqrt(dist1) < th), recall = mean(sqrt(dist2) < th), F = 2pr/(p+r) (0 if p+r == 0),
+    averaged over the batch (metrics.py:67-90).  The reference measures distances in float64 with open3d; here they
+    are FP32, so a point within ~1e-7 of the threshold may be classified differently (tolerance in tests).
+  * EMDistance is outside the accelerated path: a zero tensor unless ``require_emd`` and the reference's
+    ``extensions.emd`` package is importable.
+``MetricAccumulator`` adds what the reference leaves unimplemented (distributed test, runner.py:474-475):
+per-category sums that shard over ranks and reduce with one all-reduce.
+"""
+from __future__ import annotations
+
+import logging
+
+import torch
+
+from .. import chamfer
+from ..extensions.chamfer_dist import ChamferDistanceL1, ChamferDistanceL2
+from . import dist_utils
+
+
+def _search(pred, gt):
+    with torch.no_grad():
+        dist1, dist2, _, _ = chamfer.forward(pred, gt)
+    return dist1, dist2
+
+
+def _cd_from_sums(sums, N, M):
+    """sums [B,4] -> (CDL1, CDL2) 0-dim tensors with the reference's reductions over ALL B*N / B*M elements."""
+    B = sums.size(0)
+    tot = sums.sum(dim=0)
+    cdl2 = tot[0] / (B * N) + tot[1] / (B * M)
+    cdl1 = (tot[2] / (B * N) + tot[3] / (B * M)) / 2
+    return cdl1, cdl2
+
+
+def _f_from_counts(counts, N, M):
+    """counts [B,2] -> mean over the batch of per-cloud F (metrics.py:67-90)."""
+    precision = counts[:, 0].to(torch.float64) / float(N)
+    recall = counts[:, 1].to(torch.float64) / float(M)
+    s = precision + recall
+    f = torch.where(s > 0, 2 * recall * precision / torch.where(s > 0, s, torch.ones_like(s)), torch.zeros_like(s))
+    return f.mean().to(torch.float32)
+
+
+class Metrics(object):
+    ITEMS = [{
+        'name': 'F-Score',
+        'enabled': True,
+        'eval_func': 'cls._get_f_score',
+        'is_greater_better': True,
+        'init_value': 0
+    }, {
+        'name': 'CDL1',
+        'enabled': True,
+        'eval_func': 'cls._get_chamfer_distancel1',
+        'eval_object': ChamferDistanceL1(ignore_zeros=True),
+        'is_greater_better': False,
+        'init_value': 32767
+    }, {
+        'name': 'CDL2',
+        'enabled': True,
+        'eval_func': 'cls._get_chamfer_distancel2',
+        'eval_object': ChamferDistanceL2(ignore_zeros=True),
+        'is_greater_better': False,
+        'init_value': 32767
+    }, {
+        'name': 'EMDistance',
+        'enabled': True,
+        'eval_func': 'cls._get_emd_distance',
+        'eval_object': None,
+        'is_greater_better': False,
+        'init_value': 32767
+    }]
+
+    _emd_warned = False
+
+    @classmethod
+    def get(cls, pred, gt, require_emd=False, th=0.01):
+        """One search -> [F-Score, CDL1, CDL2, EMDistance] (0-dim tensors on gt.device), enabled items only."""
+        values = cls.get_dict(pred, gt, require_emd=require_emd, th=th)
+        return [values[item['name']] for item in cls.items()]
+
+    @classmethod
+    def get_dict(cls, pred, gt, require_emd=False, th=0.01):
+        assert pred.size(0) == gt.size(0)
+        B, N, _ = pred.shape
+        M = gt.size(1)
+        dist1, dist2 = _search(pred, gt)
+        f = _f_from_counts(chamfer.fscore_counts(dist1, dist2, th), N, M)
+        filtered = False
+        if B == 1:  # ignore_zeros=True only acts for batch size 1 (chamfer_dist/__init__.py:36-41)
+            nz1 = torch.sum(pred, dim=2).ne(0)
+            nz2 = torch.sum(gt, dim=2).ne(0)
+            filtered = not bool(torch.logical_and(nz1.all(), nz2.all()))
+        if filtered:
+            p2, g2 = pred[nz1].unsqueeze(0), gt[nz2].unsqueeze(0)
+            d1, d2 = _search(p2, g2)
+            cdl1, cdl2 = _cd_from_sums(chamfer.reduce_sums(d1, d2), p2.size(1), g2.size(1))
+        else:
+            cdl1, cdl2 = _cd_from_sums(chamfer.reduce_sums(dist1, dist2), N, M)
+        out = {'F-Score': f.to(gt.device), 'CDL1': cdl1 * 1000, 'CDL2': cdl2 * 1000}
+        out['EMDistance'] = cls._get_emd_distance(pred, gt) if require_emd else torch.tensor(0.).to(gt.device)
+        return out
+
+    @classmethod
+    def items(cls):
+        return [i for i in cls.ITEMS if i['enabled']]
+
+    @classmethod
+    def names(cls):
+        return [i['name'] for i in cls.items()]
+
+    @classmethod
+    def _get_f_score(cls, pred, gt, th=0.01):
+        B, N, _ = pred.shape
+        dist1, dist2 = _search(pred, gt)
+        return _f_from_counts(chamfer.fscore_counts(dist1, dist2, th), N, gt.size(1)).to(pred.device)
+
+    @classmethod
+    def _get_chamfer_distancel1(cls, pred, gt):
+        return cls.ITEMS[1]['eval_object'](pred, gt) * 1000
+
+    @classmethod
+    def _get_chamfer_distancel2(cls, pred, gt):
+        return cls.ITEMS[2]['eval_object'](pred, gt) * 1000
+
+    @classmethod
+    def _get_emd_distance(cls, pred, gt, eps=0.005, iterations=100):
+        try:  # the reference's own auction-EMD extension, if the user has built it (out of scope here)
+            from extensions.emd import emd_module as emd  # type: ignore
+        except Exception:
+            if not cls._emd_warned:
+                logging.warning('EMDistance requested but the reference extensions.emd is not importable; '
+                                'returning 0 (EMD is outside the accelerated hot path)')
+                cls._emd_warned = True
+            return torch.tensor(0.).to(gt.device)
+        dist, _ = emd.emdModule()(pred, gt, eps, iterations)
+        return torch.mean(torch.sqrt(dist)) * 1000
+
+    def __init__(self, metric_name, values):
+        self._items = Metrics.items()
+        self._values = [item['init_value'] for item in self._items]
+        self.metric_name = metric_name
+
+        if isinstance(values, list):
+            self._values = values
+        elif isinstance(values, dict):
+            metric_indexes = {item['name']: idx for idx, item in enumerate(self._items)}
+            for k, v in values.items():
+                if k not in metric_indexes:
+                    logging.warning('Ignore Metric[Name=%s] due to disability.' % k)
+                    continue
+                self._values[metric_indexes[k]] = v
+        else:
+            raise Exception('Unsupported value type: %s' % type(values))
+
+    def state_dict(self):
+        return {self._items[i]['name']: self._values[i] for i in range(len(self._items))}
+
+    def __repr__(self):
+        return str(self.state_dict())
+
+    def better_than(self, other):
+        if other is None:
+            return True
+        _index = -1
+        for i, _item in enumerate(self._items):
+            if _item['name'] == self.metric_name:
+                _index = i
+                break
+        if _index == -1:
+            raise Exception('Invalid metric name to compare.')
+        _metric = self._items[_index]
+        _value = self._values[_index]
+        other_value = other._values[_index]
+        return _value > other_value if _metric['is_greater_better'] else _value < other_value
+
+
+class MetricAccumulator:
+    """Per-category running sums of [F-Score, CDL1, CDL2] for a (possibly rank-sharded) test sweep.
+
+    Mirrors tools/runner.py:562-564,676-678: per-cloud metrics are averaged inside each category, then the
+    categories are macro-averaged.  Each rank adds the clouds of its shard; ``reduce()`` performs the path's single
+    collective - an all-reduce of the [n_categories, 4] (sum F, sum CDL1, sum CDL2, count) matrix.
+    """
+
+    def __init__(self, n_categories: int, device):
+        self.table = torch.zeros((n_categories, 4), dtype=torch.float64, device=device)
+
+    def update(self, category: int, f, cdl1, cdl2):
+        row = torch.stack([f.double(), cdl1.double(), cdl2.double(), torch.ones((), dtype=torch.float64, device=f.device)])
+        self.table[category] += row.to(self.table.device)
+
+    def update_batch(self, categories: torch.Tensor, f, cdl1, cdl2):
+        """categories int64 [b]; f / cdl1 / cdl2 per-cloud [b] tensors."""
+        rows = torch.stack([f.double(), cdl1.double(), cdl2.double(), torch.ones_like(f, dtype=torch.float64)], dim=1)
+        self.table.index_add_(0, categories.to(self.table.device), rows.to(self.table.device))
+
+    def reduce(self):
+        self.table = dist_utils.allreduce_sums(self.table)
+        return self
+
+    def per_category(self):
+        cnt = self.table[:, 3:4].clamp_min(1)
+        return self.table[:, :3] / cnt
+
+    def overall(self):
+        """Macro average over the categories that hold at least one cloud (runner.py:676-678)."""
+        have = self.table[:, 3] > 0
+        return self.per_category()[have].mean(dim=0)
+
+
+def per_cloud_metrics(pred, gt, th=0.01):
+    """Batched per-cloud (F, CDL1*1000, CDL2*1000) from one search - the kernel-side unit of the C4 metric sweep.
+    Equals ``Metrics.get`` called cloud by cloud when no point has a zero coordinate sum."""
+    B, N, _ = pred.shape
+    M = gt.size(1)
+    dist1, dist2 = _search(pred, gt)
+    sums = chamfer.reduce_sums(dist1, dist2)
+    counts = chamfer.fscore_counts(dist1, dist2, th)
+    precision = counts[:, 0].to(torch.float64) / float(N)
+    recall = counts[:, 1].to(torch.float64) / float(M)
+    s = precision + recall
+    f = torch.where(s > 0, 2 * recall * precision / torch.where(s > 0, s, torch.ones_like(s)), torch.zeros_like(s))
+    cdl2 = (sums[:, 0] / N + sums[:, 1] / M) * 1000
+    cdl1 = (sums[:, 2] / N + sums[:, 3] / M) / 2 * 1000
+    return f.to(torch.float32), cdl1, cdl2

@@ -1,0 +1,114 @@
+/*
+ * iapt_b200.h - C ABI of libiapt_b200.so: hand-written sm_100a kernels for ImgAdaPoinTr's point-cloud
+ * geometry hot path (Chamfer nearest-neighbour search fwd/bwd, furthest-point sampling, gather, kNN).
+ *
+ * This header is the drop-in boundary.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference repo root); INTEGRATION.md shows the reference-side bindings.
+ *
+ * Conventions (all entry points)
+ *   - plain C types only: device pointers, sizes and a stream; no torch / C++ types cross the boundary;
+ *   - every pointer is a DEVICE pointer to contiguous row-major memory on the current CUDA device unless the
+ *     name ends in `_host`; float = IEEE binary32, indices int32 (int64 for kNN, as the reference returns);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); work is enqueued, not synchronised;
+ *   - return value: 0 on success, a positive cudaError_t value for CUDA failures, a negative IAPT_E* code for
+ *     argument errors (the reference printf()s CUDA errors and continues, chamfer.cu:166-169 - we return them);
+ *     iapt_error_string() describes any of them;
+ *   - workspaces are caller-allocated (so a framework's caching allocator owns all memory); the *_workspace_bytes
+ *     functions are pure host arithmetic and never touch the GPU.
+ */
+#ifndef IAPT_B200_H_
+#define IAPT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IAPT_ABI_VERSION 1
+
+#define IAPT_EINVAL (-1)     /* bad size / null pointer */
+#define IAPT_EWORKSPACE (-2) /* workspace too small */
+#define IAPT_EUNSUPPORTED (-3)
+
+typedef void* iapt_stream_t; /* cudaStream_t */
+
+int iapt_abi_version(void);
+const char* iapt_error_string(int code);
+/* Number of kernels launched through this library by the calling process so far (bench.py's gpu_launches). */
+unsigned long long iapt_launch_count(void);
+
+/* ---- Chamfer nearest-neighbour search --------------------------------------------------------------------
+ * Replaces chamfer.forward -> chamfer_cuda_forward (extensions/chamfer_dist/chamfer_cuda.cpp:22-25,
+ * chamfer.cu:147-171; kernel chamfer.cu:15-145).
+ *   xyz1 [B,N,3], xyz2 [B,M,3]  ->  dist1 [B,N] = min_k |xyz1[b,j]-xyz2[b,k]|^2, idx1 [B,N] = lowest argmin k,
+ *                                   dist2 [B,M], idx2 [B,M] with the roles swapped.
+ * Arithmetic: d = fma(dz,dz, fma(dx,dx, dy*dy)) in FP32 - bit-identical to the reference kernel as compiled by
+ * nvcc 12.9 - so dist AND idx match the reference bit for bit (lowest index on exact ties, chamfer.cu:47-50,137-140).
+ * N == 0 or M == 0 leaves zero-filled outputs like the reference's torch::zeros.  Coordinates must be finite
+ * with |x| < 1e15 (NaN/Inf are outside the reference's contract as well).
+ * Either output pair may be NULL (dist1/idx1 or dist2/idx2) to skip that direction's final write-out. */
+size_t iapt_chamfer_forward_workspace_bytes(int B, int N, int M);
+int iapt_chamfer_forward(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1, float* dist2,
+                         int32_t* idx1, int32_t* idx2, void* workspace, size_t workspace_bytes,
+                         iapt_stream_t stream);
+
+/* Replaces chamfer.backward -> chamfer_cuda_backward (chamfer_cuda.cpp:27-34, chamfer.cu:203-229; kernel :173-201).
+ *   grad_xyz1[b,j] = 2 g1[b,j] (x1_j - x2_idx1[j]) - sum_{k: idx2[k]==j} 2 g2[b,k] (x2_k - x1_j), and symmetrically
+ *   for grad_xyz2.  Deterministic and free of floating-point atomics: every output point is owned by one warp
+ *   that adds its fan-in in ascending source index.  Outputs are fully written (no pre-zeroing needed). */
+int iapt_chamfer_backward(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
+                          const float* grad_dist1, const float* grad_dist2, int B, int N, int M, float* grad_xyz1,
+                          float* grad_xyz2, iapt_stream_t stream);
+
+/* Fused loss epilogue for ChamferDistanceL1 / L2 / L2_split / L1_PM (extensions/chamfer_dist/__init__.py:28-103):
+ * from dist1/dist2 computes, per cloud b, sums[b] = { sum_j dist1, sum_k dist2, sum_j sqrt(dist1), sum_k sqrt(dist2) }
+ * (FP32 sums in a fixed order -> deterministic) so the host forms mean(.) without extra elementwise launches.
+ * sums is [B,4] float. */
+int iapt_chamfer_reduce(const float* dist1, const float* dist2, int B, int N, int M, float* sums,
+                        iapt_stream_t stream);
+
+/* F-Score pieces (utils/metrics.py:67-90) from the same search: counts[b] = { #{j: sqrt(dist1[b,j]) < th},
+ * #{k: sqrt(dist2[b,k]) < th} } as int32 [B,2]. */
+int iapt_fscore_counts(const float* dist1, const float* dist2, int B, int N, int M, float th, int32_t* counts,
+                       iapt_stream_t stream);
+
+/* ---- Furthest point sampling -----------------------------------------------------------------------------
+ * Replaces pointnet2_ops.pointnet2_utils.furthest_point_sample -> _ext.furthest_point_sampling
+ * (third-party pointnet2_ops_lib, not vendored in the reference; call sites utils/misc.py:37,
+ * models/base_blocks.py:550).   xyz [B,N,3] -> idx [B,npoint] int32.
+ * Semantics: start at index 0, running min distance initialised to 1e10, d = fma(dz,dz,fma(dx,dx,dy*dy)),
+ * next = argmax with the LOWEST index on ties; flag IAPT_FPS_SKIP_NEAR_ORIGIN reproduces upstream's
+ * `if (|p|^2 <= 1e-3) continue;` (points that are never updated nor selected - PCN zero padding). */
+#define IAPT_FPS_SKIP_NEAR_ORIGIN 1
+size_t iapt_fps_workspace_bytes(int B, int N, int npoint);
+int iapt_fps(const float* xyz, int B, int N, int npoint, int flags, int32_t* idx, void* workspace,
+             size_t workspace_bytes, iapt_stream_t stream);
+
+/* Replaces pointnet2_utils.gather_operation -> _ext.gather_points / gather_points_grad
+ * (call sites utils/misc.py:38, models/base_blocks.py:555-558).
+ *   features [B,C,N], idx [B,npoint] -> out [B,C,npoint];  grad: grad_out [B,C,npoint] -> grad_features [B,C,N]
+ *   (fully written, deterministic: one owner per output element, ascending source order). */
+int iapt_gather(const float* features, const int32_t* idx, int B, int C, int N, int npoint, float* out,
+                iapt_stream_t stream);
+int iapt_gather_grad(const float* grad_out, const int32_t* idx, int B, int C, int N, int npoint,
+                     float* grad_features, iapt_stream_t stream);
+/* utils.misc.fps fused (utils/misc.py:32-40): xyz [B,N,3], idx [B,npoint] -> out [B,npoint,3] without the two
+ * transpose().contiguous() copies the reference makes around gather_operation. */
+int iapt_gather_xyz(const float* xyz, const int32_t* idx, int B, int N, int npoint, float* out,
+                    iapt_stream_t stream);
+
+/* ---- kNN grouping ----------------------------------------------------------------------------------------
+ * Replaces models/Transformer_utils.py:19-30 knn_point(nsample, xyz, new_xyz) (= square_distance :32-51 +
+ * torch.topk(largest=False, sorted=False)) without materialising the [B,Q,R] matrix.
+ *   ref [B,R,3], query [B,Q,3] -> idx [B,Q,k] int64 ascending by (distance, index); dist [B,Q,k] optional (NULL).
+ * 1 <= k <= 64 and k <= R. */
+#define IAPT_KNN_MAX_K 64
+int iapt_knn(const float* ref, const float* query, int B, int R, int Q, int k, int64_t* idx, float* dist,
+             iapt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IAPT_B200_H_ */

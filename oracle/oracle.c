@@ -1,0 +1,382 @@
+/*
+ * oracle.c - CPU restatement of the reference's point-cloud geometry hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under imgadapointr_b200/ may import, link or call this file;
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it,
+ * and only as the checker.  The product path is the CUDA library and fails loudly without it.
+ *
+ * Every function cites the reference lines it follows (paths relative to /root/reference):
+ *   chamfer forward  : extensions/chamfer_dist/chamfer.cu:15-145 (values :42-45, tie rule :47-50,:137-140)
+ *   chamfer backward : extensions/chamfer_dist/chamfer.cu:173-201
+ *   FPS              : call contract utils/misc.py:32-40, models/base_blocks.py:547-563; the arithmetic is
+ *                      pointnet2_ops (erikwijmans/Pointnet2_PyTorch pointnet2_ops_lib 3.0.0,
+ *                      _ext-src/src/sampling_gpu.cu, furthest_point_sampling_kernel) - a third-party
+ *                      dependency that is NOT vendored under /root/reference and pinned nowhere
+ *                       => FPS parity is "unpinned": restated from the published algorithm.
+ *   gather           : utils/misc.py:38, models/base_blocks.py:552-558 (pointnet2_ops gather_points_kernel)
+ *   kNN              : models/Transformer_utils.py:19-51 (selection restated with an explicit
+ *                      (distance, index) order because torch.topk(sorted=False) defines none)
+ *   F-Score          : utils/metrics.py:67-90
+ *
+ * Rounding: the reference kernel's `x2*x2 + y2*y2 + z2*z2` is contracted by nvcc 12.9 for sm_100a to
+ * fma(dz,dz, fma(dx,dx, dy*dy)) (checked with cuobjdump -sass); sqdist_f32() below
+ * reproduces exactly that with fmaf, so distances and therefore argmins are bit-comparable.
+ *
+ * Pinning status: chamfer forward/backward are pinned against the reference's own compiled kernel
+ * (oracle/_ref/chamfer*.so run on the B200 box, tests/test_gpu_parity_reference_so.py) and against the
+ * reference's one test (float64 gradcheck, extensions/chamfer_dist/test.py:23-29, restated in
+ * tests/test_oracle.py).  FPS / gather / kNN / F-Score: PARITY UNPINNED (the reference holds no golden
+ * vectors or tests for them and pointnet2_ops / open3d are absent); kNN is additionally checked against
+ * the verbatim torch formulation on exactly-representable inputs.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+
+#include <pthread.h>
+#include <unistd.h>
+
+/* Minimal parallel-for on pthreads (this image's gcc has no libgomp): work items are handed out through an
+ * atomic counter; every item writes disjoint outputs, so results do not depend on the thread count. */
+typedef void (*item_fn)(int item, void *ctx);
+typedef struct {
+  item_fn fn;
+  void *ctx;
+  int n;
+  int next;
+} pf_t;
+
+static void *pf_worker(void *arg) {
+  pf_t *p = (pf_t *)arg;
+  for (;;) {
+    int i = __atomic_fetch_add(&p->next, 1, __ATOMIC_RELAXED);
+    if (i >= p->n) break;
+    p->fn(i, p->ctx);
+  }
+  return NULL;
+}
+
+static int g_threads = 0;
+
+int oracle_num_threads(void) {
+  if (g_threads > 0) return g_threads;
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  const char *e = getenv("ORACLE_NUM_THREADS");
+  if (e && atoi(e) > 0) n = atoi(e);
+  if (n < 1) n = 1;
+  if (n > 256) n = 256;
+  return (int)n;
+}
+
+void oracle_set_num_threads(int n) { g_threads = n; }
+
+static void parallel_for(int n, item_fn fn, void *ctx) {
+  int nt = oracle_num_threads();
+  if (nt > n) nt = n;
+  pf_t p = {fn, ctx, n, 0};
+  if (nt <= 1) {
+    pf_worker(&p);
+    return;
+  }
+  pthread_t th[256];
+  int started = 0;
+  for (int t = 0; t < nt - 1; ++t)
+    if (pthread_create(&th[started], NULL, pf_worker, &p) == 0) started++;
+  pf_worker(&p);
+  for (int t = 0; t < started; ++t) pthread_join(th[t], NULL);
+}
+
+/* chamfer.cu:42-45 as compiled (see header): d = fma(dz,dz, fma(dx,dx, dy*dy)), differences = ref - query. */
+static inline float sqdist_f32(const float *q, const float *r) {
+  float dx = r[0] - q[0];
+  float dy = r[1] - q[1];
+  float dz = r[2] - q[2];
+  float t = dy * dy;
+  t = fmaf(dx, dx, t);
+  t = fmaf(dz, dz, t);
+  return t;
+}
+
+/* One direction of chamfer.cu:15-145: for each query j the minimum squared distance over the m points of
+ * `refs` and the LOWEST index attaining it (strict `<` inside a tile :47-50, strict `>` across tiles :137-140).
+ * m == 0 leaves the zero-initialised outputs untouched (torch::zeros, chamfer.cu:152-157). */
+static void nn_one_direction(const float *qry, int n, const float *refs, int m, float *dist, int32_t *idx) {
+  for (int j = 0; j < n; ++j) {
+    float best = 0.f;
+    int32_t besti = 0;
+    for (int k = 0; k < m; ++k) {
+      float d = sqdist_f32(qry + 3 * (size_t)j, refs + 3 * (size_t)k);
+      if (k == 0 || d < best) {
+        best = d;
+        besti = k;
+      }
+    }
+    dist[j] = best;
+    idx[j] = besti;
+  }
+}
+
+/* Work item = one slab of CF_SLAB queries of one cloud in one direction (queries are independent). */
+#define CF_SLAB 256
+typedef struct {
+  const float *xyz1, *xyz2;
+  int N, M;
+  float *dist1, *dist2;
+  int32_t *idx1, *idx2;
+  int slabs1, slabs2;
+} cf_ctx;
+
+static void cf_item(int item, void *vctx) {
+  cf_ctx *c = (cf_ctx *)vctx;
+  int per = c->slabs1 + c->slabs2;
+  int b = item / per, s = item % per;
+  const float *a = c->xyz1 + (size_t)b * c->N * 3;
+  const float *g = c->xyz2 + (size_t)b * c->M * 3;
+  if (s < c->slabs1) {
+    int j0 = s * CF_SLAB, n = c->N - j0 < CF_SLAB ? c->N - j0 : CF_SLAB;
+    nn_one_direction(a + 3 * (size_t)j0, n, g, c->M, c->dist1 + (size_t)b * c->N + j0, c->idx1 + (size_t)b * c->N + j0);
+  } else {
+    int j0 = (s - c->slabs1) * CF_SLAB, n = c->M - j0 < CF_SLAB ? c->M - j0 : CF_SLAB;
+    nn_one_direction(g + 3 * (size_t)j0, n, a, c->N, c->dist2 + (size_t)b * c->M + j0, c->idx2 + (size_t)b * c->M + j0);
+  }
+}
+
+/* chamfer_cuda_forward, chamfer.cu:147-171. */
+void oracle_chamfer_forward(const float *xyz1, const float *xyz2, int B, int N, int M, float *dist1, float *dist2,
+                            int32_t *idx1, int32_t *idx2) {
+  memset(dist1, 0, sizeof(float) * (size_t)B * N);
+  memset(dist2, 0, sizeof(float) * (size_t)B * M);
+  memset(idx1, 0, sizeof(int32_t) * (size_t)B * N);
+  memset(idx2, 0, sizeof(int32_t) * (size_t)B * M);
+  cf_ctx c = {xyz1, xyz2, N, M, dist1, dist2, idx1, idx2, 0, 0};
+  int n_items = 0;
+  for (int b = 0; b < B; ++b) n_items += (N + CF_SLAB - 1) / CF_SLAB + (M + CF_SLAB - 1) / CF_SLAB;
+  c.slabs1 = (N + CF_SLAB - 1) / CF_SLAB;
+  c.slabs2 = (M + CF_SLAB - 1) / CF_SLAB;
+  parallel_for(n_items, cf_item, &c);
+}
+
+/* chamfer_cuda_backward, chamfer.cu:173-229.  The reference accumulates with float atomicAdd in an
+ * unspecified order; the oracle accumulates in float64 and rounds once, which every order matches to
+ * well under the 1e-5 relative tolerance of the parity contract. */
+void oracle_chamfer_backward(const float *xyz1, const float *xyz2, const int32_t *idx1, const int32_t *idx2,
+                             const float *grad_dist1, const float *grad_dist2, int B, int N, int M, float *grad_xyz1,
+                             float *grad_xyz2) {
+  for (int b = 0; b < B; ++b) {
+    const float *a = xyz1 + (size_t)b * N * 3;
+    const float *c = xyz2 + (size_t)b * M * 3;
+    double *g1 = (double *)calloc((size_t)N * 3 + 1, sizeof(double));
+    double *g2 = (double *)calloc((size_t)M * 3 + 1, sizeof(double));
+    for (int j = 0; j < N && M > 0; ++j) { /* first launch, chamfer.cu:215-218 */
+      int j2 = idx1[(size_t)b * N + j];
+      float g = grad_dist1[(size_t)b * N + j] * 2;
+      for (int c3 = 0; c3 < 3; ++c3) {
+        float v = g * (a[3 * j + c3] - c[3 * j2 + c3]);
+        g1[3 * j + c3] += v;
+        g2[3 * j2 + c3] -= v;
+      }
+    }
+    for (int k = 0; k < M && N > 0; ++k) { /* second launch with roles swapped, chamfer.cu:219-222 */
+      int k2 = idx2[(size_t)b * M + k];
+      float g = grad_dist2[(size_t)b * M + k] * 2;
+      for (int c3 = 0; c3 < 3; ++c3) {
+        float v = g * (c[3 * k + c3] - a[3 * k2 + c3]);
+        g2[3 * k + c3] += v;
+        g1[3 * k2 + c3] -= v;
+      }
+    }
+    for (size_t i = 0; i < (size_t)N * 3; ++i) grad_xyz1[(size_t)b * N * 3 + i] = (float)g1[i];
+    for (size_t i = 0; i < (size_t)M * 3; ++i) grad_xyz2[(size_t)b * M * 3 + i] = (float)g2[i];
+    free(g1);
+    free(g2);
+  }
+}
+
+/* Furthest point sampling (pointnet2_ops furthest_point_sampling_kernel, restated; see header).
+ *   start at index 0; temp[k] = 1e10; each round: for every point k with |p_k|^2 > 1e-3 (when skip_near_origin)
+ *   d = |p_k - p_old|^2, temp[k] = min(temp[k], d); next = argmax_k temp[k].
+ * Tie rule (ours, documented): the LOWEST index among equal maxima.  (Upstream keeps the lowest
+ * (k mod blockDim, k) - it differs only on exact ties of the running minimum, e.g. duplicated points,
+ * where the selected coordinates are identical anyway.)  If no point is eligible the result is index 0.
+ * The `mag <= 1e-3` test compares the float magnitude against the DOUBLE literal, as upstream's C does. */
+typedef struct {
+  const float *xyz;
+  int N, npoint, skip;
+  int32_t *idx;
+} fps_ctx;
+
+static void fps_item(int b, void *vctx) {
+  fps_ctx *c = (fps_ctx *)vctx;
+  const float *xyz = c->xyz;
+  int N = c->N, npoint = c->npoint, skip_near_origin = c->skip;
+  int32_t *idx = c->idx;
+  {
+    const float *p = xyz + (size_t)b * N * 3;
+    int32_t *out = idx + (size_t)b * npoint;
+    if (npoint <= 0) return;
+    float *temp = (float *)malloc(sizeof(float) * (size_t)(N > 0 ? N : 1));
+    for (int k = 0; k < N; ++k) temp[k] = 1e10f;
+    int old = 0;
+    out[0] = 0;
+    for (int j = 1; j < npoint; ++j) {
+      int besti = 0;
+      float best = -1.f;
+      for (int k = 0; k < N; ++k) {
+        const float *pk = p + 3 * (size_t)k;
+        if (skip_near_origin) {
+          float mag = fmaf(pk[2], pk[2], fmaf(pk[0], pk[0], pk[1] * pk[1]));
+          if ((double)mag <= 1e-3) continue;
+        }
+        float d = sqdist_f32(p + 3 * (size_t)old, pk);
+        float d2 = d < temp[k] ? d : temp[k];
+        temp[k] = d2;
+        if (d2 > best) {
+          best = d2;
+          besti = k;
+        }
+      }
+      old = besti;
+      out[j] = old;
+    }
+    free(temp);
+  }
+}
+
+void oracle_fps(const float *xyz, int B, int N, int npoint, int skip_near_origin, int32_t *idx) {
+  fps_ctx c = {xyz, N, npoint, skip_near_origin, idx};
+  parallel_for(B, fps_item, &c);
+}
+
+/* gather_operation forward (pointnet2_ops gather_points_kernel): out[b,c,j] = features[b,c,idx[b,j]]. */
+void oracle_gather(const float *features, const int32_t *idx, int B, int C, int N, int npoint, float *out) {
+  for (int b = 0; b < B; ++b)
+    for (int c = 0; c < C; ++c)
+      for (int j = 0; j < npoint; ++j)
+        out[((size_t)b * C + c) * npoint + j] = features[((size_t)b * C + c) * N + idx[(size_t)b * npoint + j]];
+}
+
+/* gather_operation backward (gather_points_grad_kernel): grad_features[b,c,idx[b,j]] += grad_out[b,c,j]
+ * (float64 accumulation, rounded once; upstream uses float atomicAdd in unspecified order). */
+void oracle_gather_grad(const float *grad_out, const int32_t *idx, int B, int C, int N, int npoint,
+                        float *grad_features) {
+  double *acc = (double *)malloc(sizeof(double) * (size_t)(N > 0 ? N : 1));
+  for (int b = 0; b < B; ++b)
+    for (int c = 0; c < C; ++c) {
+      for (int k = 0; k < N; ++k) acc[k] = 0.0;
+      for (int j = 0; j < npoint; ++j) acc[idx[(size_t)b * npoint + j]] += grad_out[((size_t)b * C + c) * npoint + j];
+      for (int k = 0; k < N; ++k) grad_features[((size_t)b * C + c) * N + k] = (float)acc[k];
+    }
+  free(acc);
+}
+
+typedef struct {
+  double d;
+  int32_t i;
+} cand_t;
+
+static int cand_cmp(const void *a, const void *b) {
+  const cand_t *x = (const cand_t *)a, *y = (const cand_t *)b;
+  if (x->d < y->d) return -1;
+  if (x->d > y->d) return 1;
+  return (x->i > y->i) - (x->i < y->i);
+}
+
+/* kNN (models/Transformer_utils.py:19-30): the k references with the smallest squared distance to each
+ * query, returned ascending by (distance, index) - one valid instance of topk(sorted=False), with the
+ * lowest-index rule on exact ties (torch.topk defines none).
+ *   use_f64 = 0: distances in FP32 direct form (sqdist_f32, the arithmetic our kernel uses);
+ *   use_f64 = 1: distances in float64 from the float inputs (the "true" ordering used to classify
+ *                FP32 near-ties on continuous inputs).
+ * dist_out may be NULL. */
+typedef struct {
+  const float *ref, *qry;
+  int R, Q, k, use_f64;
+  int64_t *idx;
+  float *dist_out;
+} knn_ctx;
+
+static void knn_item(int w, void *vctx) {
+  knn_ctx *kc = (knn_ctx *)vctx;
+  const float *ref = kc->ref, *qry = kc->qry;
+  int R = kc->R, Q = kc->Q, k = kc->k, use_f64 = kc->use_f64;
+  int64_t *idx = kc->idx;
+  float *dist_out = kc->dist_out;
+  {
+    int b = w / Q, s = w % Q;
+    const float *q = qry + ((size_t)b * Q + s) * 3;
+    cand_t *c = (cand_t *)malloc(sizeof(cand_t) * (size_t)(R > 0 ? R : 1));
+    for (int r = 0; r < R; ++r) {
+      const float *p = ref + ((size_t)b * R + r) * 3;
+      if (use_f64) {
+        double dx = (double)p[0] - q[0], dy = (double)p[1] - q[1], dz = (double)p[2] - q[2];
+        c[r].d = dx * dx + dy * dy + dz * dz;
+      } else {
+        c[r].d = (double)sqdist_f32(q, p);
+      }
+      c[r].i = r;
+    }
+    qsort(c, (size_t)R, sizeof(cand_t), cand_cmp);
+    for (int j = 0; j < k; ++j) {
+      idx[((size_t)b * Q + s) * k + j] = c[j].i;
+      if (dist_out) dist_out[((size_t)b * Q + s) * k + j] = (float)c[j].d;
+    }
+    free(c);
+  }
+}
+
+void oracle_knn(const float *ref, const float *qry, int B, int R, int Q, int k, int use_f64, int64_t *idx,
+                float *dist_out) {
+  knn_ctx c = {ref, qry, R, Q, k, use_f64, idx, dist_out};
+  parallel_for(B * Q, knn_item, &c);
+}
+
+/* F-Score pieces (utils/metrics.py:67-90): open3d's compute_point_cloud_distance is the float64 Euclidean
+ * nearest-neighbour distance; the metric counts distances strictly below `th`.  Returns per cloud
+ * counts[b][0] = #{pred points with NN distance to gt < th}, counts[b][1] = #{gt points ... to pred < th},
+ * and boundary[b] = number of points with |d - th| < 1e-6 (whose FP32 classification may legitimately flip). */
+typedef struct {
+  const float *pred, *gt;
+  int N, M;
+  double th;
+  int64_t *counts, *boundary2;
+} fs_ctx;
+
+static void fs_item(int w, void *vctx) {
+  fs_ctx *fc = (fs_ctx *)vctx;
+  const float *pred = fc->pred, *gt = fc->gt;
+  int N = fc->N, M = fc->M;
+  double th = fc->th;
+  int64_t *counts = fc->counts;
+  {
+    int b = w >> 1, dir = w & 1;
+    const float *a = dir == 0 ? pred + (size_t)b * N * 3 : gt + (size_t)b * M * 3;
+    const float *c = dir == 0 ? gt + (size_t)b * M * 3 : pred + (size_t)b * N * 3;
+    int na = dir == 0 ? N : M, nc = dir == 0 ? M : N;
+    int64_t cnt = 0, bnd = 0;
+    for (int j = 0; j < na; ++j) {
+      double best = DBL_MAX;
+      for (int k = 0; k < nc; ++k) {
+        double dx = (double)a[3 * j] - c[3 * k], dy = (double)a[3 * j + 1] - c[3 * k + 1],
+               dz = (double)a[3 * j + 2] - c[3 * k + 2];
+        double d = dx * dx + dy * dy + dz * dz;
+        if (d < best) best = d;
+      }
+      double e = sqrt(best);
+      if (e < th) cnt++;
+      if (fabs(e - th) < 1e-6) bnd++;
+    }
+    counts[2 * b + dir] = cnt;
+    fc->boundary2[2 * b + dir] = bnd;
+  }
+}
+
+void oracle_fscore_counts(const float *pred, const float *gt, int B, int N, int M, double th, int64_t *counts,
+                          int64_t *boundary) {
+  int64_t *b2 = (int64_t *)calloc((size_t)2 * (B > 0 ? B : 1), sizeof(int64_t));
+  fs_ctx c = {pred, gt, N, M, th, counts, b2};
+  parallel_for(2 * B, fs_item, &c);
+  for (int b = 0; b < B; ++b) boundary[b] = b2[2 * b] + b2[2 * b + 1];
+  free(b2);
+}
