@@ -22,8 +22,19 @@ def install(override_extensions: bool = True) -> None:
     sys.modules["pointnet2_ops"] = pointnet2_ops
     sys.modules["pointnet2_ops.pointnet2_utils"] = pointnet2_utils
     if override_extensions:
+        import importlib.util
+
+        from . import extensions as our_extensions
+
         sys.modules["extensions.chamfer_dist"] = chamfer_dist
         ext = sys.modules.get("extensions")
+        if ext is None:
+            try:
+                found = importlib.util.find_spec("extensions") is not None
+            except (ImportError, ValueError):
+                found = False
+            if not found:  # reference tree not on sys.path: our package stands in for the parent too
+                sys.modules["extensions"] = ext = our_extensions
         if ext is not None:
             setattr(ext, "chamfer_dist", chamfer_dist)
 
