@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py - the driver's measurement contract for the geometry hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): PCN training-loss shape -
+``ChamferDistanceL1(pred, gt)`` forward + backward with pred, gt = [48, 16384, 3] FP32 per GPU, synthetic PCN-shaped
+clouds (imgadapointr_b200.utils.synthetic.pcn_pair, seed 202 + rank).  Every cloud is independent, so ranks hold their
+own 48 clouds (weak scaling) and the only collective is one NCCL all-reduce per step of the [sum sqrt(d1), sum
+sqrt(d2), n1, n2] vector that forms the global mean loss.
+
+Metric: Chamfer-L1 fwd+bwd point-pairs/s (pairs = B*N*M summed over ranks) and its fraction of the FP32-FMA roofline
+(algorithmic FLOPs = 16*B*N*M: 8 per ordered pair, both directions - SURVEY.md section 8d; our kernel evaluates each
+unordered pair once, i.e. 8*B*N*M real FLOPs, and is still scored with the algorithmic 16).
+
+One JSON line on stdout (rank 0).  ``value`` = device-resident throughput; ``e2e`` = the same through the public
+API from pinned HOST buffers (H2D of pred+gt and D2H of the loss inside the timed region); ``roofline`` = the dominant
+kernel (chamfer_pair_kernel) timed with CUDA events on its launch stream inside the timed region;
+``cpu_baseline`` = the reference's PyTorch CPU formulation (oracle.torch_formulation) on a bounded sample.
+``--impl reference`` times that CPU formulation alone with all host threads (the reference has no CPU Chamfer of its
+own: its only implementation is the CUDA extension, which is timed on the GPU as ``ref_cuda_kernel`` in our arm).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+B_PER_GPU = 48
+N_PTS = 16384
+METRIC = "chamfer_l1_fwd_bwd_point_pairs_per_s"
+UNIT = "point-pairs/s"
+N_INPUT_SETS = 8  # 8 x 18.9 MB of inputs = 151 MB > 126 MB L2: rotating them defeats L2 reuse between steps
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # "under load": samples at >= 60 % of the max observed power
+        load = [s for s, p in zip(sm, power) if power and p >= 0.6 * max(power)] or sm
+        load.sort()
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def cpu_chamfer_l1_fwd_bwd_rate(n_clouds, threads):
+    """The reference's PyTorch CPU formulation (cdist + min + sqrt/mean + autograd backward) on `n_clouds` clouds of
+    16384 x 16384, one at a time.  Returns (pairs/s, seconds)."""
+    from imgadapointr_b200.utils import synthetic
+    from oracle import torch_formulation as tf
+
+    torch.set_num_threads(threads)
+    pred, gt = synthetic.pcn_pair(n_clouds, N_PTS, seed=202)
+    t0 = time.perf_counter()
+    for i in range(n_clouds):
+        tf.chamfer_l1_fwd_bwd(pred[i:i + 1], gt[i:i + 1])
+    dt = time.perf_counter() - t0
+    return n_clouds * N_PTS * N_PTS / dt, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU formulation with all host threads; each step = one 16384x16384 cloud fwd+bwd."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    from imgadapointr_b200.utils import synthetic
+    from oracle import torch_formulation as tf
+
+    torch.set_num_threads(threads)
+    pred, gt = synthetic.pcn_pair(1, N_PTS, seed=202)
+    for _ in range(args.warmup):
+        tf.chamfer_l1_fwd_bwd(pred, gt)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tf.chamfer_l1_fwd_bwd(pred, gt)
+    dt = time.perf_counter() - t0
+    value = args.steps * N_PTS * N_PTS / dt
+    sample = f"1 cloud of {N_PTS}x{N_PTS} per step (of the {B_PER_GPU}-cloud batch), torch.cdist+min+autograd, float32"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Chamfer-L1 fwd+bwd, B={B_PER_GPU}/GPU x {N_PTS} pred x {N_PTS} gt (BASELINE configs[1])",
+                   "reference_arm": "PyTorch CPU formulation on host cores; bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def time_ref_cuda_kernel(pred, gt, iters=3):
+    """The reference's own CUDA extension (oracle/_ref, built unmodified for sm_100a) on the same inputs: the
+    'kernel to beat'.  Returns ms per fwd+bwd or None if the .so is absent."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(ref_dir) or not any(f.startswith("chamfer") and f.endswith(".so") for f in os.listdir(ref_dir)):
+        return None
+    sys.path.insert(0, ref_dir)
+    try:
+        import chamfer as ref_chamfer  # the reference pybind module
+    except Exception:
+        return None
+    finally:
+        sys.path.pop(0)
+
+    def step():
+        d1, d2, i1, i2 = ref_chamfer.forward(pred, gt)
+        g1 = 0.25 / torch.sqrt(d1) / d1.numel()
+        g2 = 0.25 / torch.sqrt(d2) / d2.numel()
+        ref_chamfer.backward(pred, gt, i1, i2, g1, g2)
+
+    step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the reference launches on the legacy default stream; torch's current stream is the default stream here too
+    a.record()
+    for _ in range(iters):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3 if args.impl == "ours" else 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+
+    from imgadapointr_b200 import _lib, chamfer
+    from imgadapointr_b200.extensions.chamfer_dist import ChamferFunction
+    from imgadapointr_b200.utils import synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group(backend="nccl", device_id=dev)
+
+    B, N, M = B_PER_GPU, N_PTS, N_PTS
+    # ---- inputs: N_INPUT_SETS distinct (pred, gt) sets, resident in HBM; pinned host copies for the e2e leg -------
+    base_pred, base_gt = synthetic.pcn_pair(B, N, seed=202 + rank)
+    host_sets, dev_sets = [], []
+    for s in range(N_INPUT_SETS):
+        # cheap distinct sets: roll the batch and add a tiny deterministic offset (keeps the PCN shape)
+        hp = (base_pred.roll(s, 0) + 1e-4 * s).contiguous().pin_memory()
+        hg = base_gt.roll(s, 0).contiguous().pin_memory()
+        host_sets.append((hp, hg))
+        dev_sets.append((hp.to(dev), hg.to(dev)))
+    red = torch.zeros(4, device=dev, dtype=torch.float64)
+
+    def step(pred, gt):
+        """ChamferDistanceL1(pred, gt) fwd + bwd (extensions/chamfer_dist/__init__.py:64-84) + the loss all-reduce."""
+        p = pred.detach().requires_grad_(True)
+        d1, d2 = ChamferFunction.apply(p, gt)
+        s1, s2 = torch.sqrt(d1), torch.sqrt(d2)
+        loss = (torch.mean(s1) + torch.mean(s2)) / 2
+        loss.backward()
+        if distributed:  # global mean = all-reduced sums / counts (utils/dist_utils.py:41-48 semantics)
+            red[0], red[1] = s1.sum(), s2.sum()
+            red[2], red[3] = float(s1.numel()), float(s2.numel())
+            dist.all_reduce(red)
+            loss = (red[0] / red[2] + red[1] / red[3]) / 2
+        return loss, p.grad
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        step(*dev_sets[w % N_INPUT_SETS])
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events on the launch stream, max over ranks -------------------------
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_enable(True)
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for k in range(args.steps):
+        loss, grad = step(*dev_sets[k % N_INPUT_SETS])
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    kern_ms, kern_n = _lib.profile_collect()
+    _lib.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if distributed:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    pairs_per_step = world * B * N * M
+    value = pairs_per_step / (ms_per_step * 1e-3)
+
+    # ---- e2e: same step from pinned host buffers, H2D + D2H inside the timed region ------------------------------
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream(device=dev)
+        bufs = [(torch.empty_like(dev_sets[0][0]), torch.empty_like(dev_sets[0][1])) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+
+        def e2e_run(n_steps):
+            """Double-buffered: the H2D copy of step k+1 runs on a copy stream under the kernels of step k."""
+            main = torch.cuda.current_stream(dev)
+            with torch.cuda.stream(copy_stream):
+                bufs[0][0].copy_(host_sets[0][0], non_blocking=True)
+                bufs[0][1].copy_(host_sets[0][1], non_blocking=True)
+                ready[0].record(copy_stream)
+            val = 0.0
+            for k in range(n_steps):
+                cur, nxt = k & 1, (k + 1) & 1
+                if k + 1 < n_steps:
+                    with torch.cuda.stream(copy_stream):
+                        if k >= 1:
+                            copy_stream.wait_event(freed[nxt])
+                        hs = host_sets[(k + 1) % N_INPUT_SETS]
+                        bufs[nxt][0].copy_(hs[0], non_blocking=True)
+                        bufs[nxt][1].copy_(hs[1], non_blocking=True)
+                        ready[nxt].record(copy_stream)
+                main.wait_event(ready[cur])
+                loss, _ = step(*bufs[cur])
+                freed[cur].record(main)
+                host_loss.copy_(loss.detach().to(torch.float32), non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()  # the user reads the loss every step
+                val = float(host_loss)
+            return val
+
+        e2e_run(max(2, min(args.warmup, 3)))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        e2e_run(args.steps)
+        e1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e_ms = max(e0.elapsed_time(e1), 0.0)
+        if distributed:
+            t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        e2e = {"value": pairs_per_step / (e_ms / args.steps * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(world * (host_sets[0][0].numel() + host_sets[0][1].numel()) * 4),
+               "d2h_bytes_per_step": int(world * 4), "ms_per_step": e_ms / args.steps,
+               "wall_ms_per_step": wall_ms / args.steps,
+               "note": "pinned host pred+gt -> device each step (copy stream, double buffered), loss read back each step"}
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------------
+    peaks, peak_src = measured_peaks()
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    fp32_peak = n_sm * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s: SMs x FP32 lanes x 2 (FMA) x max SM clock
+    alg_flops = 16.0 * B * N * M  # per launch (one rank): 8 FLOP per ordered pair, both directions
+    kern_avg_ms = kern_ms / max(kern_n, 1)
+    achieved = alg_flops / (kern_avg_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("chamfer_pair_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "fp32_fma", "kernel": "chamfer_pair_kernel", "achieved": achieved, "peak": fp32_peak,
+        "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": traffic,
+        "peak_source": f"{n_sm} SMs x 128 FP32 lanes x 2 x sm_max_mhz={sm_max:.0f} ({peak_src} MEASURED_PEAKS.json; it "
+                       "holds no FP32 figure, so the FMA peak is derived from its max SM clock)",
+        "algorithmic_flops_per_launch": alg_flops, "real_flops_per_launch": alg_flops / 2,
+        "kernel_ms_avg": kern_avg_ms, "kernel_launches_timed": kern_n,
+        "kernel_share_of_step": kern_avg_ms / ms_per_step,
+        "hbm": {"bound": "hbm", "achieved": 20.0 * B * (N + M) / (kern_avg_ms * 1e-3) / 1e9,
+                "peak": float(peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
+                "note": "algorithmic bytes 20*B*(N+M): three orders of magnitude below the HBM roof - not the bound"},
+    }
+    if clocks and clocks.get("sm_mhz"):
+        roofline["frac_at_observed_clock"] = achieved / (n_sm * 128 * 2 * clocks["sm_mhz"] * 1e6 / 1e12)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"Chamfer-L1 fwd+bwd, B={B}/GPU x {N} pred x {M} gt (BASELINE configs[1], PCN training-loss shape)",
+                   "global_batch": world * B, "points": [N, M], "parallelism": f"batch-sharded x{world}",
+                   "l2_policy": f"rotating {N_INPUT_SETS} input sets = {N_INPUT_SETS * 2 * B * N * 12 / 1e6:.0f} MB > 126 MB L2",
+                   "collective": "one all_reduce of [sum sqrt d1, sum sqrt d2, n1, n2] per step" if distributed else "none (1 GPU)"},
+        "frac_fp32_peak": 16.0 * pairs_per_step / world / (ms_per_step * 1e-3) / 1e12 / fp32_peak,
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "loss": float(loss),
+    }
+
+    ref_ms = time_ref_cuda_kernel(dev_sets[0][0], dev_sets[0][1])
+    if ref_ms is not None:
+        out["ref_cuda_kernel"] = {"ms_per_step": ref_ms, "value": B * N * M / (ref_ms * 1e-3), "unit": UNIT,
+                                  "what": "reference extensions/chamfer_dist CUDA ext, unmodified, built for sm_100a "
+                                          "(oracle/_ref), forward+backward on the same inputs, 1 GPU"}
+    if distributed:
+        dist.destroy_process_group()
+
+    if not args.no_cpu_baseline and world >= 1:
+        threads = os.cpu_count() or 1
+        n_clouds = 4
+        v, secs = cpu_chamfer_l1_fwd_bwd_rate(n_clouds, threads)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"{n_clouds} of the {B} clouds ({N}x{M} each), torch.cdist+min+autograd fwd+bwd, "
+                                         f"{secs:.1f} s"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -26,6 +26,8 @@ SIGNATURES = {
     "iapt_abi_version": (_c_int, []),
     "iapt_error_string": (ctypes.c_char_p, [_c_int]),
     "iapt_launch_count": (ctypes.c_ulonglong, []),
+    "iapt_profile_enable": (_c_int, [_c_int]),
+    "iapt_profile_collect": (_c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_c_int)]),
     "iapt_chamfer_forward_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "iapt_chamfer_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
                                       _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
@@ -73,6 +75,17 @@ def check(code: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib().iapt_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().iapt_profile_enable(1 if on else 0), "iapt_profile_enable")
+
+
+def profile_collect():
+    """(total device ms of the dominant Chamfer kernel, number of launches) since profile_enable(True)."""
+    ms, n = ctypes.c_double(0.0), ctypes.c_int(0)
+    check(lib().iapt_profile_collect(ctypes.byref(ms), ctypes.byref(n)), "iapt_profile_collect")
+    return float(ms.value), int(n.value)
 
 
 def require_cuda_f32(t: torch.Tensor, name: str, ndim: int) -> None:

@@ -15,6 +15,8 @@ int chamfer_forward_launch(const float*, const float*, int, int, int, float*, fl
 int chamfer_backward_launch(const float*, const float*, const int32_t*, const int32_t*, const float*, const float*, int,
                             int, int, float*, float*, cudaStream_t);
 int chamfer_metrics_launch(const float*, const float*, int, int, int, float, float*, int32_t*, cudaStream_t);
+void profile_enable(bool on);
+int profile_collect(double* total_ms, int* launches);
 size_t fps_workspace_bytes(int B, int N, int npoint);
 int fps_launch(const float*, int, int, int, int, int32_t*, void*, cudaStream_t);
 int gather_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
@@ -45,6 +47,13 @@ const char* iapt_error_string(int code) {
 }
 
 unsigned long long iapt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int iapt_profile_enable(int on) {
+  profile_enable(on != 0);
+  return 0;
+}
+
+int iapt_profile_collect(double* total_ms, int* launches) { return profile_collect(total_ms, launches); }
 
 size_t iapt_chamfer_forward_workspace_bytes(int B, int N, int M) {
   if (B <= 0 || N <= 0 || M <= 0) return 0;

@@ -19,6 +19,9 @@
 //    chunk/group with the SAME rounding and returns the first exact match.
 //  * Work items = (cloud, 2048-point A tile, S split), handed to a persistent grid (2 CTAs per SM) through an
 //    atomic ticket so B = 48 does not quantise badly over 148 SMs (the reference strides batches over gridDim.x=32).
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 
 namespace iapt {
@@ -290,6 +293,36 @@ __global__ void __launch_bounds__(256) chamfer_resolve_kernel(const float* __res
   }
 }
 
+// ---- optional per-launch timing of chamfer_pair_kernel (bench.py's roofline.achieved) ------------------------
+// CUDA events are recorded on the launch stream immediately around the kernel; nothing is synchronised until collect.
+static bool g_profile = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
+
+void profile_enable(bool on) {
+  for (auto& e : g_events) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  g_events.clear();
+  g_profile = on;
+}
+
+int profile_collect(double* total_ms, int* launches) {
+  double tot = 0.0;
+  int n = 0;
+  for (auto& e : g_events) {
+    cudaError_t err = cudaEventSynchronize(e.second);
+    if (err != cudaSuccess) return (int)err;
+    float ms = 0.f;
+    if ((err = cudaEventElapsedTime(&ms, e.first, e.second)) != cudaSuccess) return (int)err;
+    tot += ms;
+    ++n;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = n;
+  return 0;
+}
+
 size_t chamfer_forward_workspace_bytes(int B, int N, int M) {
   return sizeof(u64) * ((size_t)B * N + (size_t)B * M) + 256;
 }
@@ -354,8 +387,18 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
   p.total_items = (int)(base_items * p.s_splits);
 
   const int grid = (int)((long long)p.total_items < (long long)slots ? p.total_items : slots);
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (g_profile) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, stream);
+  }
   chamfer_pair_kernel<true><<<grid, kThreads, sizeof(FwdSmem), stream>>>(p);
   count_launch();
+  if (g_profile) {
+    cudaEventRecord(ev1, stream);
+    g_events.emplace_back(ev0, ev1);
+  }
   if ((err = cudaGetLastError()) != cudaSuccess) return (int)err;
 
   const long long pts = (long long)B * NA + (long long)B * NS;

@@ -39,6 +39,13 @@ const char* iapt_error_string(int code);
 /* Number of kernels launched through this library by the calling process so far (bench.py's gpu_launches). */
 unsigned long long iapt_launch_count(void);
 
+/* Measurement hook (bench.py roofline): when enabled, every iapt_chamfer_forward records a CUDA-event pair on its
+ * launch stream tightly around the dominant kernel (chamfer_pair_kernel).  iapt_profile_collect() synchronises those
+ * events and returns the summed device time in ms and the number of launches; enabling (or disabling) clears the
+ * records.  Not thread-safe; for benchmarking only. */
+int iapt_profile_enable(int on);
+int iapt_profile_collect(double* total_ms, int* launches);
+
 /* ---- Chamfer nearest-neighbour search --------------------------------------------------------------------
  * Replaces chamfer.forward -> chamfer_cuda_forward (extensions/chamfer_dist/chamfer_cuda.cpp:22-25,
  * chamfer.cu:147-171; kernel chamfer.cu:15-145).

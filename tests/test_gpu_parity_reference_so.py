@@ -1,0 +1,74 @@
+"""GPU parity against the REFERENCE'S OWN compiled kernel: extensions/chamfer_dist/{chamfer.cu,chamfer_cuda.cpp}
+built unmodified for sm_100a by oracle/build_ref.sh into oracle/_ref/ (travels to the GPU box as a built .so).
+This is what pins the oracle and our kernels for Chamfer: dist AND idx must be bit-identical to the reference kernel
+on continuous inputs too (same fma(dz,dz,fma(dx,dx,dy*dy)) rounding, same lowest-index tie rule)."""
+import glob
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from imgadapointr_b200 import chamfer
+from imgadapointr_b200.utils import synthetic
+
+pytestmark = pytest.mark.gpu
+REF_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    so = glob.glob(os.path.join(REF_DIR, "chamfer*.so"))
+    if not so:
+        pytest.skip("oracle/_ref/chamfer*.so not built (run oracle/build_ref.sh where /root/reference exists)")
+    spec = importlib.util.spec_from_file_location("chamfer", so[0])  # PyInit_chamfer
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+CASES = [("uniform", 2, 700, 1300), ("uniform", 1, 2048, 16384), ("pcn", 2, 8192, 8192), ("pcn", 1, 16384, 16384),
+         ("grid", 2, 3000, 2500), ("partial", 1, 2048, 16384)]
+
+
+def _inputs(kind, B, N, M):
+    if kind == "uniform":
+        return synthetic.uniform(B, N, 1), synthetic.uniform(B, M, 2)
+    if kind == "grid":
+        return synthetic.grid(B, N, 3, 5, 0.2, 0.1), synthetic.grid(B, M, 4, 5, 0.2, 0.1)
+    if kind == "pcn":
+        p, g = synthetic.pcn_pair(B, max(N, M), 5)
+        return p[:, :N].contiguous(), g[:, :M].contiguous()
+    gt = synthetic.pcn_gt(B, M, 6)
+    return synthetic.pcn_partial(gt, N, 7), gt
+
+
+@pytest.mark.parametrize("kind,B,N,M", CASES)
+def test_forward_bit_identical_to_reference_kernel(dev, ref, kind, B, N, M):
+    x1, x2 = _inputs(kind, B, N, M)
+    a, b = x1.to(dev), x2.to(dev)
+    rd1, rd2, ri1, ri2 = ref.forward(a, b)
+    torch.cuda.synchronize()
+    d1, d2, i1, i2 = chamfer.forward(a, b)
+    assert torch.equal(d1, rd1) and torch.equal(d2, rd2)
+    assert torch.equal(i1, ri1) and torch.equal(i2, ri2)
+    if N * M <= 2048 * 16384:  # and the CPU oracle agrees with both (pins the oracle itself)
+        od1, od2, oi1, oi2 = oracle.chamfer_forward(x1.numpy(), x2.numpy())
+        assert np.array_equal(od1, rd1.cpu().numpy()) and np.array_equal(oi1, ri1.cpu().numpy())
+        assert np.array_equal(od2, rd2.cpu().numpy()) and np.array_equal(oi2, ri2.cpu().numpy())
+
+
+@pytest.mark.parametrize("kind,B,N,M", CASES[:4])
+def test_backward_matches_reference_kernel(dev, ref, kind, B, N, M):
+    x1, x2 = _inputs(kind, B, N, M)
+    a, b = x1.to(dev), x2.to(dev)
+    d1, d2, i1, i2 = chamfer.forward(a, b)
+    g1 = torch.randn(d1.shape, generator=torch.Generator().manual_seed(1)).to(dev)
+    g2 = torch.randn(d2.shape, generator=torch.Generator().manual_seed(2)).to(dev)
+    r1, r2 = ref.backward(a, b, i1, i2, g1, g2)
+    torch.cuda.synchronize()
+    o1, o2 = chamfer.backward(a, b, i1, i2, g1, g2)
+    for got, want in ((o1, r1), (o2, r2)):
+        assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
