@@ -54,7 +54,9 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region.  NVML is polled from a thread every ~2 ms
+    (the timed region of a short run is only tens of ms - `nvidia-smi -lms 200` would miss it); if NVML is not
+    importable the recipe's nvidia-smi query is used instead."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -62,51 +64,94 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []  # (sm_mhz, power_w, reasons_bitmask)
+        self.sm_max = None
+        self._stop = threading.Event()
+        self.thread = None
+        self.mode = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        try:
+                            rs = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            rs = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.samples.append((sm, pw, rs))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.mode = "smi"
+            try:
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                     "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.lines = []
+                self.thread = threading.Thread(target=lambda: [self.lines.append(l.strip()) for l in self.proc.stdout],
+                                               daemon=True)
+                self.thread.start()
+            except Exception:
+                self.mode = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = set()
+        if self.mode == "nvml":
+            self._stop.set()
+            self.thread.join(timeout=2)
+            for _, _, rs in self.samples:
+                for bit, n in names.items():
+                    if rs & bit:
+                        reasons.add(n)
+        elif self.mode == "smi":
+            self.proc.terminate()
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            for ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    self.samples.append((float(f[1]), float(f[3]), 0))
+                    self.sm_max = float(f[2])
+                except ValueError:
+                    continue
+                for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        sm = [s[0] for s in self.samples]
+        power = [s[1] for s in self.samples]
         # "under load": samples at >= 60 % of the max observed power
-        load = [s for s, p in zip(sm, power) if power and p >= 0.6 * max(power)] or sm
-        load.sort()
-        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+        load = sorted(s for s, p in zip(sm, power) if p >= 0.6 * max(power)) if power else []
+        load = load or sorted(sm)
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": self.sm_max, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None, "source": self.mode}
 
 
 def cpu_chamfer_l1_fwd_bwd_rate(n_clouds, threads):
@@ -254,7 +299,7 @@ def main():
     barrier()
 
     # ---- timed region: exactly K steps, CUDA events on the launch stream, max over ranks -------------------------
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     _lib.profile_enable(True)
@@ -379,7 +424,7 @@ def main():
                    "collective": "one all_reduce of [sum sqrt d1, sum sqrt d2, n1, n2] per step" if distributed else "none (1 GPU)"},
         "frac_fp32_peak": 16.0 * pairs_per_step / world / (ms_per_step * 1e-3) / 1e12 / fp32_peak,
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "loss": float(loss),
+        "loss": float(loss.detach()),
     }
 
     ref_ms = time_ref_cuda_kernel(dev_sets[0][0], dev_sets[0][1])
