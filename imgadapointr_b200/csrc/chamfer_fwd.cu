@@ -6,19 +6,21 @@
 //  * ONE pass evaluates every unordered (a, s) pair once and feeds BOTH directions: the row minimum (nearest
 //    streamed point for each register point) and the column minimum (nearest register point for each streamed
 //    point).  The reference evaluates each pair twice (two launches with the roles swapped).
-//  * "A side" points live in registers, 8 per thread, packed two-per-f32x2 so the 3 SUB + 1 MUL + 2 FMA of the
-//    direct form issue as FADD2/FMUL2/FFMA2 (half the FP32 issue slots).  "S side" points are streamed through
-//    double-buffered shared memory in a duplicated (x,x,y,y | z,z) layout and read with broadcast LDS.128/LDS.64.
+//  * "A side" points live in registers, QT (8 or 16) per thread, packed two-per-f32x2 so the 3 SUB + 1 MUL + 2 FMA
+//    of the direct form issue as FADD2/FMUL2/FFMA2 (half the FP32 issue slots).  "S side" points are streamed
+//    through double-buffered shared memory in a duplicated (x,x,y,y | z,z) layout and read with broadcast LDS.128.
 //  * No per-pair argmin bookkeeping.  Only minima are tracked in the hot loop (FMNMX3: one ALU slot per two
 //    pairs per direction); the index is recovered exactly afterwards:
-//      rows   : per 32-point chunk "did my running minimum strictly decrease?" -> remember the FIRST such chunk;
-//      columns: REDUX.MIN over the warp + ballot of the lanes that hold the minimum -> lowest 8-point group;
+//      rows   : per 32-point chunk "did my running minimum strictly decrease?" -> remember the FIRST such chunk
+//               (the snapshot and the chunk id live in shared memory, not registers);
+//      columns: REDUX.MIN over the warp + ballot of the lanes that hold the minimum -> lowest QT-point group;
 //    both are folded across tiles/CTAs with a 64-bit atomicMin on (distance bits << 32 | coarse id), whose
 //    unsigned order is the lexicographic (distance, id) order = the reference's lowest-index tie rule
 //    (chamfer.cu:47-50,137-140).  chamfer_resolve_kernel then re-evaluates the <= 32 candidates of the winning
 //    chunk/group with the SAME rounding and returns the first exact match.
-//  * Work items = (cloud, 2048-point A tile, S split), handed to a persistent grid (2 CTAs per SM) through an
+//  * Work items = (cloud, A tile of 256*QT points, S split), handed to a persistent grid (2 CTAs per SM) through an
 //    atomic ticket so B = 48 does not quantise badly over 148 SMs (the reference strides batches over gridDim.x=32).
+#include <cstdlib>
 #include <utility>
 #include <vector>
 
@@ -28,11 +30,14 @@ namespace iapt {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kQT = 8;                  // A-side points per thread
-constexpr int kATile = kThreads * kQT;  // 2048
-constexpr int kSStage = 512;            // streamed points per smem stage
-constexpr int kChunk = 32;              // streamed points per row-index chunk
-constexpr int kGroup = kQT;             // A-side points per column-index group (= one thread's points)
+constexpr int kSStage = 512;  // streamed points per smem stage
+constexpr int kChunk = 32;    // streamed points per row-index chunk
+#ifndef IAPT_DEFAULT_QT_LARGE
+#define IAPT_DEFAULT_QT_LARGE 16
+#endif
+#ifndef IAPT_DEFAULT_PREFETCH
+#define IAPT_DEFAULT_PREFETCH 0
+#endif
 
 struct FwdParams {
   const float* A;  // [B, NA, 3] register side
@@ -40,21 +45,25 @@ struct FwdParams {
   int B, NA, NS;
   u64* PA;  // [B, NA] packed (dist, chunk id of S)
   u64* PS;  // [B, NS] packed (dist, group id of A)
-  unsigned* ticket;
+  unsigned* ticket;  // starts at 0xFFFFFFFF (same memset as the keys); item = atomicAdd(ticket, 1) + 1
   int a_tiles, s_splits, stages_per_split, total_items;
 };
 
+template <int QT>
 struct __align__(16) FwdSmem {
-  ulonglong2 sxy[2][kSStage];         // (x,x),(y,y)
-  u64 sz[2][kSStage];                 // (z,z)
-  uint4 col[kWarps][kSStage / 2];     // per warp, per streamed point pair: (min bits, ballot) x2
+  ulonglong2 sxy[2][kSStage + 2];   // (x,x),(y,y)      (+2: the register prefetch reads one pair past the stage)
+  ulonglong2 szz[2][kSStage / 2 + 1];  // (z,z) of two consecutive points
+  uint4 col[kWarps][kSStage / 2];   // per warp, per streamed point pair: (min bits, ballot) x2
+  float4 prev[QT / 4][kThreads];    // running minima at the last chunk boundary
+  unsigned bestc[QT][kThreads];     // first chunk in which the running minimum strictly decreased
   unsigned next_item;
 };
 
-__device__ __forceinline__ void stage_fill_load(const float* __restrict__ Sb, int NS, int base, int tid, float (&v)[2][3]) {
+__device__ __forceinline__ void stage_fill_load(const float* __restrict__ Sb, int NS, int base, int tid,
+                                                float (&v)[2][3]) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    int s = base + tid + h * kThreads;
+    int s = base + 2 * tid + h;
     if (s < NS) {
       v[h][0] = __ldg(Sb + 3 * (size_t)s + 0);
       v[h][1] = __ldg(Sb + 3 * (size_t)s + 1);
@@ -65,22 +74,28 @@ __device__ __forceinline__ void stage_fill_load(const float* __restrict__ Sb, in
   }
 }
 
-__device__ __forceinline__ void stage_fill_store(FwdSmem& sm, int buf, int tid, const float (&v)[2][3]) {
+template <int QT>
+__device__ __forceinline__ void stage_fill_store(FwdSmem<QT>& sm, int buf, int tid, const float (&v)[2][3]) {
+  ulonglong2 zz;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    int r = tid + h * kThreads;
     ulonglong2 xy;
     xy.x = pack2(v[h][0], v[h][0]);
     xy.y = pack2(v[h][1], v[h][1]);
-    sm.sxy[buf][r] = xy;
-    sm.sz[buf][r] = pack2(v[h][2], v[h][2]);
+    sm.sxy[buf][2 * tid + h] = xy;
   }
+  zz.x = pack2(v[0][2], v[0][2]);
+  zz.y = pack2(v[1][2], v[1][2]);
+  sm.szz[buf][tid] = zz;
 }
 
-template <bool kCols>
+// QT: A-side points per thread (8 or 16).  kPrefetch: keep the NEXT pair of streamed points in registers.
+template <int QT, bool kPrefetch>
 __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
+  FwdSmem<QT>& sm = *reinterpret_cast<FwdSmem<QT>*>(smem_raw);
+  constexpr int kATile = kThreads * QT;
+  constexpr int kPairs = QT / 2;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
@@ -88,7 +103,7 @@ __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) 
 
   for (;;) {
     __syncthreads();  // everyone is done with smem (incl. next_item) of the previous item
-    if (tid == 0) sm.next_item = atomicAdd(p.ticket, 1u);
+    if (tid == 0) sm.next_item = atomicAdd(p.ticket, 1u) + 1u;
     __syncthreads();
     const int item = (int)sm.next_item;
     if (item >= p.total_items) break;
@@ -101,11 +116,11 @@ __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) 
     const float* __restrict__ Ab = p.A + (size_t)b * p.NA * 3;
     const float* __restrict__ Sb = p.S + (size_t)b * p.NS * 3;
 
-    // ---- this thread's 8 consecutive A points -> 4 f32x2 pairs per coordinate --------------------------------
-    const int a0 = at * kATile + tid * kQT;
-    u64 qx[kQT / 2], qy[kQT / 2], qz[kQT / 2];
+    // ---- this thread's QT consecutive A points -> QT/2 f32x2 pairs per coordinate -----------------------------
+    const int a0 = at * kATile + tid * QT;
+    u64 qx[kPairs], qy[kPairs], qz[kPairs];
 #pragma unroll
-    for (int i = 0; i < kQT / 2; ++i) {
+    for (int i = 0; i < kPairs; ++i) {
       float c[2][3];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -122,13 +137,14 @@ __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) 
       qy[i] = pack2(c[0][1], c[1][1]);
       qz[i] = pack2(c[0][2], c[1][2]);
     }
-    float m[kQT];
-    unsigned bestc[kQT];
+    float m[QT];
 #pragma unroll
-    for (int i = 0; i < kQT; ++i) {
+    for (int i = 0; i < QT; ++i) {
       m[i] = kInf;
-      bestc[i] = 0u;
+      sm.bestc[i][tid] = 0u;
     }
+#pragma unroll
+    for (int i = 0; i < QT / 4; ++i) sm.prev[i][tid] = make_float4(kInf, kInf, kInf, kInf);
 
     const int stage0 = ss * p.stages_per_split;
     const int total_stages = (p.NS + kSStage - 1) / kSStage;
@@ -137,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) 
     {  // prologue: first stage -> buffer 0
       float v[2][3];
       stage_fill_load(Sb, p.NS, stage0 * kSStage, tid, v);
-      stage_fill_store(sm, 0, tid, v);
+      stage_fill_store<QT>(sm, 0, tid, v);
     }
     __syncthreads();
 
@@ -152,55 +168,63 @@ __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) 
       const int n_valid = min(kSStage, p.NS - s_base);
       const int n_chunks = (n_valid + kChunk - 1) / kChunk;
       const ulonglong2* __restrict__ sxy = sm.sxy[buf];
-      const u64* __restrict__ sz = sm.sz[buf];
+      const ulonglong2* __restrict__ szz = sm.szz[buf];
 
+      ulonglong2 xy0 = sxy[0], xy1 = sxy[1], zz = szz[0];
       for (int c = 0; c < n_chunks; ++c) {
-        float prev[kQT];
-#pragma unroll
-        for (int i = 0; i < kQT; ++i) prev[i] = m[i];
 #pragma unroll 4
         for (int rr = 0; rr < kChunk; rr += 2) {
           const int r = c * kChunk + rr;
-          const ulonglong2 xy0 = sxy[r];
-          const ulonglong2 xy1 = sxy[r + 1];
-          const u64 z0 = sz[r];
-          const u64 z1 = sz[r + 1];
-          float dl[kQT / 2], dh[kQT / 2], el[kQT / 2], eh[kQT / 2];
+          ulonglong2 cxy0, cxy1, czz;
+          if (kPrefetch) {
+            cxy0 = xy0;
+            cxy1 = xy1;
+            czz = zz;
+            xy0 = sxy[r + 2];  // next pair (the arrays are padded, the last prefetch is never used)
+            xy1 = sxy[r + 3];
+            zz = szz[(r >> 1) + 1];
+          } else {
+            cxy0 = sxy[r];
+            cxy1 = sxy[r + 1];
+            czz = szz[r >> 1];
+          }
+          float c0 = kInf, c1 = kInf;
 #pragma unroll
-          for (int i = 0; i < kQT / 2; ++i) {
-            u64 d = sqdist2(qx[i], qy[i], qz[i], xy0.x, xy0.y, z0);
-            u64 e = sqdist2(qx[i], qy[i], qz[i], xy1.x, xy1.y, z1);
-            unpack2(d, dl[i], dh[i]);
-            unpack2(e, el[i], eh[i]);
-            m[2 * i] = fmin3(m[2 * i], dl[i], el[i]);
-            m[2 * i + 1] = fmin3(m[2 * i + 1], dh[i], eh[i]);
+          for (int i = 0; i < kPairs; ++i) {
+            const u64 d = sqdist2(qx[i], qy[i], qz[i], cxy0.x, cxy0.y, czz.x);
+            const u64 e = sqdist2(qx[i], qy[i], qz[i], cxy1.x, cxy1.y, czz.y);
+            float dl, dh, el, eh;
+            unpack2(d, dl, dh);
+            unpack2(e, el, eh);
+            m[2 * i] = fmin3(m[2 * i], dl, el);
+            m[2 * i + 1] = fmin3(m[2 * i + 1], dh, eh);
+            c0 = fmin3(c0, dl, dh);
+            c1 = fmin3(c1, el, eh);
           }
-          if (kCols) {
-            float c0 = fmin3(dl[0], dh[0], dl[1]);
-            c0 = fmin3(c0, dh[1], dl[2]);
-            c0 = fmin3(c0, dh[2], dl[3]);
-            c0 = fminf(c0, dh[3]);
-            float c1 = fmin3(el[0], eh[0], el[1]);
-            c1 = fmin3(c1, eh[1], el[2]);
-            c1 = fmin3(c1, eh[2], el[3]);
-            c1 = fminf(c1, eh[3]);
-            const unsigned u0 = __float_as_uint(c0), u1 = __float_as_uint(c1);
-            const unsigned w0 = redux_min_u32(u0);
-            const unsigned w1 = redux_min_u32(u1);
-            const unsigned b0 = __ballot_sync(0xffffffffu, u0 == w0);
-            const unsigned b1 = __ballot_sync(0xffffffffu, u1 == w1);
-            if (lane == 0) sm.col[warp][r >> 1] = make_uint4(w0, b0, w1, b1);
-          }
+          const unsigned u0 = __float_as_uint(c0), u1 = __float_as_uint(c1);
+          const unsigned w0 = redux_min_u32(u0);
+          const unsigned w1 = redux_min_u32(u1);
+          const unsigned b0 = __ballot_sync(0xffffffffu, u0 == w0);
+          const unsigned b1 = __ballot_sync(0xffffffffu, u1 == w1);
+          if (lane == 0) sm.col[warp][r >> 1] = make_uint4(w0, b0, w1, b1);
         }
+        // chunk boundary: which running minima strictly decreased inside this chunk?
         const unsigned gchunk = (unsigned)((s_base >> 5) + c);
 #pragma unroll
-        for (int i = 0; i < kQT; ++i) bestc[i] = (m[i] < prev[i]) ? gchunk : bestc[i];
+        for (int i = 0; i < QT / 4; ++i) {
+          const float4 pv = sm.prev[i][tid];
+          if (m[4 * i + 0] < pv.x) sm.bestc[4 * i + 0][tid] = gchunk;
+          if (m[4 * i + 1] < pv.y) sm.bestc[4 * i + 1][tid] = gchunk;
+          if (m[4 * i + 2] < pv.z) sm.bestc[4 * i + 2][tid] = gchunk;
+          if (m[4 * i + 3] < pv.w) sm.bestc[4 * i + 3][tid] = gchunk;
+          sm.prev[i][tid] = make_float4(m[4 * i + 0], m[4 * i + 1], m[4 * i + 2], m[4 * i + 3]);
+        }
       }
 
-      if (has_next) stage_fill_store(sm, buf ^ 1, tid, nxt);
+      if (has_next) stage_fill_store<QT>(sm, buf ^ 1, tid, nxt);
       __syncthreads();  // col[][] of this stage complete; next stage's points visible
 
-      if (kCols) {
+      {
         // fold the 8 warps' column minima (lowest warp wins ties -> lowest A index) and publish
         const uint2* colp = reinterpret_cast<const uint2*>(&sm.col[0][0]);
 #pragma unroll
@@ -219,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) 
             }
             const int s = s_base + r;
             if (s < p.NS) {
-              const unsigned gid = (unsigned)(at * (kATile / kGroup) + bw * 32 + (__ffs(best.y) - 1));
+              const unsigned gid = (unsigned)(at * kThreads + bw * 32 + (__ffs(best.y) - 1));
               atomicMin(p.PS + (size_t)b * p.NS + s, ((u64)best.x << 32) | gid);
             }
           }
@@ -230,65 +254,108 @@ __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) 
 
     // ---- publish row minima ------------------------------------------------------------------------------
 #pragma unroll
-    for (int i = 0; i < kQT; ++i) {
+    for (int i = 0; i < QT; ++i) {
       const int a = a0 + i;
-      if (a < p.NA) atomicMin(p.PA + (size_t)b * p.NA + a, pack_key(m[i], bestc[i]));
+      if (a < p.NA) atomicMin(p.PA + (size_t)b * p.NA + a, pack_key(m[i], sm.bestc[i][tid]));
     }
   }
 }
 
-// Index resolution + unpack.  One thread per point of either side.
-//   A side: candidates are the 32 streamed points of chunk `id`;  S side: the 8 register-side points of group `id`.
+// Index resolution + unpack, warp-cooperative: the lanes of a warp evaluate the candidates of one point in
+// parallel (coalesced candidate reads), a ballot of the exact matches gives the first (lowest-index) one.
+//   A side: candidates are the 32 streamed points of chunk `id` (one point per warp step);
+//   S side: the `group` register-side points of group `id` (32/group points per warp step).
 // The candidate distance is evaluated with the identical instruction sequence as the search, so exactly-equal
-// compares are well defined; the first (lowest index) match is the reference's answer.
+// compares are well defined.
 __global__ void __launch_bounds__(256) chamfer_resolve_kernel(const float* __restrict__ A, const float* __restrict__ S,
-                                                              int B, int NA, int NS, const u64* __restrict__ PA,
-                                                              const u64* __restrict__ PS, float* __restrict__ distA,
-                                                              int32_t* __restrict__ idxA, float* __restrict__ distS,
-                                                              int32_t* __restrict__ idxS) {
+                                                              int B, int NA, int NS, int group,
+                                                              const u64* __restrict__ PA, const u64* __restrict__ PS,
+                                                              float* __restrict__ distA, int32_t* __restrict__ idxA,
+                                                              float* __restrict__ distS, int32_t* __restrict__ idxS) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long totalA = (long long)B * NA;
-  const long long total = totalA + (long long)B * NS;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    if (t < totalA) {
-      if (distA == nullptr) continue;
-      const int b = (int)(t / NA);
-      const u64 key = PA[t];
-      const float d = __uint_as_float((unsigned)(key >> 32));
-      const int c0 = (int)(unsigned)key * kChunk;
-      const float ax = A[3 * t], ay = A[3 * t + 1], az = A[3 * t + 2];
-      const float* Sb = S + (size_t)b * NS * 3;
-      const int c1 = min(NS, c0 + kChunk);
-      int found = c0;
-      for (int j = c0; j < c1; ++j) {
-        const float e = sqdist(ax, ay, az, Sb[3 * j], Sb[3 * j + 1], Sb[3 * j + 2]);
-        if (e == d) {
-          found = j;
-          break;
+  const long long totalS = (long long)B * NS;
+
+  // ---- A side: 32 points per warp iteration, one candidate chunk per point -------------------------------------
+  if (distA != nullptr) {
+    for (long long t0 = warp_global * 32; t0 < totalA; t0 += n_warps * 32) {
+      const long long t = t0 + lane;
+      u64 key = ~0ull;
+      float ax = 0.f, ay = 0.f, az = 0.f;
+      if (t < totalA) {
+        key = PA[t];
+        ax = A[3 * t];
+        ay = A[3 * t + 1];
+        az = A[3 * t + 2];
+      }
+      int myidx = 0;
+      const int n_here = (int)min((long long)32, totalA - t0);
+      for (int j = 0; j < n_here; ++j) {
+        const u64 kj = __shfl_sync(0xffffffffu, key, j);
+        const float x = __shfl_sync(0xffffffffu, ax, j);
+        const float y = __shfl_sync(0xffffffffu, ay, j);
+        const float z = __shfl_sync(0xffffffffu, az, j);
+        const int b = (int)((t0 + j) / NA);
+        const int cand = (int)(unsigned)kj * kChunk + lane;
+        bool eq = false;
+        if (cand < NS) {
+          const float* c = S + ((size_t)b * NS + cand) * 3;
+          eq = sqdist(x, y, z, c[0], c[1], c[2]) == __uint_as_float((unsigned)(kj >> 32));
+        }
+        const unsigned hits = __ballot_sync(0xffffffffu, eq);
+        const int first = hits ? (__ffs(hits) - 1) : 0;
+        if (lane == j) myidx = (int)(unsigned)kj * kChunk + first;
+      }
+      if (t < totalA) {
+        distA[t] = __uint_as_float((unsigned)(key >> 32));
+        idxA[t] = myidx;
+      }
+    }
+  }
+  // ---- S side: `group` lanes per point, 32/group points per step ----------------------------------------------
+  if (distS != nullptr) {
+    const int per_step = 32 / group;  // group is 8 or 16
+    const int sub = lane / group, off = lane % group;
+    for (long long u0 = warp_global * 32; u0 < totalS; u0 += n_warps * 32) {
+      const long long u = u0 + lane;
+      u64 key = ~0ull;
+      float sx = 0.f, sy = 0.f, sz = 0.f;
+      if (u < totalS) {
+        key = PS[u];
+        sx = S[3 * u];
+        sy = S[3 * u + 1];
+        sz = S[3 * u + 2];
+      }
+      int myidx = 0;
+      for (int j0 = 0; j0 < 32; j0 += per_step) {
+        const int j = j0 + sub;  // the point this lane helps with
+        const u64 kj = __shfl_sync(0xffffffffu, key, j);
+        const float x = __shfl_sync(0xffffffffu, sx, j);
+        const float y = __shfl_sync(0xffffffffu, sy, j);
+        const float z = __shfl_sync(0xffffffffu, sz, j);
+        bool eq = false;
+        if (u0 + j < totalS) {
+          const int b = (int)((u0 + j) / NS);
+          const int cand = (int)(unsigned)kj * group + off;
+          if (cand < NA) {
+            const float* c = A + ((size_t)b * NA + cand) * 3;
+            eq = sqdist(c[0], c[1], c[2], x, y, z) == __uint_as_float((unsigned)(kj >> 32));
+          }
+        }
+        const unsigned hits = __ballot_sync(0xffffffffu, eq);
+        // every lane extracts the sub-mask of the point it OWNS in this step, if any
+        const int owner_sub = lane - j0;  // lane j0 + s owns sub-group s
+        if (owner_sub >= 0 && owner_sub < per_step) {
+          const unsigned mine = (hits >> (owner_sub * group)) & ((group == 32) ? 0xffffffffu : ((1u << group) - 1u));
+          myidx = (int)(unsigned)key * group + (mine ? (__ffs(mine) - 1) : 0);
         }
       }
-      distA[t] = d;
-      idxA[t] = found;
-    } else {
-      if (distS == nullptr) continue;
-      const long long u = t - totalA;
-      const int b = (int)(u / NS);
-      const u64 key = PS[u];
-      const float d = __uint_as_float((unsigned)(key >> 32));
-      const int g0 = (int)(unsigned)key * kGroup;
-      const float sx = S[3 * u], sy = S[3 * u + 1], sz = S[3 * u + 2];
-      const float* Ab = A + (size_t)b * NA * 3;
-      const int g1 = min(NA, g0 + kGroup);
-      int found = g0;
-      for (int j = g0; j < g1; ++j) {
-        const float e = sqdist(Ab[3 * j], Ab[3 * j + 1], Ab[3 * j + 2], sx, sy, sz);
-        if (e == d) {
-          found = j;
-          break;
-        }
+      if (u < totalS) {
+        distS[u] = __uint_as_float((unsigned)(key >> 32));
+        idxS[u] = myidx;
       }
-      distS[u] = d;
-      idxS[u] = found;
     }
   }
 }
@@ -327,10 +394,42 @@ size_t chamfer_forward_workspace_bytes(int B, int N, int M) {
   return sizeof(u64) * ((size_t)B * N + (size_t)B * M) + 256;
 }
 
+// Variant selection.  Default: QT=16 when the register side is large enough to fill 4096-point tiles, else QT=8.
+// IAPT_FWD_VARIANT (development knob, read once): "8", "8p", "16", "16p" force a variant (p = register prefetch).
+struct Variant {
+  int qt;
+  bool prefetch;
+};
+
+static Variant pick_variant(int NA) {
+  static int forced = -1;
+  if (forced < 0) {
+    forced = 0;
+    if (const char* e = std::getenv("IAPT_FWD_VARIANT")) {
+      const int q = std::atoi(e);
+      if (q == 8 || q == 16) forced = q | ((e[0] && (e[1] == 'p' || (e[1] && e[2] == 'p'))) ? 0x100 : 0);
+    }
+  }
+  if (forced > 0) return Variant{forced & 0xff, (forced & 0x100) != 0};
+  return Variant{NA >= 8192 ? IAPT_DEFAULT_QT_LARGE : 8, IAPT_DEFAULT_PREFETCH != 0};
+}
+
+template <int QT, bool kPrefetch>
+static cudaError_t launch_pair(const FwdParams& p, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(chamfer_pair_kernel<QT, kPrefetch>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(FwdSmem<QT>));
+    configured = true;
+  }
+  chamfer_pair_kernel<QT, kPrefetch><<<grid, kThreads, sizeof(FwdSmem<QT>), stream>>>(p);
+  return cudaGetLastError();
+}
+
 // Host launcher.  Returns cudaError_t.
 int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1, float* dist2,
                            int32_t* idx1, int32_t* idx2, void* workspace, cudaStream_t stream) {
-  // Register side = the larger cloud (its tile is 2048 points; the streamed side pads only to 32).
+  // Register side = the larger cloud (its tile is 256*QT points; the streamed side pads only to 32).
   const bool swap = N < M;
   const float* A = swap ? xyz2 : xyz1;
   const float* S = swap ? xyz1 : xyz2;
@@ -347,8 +446,8 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
   unsigned* ticket = reinterpret_cast<unsigned*>(ws + key_bytes);
 
   cudaError_t err;
-  if ((err = cudaMemsetAsync(ws, 0xFF, key_bytes, stream)) != cudaSuccess) return (int)err;
-  if ((err = cudaMemsetAsync(ticket, 0, 256, stream)) != cudaSuccess) return (int)err;
+  // one memset: keys = +inf-like all-ones, ticket = 0xFFFFFFFF (the kernel uses atomicAdd(ticket,1)+1)
+  if ((err = cudaMemsetAsync(ws, 0xFF, key_bytes + 256, stream)) != cudaSuccess) return (int)err;
 
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -356,9 +455,9 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
-    cudaFuncSetAttribute(chamfer_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem));
-    cudaFuncSetAttribute(chamfer_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem));
   }
+  const Variant v = pick_variant(NA);
+  const int a_tile = kThreads * v.qt;
 
   FwdParams p;
   p.A = A;
@@ -369,7 +468,7 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
   p.PA = PA;
   p.PS = PS;
   p.ticket = ticket;
-  p.a_tiles = (NA + kATile - 1) / kATile;
+  p.a_tiles = (NA + a_tile - 1) / a_tile;
   const int total_stages = (NS + kSStage - 1) / kSStage;
   const int slots = num_sms * 2;
   const long long base_items = (long long)B * p.a_tiles;
@@ -393,18 +492,22 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
     cudaEventCreate(&ev1);
     cudaEventRecord(ev0, stream);
   }
-  chamfer_pair_kernel<true><<<grid, kThreads, sizeof(FwdSmem), stream>>>(p);
+  if (v.qt == 16)
+    err = v.prefetch ? launch_pair<16, true>(p, grid, stream) : launch_pair<16, false>(p, grid, stream);
+  else
+    err = v.prefetch ? launch_pair<8, true>(p, grid, stream) : launch_pair<8, false>(p, grid, stream);
   count_launch();
   if (g_profile) {
     cudaEventRecord(ev1, stream);
     g_events.emplace_back(ev0, ev1);
   }
-  if ((err = cudaGetLastError()) != cudaSuccess) return (int)err;
+  if (err != cudaSuccess) return (int)err;
 
   const long long pts = (long long)B * NA + (long long)B * NS;
-  long long rblocks = (pts + 255) / 256;
-  if (rblocks > num_sms * 32LL) rblocks = num_sms * 32LL;
-  chamfer_resolve_kernel<<<(int)rblocks, 256, 0, stream>>>(A, S, B, NA, NS, PA, PS, distA, idxA, distS, idxS);
+  long long rblocks = (pts / 32 + 7) / 8;  // one warp per 32 points
+  if (rblocks > num_sms * 16LL) rblocks = num_sms * 16LL;
+  if (rblocks < 1) rblocks = 1;
+  chamfer_resolve_kernel<<<(int)rblocks, 256, 0, stream>>>(A, S, B, NA, NS, v.qt, PA, PS, distA, idxA, distS, idxS);
   count_launch();
   return (int)cudaGetLastError();
 }
