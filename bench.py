@@ -8,8 +8,8 @@
 Workload (BASELINE.json configs[1], the configuration the metric is quoted on): PCN training-loss shape -
 ``ChamferDistanceL1(pred, gt)`` forward + backward with pred, gt = [48, 16384, 3] FP32 per GPU, synthetic PCN-shaped
 clouds (imgadapointr_b200.utils.synthetic.pcn_pair, seed 202 + rank).  Every cloud is independent, so ranks hold their
-own 48 clouds (weak scaling) and the only collective is one NCCL all-reduce per step of the [sum sqrt(d1), sum
-sqrt(d2), n1, n2] vector that forms the global mean loss.
+own 48 clouds (weak scaling) and the only collective is one NCCL all-reduce per step of the scalar loss
+(the reference's reduce_tensor, utils/dist_utils.py:41-48).
 
 Metric: Chamfer-L1 fwd+bwd point-pairs/s (pairs = B*N*M summed over ranks) and its fraction of the FP32-FMA roofline
 (algorithmic FLOPs = 16*B*N*M: 8 per ordered pair, both directions - SURVEY.md section 8d; our kernel evaluates each
@@ -252,8 +252,8 @@ def main():
     import torch.distributed as dist
 
     from imgadapointr_b200 import _lib, chamfer
-    from imgadapointr_b200.extensions.chamfer_dist import ChamferFunction
-    from imgadapointr_b200.utils import synthetic
+    from imgadapointr_b200.extensions.chamfer_dist import ChamferDistanceL1
+    from imgadapointr_b200.utils import dist_utils, synthetic
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
@@ -273,20 +273,17 @@ def main():
         hg = base_gt.roll(s, 0).contiguous().pin_memory()
         host_sets.append((hp, hg))
         dev_sets.append((hp.to(dev), hg.to(dev)))
-    red = torch.zeros(4, device=dev, dtype=torch.float64)
+
+    loss_mod = ChamferDistanceL1()  # extensions/chamfer_dist/__init__.py:64-84 (fused search+loss+gradient path)
 
     def step(pred, gt):
-        """ChamferDistanceL1(pred, gt) fwd + bwd (extensions/chamfer_dist/__init__.py:64-84) + the loss all-reduce."""
+        """ChamferDistanceL1(pred, gt) forward + backward, then the reference's loss all-reduce
+        (tools/runner.py:217-219 -> utils/dist_utils.py:41-48: all_reduce(SUM) / world_size)."""
         p = pred.detach().requires_grad_(True)
-        d1, d2 = ChamferFunction.apply(p, gt)
-        s1, s2 = torch.sqrt(d1), torch.sqrt(d2)
-        loss = (torch.mean(s1) + torch.mean(s2)) / 2
+        loss = loss_mod(p, gt)
         loss.backward()
-        if distributed:  # global mean = all-reduced sums / counts (utils/dist_utils.py:41-48 semantics)
-            red[0], red[1] = s1.sum(), s2.sum()
-            red[2], red[3] = float(s1.numel()), float(s2.numel())
-            dist.all_reduce(red)
-            loss = (red[0] / red[2] + red[1] / red[3]) / 2
+        if distributed:
+            loss = dist_utils.reduce_tensor(loss.detach())
         return loss, p.grad
 
     def barrier():
@@ -421,7 +418,7 @@ def main():
         "config": {"workload": f"Chamfer-L1 fwd+bwd, B={B}/GPU x {N} pred x {M} gt (BASELINE configs[1], PCN training-loss shape)",
                    "global_batch": world * B, "points": [N, M], "parallelism": f"batch-sharded x{world}",
                    "l2_policy": f"rotating {N_INPUT_SETS} input sets = {N_INPUT_SETS * 2 * B * N * 12 / 1e6:.0f} MB > 126 MB L2",
-                   "collective": "one all_reduce of [sum sqrt d1, sum sqrt d2, n1, n2] per step" if distributed else "none (1 GPU)"},
+                   "collective": "one all_reduce(SUM)/world of the scalar loss per step (utils/dist_utils.py:41-48)" if distributed else "none (1 GPU)"},
         "frac_fp32_peak": 16.0 * pairs_per_step / world / (ms_per_step * 1e-3) / 1e12 / fp32_peak,
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "loss": float(loss.detach()),

@@ -33,6 +33,9 @@ SIGNATURES = {
                                       _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "iapt_chamfer_backward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                                        _c_int, _c_void_p, _c_void_p, _c_void_p]),
+    "iapt_chamfer_loss": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
+    "iapt_chamfer_backward_fused": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
+                                             _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "iapt_chamfer_reduce": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
     "iapt_fscore_counts": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p]),
     "iapt_fps_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),

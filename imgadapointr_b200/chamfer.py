@@ -92,3 +92,40 @@ def fscore_counts(dist1: torch.Tensor, dist2: torch.Tensor, th: float) -> torch.
         _lib.check(_lib.lib().iapt_fscore_counts(_lib.ptr(dist1), _lib.ptr(dist2), B, N, M, float(th),
                                                  _lib.ptr(counts), _lib.stream_ptr(dev)), "iapt_fscore_counts")
     return counts
+
+
+LOSS_L1, LOSS_L2, LOSS_L2_SPLIT, LOSS_L1_PM = 1, 2, 3, 4
+
+
+def loss_forward(dist1: torch.Tensor, dist2: torch.Tensor, kind: int):
+    """(loss[2], sums[B,4]) - the reference modules' reductions in two small launches (iapt_chamfer_loss)."""
+    B, N = dist1.shape
+    M = dist2.size(1)
+    dev = dist1.device
+    with torch.cuda.device(dev):
+        sums = torch.empty((B, 4), dtype=torch.float32, device=dev)
+        loss = torch.empty((2,), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().iapt_chamfer_loss(_lib.ptr(dist1), _lib.ptr(dist2), B, N, M, int(kind), _lib.ptr(sums),
+                                                _lib.ptr(loss), _lib.stream_ptr(dev)), "iapt_chamfer_loss")
+    return loss, sums
+
+
+def loss_backward(xyz1, xyz2, idx1, idx2, dist1, dist2, kind: int, grad_loss):
+    """Gradient of the fused loss w.r.t. (xyz1, xyz2) in one kernel (iapt_chamfer_backward_fused).
+    grad_loss: CUDA float32 tensor with 1 element (2 for LOSS_L2_SPLIT) or None (= 1)."""
+    B, N, _ = xyz1.shape
+    M = xyz2.size(1)
+    dev = xyz1.device
+    if grad_loss is not None:
+        grad_loss = grad_loss.to(torch.float32).contiguous()
+        if grad_loss.numel() != (2 if kind == LOSS_L2_SPLIT else 1):
+            raise _lib.IaptError("loss_backward: grad_loss has the wrong number of elements")
+    with torch.cuda.device(dev):
+        gx1 = torch.empty_like(xyz1)
+        gx2 = torch.empty_like(xyz2)
+        _lib.check(
+            _lib.lib().iapt_chamfer_backward_fused(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(idx1), _lib.ptr(idx2),
+                                                   _lib.ptr(dist1), _lib.ptr(dist2), int(kind), _lib.ptr(grad_loss), B, N,
+                                                   M, _lib.ptr(gx1), _lib.ptr(gx2), _lib.stream_ptr(dev)),
+            "iapt_chamfer_backward_fused")
+    return gx1, gx2

@@ -15,6 +15,9 @@ int chamfer_forward_launch(const float*, const float*, int, int, int, float*, fl
 int chamfer_backward_launch(const float*, const float*, const int32_t*, const int32_t*, const float*, const float*, int,
                             int, int, float*, float*, cudaStream_t);
 int chamfer_metrics_launch(const float*, const float*, int, int, int, float, float*, int32_t*, cudaStream_t);
+int chamfer_loss_launch(const float*, const float*, int, int, int, int, float*, float*, cudaStream_t);
+int chamfer_backward_fused_launch(const float*, const float*, const int32_t*, const int32_t*, const float*, const float*,
+                                  int, float, float, const float*, int, int, int, int, float*, float*, cudaStream_t);
 void profile_enable(bool on);
 int profile_collect(double* total_ms, int* launches);
 size_t fps_workspace_bytes(int B, int N, int npoint);
@@ -99,6 +102,31 @@ int iapt_chamfer_backward(const float* xyz1, const float* xyz2, const int32_t* i
   }
   IAPT_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && grad_xyz1 && grad_xyz2);
   return chamfer_backward_launch(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2, B, N, M, grad_xyz1, grad_xyz2, st);
+}
+
+int iapt_chamfer_loss(const float* dist1, const float* dist2, int B, int N, int M, int kind, float* sums, float* loss,
+                      iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 1 && N >= 1 && M >= 1 && kind >= IAPT_LOSS_L1 && kind <= IAPT_LOSS_L1_PM);
+  IAPT_REQUIRE(dist1 && dist2 && sums && loss);
+  return chamfer_loss_launch(dist1, dist2, B, N, M, kind, sums, loss, (cudaStream_t)stream);
+}
+
+int iapt_chamfer_backward_fused(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
+                                const float* dist1, const float* dist2, int kind, const float* grad_loss, int B, int N,
+                                int M, float* grad_xyz1, float* grad_xyz2, iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 1 && N >= 1 && M >= 1 && kind >= IAPT_LOSS_L1 && kind <= IAPT_LOSS_L1_PM);
+  IAPT_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && dist1 && dist2 && grad_xyz1 && grad_xyz2);
+  const float n1 = (float)B * (float)N, n2 = (float)B * (float)M;
+  int mode = 1, stride = 0;
+  float s1 = 0.f, s2 = 0.f;
+  switch (kind) {
+    case IAPT_LOSS_L1: mode = 1; s1 = 0.25f / n1; s2 = 0.25f / n2; break;       // ((q1+q2)/2, d sqrt = 0.5/sqrt)
+    case IAPT_LOSS_L2: mode = 2; s1 = 1.f / n1; s2 = 1.f / n2; break;
+    case IAPT_LOSS_L2_SPLIT: mode = 2; s1 = 1.f / n1; s2 = 1.f / n2; stride = 1; break;
+    default: mode = 1; s1 = 0.5f / n1; s2 = 0.f; break;                           // L1_PM: mean sqrt(dist1) only
+  }
+  return chamfer_backward_fused_launch(xyz1, xyz2, idx1, idx2, dist1, dist2, mode, s1, s2, grad_loss, stride, B, N, M,
+                                       grad_xyz1, grad_xyz2, (cudaStream_t)stream);
 }
 
 int iapt_chamfer_reduce(const float* dist1, const float* dist2, int B, int N, int M, float* sums,

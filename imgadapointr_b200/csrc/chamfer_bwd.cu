@@ -7,34 +7,57 @@
 // Owner-computes formulation.  For output point j of cloud side X (other side Y):
 //     grad_X[j] = 2 gX[j] (x_j - y_{idxX[j]})                      "own" term   (chamfer.cu:193-195)
 //               - sum_{k : idxY[k] == j} 2 gY[k] (y_k - x_j)       fan-in term  (chamfer.cu:196-198, roles swapped)
-// A warp owns kBins consecutive output points, keeps their fan-in accumulators in shared memory, and scans the
-// other side's index array idxY[b, :] in ascending k (coalesced 128 B loads; hits are rare: kBins / N per key).
-// Lanes that hit the same bin in one step are serialised in lane order, so every accumulator receives its
-// contributions in ascending k: the result is bit-reproducible and independent of the launch geometry.
-// Cost: each key is read N / kBins times from L2 - ~1 % of the forward search's work - and worst-case fan-in
-// (all keys in one bin) degrades to a sequential sum inside one warp, never to atomics.
+// A warp owns kBins consecutive output points and keeps their fan-in accumulators in shared memory.  It scans the
+// other side's index array idxY[b, :] in ascending k (coalesced 128 B loads, 8 in flight per lane) and only
+// COMPACTS the hits (k, bin) into a small shared-memory list; whenever the list fills it is drained 32 hits at a
+// time: the lanes gather gY[k], y_k, x_j in parallel (one round trip to L2 for 32 hits instead of one per hit) and
+// lanes that hit the same bin are then serialised in list order.  Every accumulator therefore receives its
+// contributions in ascending k: the result is bit-reproducible and independent of the launch geometry, with no
+// floating-point atomics.  Each key is read N / kBins times from L2 (~1 % of the forward search's work) and
+// worst-case fan-in (all keys in one bin) degrades to a sequential sum inside one warp.
+//
+// Optional fused loss mode (iapt_chamfer_backward_fused): instead of reading grad_dist arrays the kernel forms
+// g = scale / sqrt(dist) (L1) or g = scale (L2) on the fly from the saved distances - the analytic gradient of the
+// reference's sqrt/mean epilogues (extensions/chamfer_dist/__init__.py:82-84) - times the upstream scalar gradient.
 #include "common.cuh"
 
 namespace iapt {
 
 constexpr int kBwdThreads = 256;
 constexpr int kBwdWarps = kBwdThreads / 32;
-constexpr int kBins = 256;  // output points per warp
+constexpr int kBins = 256;     // output points per warp
+constexpr int kHitCap = 256;   // compacted hits per warp before a drain (>= 128 + 32)
 
 struct BwdParams {
   const float* xyz[2];     // [B, n[s], 3]
   const int32_t* idx[2];   // [B, n[s]]   idx[s][j] indexes into side 1-s
-  const float* gdist[2];   // [B, n[s]]   (may be null = zeros)
+  const float* gdist[2];   // plain mode: grad_dist [B, n[s]] (null = zeros).  fused mode: dist [B, n[s]]
   float* grad[2];          // [B, n[s], 3]
   int n[2];
   int B;
   int blocks_per_cloud[2];  // ceil(n[s] / kBins)
   long long warps_side0;    // B * blocks_per_cloud[0]
   long long total_warps;
+  // fused loss mode: g[s] = upstream * scale[s] * (mode == 1 ? 1/sqrt(dist) : 1); upstream read from *grad_out
+  int mode;                 // 0 plain, 1 L1 (sqrt), 2 L2
+  float scale[2];
+  const float* grad_out;    // device: upstream[side] = grad_out[side * grad_out_stride] (null = 1)
+  int grad_out_stride;
 };
+
+__device__ __forceinline__ float point_weight(const BwdParams& p, int side, const float* __restrict__ g, int i,
+                                              const float (&upstream)[2]) {
+  // returns 2 * dLoss/d dist[i]
+  if (p.mode == 0) return __fmul_rn(__ldg(g + i), 2.f);
+  float w = __fmul_rn(upstream[side], p.scale[side]);
+  if (p.mode == 1) w = __fdiv_rn(w, sqrtf(__ldg(g + i)));  // d/dd sqrt(d) = 0.5/sqrt(d); the 0.5 is in scale
+  return __fmul_rn(w, 2.f);
+}
 
 __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
   __shared__ float acc[kBwdWarps][kBins * 3];
+  __shared__ int hit_k[kBwdWarps][kHitCap];
+  __shared__ unsigned short hit_bin[kBwdWarps][kHitCap];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long gw = (long long)blockIdx.x * kBwdWarps + warp;
@@ -61,49 +84,79 @@ __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
   const float* __restrict__ gY = p.gdist[other] ? p.gdist[other] + (size_t)b * nY : nullptr;
   float* __restrict__ out = p.grad[side] + (size_t)b * nX * 3;
   float* a = acc[warp];
+  int* hk = hit_k[warp];
+  unsigned short* hb = hit_bin[warp];
+  float upstream[2] = {1.f, 1.f};
+  if (p.mode != 0 && p.grad_out != nullptr) {
+    upstream[0] = __ldg(p.grad_out);
+    upstream[1] = __ldg(p.grad_out + p.grad_out_stride);
+  }
+  const unsigned lt_mask = (1u << lane) - 1u;
 
   for (int i = lane; i < kBins * 3; i += 32) a[i] = 0.f;
   __syncwarp();
 
+  int count = 0;  // warp-uniform
+  auto drain = [&]() {
+    for (int i0 = 0; i0 < count; i0 += 32) {
+      const int i = i0 + lane;
+      const bool on = i < count;
+      float cx = 0.f, cy = 0.f, cz = 0.f;
+      unsigned bin = 0, rank = 0;
+      const unsigned active = __ballot_sync(0xffffffffu, on);
+      if (on) {
+        const int k = hk[i];
+        bin = hb[i];
+        const int j = j0 + (int)bin;
+        const float g = point_weight(p, other, gY, k, upstream);
+        cx = __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 0), __ldg(X + 3 * (size_t)j + 0)));
+        cy = __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 1), __ldg(X + 3 * (size_t)j + 1)));
+        cz = __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 2), __ldg(X + 3 * (size_t)j + 2)));
+        const unsigned peers = __match_any_sync(active, bin);
+        rank = __popc(peers & lt_mask);
+      }
+      // hits of the same bin take turns in list (= ascending k) order
+      for (unsigned r = 0;; ++r) {
+        if (on && rank == r) {
+          a[bin * 3 + 0] = __fadd_rn(a[bin * 3 + 0], cx);
+          a[bin * 3 + 1] = __fadd_rn(a[bin * 3 + 1], cy);
+          a[bin * 3 + 2] = __fadd_rn(a[bin * 3 + 2], cz);
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, on && rank > r)) break;
+      }
+    }
+    count = 0;
+  };
+
   if (gY != nullptr) {
-    // ---- scan the other side's nearest-neighbour indices, 128 keys per step, ascending k ---------------------
-    for (int k0 = 0; k0 < nY; k0 += 128) {
-      int key[4];
+    // ---- scan the other side's nearest-neighbour indices, 256 keys per step, ascending k ---------------------
+    for (int k0 = 0; k0 < nY; k0 += 256) {
+      int key[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < 8; ++e) {
         const int k = k0 + e * 32 + lane;
         key[e] = (k < nY) ? __ldg(idxY + k) : -1;
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < 8; ++e) {
         const unsigned bin = (unsigned)(key[e] - j0);
         const bool hit = (key[e] >= 0) && (bin < (unsigned)kBins) && ((int)bin + j0 < nX);
         const unsigned mask = __ballot_sync(0xffffffffu, hit);
-        if (mask == 0u) continue;  // warp-uniform
-        float cx = 0.f, cy = 0.f, cz = 0.f;
-        unsigned rank = 0;
-        if (hit) {
-          const int k = k0 + e * 32 + lane;
-          const int j = j0 + (int)bin;
-          const float g = __fmul_rn(__ldg(gY + k), 2.f);
-          cx = __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 0), __ldg(X + 3 * (size_t)j + 0)));
-          cy = __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 1), __ldg(X + 3 * (size_t)j + 1)));
-          cz = __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 2), __ldg(X + 3 * (size_t)j + 2)));
-          const unsigned peers = __match_any_sync(mask, bin);
-          rank = __popc(peers & ((1u << lane) - 1u));
-        }
-        // lanes with the same bin take turns in lane (= ascending k) order
-        for (unsigned r = 0;; ++r) {
-          if (hit && rank == r) {
-            a[bin * 3 + 0] = __fadd_rn(a[bin * 3 + 0], cx);
-            a[bin * 3 + 1] = __fadd_rn(a[bin * 3 + 1], cy);
-            a[bin * 3 + 2] = __fadd_rn(a[bin * 3 + 2], cz);
+        if (mask != 0u) {  // warp-uniform
+          if (hit) {
+            const int pos = count + __popc(mask & lt_mask);
+            hk[pos] = k0 + e * 32 + lane;
+            hb[pos] = (unsigned short)bin;
           }
+          count += __popc(mask);
           __syncwarp();
-          if (!__any_sync(0xffffffffu, hit && rank > r)) break;
+          if (count > kHitCap - 32) drain();
         }
       }
     }
+    __syncwarp();
+    drain();
   }
   __syncwarp();
 
@@ -114,7 +167,7 @@ __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
     float ox = 0.f, oy = 0.f, oz = 0.f;
     if (gX != nullptr) {
       const int j2 = __ldg(idxX + j);
-      const float g = __fmul_rn(__ldg(gX + j), 2.f);
+      const float g = point_weight(p, side, gX, j, upstream);
       ox = __fmul_rn(g, __fsub_rn(__ldg(X + 3 * (size_t)j + 0), __ldg(Y + 3 * (size_t)j2 + 0)));
       oy = __fmul_rn(g, __fsub_rn(__ldg(X + 3 * (size_t)j + 1), __ldg(Y + 3 * (size_t)j2 + 1)));
       oz = __fmul_rn(g, __fsub_rn(__ldg(X + 3 * (size_t)j + 2), __ldg(Y + 3 * (size_t)j2 + 2)));
@@ -123,6 +176,20 @@ __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
     out[3 * (size_t)j + 1] = __fsub_rn(oy, a[i * 3 + 1]);
     out[3 * (size_t)j + 2] = __fsub_rn(oz, a[i * 3 + 2]);
   }
+}
+
+static int bwd_launch_common(BwdParams& p, int B, int N, int M, cudaStream_t stream) {
+  p.n[0] = N;
+  p.n[1] = M;
+  p.B = B;
+  p.blocks_per_cloud[0] = (N + kBins - 1) / kBins;
+  p.blocks_per_cloud[1] = (M + kBins - 1) / kBins;
+  p.warps_side0 = (long long)B * p.blocks_per_cloud[0];
+  p.total_warps = p.warps_side0 + (long long)B * p.blocks_per_cloud[1];
+  const long long blocks = (p.total_warps + kBwdWarps - 1) / kBwdWarps;
+  chamfer_bwd_kernel<<<(unsigned)blocks, kBwdThreads, 0, stream>>>(p);
+  count_launch();
+  return (int)cudaGetLastError();
 }
 
 int chamfer_backward_launch(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
@@ -137,17 +204,34 @@ int chamfer_backward_launch(const float* xyz1, const float* xyz2, const int32_t*
   p.gdist[1] = grad_dist2;
   p.grad[0] = grad_xyz1;
   p.grad[1] = grad_xyz2;
-  p.n[0] = N;
-  p.n[1] = M;
-  p.B = B;
-  p.blocks_per_cloud[0] = (N + kBins - 1) / kBins;
-  p.blocks_per_cloud[1] = (M + kBins - 1) / kBins;
-  p.warps_side0 = (long long)B * p.blocks_per_cloud[0];
-  p.total_warps = p.warps_side0 + (long long)B * p.blocks_per_cloud[1];
-  const long long blocks = (p.total_warps + kBwdWarps - 1) / kBwdWarps;
-  chamfer_bwd_kernel<<<(unsigned)blocks, kBwdThreads, 0, stream>>>(p);
-  count_launch();
-  return (int)cudaGetLastError();
+  p.mode = 0;
+  p.scale[0] = p.scale[1] = 1.f;
+  p.grad_out = nullptr;
+  p.grad_out_stride = 0;
+  return bwd_launch_common(p, B, N, M, stream);
+}
+
+// mode 1: loss = scale1 * sum sqrt(dist1) + scale2 * sum sqrt(dist2);  mode 2: loss = scale1 * sum dist1 + scale2 * sum dist2.
+// (scale already contains the 1/(B*N) of the mean and, for mode 1, the 0.5 of d sqrt.)  A zero scale skips that direction.
+int chamfer_backward_fused_launch(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
+                                  const float* dist1, const float* dist2, int mode, float scale1, float scale2,
+                                  const float* grad_out, int grad_out_stride, int B, int N, int M, float* grad_xyz1,
+                                  float* grad_xyz2, cudaStream_t stream) {
+  BwdParams p;
+  p.xyz[0] = xyz1;
+  p.xyz[1] = xyz2;
+  p.idx[0] = idx1;
+  p.idx[1] = idx2;
+  p.gdist[0] = scale1 != 0.f ? dist1 : nullptr;
+  p.gdist[1] = scale2 != 0.f ? dist2 : nullptr;
+  p.grad[0] = grad_xyz1;
+  p.grad[1] = grad_xyz2;
+  p.mode = mode;
+  p.scale[0] = scale1;
+  p.scale[1] = scale2;
+  p.grad_out = grad_out;
+  p.grad_out_stride = grad_out_stride;
+  return bwd_launch_common(p, B, N, M, stream);
 }
 
 }  // namespace iapt

@@ -64,6 +64,49 @@ __global__ void __launch_bounds__(512) chamfer_metrics_kernel(const float* __res
   }
 }
 
+// Fixed-order fold of the per-cloud sums into the loss scalars of the four reference modules
+// (extensions/chamfer_dist/__init__.py:43-44,61-62,82-84,101-103).  kind: 1 L1, 2 L2, 3 L2_split, 4 L1_PM.
+__global__ void __launch_bounds__(128) chamfer_loss_finalize_kernel(const float* __restrict__ sums, int B, int N, int M,
+                                                                   int kind, float* __restrict__ loss) {
+  __shared__ float sh[4][4];
+  const int c = threadIdx.x & 3, part = threadIdx.x >> 2;  // 32 partial accumulators per column
+  float v = 0.f;
+  for (int b = part; b < B; b += 32) v = __fadd_rn(v, sums[b * 4 + c]);
+  // fold the 32 parts of each column in a fixed order: lanes with equal c are 4 apart
+#pragma unroll
+  for (int o = 16; o >= 4; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) < 4) sh[threadIdx.x >> 5][c] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t[4];
+    for (int k = 0; k < 4; ++k) t[k] = __fadd_rn(__fadd_rn(sh[0][k], sh[1][k]), __fadd_rn(sh[2][k], sh[3][k]));
+    const float n1 = (float)B * (float)N, n2 = (float)B * (float)M;
+    const float m1 = t[0] / n1, m2 = t[1] / n2, q1 = t[2] / n1, q2 = t[3] / n2;
+    if (kind == 1) {
+      loss[0] = (q1 + q2) / 2;
+      loss[1] = 0.f;
+    } else if (kind == 2) {
+      loss[0] = m1 + m2;
+      loss[1] = 0.f;
+    } else if (kind == 3) {
+      loss[0] = m1;
+      loss[1] = m2;
+    } else {
+      loss[0] = q1;
+      loss[1] = 0.f;
+    }
+  }
+}
+
+int chamfer_loss_launch(const float* dist1, const float* dist2, int B, int N, int M, int kind, float* sums, float* loss,
+                        cudaStream_t stream) {
+  dim3 grid(B, 2);
+  chamfer_metrics_kernel<<<grid, 512, 0, stream>>>(dist1, dist2, N, M, 0.f, sums, nullptr);
+  chamfer_loss_finalize_kernel<<<1, 128, 0, stream>>>(sums, B, N, M, kind, loss);
+  count_launch(2);
+  return (int)cudaGetLastError();
+}
+
 int chamfer_metrics_launch(const float* dist1, const float* dist2, int B, int N, int M, float th, float* sums,
                            int32_t* counts, cudaStream_t stream) {
   dim3 grid(B, 2);

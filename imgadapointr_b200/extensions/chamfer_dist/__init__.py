@@ -24,6 +24,34 @@ class ChamferFunction(torch.autograd.Function):
         return grad_xyz1, grad_xyz2
 
 
+class FusedChamferLoss(torch.autograd.Function):
+    """Search + loss reduction + analytic gradient as 5 kernels, no sqrt/mean autograd chain (SURVEY.md section 8f
+    rank 1).  Same values as composing ChamferFunction with torch.sqrt / torch.mean (tests compare both paths);
+    returns a 0-dim tensor (a pair for L2_split)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, kind):
+        dist1, dist2, idx1, idx2 = chamfer.forward(xyz1, xyz2)
+        loss, _ = chamfer.loss_forward(dist1, dist2, kind)
+        ctx.save_for_backward(xyz1, xyz2, idx1, idx2, dist1, dist2)
+        ctx.kind = kind
+        if kind == chamfer.LOSS_L2_SPLIT:
+            return loss[0], loss[1]
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, *grads):
+        xyz1, xyz2, idx1, idx2, dist1, dist2 = ctx.saved_tensors
+        if ctx.kind == chamfer.LOSS_L2_SPLIT:
+            g = torch.stack([grads[0] if grads[0] is not None else torch.zeros_like(dist1[0, 0]),
+                             grads[1] if grads[1] is not None else torch.zeros_like(dist1[0, 0])])
+        else:
+            g = grads[0].reshape(1)
+        gx1, gx2 = chamfer.loss_backward(xyz1.detach().contiguous(), xyz2.detach().contiguous(), idx1, idx2, dist1,
+                                         dist2, ctx.kind, g)
+        return gx1, gx2, None
+
+
 def _filter_zeros(xyz1, xyz2, ignore_zeros):
     batch_size = xyz1.size(0)
     if batch_size == 1 and ignore_zeros:
@@ -35,6 +63,10 @@ def _filter_zeros(xyz1, xyz2, ignore_zeros):
 
 
 class _ChamferBase(torch.nn.Module):
+    #: use the fused search+loss+gradient path (set False to compose ChamferFunction with torch.sqrt/mean exactly
+    #: like the reference's module source does; both paths are parity-tested against each other)
+    fused = True
+
     def __init__(self, ignore_zeros=False):
         super().__init__()
         self.ignore_zeros = ignore_zeros
@@ -43,11 +75,19 @@ class _ChamferBase(torch.nn.Module):
         xyz1, xyz2 = _filter_zeros(xyz1, xyz2, self.ignore_zeros)
         return ChamferFunction.apply(xyz1, xyz2)
 
+    def _fused(self, xyz1, xyz2, kind):
+        xyz1, xyz2 = _filter_zeros(xyz1, xyz2, self.ignore_zeros)
+        if xyz1.size(1) == 0 or xyz2.size(1) == 0:
+            return None  # degenerate: let the composed path reproduce the reference's NaN-from-empty-mean behaviour
+        return FusedChamferLoss.apply(xyz1, xyz2, kind)
+
 
 class ChamferDistanceL2(_ChamferBase):
     """mean(dist1) + mean(dist2)   (__init__.py:28-44)"""
 
     def forward(self, xyz1, xyz2):
+        if self.fused and (out := self._fused(xyz1, xyz2, chamfer.LOSS_L2)) is not None:
+            return out
         dist1, dist2 = self._dists(xyz1, xyz2)
         return torch.mean(dist1) + torch.mean(dist2)
 
@@ -56,6 +96,8 @@ class ChamferDistanceL2_split(_ChamferBase):
     """(mean(dist1), mean(dist2))   (__init__.py:46-62)"""
 
     def forward(self, xyz1, xyz2):
+        if self.fused and (out := self._fused(xyz1, xyz2, chamfer.LOSS_L2_SPLIT)) is not None:
+            return out
         dist1, dist2 = self._dists(xyz1, xyz2)
         return torch.mean(dist1), torch.mean(dist2)
 
@@ -64,6 +106,8 @@ class ChamferDistanceL1(_ChamferBase):
     """(mean(sqrt(dist1)) + mean(sqrt(dist2))) / 2   (__init__.py:64-84)"""
 
     def forward(self, xyz1, xyz2):
+        if self.fused and (out := self._fused(xyz1, xyz2, chamfer.LOSS_L1)) is not None:
+            return out
         dist1, dist2 = self._dists(xyz1, xyz2)
         dist1 = torch.sqrt(dist1)
         dist2 = torch.sqrt(dist2)
@@ -74,6 +118,8 @@ class ChamferDistanceL1_PM(_ChamferBase):
     """mean(sqrt(dist1))   (__init__.py:86-103)"""
 
     def forward(self, xyz1, xyz2):
+        if self.fused and (out := self._fused(xyz1, xyz2, chamfer.LOSS_L1_PM)) is not None:
+            return out
         dist1, _ = self._dists(xyz1, xyz2)
         dist1 = torch.sqrt(dist1)
         return torch.mean(dist1)

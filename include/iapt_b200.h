@@ -76,6 +76,27 @@ int iapt_chamfer_backward(const float* xyz1, const float* xyz2, const int32_t* i
 int iapt_chamfer_reduce(const float* dist1, const float* dist2, int B, int N, int M, float* sums,
                         iapt_stream_t stream);
 
+/* Fused loss modules (extensions/chamfer_dist/__init__.py:28-103) - the "next" row of SURVEY.md section 8f.
+ * iapt_chamfer_loss: from dist1/dist2 writes the per-cloud sums [B,4] (as iapt_chamfer_reduce) AND the final loss
+ * scalars loss[2] with the reference's reductions over ALL B*N / B*M elements:
+ *   IAPT_LOSS_L1       loss[0] = (mean sqrt d1 + mean sqrt d2) / 2          (ChamferDistanceL1,       :64-84)
+ *   IAPT_LOSS_L2       loss[0] =  mean d1 + mean d2                         (ChamferDistanceL2,       :28-44)
+ *   IAPT_LOSS_L2_SPLIT loss[0] =  mean d1, loss[1] = mean d2                (ChamferDistanceL2_split, :46-62)
+ *   IAPT_LOSS_L1_PM    loss[0] =  mean sqrt d1                              (ChamferDistanceL1_PM,    :86-103)
+ * iapt_chamfer_backward_fused: the gradient of that loss w.r.t. xyz1/xyz2 in ONE kernel - iapt_chamfer_backward with
+ * grad_dist formed on the fly (upstream * 0.5/sqrt(d)/count resp. upstream/count), replacing the sqrt/mean autograd
+ * chain.  grad_loss points to the upstream gradient scalar(s) on the device (2 floats for L2_SPLIT, 1 otherwise;
+ * NULL = 1).  A zero distance under L1 yields inf*0 = NaN exactly like the reference's sqrt backward. */
+#define IAPT_LOSS_L1 1
+#define IAPT_LOSS_L2 2
+#define IAPT_LOSS_L2_SPLIT 3
+#define IAPT_LOSS_L1_PM 4
+int iapt_chamfer_loss(const float* dist1, const float* dist2, int B, int N, int M, int kind, float* sums, float* loss,
+                      iapt_stream_t stream);
+int iapt_chamfer_backward_fused(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
+                                const float* dist1, const float* dist2, int kind, const float* grad_loss, int B, int N,
+                                int M, float* grad_xyz1, float* grad_xyz2, iapt_stream_t stream);
+
 /* F-Score pieces (utils/metrics.py:67-90) from the same search: counts[b] = { #{j: sqrt(dist1[b,j]) < th},
  * #{k: sqrt(dist2[b,k]) < th} } as int32 [B,2]. */
 int iapt_fscore_counts(const float* dist1, const float* dist2, int B, int N, int M, float th, int32_t* counts,

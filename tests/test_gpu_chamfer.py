@@ -174,3 +174,42 @@ def test_ignore_zeros_quirk(dev):
     both = torch.cat([partial, partial]).to(dev)
     gt2 = torch.cat([gt, gt]).to(dev)
     assert float(ChamferDistanceL1(ignore_zeros=True)(both, gt2)) == float(ChamferDistanceL1()(both, gt2))
+
+
+@pytest.mark.parametrize("cls", [ChamferDistanceL1, ChamferDistanceL2, ChamferDistanceL2_split, ChamferDistanceL1_PM])
+@pytest.mark.parametrize("B,N,M", [(3, 1024, 1024), (2, 700, 2500), (1, 16384, 2048)])
+def test_fused_loss_path_equals_composed_path(dev, cls, B, N, M):
+    """The fused search+loss+gradient path (default) against the reference-style composition ChamferFunction +
+    torch.sqrt/mean + autograd, values and gradients w.r.t. BOTH clouds, with non-trivial upstream weights."""
+    pred, gt = synthetic.pcn_pair(B, max(N, M), 81)
+    pred, gt = pred[:, :N].contiguous(), gt[:, :M].contiguous()
+    res = {}
+    for fused in (True, False):
+        mod = cls()
+        mod.fused = fused
+        p = pred.to(dev).requires_grad_(True)
+        g = gt.to(dev).requires_grad_(True)
+        out = mod(p, g)
+        out = torch.stack(list(out)) if isinstance(out, tuple) else out.reshape(1)
+        w = torch.tensor([0.7, -1.3], device=dev)[: out.numel()]
+        (out * w).sum().backward()
+        res[fused] = (out.detach(), p.grad.clone(), g.grad.clone() if g.grad is not None else torch.zeros_like(g))
+    a, b = res[True], res[False]
+    assert torch.allclose(a[0], b[0], rtol=1e-6, atol=0)
+    for x, y in ((a[1], b[1]), (a[2], b[2])):
+        assert float((x - y).abs().max()) <= GRAD_RTOL * max(float(y.abs().max()), 1e-30)
+
+
+def test_fused_l1_zero_distance_nan_quirk(dev):
+    """SURVEY hard part 5: a predicted point that coincides exactly with a target makes the reference's L1 backward
+    produce inf * 0 = NaN for that point; the fused path must reproduce it, not hide it."""
+    pred, gt = synthetic.pcn_pair(1, 512, 91)
+    pred[0, 7] = gt[0, 100]
+    nan_sets = []
+    for fused in (True, False):
+        mod = ChamferDistanceL1()
+        mod.fused = fused
+        p = pred.to(dev).requires_grad_(True)
+        mod(p, gt.to(dev)).backward()
+        nan_sets.append(torch.isnan(p.grad).any(dim=-1).cpu())
+    assert bool(nan_sets[0][0, 7]) and torch.equal(nan_sets[0], nan_sets[1])
