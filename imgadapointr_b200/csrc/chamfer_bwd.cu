@@ -7,10 +7,9 @@
 // Owner-computes formulation.  For output point j of cloud side X (other side Y):
 //     grad_X[j] = 2 gX[j] (x_j - y_{idxX[j]})                      "own" term   (chamfer.cu:193-195)
 //               - sum_{k : idxY[k] == j} 2 gY[k] (y_k - x_j)       fan-in term  (chamfer.cu:196-198, roles swapped)
-// A warp owns kBins consecutive output points and keeps their fan-in accumulators in shared memory.  The 8 warps of
-// a CTA own 8 consecutive bin blocks of one (cloud, side) and share the key stream: idxY[b, :] is staged through
-// shared memory once per CTA (register double-buffered 2048-key tiles) and every warp scans it from there in
-// ascending k and only COMPACTS the hits (k, bin) into a small shared-memory list; whenever the list fills it is drained 32 hits at a
+// A warp owns kBins consecutive output points and keeps their fan-in accumulators in shared memory.  It scans the
+// other side's index array idxY[b, :] in ascending k (coalesced 128 B loads, 8 in flight per lane) and only
+// COMPACTS the hits (k, bin) into a small shared-memory list; whenever the list fills it is drained 32 hits at a
 // time: the lanes gather gY[k], y_k, x_j in parallel (one round trip to L2 for 32 hits instead of one per hit) and
 // lanes that hit the same bin are then serialised in list order.  Every accumulator therefore receives its
 // contributions in ascending k: the result is bit-reproducible and independent of the launch geometry, with no
@@ -27,8 +26,7 @@ namespace iapt {
 constexpr int kBwdThreads = 256;
 constexpr int kBwdWarps = kBwdThreads / 32;
 constexpr int kBins = 256;     // output points per warp
-constexpr int kHitCap = 256;   // compacted hits per warp before a drain
-constexpr int kKeyTile = 2048; // keys staged per CTA per step (8 KB)
+constexpr int kHitCap = 256;   // compacted hits per warp before a drain (>= 128 + 32)
 
 struct BwdParams {
   const float* xyz[2];     // [B, n[s], 3]
@@ -37,9 +35,9 @@ struct BwdParams {
   float* grad[2];          // [B, n[s], 3]
   int n[2];
   int B;
-  int ctas_per_cloud[2];    // ceil(n[s] / (kBins * kBwdWarps))
-  long long ctas_side0;     // B * ctas_per_cloud[0]
-  long long total_ctas;
+  int blocks_per_cloud[2];  // ceil(n[s] / kBins)
+  long long warps_side0;    // B * blocks_per_cloud[0]
+  long long total_warps;
   // fused loss mode: g[s] = upstream * scale[s] * (mode == 1 ? 1/sqrt(dist) : 1); upstream read from *grad_out
   int mode;                 // 0 plain, 1 L1 (sqrt), 2 L2
   float scale[2];
@@ -56,29 +54,26 @@ __device__ __forceinline__ float point_weight(int mode, float scaled_upstream, c
 }
 
 __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
-  // A CTA = 8 warps = 8 consecutive bin blocks of ONE (cloud, side): the key stream idxY[b, :] is staged once per
-  // CTA in shared memory (register double-buffered tiles) and scanned by all 8 warps from there.
   __shared__ float acc[kBwdWarps][kBins * 3];
   __shared__ int hit_k[kBwdWarps][kHitCap];
   __shared__ unsigned short hit_bin[kBwdWarps][kHitCap];
-  __shared__ int skeys[kKeyTile];
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * kBwdWarps + warp;
+  if (gw >= p.total_warps) return;  // whole warp exits together; no block-level sync below
 
   int side;
-  long long c = blockIdx.x;
-  if (c < p.ctas_side0) {
+  long long w = gw;
+  if (w < p.warps_side0) {
     side = 0;
   } else {
     side = 1;
-    c -= p.ctas_side0;
+    w -= p.warps_side0;
   }
-  const int cpc = side ? p.ctas_per_cloud[1] : p.ctas_per_cloud[0];
-  const int b = (int)(c / cpc);
-  const int j0 = ((int)(c - (long long)b * cpc) * kBwdWarps + warp) * kBins;
+  const int bpc = side ? p.blocks_per_cloud[1] : p.blocks_per_cloud[0];
+  const int b = (int)(w / bpc);
+  const int j0 = (int)(w - (long long)b * bpc) * kBins;
   const int nX = side ? p.n[1] : p.n[0], nY = side ? p.n[0] : p.n[1];
-  const bool warp_on = j0 < nX;  // ragged tail: idle warps still take part in the block barriers
   const float* __restrict__ X = (side ? p.xyz[1] : p.xyz[0]) + (size_t)b * nX * 3;
   const float* __restrict__ Y = (side ? p.xyz[0] : p.xyz[1]) + (size_t)b * nY * 3;
   const int32_t* __restrict__ idxX = (side ? p.idx[1] : p.idx[0]) + (size_t)b * nX;
@@ -98,7 +93,7 @@ __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
     up1 = __ldg(p.grad_out + p.grad_out_stride);
   }
   const int mode = p.mode;
-  const float wX = __fmul_rn(side ? up1 : up0, scaleX);  // upstream * scale of this side / the other side
+  const float wX = __fmul_rn(side ? up1 : up0, scaleX);  // upstream * scale of this side / of the other side
   const float wY = __fmul_rn(side ? up0 : up1, scaleY);
   const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -139,52 +134,35 @@ __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
   };
 
   if (gY != nullptr) {
-    constexpr int kPerThread = kKeyTile / kBwdThreads;
-    int reg[kPerThread];
-    auto load_tile = [&](int t0) {
+    // ---- scan the other side's nearest-neighbour indices, 256 keys per step, ascending k ---------------------
+    for (int k0 = 0; k0 < nY; k0 += 256) {
+      int key[8];
 #pragma unroll
-      for (int e = 0; e < kPerThread; ++e) {
-        const int k = t0 + e * kBwdThreads + tid;
-        reg[e] = (k < nY) ? __ldg(idxY + k) : -1;
+      for (int e = 0; e < 8; ++e) {
+        const int k = k0 + e * 32 + lane;
+        key[e] = (k < nY) ? __ldg(idxY + k) : -1;
       }
-    };
-    load_tile(0);
-    for (int t0 = 0; t0 < nY; t0 += kKeyTile) {
-      __syncthreads();  // previous tile fully scanned
 #pragma unroll
-      for (int e = 0; e < kPerThread; ++e) skeys[e * kBwdThreads + tid] = reg[e];
-      __syncthreads();
-      if (t0 + kKeyTile < nY) load_tile(t0 + kKeyTile);  // in flight while this tile is scanned
-      if (warp_on) {
-        const int tn = min(kKeyTile, nY - t0);
-        for (int s0 = 0; s0 < tn; s0 += 256) {
-          int key[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) key[e] = skeys[s0 + e * 32 + lane];  // tail entries are -1
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const unsigned bin = (unsigned)(key[e] - j0);
-            const bool hit = (key[e] >= 0) && (bin < (unsigned)kBins) && ((int)bin + j0 < nX);
-            const unsigned mask = __ballot_sync(0xffffffffu, hit);
-            if (mask != 0u) {  // warp-uniform
-              if (hit) {
-                const int pos = count + __popc(mask & lt_mask);
-                hk[pos] = t0 + s0 + e * 32 + lane;
-                hb[pos] = (unsigned short)bin;
-              }
-              count += __popc(mask);
-              __syncwarp();
-              if (count > kHitCap - 32) drain();
-            }
+      for (int e = 0; e < 8; ++e) {
+        const unsigned bin = (unsigned)(key[e] - j0);
+        const bool hit = (key[e] >= 0) && (bin < (unsigned)kBins) && ((int)bin + j0 < nX);
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask != 0u) {  // warp-uniform
+          if (hit) {
+            const int pos = count + __popc(mask & lt_mask);
+            hk[pos] = k0 + e * 32 + lane;
+            hb[pos] = (unsigned short)bin;
           }
+          count += __popc(mask);
+          __syncwarp();
+          if (count > kHitCap - 32) drain();
         }
       }
     }
     __syncwarp();
-    if (warp_on) drain();
+    drain();
   }
   __syncwarp();
-  if (!warp_on) return;
 
   // ---- own term and write-out ------------------------------------------------------------------------------
   for (int i = lane; i < kBins; i += 32) {
@@ -208,12 +186,12 @@ static int bwd_launch_common(BwdParams& p, int B, int N, int M, cudaStream_t str
   p.n[0] = N;
   p.n[1] = M;
   p.B = B;
-  constexpr int kPerCta = kBins * kBwdWarps;
-  p.ctas_per_cloud[0] = (N + kPerCta - 1) / kPerCta;
-  p.ctas_per_cloud[1] = (M + kPerCta - 1) / kPerCta;
-  p.ctas_side0 = (long long)B * p.ctas_per_cloud[0];
-  p.total_ctas = p.ctas_side0 + (long long)B * p.ctas_per_cloud[1];
-  chamfer_bwd_kernel<<<(unsigned)p.total_ctas, kBwdThreads, 0, stream>>>(p);
+  p.blocks_per_cloud[0] = (N + kBins - 1) / kBins;
+  p.blocks_per_cloud[1] = (M + kBins - 1) / kBins;
+  p.warps_side0 = (long long)B * p.blocks_per_cloud[0];
+  p.total_warps = p.warps_side0 + (long long)B * p.blocks_per_cloud[1];
+  const long long blocks = (p.total_warps + kBwdWarps - 1) / kBwdWarps;
+  chamfer_bwd_kernel<<<(unsigned)blocks, kBwdThreads, 0, stream>>>(p);
   count_launch();
   return (int)cudaGetLastError();
 }
