@@ -1,0 +1,240 @@
+#!/usr/bin/env python
+"""bench_extra.py - the secondary BASELINE.json configs (parity-test / evidence runs, NOT the driver's bench line).
+
+    python bench_extra.py [--configs 1,3,4,5] [--out gpurun_out/extra.json]
+    torchrun --nproc-per-node N ... bench_extra.py --configs 4,5        (batch-sharded over N GPUs)
+
+  C1  one PCN-shaped cloud pair (2048 partial / 16384 gt): Chamfer-L1/L2 + FPS 2048->512 + kNN k=16, beside the
+      PyTorch CPU formulation on the host cores
+  C3  AdaPoinTr encoder geometry at B=48: FPS 2048->512 + DGCNN kNN k=16 (4 shapes) + transformer kNN k=8 (3 shapes),
+      beside the reference formulation (square_distance + topk) run on the same GPU
+  C4  PCN test-set metric sweep: 1200 synthetic clouds (8 categories x 150), CD-L1 / CD-L2 / F-Score@1% per cloud from
+      one search, batch-sharded over the ranks, one all-reduce of the [8 x 4] table
+  C5  scaling stress: Chamfer-L2 fwd+bwd B=256 x 16384^2 and B=16 x 65536^2, batch-sharded over the ranks
+All timings are CUDA events after warm-up, max over ranks; results go to one JSON file (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from imgadapointr_b200 import chamfer  # noqa: E402
+from imgadapointr_b200.extensions.chamfer_dist import ChamferDistanceL1, ChamferDistanceL2  # noqa: E402
+from imgadapointr_b200.models.Transformer_utils import knn_point  # noqa: E402
+from imgadapointr_b200.pointnet2_ops import pointnet2_utils  # noqa: E402
+from imgadapointr_b200.utils import dist_utils, misc, synthetic  # noqa: E402
+from imgadapointr_b200.utils.metrics import MetricAccumulator, per_cloud_metrics  # noqa: E402
+
+FP32_PEAK = 148 * 128 * 2 * 1.965e9
+
+
+def gpu_time(fn, warm=3, iters=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def cpu_time(fn, iters=3):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        fn()
+    return (time.perf_counter() - t0) / iters * 1e3
+
+
+def max_over_ranks(ms, dev):
+    if dist.is_initialized():
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def config1(dev):
+    from oracle import torch_formulation as tf
+
+    gt = synthetic.pcn_gt(1, 16384, 101)
+    partial = synthetic.pcn_partial(gt, 2048, 102)
+    p, g = partial.to(dev), gt.to(dev)
+    l1, l2 = ChamferDistanceL1(), ChamferDistanceL2()
+
+    def fwd_bwd(mod):
+        x = p.detach().requires_grad_(True)
+        mod(x, g).backward()
+
+    out = {"gpu_ms": {}, "cpu_ms": {}, "cpu_threads": torch.get_num_threads()}
+    out["gpu_ms"]["chamfer_l1_fwd_bwd"] = gpu_time(lambda: fwd_bwd(l1))
+    out["gpu_ms"]["chamfer_l2_fwd_bwd"] = gpu_time(lambda: fwd_bwd(l2))
+    out["gpu_ms"]["fps_2048_512"] = gpu_time(lambda: pointnet2_utils.furthest_point_sample(p, 512))
+    out["gpu_ms"]["knn_k16_2048x2048"] = gpu_time(lambda: knn_point(16, p, p))
+
+    def cpu_l1():
+        x = partial.clone().requires_grad_(True)
+        tf.chamfer_l1(x, gt).backward()
+
+    out["cpu_ms"]["chamfer_l1_fwd_bwd"] = cpu_time(cpu_l1)
+    out["cpu_ms"]["fps_2048_512"] = cpu_time(lambda: tf.fps_loop(partial, 512), iters=1)
+    out["cpu_ms"]["knn_k16_2048x2048"] = cpu_time(lambda: tf.knn_point(16, partial, partial))
+    return out
+
+
+ENC_KNN = [(16, 2048, 2048), (16, 2048, 512), (16, 512, 512), (16, 512, 256), (8, 256, 256), (8, 512, 512), (8, 256, 512)]
+# (k, R = #reference points, Q = #queries): base_blocks.py:606,611,616,621 (DGCNN) and :331,361,364 (transformer)
+
+
+def config3(dev, B=48):
+    from oracle import torch_formulation as tf
+
+    gt = synthetic.pcn_gt(B, 16384, 303)
+    xyz = synthetic.pcn_partial(gt, 2048, 304).to(dev)
+    out = {"B": B, "per_op_ms": {}}
+    out["per_op_ms"]["fps_2048_512"] = gpu_time(lambda: pointnet2_utils.furthest_point_sample(xyz, 512))
+    out["per_op_ms"]["misc_fps_2048_256"] = gpu_time(lambda: misc.fps(xyz, 256))
+    c512 = misc.fps(xyz, 512)
+    c256 = misc.fps(c512, 256)
+    clouds = {2048: xyz, 512: c512, 256: c256}
+    tot_ours = tot_ref = 0.0
+    for (k, R, Q) in ENC_KNN:
+        ref_pts, qry = clouds[R], clouds[Q]
+        ours = gpu_time(lambda: knn_point(k, ref_pts, qry))
+        refgpu = gpu_time(lambda: tf.knn_point(k, ref_pts, qry))
+        out["per_op_ms"][f"knn_k{k}_R{R}_Q{Q}"] = {"ours": ours, "reference_formulation_on_gpu": refgpu}
+        tot_ours += ours
+        tot_ref += refgpu
+
+    def sequence():
+        pointnet2_utils.furthest_point_sample(xyz, 512)
+        pointnet2_utils.furthest_point_sample(c512, 256)
+        for (k, R, Q) in ENC_KNN:
+            knn_point(k, clouds[R], clouds[Q])
+
+    seq = gpu_time(sequence)
+    out["sequence_ms"] = seq
+    out["clouds_per_s_whole_sequence"] = B / (seq * 1e-3)
+    out["knn_total_ms"] = {"ours": tot_ours, "reference_formulation_on_gpu": tot_ref}
+    out["fps_clouds_per_s"] = B / (out["per_op_ms"]["fps_2048_512"] * 1e-3)
+    return out
+
+
+def config4(dev, rank, world, n_per_cat=150, n_cat=8, chunk=25):
+    total = n_per_cat * n_cat
+    b, e = dist_utils.shard_range(total, rank, world)
+    acc = MetricAccumulator(n_cat, dev)
+    # generate this rank's clouds (seed 404 + global index), category = index // n_per_cat
+    t_gen = time.perf_counter()
+    preds, gts, cats = [], [], []
+    for i in range(b, e):
+        p, g = synthetic.pcn_pair(1, 16384, 404 + i, noise=0.004 + 0.001 * (i % 7))
+        preds.append(p)
+        gts.append(g)
+        cats.append(i // n_per_cat)
+    t_gen = time.perf_counter() - t_gen
+    preds = torch.cat(preds).to(dev)
+    gts = torch.cat(gts).to(dev)
+    cats = torch.tensor(cats, device=dev)
+
+    def sweep():
+        acc.table.zero_()
+        for s in range(0, e - b, chunk):
+            f, c1, c2 = per_cloud_metrics(preds[s:s + chunk], gts[s:s + chunk])
+            acc.update_batch(cats[s:s + chunk], f, c1, c2)
+        acc.reduce()
+
+    sweep()
+    torch.cuda.synchronize()
+    if dist.is_initialized():
+        dist.barrier()
+    a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    sweep()
+    z.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(a.elapsed_time(z), dev)
+    overall = acc.overall().tolist()
+    return {"clouds": total, "world": world, "sweep_ms": ms, "clouds_per_s": total / (ms * 1e-3),
+            "overall_F_CDL1_CDL2": overall, "host_generation_s_per_rank": t_gen,
+            "note": "one NN search per cloud yields CD-L1, CD-L2 and F-Score (the reference runs 4 searches + 2 KD-tree "
+                    "passes per cloud, tools/runner.py:552-560)"}
+
+
+def config5(dev, rank, world):
+    out = {}
+    l2 = ChamferDistanceL2()
+    for name, B, N in (("B256_16384", 256, 16384), ("B16_65536", 16, 65536)):
+        b, e = dist_utils.shard_range(B, rank, world)
+        nb = e - b
+        x = (torch.rand((nb, N, 3), generator=torch.Generator().manual_seed(505 + rank)) - 0.5).to(dev)
+        y = (torch.rand((nb, N, 3), generator=torch.Generator().manual_seed(605 + rank)) - 0.5).to(dev)
+
+        def step():
+            p = x.detach().requires_grad_(True)
+            loss = l2(p, y)
+            loss.backward()
+            if dist.is_initialized():
+                dist_utils.reduce_tensor(loss.detach())
+
+        ms = max_over_ranks(gpu_time(step, warm=2, iters=5), dev)
+        pairs = B * N * N
+        out[name] = {"global_batch": B, "clouds_per_rank": nb, "ms_per_step": ms, "point_pairs_per_s": pairs / (ms * 1e-3),
+                     "frac_fp32_peak_aggregate": 16 * pairs / (ms * 1e-3) / (FP32_PEAK * world)}
+        del x, y
+        torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,3,4,5")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "extra.json"))
+    ap.add_argument("--c4-per-cat", type=int, default=150)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    want = {int(c) for c in args.configs.split(",")}
+    res = {"world": world, "gpu": torch.cuda.get_device_name(dev), "host_cores": os.cpu_count()}
+    if 1 in want and rank == 0:
+        res["config1"] = config1(dev)
+    if 3 in want and rank == 0:
+        res["config3"] = config3(dev)
+    if world > 1:
+        dist.barrier()
+    if 4 in want:
+        res["config4"] = config4(dev, rank, world, n_per_cat=args.c4_per_cat)
+    if 5 in want:
+        res["config5"] = config5(dev, rank, world)
+    if rank == 0:
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        with open(args.out, "w") as f:
+            json.dump(res, f, indent=1)
+        print(json.dumps(res, indent=1))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
