@@ -33,12 +33,12 @@ def forward(xyz1: torch.Tensor, xyz2: torch.Tensor):
     M = xyz2.size(1)
     dev = xyz1.device
     L = _lib.lib()
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         dist1 = torch.empty((B, N), dtype=torch.float32, device=dev)
         dist2 = torch.empty((B, M), dtype=torch.float32, device=dev)
         idx1 = torch.empty((B, N), dtype=torch.int32, device=dev)
         idx2 = torch.empty((B, M), dtype=torch.int32, device=dev)
-        ws_bytes = int(L.iapt_chamfer_forward_workspace_bytes(B, N, M))
+        ws_bytes = 8 * B * (N + M) + 256 if (B > 0 and N > 0 and M > 0) else 0  # == iapt_chamfer_forward_workspace_bytes
         ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev)
         _lib.check(
             L.iapt_chamfer_forward(_lib.ptr(xyz1), _lib.ptr(xyz2), B, N, M, _lib.ptr(dist1), _lib.ptr(dist2),
@@ -60,7 +60,7 @@ def backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
     if tuple(g1.shape) != (B, N) or tuple(g2.shape) != (B, M) or tuple(idx1.shape) != (B, N) or tuple(idx2.shape) != (B, M):
         raise _lib.IaptError("backward: shape mismatch between xyz, idx and grad_dist")
     L = _lib.lib()
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         gx1 = torch.empty_like(xyz1)
         gx2 = torch.empty_like(xyz2)
         _lib.check(
@@ -75,7 +75,7 @@ def reduce_sums(dist1: torch.Tensor, dist2: torch.Tensor) -> torch.Tensor:
     B, N = dist1.shape
     M = dist2.size(1)
     dev = dist1.device
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         sums = torch.empty((B, 4), dtype=torch.float32, device=dev)
         _lib.check(_lib.lib().iapt_chamfer_reduce(_lib.ptr(dist1), _lib.ptr(dist2), B, N, M, _lib.ptr(sums),
                                                   _lib.stream_ptr(dev)), "iapt_chamfer_reduce")
@@ -87,7 +87,7 @@ def fscore_counts(dist1: torch.Tensor, dist2: torch.Tensor, th: float) -> torch.
     B, N = dist1.shape
     M = dist2.size(1)
     dev = dist1.device
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         counts = torch.empty((B, 2), dtype=torch.int32, device=dev)
         _lib.check(_lib.lib().iapt_fscore_counts(_lib.ptr(dist1), _lib.ptr(dist2), B, N, M, float(th),
                                                  _lib.ptr(counts), _lib.stream_ptr(dev)), "iapt_fscore_counts")
@@ -102,7 +102,7 @@ def loss_forward(dist1: torch.Tensor, dist2: torch.Tensor, kind: int):
     B, N = dist1.shape
     M = dist2.size(1)
     dev = dist1.device
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         sums = torch.empty((B, 4), dtype=torch.float32, device=dev)
         loss = torch.empty((2,), dtype=torch.float32, device=dev)
         _lib.check(_lib.lib().iapt_chamfer_loss(_lib.ptr(dist1), _lib.ptr(dist2), B, N, M, int(kind), _lib.ptr(sums),
@@ -120,7 +120,7 @@ def loss_backward(xyz1, xyz2, idx1, idx2, dist1, dist2, kind: int, grad_loss):
         grad_loss = grad_loss.to(torch.float32).contiguous()
         if grad_loss.numel() != (2 if kind == LOSS_L2_SPLIT else 1):
             raise _lib.IaptError("loss_backward: grad_loss has the wrong number of elements")
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         gx1 = torch.empty_like(xyz1)
         gx2 = torch.empty_like(xyz2)
         _lib.check(

@@ -401,7 +401,7 @@ struct Variant {
   bool prefetch;
 };
 
-static Variant pick_variant(int NA) {
+static Variant pick_variant(int B, int NA, int NS, int slots) {
   static int forced = -1;
   if (forced < 0) {
     forced = 0;
@@ -411,7 +411,12 @@ static Variant pick_variant(int NA) {
     }
   }
   if (forced > 0) return Variant{forced & 0xff, (forced & 0x100) != 0};
-  return Variant{NA >= 8192 ? IAPT_DEFAULT_QT_LARGE : 8, IAPT_DEFAULT_PREFETCH != 0};
+  // QT=16 halves the per-pair LDS/REDUX overhead but makes 4096-point tiles: use it only when even one-stage items
+  // of that size would still oversubscribe the persistent grid 4x (large batches); otherwise QT=8 (2048-point tiles).
+  const long long tiles16 = (NA + kThreads * 16 - 1) / (kThreads * 16);
+  const long long stages = (NS + kSStage - 1) / kSStage;
+  const bool big = NA >= 4096 && (long long)B * tiles16 * stages >= 4LL * slots;
+  return Variant{big ? IAPT_DEFAULT_QT_LARGE : 8, IAPT_DEFAULT_PREFETCH != 0};
 }
 
 template <int QT, bool kPrefetch>
@@ -456,7 +461,8 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  const Variant v = pick_variant(NA);
+  const int slots = num_sms * 2;
+  const Variant v = pick_variant(B, NA, NS, slots);
   const int a_tile = kThreads * v.qt;
 
   FwdParams p;
@@ -470,15 +476,13 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
   p.ticket = ticket;
   p.a_tiles = (NA + a_tile - 1) / a_tile;
   const int total_stages = (NS + kSStage - 1) / kSStage;
-  const int slots = num_sms * 2;
   const long long base_items = (long long)B * p.a_tiles;
-  // Split the streamed side until there are >= 16 items per resident CTA slot (tail < ~3 %), but keep >= 2 stages
-  // (1024 streamed points) per item so the per-item prologue stays negligible.
+  // Split the streamed side until there are >= 16 items per resident CTA slot (tail < ~3 %); an item never gets
+  // less than one 512-point stage.
   int splits = 1;
   if (base_items < 16LL * slots) {
     splits = (int)((16LL * slots + base_items - 1) / base_items);
-    const int max_splits = (total_stages + 1) / 2;
-    if (splits > max_splits) splits = max_splits;
+    if (splits > total_stages) splits = total_stages;
     if (splits < 1) splits = 1;
   }
   p.stages_per_split = (total_stages + splits - 1) / splits;

@@ -35,7 +35,7 @@ def knn_point(nsample, xyz, new_xyz, return_dist=False):
     if k > R:
         raise RuntimeError(f"knn_point: nsample={k} exceeds the number of points {R} (torch.topk raises here too)")
     dev = xyz.device
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         idx = torch.empty((B, Q, k), dtype=torch.int64, device=dev)
         dist = torch.empty((B, Q, k), dtype=torch.float32, device=dev) if return_dist else None
         _lib.check(_lib.lib().iapt_knn(_lib.ptr(xyz), _lib.ptr(new_xyz), B, R, Q, k, _lib.ptr(idx), _lib.ptr(dist),

@@ -32,7 +32,7 @@ def _fps(xyz: torch.Tensor, npoint: int, skip_near_origin: bool) -> torch.Tensor
     npoint = int(npoint)
     dev = xyz.device
     L = _lib.lib()
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         idx = torch.empty((B, npoint), dtype=torch.int32, device=dev)
         ws_bytes = int(L.iapt_fps_workspace_bytes(B, N, npoint))
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
@@ -78,7 +78,7 @@ class GatherOperation(torch.autograd.Function):
         idx = _check_idx(idx, B)
         m = idx.size(1)
         dev = features.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             out = torch.empty((B, C, m), dtype=torch.float32, device=dev)
             _lib.check(_lib.lib().iapt_gather(_lib.ptr(features), _lib.ptr(idx), B, C, N, m, _lib.ptr(out),
                                               _lib.stream_ptr(dev)), "iapt_gather")
@@ -92,7 +92,7 @@ class GatherOperation(torch.autograd.Function):
         grad_out = grad_out.to(torch.float32).contiguous()
         B, C, m = grad_out.shape
         dev = grad_out.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             gfeat = torch.empty((B, C, ctx.N), dtype=torch.float32, device=dev)
             _lib.check(_lib.lib().iapt_gather_grad(_lib.ptr(grad_out), _lib.ptr(idx), B, C, ctx.N, m, _lib.ptr(gfeat),
                                                    _lib.stream_ptr(dev)), "iapt_gather_grad")
@@ -110,7 +110,7 @@ def gather_xyz(xyz: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     idx = _check_idx(idx, B)
     m = idx.size(1)
     dev = xyz.device
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         out = torch.empty((B, m, 3), dtype=torch.float32, device=dev)
         _lib.check(_lib.lib().iapt_gather_xyz(_lib.ptr(xyz), _lib.ptr(idx), B, N, m, _lib.ptr(out),
                                               _lib.stream_ptr(dev)), "iapt_gather_xyz")

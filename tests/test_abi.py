@@ -59,6 +59,8 @@ def test_version_errors_and_workspace_arithmetic():
     assert L.iapt_error_string(0) == b"success"
     assert L.iapt_chamfer_forward_workspace_bytes(48, 16384, 16384) == 8 * 48 * 2 * 16384 + 256
     assert L.iapt_chamfer_forward_workspace_bytes(0, 5, 5) == 0
+    for (B, N, M) in [(1, 1, 1), (3, 700, 16384), (256, 16384, 16384)]:  # chamfer.py computes this inline
+        assert L.iapt_chamfer_forward_workspace_bytes(B, N, M) == 8 * B * (N + M) + 256
     assert L.iapt_fps_workspace_bytes(4, 2048, 512) == 0
     assert L.iapt_fps_workspace_bytes(2, 65536, 512) == 2 * 65536 * 4
     # argument validation happens before any CUDA call
