@@ -94,24 +94,39 @@ def kernel(rep, tag):
     old["source"] = f"{tag}: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch"
     json.dump(old, open(tpath, "w"), indent=1)
     src = ncu_csv(rep, "source")
-    h = src[1]
-    ix = {x: i for i, x in enumerate(h)}
-    data = [r for r in src[2:] if len(r) == len(h)]
-    tot = sum(int(r[ix["# Samples"]]) for r in data) or 1
-    kinds = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
-    dst = os.path.join(ROOT, "profiles", f"{tag}_{name}_stalls.txt")
-    with open(dst, "w") as f:
-        f.write(f"# warp stall sampling, {tot} samples; share by reason\n")
-        for k in sorted(kinds, key=lambda k: -sum(int(r[ix[k]]) for r in data)):
-            n = sum(int(r[ix[k]]) for r in data)
-            if n:
-                f.write(f"{k:28s} {100 * n / tot:6.2f}%\n")
-        f.write("\n# top 40 instructions by samples\n")
-        for r in sorted(data, key=lambda r: -int(r[ix["# Samples"]]))[:40]:
-            st = {k[6:]: int(r[ix[k]]) for k in kinds if int(r[ix[k]])}
-            top = ", ".join(f"{k}={v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:4])
-            f.write(f"{int(r[ix['# Samples']]):7d}  {r[ix['Source']].strip()[:64]:64s} {top}\n")
-    print("wrote", dst)
+    # the source page holds one block per profiled launch: a "Kernel Name" row, a header row, then instructions
+    blocks, cur = [], None
+    for r in src:
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "hdr": None, "rows": []}
+            blocks.append(cur)
+        elif cur is not None and cur["hdr"] is None:
+            cur["hdr"] = r
+        elif cur is not None and len(r) == len(cur["hdr"]):
+            cur["rows"].append(r)
+    seen = set()
+    for blk in blocks:
+        name = blk["name"].split("(")[0].split("::")[-1].split("<")[0].split()[-1]
+        if name in seen:
+            continue
+        seen.add(name)
+        h, data = blk["hdr"], blk["rows"]
+        ix = {x: i for i, x in enumerate(h)}
+        tot = sum(int(r[ix["# Samples"]]) for r in data) or 1
+        kinds = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
+        dst = os.path.join(ROOT, "profiles", f"{tag}_{name}_stalls.txt")
+        with open(dst, "w") as f:
+            f.write(f"# {blk['name']}\n# warp stall sampling, {tot} samples; share by reason\n")
+            for k in sorted(kinds, key=lambda k: -sum(int(r[ix[k]]) for r in data)):
+                n = sum(int(r[ix[k]]) for r in data)
+                if n:
+                    f.write(f"{k:28s} {100 * n / tot:6.2f}%\n")
+            f.write("\n# top 40 instructions by samples\n")
+            for r in sorted(data, key=lambda r: -int(r[ix["# Samples"]]))[:40]:
+                st = {k[6:]: int(r[ix[k]]) for k in kinds if int(r[ix[k]])}
+                top = ", ".join(f"{k}={v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:4])
+                f.write(f"{int(r[ix['# Samples']]):7d}  {r[ix['Source']].strip()[:64]:64s} {top}\n")
+        print("wrote", dst)
 
 
 if __name__ == "__main__":
