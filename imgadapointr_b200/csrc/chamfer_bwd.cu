@@ -25,7 +25,7 @@ namespace iapt {
 
 constexpr int kBwdThreads = 256;
 constexpr int kBwdWarps = kBwdThreads / 32;
-constexpr int kBins = 256;     // output points per warp
+constexpr int kBins = 512;     // output points per warp
 constexpr int kHitCap = 256;   // compacted hits per warp before a drain (>= 128 + 32)
 
 struct BwdParams {
@@ -45,6 +45,12 @@ struct BwdParams {
   int grad_out_stride;
 };
 
+struct BwdSmem {
+  float acc[kBwdWarps][kBins * 3];
+  int hit_k[kBwdWarps][kHitCap];
+  unsigned short hit_bin[kBwdWarps][kHitCap];
+};
+
 __device__ __forceinline__ float point_weight(int mode, float scaled_upstream, const float* __restrict__ g, int i) {
   // returns 2 * dLoss/d dist[i]
   if (mode == 0) return __fmul_rn(__ldg(g + i), 2.f);
@@ -54,9 +60,8 @@ __device__ __forceinline__ float point_weight(int mode, float scaled_upstream, c
 }
 
 __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
-  __shared__ float acc[kBwdWarps][kBins * 3];
-  __shared__ int hit_k[kBwdWarps][kHitCap];
-  __shared__ unsigned short hit_bin[kBwdWarps][kHitCap];
+  extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(bwd_smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long gw = (long long)blockIdx.x * kBwdWarps + warp;
@@ -84,9 +89,9 @@ __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
   const float* __restrict__ gY = gYb ? gYb + (size_t)b * nY : nullptr;
   float* __restrict__ out = (side ? p.grad[1] : p.grad[0]) + (size_t)b * nX * 3;
   const float scaleX = side ? p.scale[1] : p.scale[0], scaleY = side ? p.scale[0] : p.scale[1];
-  float* a = acc[warp];
-  int* hk = hit_k[warp];
-  unsigned short* hb = hit_bin[warp];
+  float* a = sm.acc[warp];
+  int* hk = sm.hit_k[warp];
+  unsigned short* hb = sm.hit_bin[warp];
   float up0 = 1.f, up1 = 1.f;
   if (p.mode != 0 && p.grad_out != nullptr) {
     up0 = __ldg(p.grad_out);
@@ -191,7 +196,12 @@ static int bwd_launch_common(BwdParams& p, int B, int N, int M, cudaStream_t str
   p.warps_side0 = (long long)B * p.blocks_per_cloud[0];
   p.total_warps = p.warps_side0 + (long long)B * p.blocks_per_cloud[1];
   const long long blocks = (p.total_warps + kBwdWarps - 1) / kBwdWarps;
-  chamfer_bwd_kernel<<<(unsigned)blocks, kBwdThreads, 0, stream>>>(p);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(chamfer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));
+    configured = true;
+  }
+  chamfer_bwd_kernel<<<(unsigned)blocks, kBwdThreads, sizeof(BwdSmem), stream>>>(p);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -279,34 +279,56 @@ __global__ void __launch_bounds__(256) chamfer_resolve_kernel(const float* __res
   const long long totalS = (long long)B * NS;
 
   // ---- A side: 32 points per warp iteration, one candidate chunk per point -------------------------------------
+  // The candidate loads of kRU consecutive points are issued together so kRU gathers are in flight per lane.
+  constexpr int kRU = 4;
   if (distA != nullptr) {
     for (long long t0 = warp_global * 32; t0 < totalA; t0 += n_warps * 32) {
       const long long t = t0 + lane;
-      u64 key = ~0ull;
+      u64 key = 0ull;
       float ax = 0.f, ay = 0.f, az = 0.f;
+      int bl = 0;
       if (t < totalA) {
         key = PA[t];
         ax = A[3 * t];
         ay = A[3 * t + 1];
         az = A[3 * t + 2];
+        bl = (int)(t / NA);
       }
       int myidx = 0;
-      const int n_here = (int)min((long long)32, totalA - t0);
-      for (int j = 0; j < n_here; ++j) {
-        const u64 kj = __shfl_sync(0xffffffffu, key, j);
-        const float x = __shfl_sync(0xffffffffu, ax, j);
-        const float y = __shfl_sync(0xffffffffu, ay, j);
-        const float z = __shfl_sync(0xffffffffu, az, j);
-        const int b = (int)((t0 + j) / NA);
-        const int cand = (int)(unsigned)kj * kChunk + lane;
-        bool eq = false;
-        if (cand < NS) {
-          const float* c = S + ((size_t)b * NS + cand) * 3;
-          eq = sqdist(x, y, z, c[0], c[1], c[2]) == __uint_as_float((unsigned)(kj >> 32));
+#pragma unroll 1
+      for (int j0 = 0; j0 < 32; j0 += kRU) {
+        if (t0 + j0 >= totalA) break;  // warp-uniform
+        float cx[kRU], cy[kRU], cz[kRU];
+        bool ok[kRU];
+        unsigned kd[kRU];
+        int base[kRU];
+#pragma unroll
+        for (int u = 0; u < kRU; ++u) {
+          const int j = j0 + u;
+          const u64 kj = __shfl_sync(0xffffffffu, key, j);
+          const int b = __shfl_sync(0xffffffffu, bl, j);
+          kd[u] = (unsigned)(kj >> 32);
+          base[u] = (int)(unsigned)kj * kChunk;
+          const int cand = base[u] + lane;
+          ok[u] = (t0 + j < totalA) && (cand < NS);
+          cx[u] = cy[u] = cz[u] = 0.f;
+          if (ok[u]) {
+            const float* c = S + ((size_t)b * NS + cand) * 3;
+            cx[u] = __ldg(c);
+            cy[u] = __ldg(c + 1);
+            cz[u] = __ldg(c + 2);
+          }
         }
-        const unsigned hits = __ballot_sync(0xffffffffu, eq);
-        const int first = hits ? (__ffs(hits) - 1) : 0;
-        if (lane == j) myidx = (int)(unsigned)kj * kChunk + first;
+#pragma unroll
+        for (int u = 0; u < kRU; ++u) {
+          const int j = j0 + u;
+          const float x = __shfl_sync(0xffffffffu, ax, j);
+          const float y = __shfl_sync(0xffffffffu, ay, j);
+          const float z = __shfl_sync(0xffffffffu, az, j);
+          const bool eq = ok[u] && (sqdist(x, y, z, cx[u], cy[u], cz[u]) == __uint_as_float(kd[u]));
+          const unsigned hits = __ballot_sync(0xffffffffu, eq);
+          if (lane == j) myidx = base[u] + (hits ? (__ffs(hits) - 1) : 0);
+        }
       }
       if (t < totalA) {
         distA[t] = __uint_as_float((unsigned)(key >> 32));
@@ -318,43 +340,61 @@ __global__ void __launch_bounds__(256) chamfer_resolve_kernel(const float* __res
   if (distS != nullptr) {
     const int per_step = 32 / group;  // group is 8 or 16
     const int sub = lane / group, off = lane % group;
+    const unsigned gmask = (1u << group) - 1u;
     for (long long u0 = warp_global * 32; u0 < totalS; u0 += n_warps * 32) {
-      const long long u = u0 + lane;
-      u64 key = ~0ull;
+      const long long uu = u0 + lane;
+      u64 key = 0ull;
       float sx = 0.f, sy = 0.f, sz = 0.f;
-      if (u < totalS) {
-        key = PS[u];
-        sx = S[3 * u];
-        sy = S[3 * u + 1];
-        sz = S[3 * u + 2];
+      int bl = 0;
+      if (uu < totalS) {
+        key = PS[uu];
+        sx = S[3 * uu];
+        sy = S[3 * uu + 1];
+        sz = S[3 * uu + 2];
+        bl = (int)(uu / NS);
       }
       int myidx = 0;
-      for (int j0 = 0; j0 < 32; j0 += per_step) {
-        const int j = j0 + sub;  // the point this lane helps with
-        const u64 kj = __shfl_sync(0xffffffffu, key, j);
-        const float x = __shfl_sync(0xffffffffu, sx, j);
-        const float y = __shfl_sync(0xffffffffu, sy, j);
-        const float z = __shfl_sync(0xffffffffu, sz, j);
-        bool eq = false;
-        if (u0 + j < totalS) {
-          const int b = (int)((u0 + j) / NS);
+#pragma unroll 1
+      for (int j0 = 0; j0 < 32; j0 += kRU * per_step) {
+        if (u0 + j0 >= totalS) break;  // warp-uniform
+        float cx[kRU], cy[kRU], cz[kRU];
+        bool ok[kRU];
+        unsigned kd[kRU];
+#pragma unroll
+        for (int q = 0; q < kRU; ++q) {
+          const int j = j0 + q * per_step + sub;  // the point this lane helps with
+          const u64 kj = __shfl_sync(0xffffffffu, key, j & 31);
+          const int b = __shfl_sync(0xffffffffu, bl, j & 31);
+          kd[q] = (unsigned)(kj >> 32);
           const int cand = (int)(unsigned)kj * group + off;
-          if (cand < NA) {
+          ok[q] = (j < 32) && (u0 + j < totalS) && (cand < NA);
+          cx[q] = cy[q] = cz[q] = 0.f;
+          if (ok[q]) {
             const float* c = A + ((size_t)b * NA + cand) * 3;
-            eq = sqdist(c[0], c[1], c[2], x, y, z) == __uint_as_float((unsigned)(kj >> 32));
+            cx[q] = __ldg(c);
+            cy[q] = __ldg(c + 1);
+            cz[q] = __ldg(c + 2);
           }
         }
-        const unsigned hits = __ballot_sync(0xffffffffu, eq);
-        // every lane extracts the sub-mask of the point it OWNS in this step, if any
-        const int owner_sub = lane - j0;  // lane j0 + s owns sub-group s
-        if (owner_sub >= 0 && owner_sub < per_step) {
-          const unsigned mine = (hits >> (owner_sub * group)) & ((group == 32) ? 0xffffffffu : ((1u << group) - 1u));
-          myidx = (int)(unsigned)key * group + (mine ? (__ffs(mine) - 1) : 0);
+#pragma unroll
+        for (int q = 0; q < kRU; ++q) {
+          const int jb = j0 + q * per_step;  // first point of this step
+          const int j = jb + sub;
+          const float x = __shfl_sync(0xffffffffu, sx, j & 31);
+          const float y = __shfl_sync(0xffffffffu, sy, j & 31);
+          const float z = __shfl_sync(0xffffffffu, sz, j & 31);
+          const bool eq = ok[q] && (sqdist(cx[q], cy[q], cz[q], x, y, z) == __uint_as_float(kd[q]));
+          const unsigned hits = __ballot_sync(0xffffffffu, eq);
+          const int owner_sub = lane - jb;  // lane jb + s owns sub-group s of this step
+          if (owner_sub >= 0 && owner_sub < per_step) {
+            const unsigned mine = (hits >> (owner_sub * group)) & gmask;
+            myidx = (int)(unsigned)key * group + (mine ? (__ffs(mine) - 1) : 0);
+          }
         }
       }
-      if (u < totalS) {
-        distS[u] = __uint_as_float((unsigned)(key >> 32));
-        idxS[u] = myidx;
+      if (uu < totalS) {
+        distS[uu] = __uint_as_float((unsigned)(key >> 32));
+        idxS[uu] = myidx;
       }
     }
   }
