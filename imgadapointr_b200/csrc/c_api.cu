@@ -26,6 +26,10 @@ int gather_launch(const float*, const int32_t*, int, int, int, int, float*, cuda
 int gather_xyz_launch(const float*, const int32_t*, int, int, int, float*, cudaStream_t);
 int gather_grad_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
 int knn_launch(const float*, const float*, int, int, int, int, int64_t*, float*, cudaStream_t);
+int graph_feature_launch(const float*, const float*, const long long*, int, int, int, int, int, float*, cudaStream_t);
+int index_points_launch(const float*, const long long*, int, int, int, long long, float*, cudaStream_t);
+size_t graph_feature_grad_workspace_bytes(int B, int Nq, int Nk, int k);
+int graph_feature_grad_launch(const float*, const long long*, int, int, int, int, int, float*, float*, void*, cudaStream_t);
 }  // namespace iapt
 
 using namespace iapt;
@@ -195,6 +199,44 @@ int iapt_knn(const float* ref, const float* query, int B, int R, int Q, int k, i
   if (B == 0 || Q == 0) return 0;
   IAPT_REQUIRE(ref && query && idx);
   return knn_launch(ref, query, B, R, Q, k, idx, dist, (cudaStream_t)stream);
+}
+
+int iapt_graph_feature(const float* x_q, const float* x_k, const int64_t* idx, int B, int C, int Nq, int Nk, int k,
+                       float* out, iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && C >= 0 && Nq >= 0 && Nk >= 1 && k >= 0 && B <= 65535);
+  if (B == 0 || C == 0 || Nq == 0 || k == 0) return 0;
+  IAPT_REQUIRE(x_q && x_k && idx && out);
+  return graph_feature_launch(x_q, x_k, (const long long*)idx, B, C, Nq, Nk, k, out, (cudaStream_t)stream);
+}
+
+size_t iapt_graph_feature_grad_workspace_bytes(int B, int Nq, int Nk, int k) {
+  if (B <= 0 || Nq <= 0 || Nk <= 0 || k <= 0) return 0;
+  return graph_feature_grad_workspace_bytes(B, Nq, Nk, k);
+}
+
+int iapt_graph_feature_grad(const float* grad_out, const int64_t* idx, int B, int C, int Nq, int Nk, int k,
+                            float* grad_x_q, float* grad_x_k, void* workspace, size_t workspace_bytes,
+                            iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && C >= 0 && Nq >= 0 && Nk >= 1 && k >= 0 && B <= 65535 && C <= 65535);
+  if (B == 0 || C == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Nq == 0 || k == 0) {
+    cudaError_t e = cudaSuccess;
+    if (grad_x_k) e = cudaMemsetAsync(grad_x_k, 0, sizeof(float) * (size_t)B * C * Nk, st);
+    return (int)e;
+  }
+  IAPT_REQUIRE(grad_out && idx);
+  if (grad_x_k && (workspace == nullptr || workspace_bytes < graph_feature_grad_workspace_bytes(B, Nq, Nk, k)))
+    return IAPT_EWORKSPACE;
+  return graph_feature_grad_launch(grad_out, (const long long*)idx, B, C, Nq, Nk, k, grad_x_q, grad_x_k, workspace, st);
+}
+
+int iapt_index_points(const float* points, const int64_t* idx, int B, int N, int C, long long S, float* out,
+                      iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && N >= 1 && C >= 0 && S >= 0);
+  if (B == 0 || C == 0 || S == 0) return 0;
+  IAPT_REQUIRE(points && idx && out);
+  return index_points_launch(points, (const long long*)idx, B, N, C, S, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

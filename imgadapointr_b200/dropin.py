@@ -45,14 +45,24 @@ def patch_reference_modules() -> list:
     from .utils import metrics as m
     from .utils import misc
 
+    from .models import base_blocks as bb
+
     patched = []
+    ref_bb = sys.modules.get("models.base_blocks")
+    grouper = getattr(ref_bb, "DGCNN_Grouper", None) if ref_bb is not None else None
+    if grouper is not None:  # geometry methods of the reference's grouper (base_blocks.py:547-588)
+        grouper.fps_downsample = staticmethod(bb.fps_downsample)
+        grouper.get_graph_feature = lambda self, coor_q, x_q, coor_k, x_k: bb.get_graph_feature(self.k, coor_q, x_q,
+                                                                                                coor_k, x_k)
+        patched += ["models.base_blocks.DGCNN_Grouper.fps_downsample", "models.base_blocks.DGCNN_Grouper.get_graph_feature"]
     for name, mod in list(sys.modules.items()):
         if mod is None or name.startswith("imgadapointr_b200"):
             continue
         root = name.split(".")[0]
         if root not in ("models", "utils", "tools", "extensions", "datasets"):
             continue
-        for attr, new in (("knn_point", tu.knn_point), ("fps", misc.fps), ("Metrics", m.Metrics)):
+        for attr, new in (("knn_point", tu.knn_point), ("index_points", tu.index_points), ("fps", misc.fps),
+                          ("Metrics", m.Metrics)):
             old = getattr(mod, attr, None)
             if old is not None and old is not new and callable(old):
                 if attr == "fps" and not name.endswith("misc") and getattr(old, "__module__", "") != "utils.misc":

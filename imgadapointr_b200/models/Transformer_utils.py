@@ -55,9 +55,24 @@ def square_distance(src, dst):
 
 
 def index_points(points, idx):
-    """points [B,N,C], idx [B,S] or [B,S,K] -> [B,S,C] / [B,S,K,C] (Transformer_utils.py:53-69), as one gather."""
+    """points [B,N,C], idx [B,S] or [B,S,K] -> [B,S,C] / [B,S,K,C] (Transformer_utils.py:53-69).
+
+    One gather kernel (iapt_index_points) instead of the reference's arange/repeat + advanced indexing; when
+    gradients w.r.t. ``points`` are needed the differentiable torch.gather formulation is used."""
     B = points.shape[0]
     C = points.shape[-1]
     flat = idx.reshape(B, -1).to(torch.int64)
+    fast = (points.is_cuda and points.dtype == torch.float32 and points.dim() == 3 and flat.is_cuda
+            and not (torch.is_grad_enabled() and points.requires_grad))
+    if fast:
+        pts = points.contiguous()
+        flat = flat.contiguous()
+        S = flat.size(1)
+        dev = pts.device
+        with _lib.on_device(dev):
+            out = torch.empty((B, S, C), dtype=torch.float32, device=dev)
+            _lib.check(_lib.lib().iapt_index_points(_lib.ptr(pts), _lib.ptr(flat), B, pts.size(1), C, S, _lib.ptr(out),
+                                                    _lib.stream_ptr(dev)), "iapt_index_points")
+        return out.reshape(*idx.shape, C)
     out = torch.gather(points, 1, flat.unsqueeze(-1).expand(-1, -1, C))
     return out.reshape(*idx.shape, C)

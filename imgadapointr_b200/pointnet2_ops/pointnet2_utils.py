@@ -55,11 +55,45 @@ class FurthestPointSampling(torch.autograd.Function):
         return None, None
 
 
+# ---- prefix reuse --------------------------------------------------------------------
+# Greedy FPS always starts at index 0, so the m-point sample of a cloud is a PREFIX of any longer sample of the same
+# cloud.  The reference samples the same tensor several times per forward (AdaPoinTr.py:113 -> 256 points, :126 -> 64
+# points of the same `xyz`); the second call is served from the first one's result.  A cached result is reused only
+# for the very same live tensor object (weak reference) at the same autograd version, i.e. provably unmodified.
+_prefix_cache = []  # [(weakref(xyz), version, skip, idx)], most recent first
+_PREFIX_CACHE_SIZE = 4
+
+
+def _prefix_lookup(xyz, npoint, skip):
+    for ref, version, sk, idx in _prefix_cache:
+        if ref() is xyz and version == xyz._version and sk == skip and idx.size(1) >= npoint and idx.device == xyz.device:
+            return idx
+    return None
+
+
 def furthest_point_sample(xyz, npoint):
-    return FurthestPointSampling.apply(xyz, npoint)
+    skip = SKIP_NEAR_ORIGIN_DEFAULT if furthest_point_sample.skip_near_origin is None \
+        else furthest_point_sample.skip_near_origin
+    if furthest_point_sample.reuse_prefix and isinstance(xyz, torch.Tensor):
+        hit = _prefix_lookup(xyz, int(npoint), skip)
+        if hit is not None:
+            furthest_point_sample.prefix_hits += 1
+            return hit[:, :int(npoint)].contiguous()
+    out = FurthestPointSampling.apply(xyz, npoint)
+    if furthest_point_sample.reuse_prefix:
+        import weakref
+
+        try:
+            _prefix_cache.insert(0, (weakref.ref(xyz), xyz._version, skip, out))
+            del _prefix_cache[_PREFIX_CACHE_SIZE:]
+        except TypeError:
+            pass
+    return out
 
 
 furthest_point_sample.skip_near_origin = None  # None -> SKIP_NEAR_ORIGIN_DEFAULT
+furthest_point_sample.reuse_prefix = True
+furthest_point_sample.prefix_hits = 0
 
 
 def _check_idx(idx, B):

@@ -136,6 +136,23 @@ int iapt_gather_xyz(const float* xyz, const int32_t* idx, int B, int N, int npoi
 int iapt_knn(const float* ref, const float* query, int B, int R, int Q, int k, int64_t* idx, float* dist,
              iapt_stream_t stream);
 
+/* ---- kNN consumers -----------------------------------------------------------------
+ * iapt_graph_feature replaces the gather / expand / cat after knn_point in DGCNN_Grouper.get_graph_feature
+ * (models/base_blocks.py:582-588):   x_q [B,C,Nq], x_k [B,C,Nk], idx [B,Nq,k] int64 (as knn_point returns)  ->
+ *   out [B,2C,Nq,k]:  out[b,c,q,j] = x_k[b,c,idx[b,q,j]] - x_q[b,c,q],   out[b,C+c,q,j] = x_q[b,c,q].
+ * iapt_graph_feature_grad: grad_out [B,2C,Nq,k] -> grad_x_q [B,C,Nq] and grad_x_k [B,C,Nk] (either may be NULL),
+ * deterministic (inverse index by a stable counting sort of idx, shared by all channels; no float atomics).
+ * iapt_index_points replaces index_points (models/Transformer_utils.py:53-69): points [B,N,C], idx [B,S] int64 (S may be
+ * the flattened Q*k) -> out [B,S,C]. */
+int iapt_graph_feature(const float* x_q, const float* x_k, const int64_t* idx, int B, int C, int Nq, int Nk, int k,
+                       float* out, iapt_stream_t stream);
+size_t iapt_graph_feature_grad_workspace_bytes(int B, int Nq, int Nk, int k);
+int iapt_graph_feature_grad(const float* grad_out, const int64_t* idx, int B, int C, int Nq, int Nk, int k,
+                            float* grad_x_q, float* grad_x_k, void* workspace, size_t workspace_bytes,
+                            iapt_stream_t stream);
+int iapt_index_points(const float* points, const int64_t* idx, int B, int N, int C, long long S, float* out,
+                      iapt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

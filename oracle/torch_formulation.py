@@ -93,3 +93,21 @@ def fscore(pred, gt, th=0.01):
         recall = float((d2 < th).sum()) / float(len(d2))
         fs.append(2 * recall * precision / (recall + precision) if recall + precision else 0.0)
     return sum(fs) / len(fs)
+
+
+def get_graph_feature(k, coor_q, x_q, coor_k, x_k, idx=None):
+    """DGCNN_Grouper.get_graph_feature restated (models/base_blocks.py:565-588): kNN under no_grad, flat gather of the
+    neighbour features, cat(feature - x_q, x_q) -> [B, 2C, Nq, k].  ``idx`` ([B,Nq,k]) overrides the kNN result."""
+    batch_size, num_dims, num_points_k = x_k.shape
+    num_points_q = x_q.size(2)
+    with torch.no_grad():
+        if idx is None:
+            idx = knn_point(k, coor_k.transpose(-1, -2).contiguous(), coor_q.transpose(-1, -2).contiguous())
+        idx = idx.transpose(-1, -2).contiguous()
+        idx_base = torch.arange(0, batch_size, device=x_q.device).view(-1, 1, 1) * num_points_k
+        idx = (idx + idx_base).view(-1)
+    xk = x_k.transpose(2, 1).contiguous()
+    feature = xk.view(batch_size * num_points_k, -1)[idx, :]
+    feature = feature.view(batch_size, k, num_points_q, num_dims).permute(0, 3, 2, 1).contiguous()
+    xq = x_q.view(batch_size, num_dims, num_points_q, 1).expand(-1, -1, -1, k)
+    return torch.cat((feature - xq, xq), dim=1)

@@ -70,11 +70,24 @@ def import_reference():
 
     ref_cd = load("ref_chamfer_dist", "extensions/chamfer_dist/__init__.py")
     ref_tu = load("ref_transformer_utils", "models/Transformer_utils.py")
-    return ref_cd, ref_tu
+    # models/base_blocks.py (DGCNN_Grouper geometry): `from models.Transformer_utils import *`, `from utils import misc`
+    # and `pointnet2_utils` are satisfied by the module loaded above, an empty stand-in and oracle-backed FPS/gather.
+    p2u.furthest_point_sample = lambda xyz, m: torch.from_numpy(oracle.fps(xyz.detach().numpy(), int(m), True))
+    p2u.gather_operation = lambda feat, idx: torch.gather(feat, 2, idx.long()[:, None, :].expand(-1, feat.size(1), -1))
+    models_pkg = types.ModuleType("models")
+    models_pkg.__path__ = []
+    utils_pkg = types.ModuleType("utils")
+    utils_pkg.__path__ = []
+    utils_pkg.misc = types.ModuleType("utils.misc")
+    sys.modules.update({"models": models_pkg, "models.Transformer_utils": ref_tu, "utils": utils_pkg,
+                        "utils.misc": utils_pkg.misc, "extensions": types.ModuleType("extensions"),
+                        "extensions.chamfer_dist": ref_cd})
+    ref_bb = load("ref_base_blocks", "models/base_blocks.py")
+    return ref_cd, ref_tu, ref_bb
 
 
 def main():
-    ref_cd, ref_tu = import_reference()
+    ref_cd, ref_tu, ref_bb = import_reference()
     torch.manual_seed(0)
     # ---- demo samples: FPS (oracle, unpinned), kNN k=16 from the reference's own knn_point -------------------
     for path in sorted(glob.glob(os.path.join(REF, "demo/samples/*/00.pcd"))):
@@ -124,6 +137,27 @@ def main():
     idx = ref_tu.knn_point(4, gt, gt[:, :50].contiguous())
     out["ip_points"], out["ip_idx"], out["ip_out"] = pts.numpy(), idx.numpy(), ref_tu.index_points(pts, idx).numpy()
     np.savez_compressed(os.path.join(HERE, "reference_losses.npz"), **out)
+    # ---- DGCNN_Grouper geometry (base_blocks.py:547-588): the reference's own methods on CPU --------------------------
+    g = torch.Generator().manual_seed(21)
+    B, C, Nk, Nq, k = 2, 8, 300, 100, 16
+    coor_k = torch.rand((B, 3, Nk), generator=g) - 0.5
+    coor_q = coor_k[:, :, :Nq].contiguous()
+    x_k = torch.randn((B, C, Nk), generator=g).requires_grad_(True)
+    x_q = torch.randn((B, C, Nq), generator=g).requires_grad_(True)
+    self_like = types.SimpleNamespace(k=k)
+    feat = ref_bb.DGCNN_Grouper.get_graph_feature(self_like, coor_q, x_q, coor_k, x_k)
+    go = torch.randn(feat.shape, generator=g)
+    feat.backward(go)
+    with torch.no_grad():
+        idx = ref_tu.knn_point(k, coor_k.transpose(-1, -2).contiguous(), coor_q.transpose(-1, -2).contiguous())
+    gg = {"coor_k": coor_k.numpy(), "coor_q": coor_q.numpy(), "x_k": x_k.detach().numpy(), "x_q": x_q.detach().numpy(),
+          "ref_idx": idx.numpy(), "feature": feat.detach().numpy(), "grad_out": go.numpy(),
+          "grad_x_k": x_k.grad.numpy(), "grad_x_q": x_q.grad.numpy()}
+    coor = torch.rand((B, 3, 200), generator=g) - 0.5
+    xf = torch.randn((B, 5, 200), generator=g)
+    nc, nx = ref_bb.DGCNN_Grouper.fps_downsample(coor, xf, 40)
+    gg.update({"fd_coor": coor.numpy(), "fd_x": xf.numpy(), "fd_new_coor": nc.numpy(), "fd_new_x": nx.numpy()})
+    np.savez_compressed(os.path.join(HERE, "reference_grouper.npz"), **gg)
     print("wrote", sorted(os.listdir(HERE)))
 
 

@@ -142,3 +142,28 @@ def test_demo_sample_fixtures(dev):
         assert np.array_equal(fi[0], z["fps512"])
         ki = knn_point(16, xyz.to(dev), xyz.to(dev)).cpu().numpy()
         assert np.array_equal(ki[0], z["knn16"])
+
+
+def test_fps_prefix_reuse_is_exact_and_safe(dev):
+    """SURVEY 8f rank 3: repeated sampling of the SAME unmodified tensor is served from the longer sample's prefix;
+    any in-place modification (autograd version bump) or a different tensor object invalidates it."""
+    fps = pointnet2_utils.furthest_point_sample
+    xyz = synthetic.uniform(3, 1500, 77).to(dev)
+    h0 = fps.prefix_hits
+    a256 = fps(xyz, 256)
+    a64 = fps(xyz, 64)
+    assert fps.prefix_hits == h0 + 1 and torch.equal(a64, a256[:, :64]) and a64.is_contiguous()
+    fps.reuse_prefix = False
+    try:
+        assert torch.equal(fps(xyz, 64), a64)  # identical to a fresh launch
+    finally:
+        fps.reuse_prefix = True
+    b300 = fps(xyz, 300)  # longer than anything cached -> computed, and consistent with the prefix property
+    assert fps.prefix_hits == h0 + 1 and torch.equal(b300[:, :256], a256)
+    xyz[0, 0, 0] += 1.0  # in-place edit bumps the version: the cache must not be used
+    c64 = fps(xyz, 64)
+    assert fps.prefix_hits == h0 + 1
+    assert np.array_equal(c64.cpu().numpy(), oracle.fps(xyz.cpu().numpy(), 64, True))
+    clone = xyz.clone()
+    fps(clone, 32)
+    assert fps.prefix_hits == h0 + 1  # a different tensor object never hits

@@ -1,0 +1,88 @@
+"""GPU parity: kNN consumers - graph feature gather/concat fwd+bwd, index_points, fps_downsample -
+against golden outputs of the REFERENCE'S OWN DGCNN_Grouper methods (tests/golden/reference_grouper.npz) and the
+torch restatement."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from imgadapointr_b200.models import base_blocks as bb
+from imgadapointr_b200.models.Transformer_utils import index_points, knn_point
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "reference_grouper.npz")
+tf = oracle.torch_formulation
+
+
+def _t(z, name, dev):
+    return torch.from_numpy(z[name]).to(dev)
+
+
+def test_graph_feature_matches_reference_golden(dev):
+    z = np.load(GOLD)
+    x_q = _t(z, "x_q", dev).requires_grad_(True)
+    x_k = _t(z, "x_k", dev).requires_grad_(True)
+    idx = _t(z, "ref_idx", dev)
+    out = bb.graph_feature(x_q, x_k, idx)
+    assert torch.equal(out.detach().cpu(), torch.from_numpy(z["feature"]))  # gather + subtract: bit exact
+    out.backward(_t(z, "grad_out", dev))
+    for got, want in ((x_q.grad, z["grad_x_q"]), (x_k.grad, z["grad_x_k"])):
+        want = torch.from_numpy(want)
+        assert float((got.cpu() - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+def test_get_graph_feature_end_to_end_and_determinism(dev):
+    z = np.load(GOLD)
+    k = z["ref_idx"].shape[-1]
+    got = bb.get_graph_feature(k, _t(z, "coor_q", dev), _t(z, "x_q", dev), _t(z, "coor_k", dev), _t(z, "x_k", dev))
+    want = torch.from_numpy(z["feature"])
+    assert got.shape == want.shape
+    # our kNN returns the same neighbour SET in (distance, index) order; every consumer reduces over k
+    # (conv1x1 + GroupNorm + max, base_blocks.py:607-608), so compare order-independently
+    assert torch.equal(got.cpu().sort(dim=-1).values, want.sort(dim=-1).values)
+    assert torch.equal(got.cpu().max(dim=-1).values, want.max(dim=-1).values)
+    # larger, duplicate-heavy case: forward equals the torch restatement for OUR idx, backward is bit-reproducible
+    B, C, Nk, Nq, kk = 4, 35, 2048, 512, 16
+    g = torch.Generator().manual_seed(3)
+    coor_k = (torch.rand((B, 3, Nk), generator=g) - 0.5).to(dev)
+    coor_q = coor_k[:, :, :Nq].contiguous()
+    x_k = torch.randn((B, C, Nk), generator=g).to(dev)
+    x_q = torch.randn((B, C, Nq), generator=g).to(dev)
+    idx = knn_point(kk, coor_k.transpose(1, 2).contiguous(), coor_q.transpose(1, 2).contiguous())
+    idx[:, :50] = 7  # heavy fan-in onto one source point
+    ref = tf.get_graph_feature(kk, coor_q, x_q, coor_k, x_k, idx=idx)
+    go = torch.randn(ref.shape, generator=g).to(dev)
+    grads = []
+    for _ in range(2):
+        a, b = x_q.clone().requires_grad_(True), x_k.clone().requires_grad_(True)
+        out = bb.graph_feature(a, b, idx)
+        assert torch.equal(out, ref)
+        out.backward(go)
+        grads.append((a.grad.clone(), b.grad.clone()))
+    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
+    a, b = x_q.clone().requires_grad_(True), x_k.clone().requires_grad_(True)
+    tf.get_graph_feature(kk, coor_q, a, coor_k, b, idx=idx).backward(go)
+    assert float((grads[0][0] - a.grad).abs().max()) <= 1e-5 * float(a.grad.abs().max())
+    assert float((grads[0][1] - b.grad).abs().max()) <= 1e-5 * float(b.grad.abs().max())
+
+
+def test_fps_downsample_matches_reference_golden(dev):
+    z = np.load(GOLD)
+    nc, nx = bb.fps_downsample(_t(z, "fd_coor", dev), _t(z, "fd_x", dev), z["fd_new_coor"].shape[-1])
+    assert torch.equal(nc.cpu(), torch.from_numpy(z["fd_new_coor"])) and torch.equal(nx.cpu(), torch.from_numpy(z["fd_new_x"]))
+
+
+def test_index_points_kernel_and_grad_path(dev):
+    g = torch.Generator().manual_seed(5)
+    pts = torch.randn((3, 400, 11), generator=g).to(dev)
+    idx2 = torch.randint(0, 400, (3, 77), generator=g).to(dev)
+    idx3 = torch.randint(0, 400, (3, 50, 8), generator=g).to(dev)
+    bi = torch.arange(3, device=dev)
+    assert torch.equal(index_points(pts, idx2), pts[bi.view(3, 1), idx2])
+    assert torch.equal(index_points(pts, idx3), pts[bi.view(3, 1, 1), idx3])
+    p = pts.clone().requires_grad_(True)
+    index_points(p, idx3).sum().backward()  # differentiable path
+    want = torch.zeros(3, 400, device=dev).scatter_add_(1, idx3.reshape(3, -1), torch.ones(3, 400, device=dev))
+    assert torch.allclose(p.grad[..., 0], want)
