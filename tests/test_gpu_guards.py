@@ -1,0 +1,95 @@
+"""GPU: out-of-bounds WRITE detection without compute-sanitizer (closed on this pool): every output and workspace of
+each C-ABI entry point is carved out of a larger guard-filled allocation, the kernel is run on ragged sizes, and the
+guard bytes on both sides must be untouched."""
+import ctypes
+
+import pytest
+import torch
+
+from imgadapointr_b200 import _lib
+from imgadapointr_b200.utils import synthetic
+
+pytestmark = pytest.mark.gpu
+GUARD = 4096  # bytes on each side
+PATTERN = 0xA5
+
+
+class Guarded:
+    def __init__(self, nbytes, dev):
+        self.n = int(nbytes)
+        self.buf = torch.full((self.n + 2 * GUARD,), PATTERN, dtype=torch.uint8, device=dev)
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + GUARD
+
+    def view(self, dtype, shape):
+        return self.buf[GUARD:GUARD + self.n].view(dtype).view(shape)
+
+    def intact(self):
+        return bool((self.buf[:GUARD] == PATTERN).all()) and bool((self.buf[GUARD + self.n:] == PATTERN).all())
+
+
+@pytest.mark.parametrize("B,N,M", [(1, 1, 1), (2, 33, 7), (3, 513, 2049), (2, 4097, 300), (1, 9000, 8191)])
+def test_chamfer_entry_points_stay_in_bounds(dev, B, N, M):
+    L = _lib.lib()
+    st = _lib.stream_ptr(dev)
+    x1 = synthetic.uniform(B, N, 1).to(dev)
+    x2 = synthetic.uniform(B, M, 2).to(dev)
+    d1, d2 = Guarded(4 * B * N, dev), Guarded(4 * B * M, dev)
+    i1, i2 = Guarded(4 * B * N, dev), Guarded(4 * B * M, dev)
+    wsn = L.iapt_chamfer_forward_workspace_bytes(B, N, M)
+    ws = Guarded(wsn, dev)
+    _lib.check(L.iapt_chamfer_forward(x1.data_ptr(), x2.data_ptr(), B, N, M, d1.ptr, d2.ptr, i1.ptr, i2.ptr, ws.ptr, wsn,
+                                      st), "fwd")
+    torch.cuda.synchronize()
+    assert all(g.intact() for g in (d1, d2, i1, i2, ws))
+    gx1, gx2 = Guarded(12 * B * N, dev), Guarded(12 * B * M, dev)
+    _lib.check(L.iapt_chamfer_backward(x1.data_ptr(), x2.data_ptr(), i1.ptr, i2.ptr, d1.ptr, d2.ptr, B, N, M, gx1.ptr,
+                                       gx2.ptr, st), "bwd")
+    sums, loss, cnt = Guarded(16 * B, dev), Guarded(8, dev), Guarded(8 * B, dev)
+    _lib.check(L.iapt_chamfer_loss(d1.ptr, d2.ptr, B, N, M, 1, sums.ptr, loss.ptr, st), "loss")
+    _lib.check(L.iapt_fscore_counts(d1.ptr, d2.ptr, B, N, M, ctypes.c_float(0.1), cnt.ptr, st), "fs")
+    gy1, gy2 = Guarded(12 * B * N, dev), Guarded(12 * B * M, dev)
+    _lib.check(L.iapt_chamfer_backward_fused(x1.data_ptr(), x2.data_ptr(), i1.ptr, i2.ptr, d1.ptr, d2.ptr, 1, None, B, N,
+                                             M, gy1.ptr, gy2.ptr, st), "bwdf")
+    torch.cuda.synchronize()
+    assert all(g.intact() for g in (gx1, gx2, sums, loss, cnt, gy1, gy2, d1, d2, i1, i2))
+    assert torch.isfinite(gx1.view(torch.float32, (B, N, 3))).all()
+
+
+@pytest.mark.parametrize("B,N,m,k", [(2, 7, 7, 3), (3, 129, 64, 16), (2, 3000, 100, 33), (1, 20000, 50, 8)])
+def test_fps_gather_knn_graph_stay_in_bounds(dev, B, N, m, k):
+    L = _lib.lib()
+    st = _lib.stream_ptr(dev)
+    xyz = synthetic.uniform(B, N, 3).to(dev)
+    idx = Guarded(4 * B * m, dev)
+    wsn = L.iapt_fps_workspace_bytes(B, N, m)
+    ws = Guarded(max(wsn, 4), dev)
+    _lib.check(L.iapt_fps(xyz.data_ptr(), B, N, m, 1, idx.ptr, ws.ptr, wsn, st), "fps")
+    out_xyz = Guarded(12 * B * m, dev)
+    _lib.check(L.iapt_gather_xyz(xyz.data_ptr(), idx.ptr, B, N, m, out_xyz.ptr, st), "gxyz")
+    C = 5
+    feat = torch.randn((B, C, N), device=dev)
+    out = Guarded(4 * B * C * m, dev)
+    _lib.check(L.iapt_gather(feat.data_ptr(), idx.ptr, B, C, N, m, out.ptr, st), "gather")
+    gfeat = Guarded(4 * B * C * N, dev)
+    _lib.check(L.iapt_gather_grad(out.ptr, idx.ptr, B, C, N, m, gfeat.ptr, st), "ggrad")
+    Q = min(N, 37)
+    qry = xyz[:, :Q].contiguous()
+    kidx, kdist = Guarded(8 * B * Q * k, dev), Guarded(4 * B * Q * k, dev)
+    _lib.check(L.iapt_knn(xyz.data_ptr(), qry.data_ptr(), B, N, Q, min(k, N), kidx.ptr, kdist.ptr, st), "knn")
+    torch.cuda.synchronize()
+    assert all(g.intact() for g in (idx, ws, out_xyz, out, gfeat, kidx, kdist))
+    kk = min(k, N)
+    xq = torch.randn((B, C, Q), device=dev)
+    gf = Guarded(4 * B * 2 * C * Q * kk, dev)
+    _lib.check(L.iapt_graph_feature(xq.data_ptr(), feat.data_ptr(), kidx.ptr, B, C, Q, N, kk, gf.ptr, st), "gf")
+    gq, gk = Guarded(4 * B * C * Q, dev), Guarded(4 * B * C * N, dev)
+    wn = L.iapt_graph_feature_grad_workspace_bytes(B, Q, N, kk)
+    w2 = Guarded(wn, dev)
+    _lib.check(L.iapt_graph_feature_grad(gf.ptr, kidx.ptr, B, C, Q, N, kk, gq.ptr, gk.ptr, w2.ptr, wn, st), "gfg")
+    ip = Guarded(4 * B * Q * kk * 3, dev)
+    _lib.check(L.iapt_index_points(xyz.data_ptr(), kidx.ptr, B, N, 3, Q * kk, ip.ptr, st), "ip")
+    torch.cuda.synchronize()
+    assert all(g.intact() for g in (gf, gq, gk, w2, ip, kidx))
