@@ -108,6 +108,7 @@ def config3(dev, B=48):
     gt = synthetic.pcn_gt(B, 16384, 303)
     xyz = synthetic.pcn_partial(gt, 2048, 304).to(dev)
     out = {"B": B, "per_op_ms": {}}
+    pointnet2_utils.furthest_point_sample.reuse_prefix = False  # time real launches, not the prefix cache
     out["per_op_ms"]["fps_2048_512"] = gpu_time(lambda: pointnet2_utils.furthest_point_sample(xyz, 512))
     out["per_op_ms"]["misc_fps_2048_256"] = gpu_time(lambda: misc.fps(xyz, 256))
     c512 = misc.fps(xyz, 512)
@@ -128,7 +129,35 @@ def config3(dev, B=48):
         for (k, R, Q) in ENC_KNN:
             knn_point(k, clouds[R], clouds[Q])
 
+    # kNN consumer (8f rank 2): DGCNN graph feature gather/concat, layer-1 shape of the grouper (C=8, Q=R=2048, k=16)
+    # and the widest one (C=64, Q=256, R=512), forward + backward, vs the reference formulation on the same GPU
+    from imgadapointr_b200.models import base_blocks as bb
+
+    out["graph_feature_ms"] = {}
+    for (C, R, Q) in ((8, 2048, 2048), (32, 2048, 512), (64, 512, 256)):
+        xk = torch.randn((B, C, R), device=dev, requires_grad=True)
+        xq = torch.randn((B, C, Q), device=dev, requires_grad=True)
+        ck = clouds[R].transpose(1, 2).contiguous()
+        cq = clouds[Q].transpose(1, 2).contiguous()
+        idx = knn_point(16, clouds[R], clouds[Q])
+        go = torch.randn((B, 2 * C, Q, 16), device=dev)
+
+        def ours_fb():
+            xk.grad = xq.grad = None
+            bb.graph_feature(xq, xk, idx).backward(go)
+
+        def ref_fb():
+            xk.grad = xq.grad = None
+            tf.get_graph_feature(16, cq, xq, ck, xk, idx=idx).backward(go)
+
+        out["graph_feature_ms"][f"C{C}_R{R}_Q{Q}_k16"] = {
+            "ours_fwd": gpu_time(lambda: bb.graph_feature(xq, xk, idx)),
+            "reference_formulation_fwd": gpu_time(lambda: tf.get_graph_feature(16, cq, xq, ck, xk, idx=idx)),
+            "ours_fwd_bwd": gpu_time(ours_fb), "reference_formulation_fwd_bwd": gpu_time(ref_fb),
+            "out_MB": B * 2 * C * Q * 16 * 4 / 1e6}
+
     seq = gpu_time(sequence)
+    pointnet2_utils.furthest_point_sample.reuse_prefix = True
     out["sequence_ms"] = seq
     out["clouds_per_s_whole_sequence"] = B / (seq * 1e-3)
     out["knn_total_ms"] = {"ours": tot_ours, "reference_formulation_on_gpu": tot_ref}

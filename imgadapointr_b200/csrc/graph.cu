@@ -8,14 +8,19 @@
 // backward: grad_x_q is a fixed-order sum over k; grad_x_k is owner-computes through a per-cloud inverse index
 // (stable counting sort of idx built once and shared by all C channels) - no floating-point atomics, whereas the
 // reference's index backward accumulates with atomicAdd in run-dependent order.
+#include <cstdint>
+
 #include "common.cuh"
 
 namespace iapt {
 
 // ---- forward: out[b,c,q,j] = x_k[b,c,idx[b,q,j]] - x_q[b,c,q];  out[b,C+c,q,j] = x_q[b,c,q] ---------------------
+// A thread owns kVec consecutive (q, j) positions (kVec = 4 when k % 4 == 0: one 128-bit store per channel half) and
+// kGfChannelsPerCta channels; all gathers of a thread are independent, so 8 * kVec loads are in flight per thread.
 constexpr int kGfThreads = 256;
 constexpr int kGfChannelsPerCta = 8;
 
+template <int kVec>
 __global__ void __launch_bounds__(kGfThreads) graph_feature_kernel(const float* __restrict__ xq,
                                                                    const float* __restrict__ xk,
                                                                    const long long* __restrict__ idx, int C, int Nq,
@@ -23,18 +28,33 @@ __global__ void __launch_bounds__(kGfThreads) graph_feature_kernel(const float* 
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * kGfChannelsPerCta;
   const long long L = (long long)Nq * k;
-  const long long pos = (long long)blockIdx.x * kGfThreads + threadIdx.x;  // flattened (q, j)
+  const long long pos = ((long long)blockIdx.x * kGfThreads + threadIdx.x) * kVec;  // flattened (q, j)
   if (pos >= L) return;
-  const int q = (int)(pos / k);
-  const int n = (int)__ldg(idx + (size_t)b * L + pos);
+  const int q = (int)(pos / k);  // kVec divides k: all kVec positions share q
+  int n[kVec];
+#pragma unroll
+  for (int v = 0; v < kVec; ++v) n[v] = (int)__ldg(idx + (size_t)b * L + pos + v);
 #pragma unroll
   for (int cc = 0; cc < kGfChannelsPerCta; ++cc) {
     const int c = c0 + cc;
     if (c >= C) break;
     const float vq = __ldg(xq + ((size_t)b * C + c) * Nq + q);
-    const float vk = __ldg(xk + ((size_t)b * C + c) * Nk + n);
-    out[((size_t)b * 2 * C + c) * L + pos] = __fsub_rn(vk, vq);
-    out[((size_t)b * 2 * C + C + c) * L + pos] = vq;
+    const float* row = xk + ((size_t)b * C + c) * Nk;
+    float d[kVec];
+#pragma unroll
+    for (int v = 0; v < kVec; ++v) d[v] = __fsub_rn(__ldg(row + n[v]), vq);
+    float* lo = out + ((size_t)b * 2 * C + c) * L + pos;
+    float* hi = out + ((size_t)b * 2 * C + C + c) * L + pos;
+    if (kVec == 4) {
+      *reinterpret_cast<float4*>(lo) = make_float4(d[0], d[1], d[2], d[3]);
+      *reinterpret_cast<float4*>(hi) = make_float4(vq, vq, vq, vq);
+    } else {
+#pragma unroll
+      for (int v = 0; v < kVec; ++v) {
+        lo[v] = d[v];
+        hi[v] = vq;
+      }
+    }
   }
 }
 
@@ -99,7 +119,7 @@ __global__ void __launch_bounds__(1024) inv_scan_kernel(int* __restrict__ counts
 
 // Step 3: stable fill.  A warp owns kInvBins consecutive bins with their write cursors in shared memory and scans
 // all L keys in ascending position; same-bin hits inside a 32-key step take consecutive slots in lane order.
-constexpr int kInvBins = 256;
+constexpr int kInvBins = 64;
 __global__ void __launch_bounds__(256) inv_fill_kernel(const long long* __restrict__ idx, long long L, int Nk,
                                                        const int* __restrict__ start, int* __restrict__ perm) {
   __shared__ int cursor[8][kInvBins];
@@ -114,15 +134,15 @@ __global__ void __launch_bounds__(256) inv_fill_kernel(const long long* __restri
   const long long* key = idx + (size_t)b * L;
   int* out = perm + (size_t)b * L;
   const unsigned lt = (1u << lane) - 1u;
-  for (long long p0 = 0; p0 < L; p0 += 128) {
-    int kk[4];
+  for (long long p0 = 0; p0 < L; p0 += 256) {
+    int kk[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < 8; ++e) {
       const long long p = p0 + e * 32 + lane;
       kk[e] = (p < L) ? (int)__ldg(key + p) : -1;
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < 8; ++e) {
       const unsigned bin = (unsigned)(kk[e] - j0);
       const bool hit = kk[e] >= 0 && bin < (unsigned)kInvBins;
       const unsigned mask = __ballot_sync(0xffffffffu, hit);
@@ -187,8 +207,14 @@ static inline int grid1d(long long total, int threads, long long cap = 148LL * 3
 int graph_feature_launch(const float* xq, const float* xk, const long long* idx, int B, int C, int Nq, int Nk, int k,
                          float* out, cudaStream_t stream) {
   const long long L = (long long)Nq * k;
-  dim3 grid((unsigned)((L + kGfThreads - 1) / kGfThreads), (C + kGfChannelsPerCta - 1) / kGfChannelsPerCta, B);
-  graph_feature_kernel<<<grid, kGfThreads, 0, stream>>>(xq, xk, idx, C, Nq, Nk, k, out);
+  const unsigned gy = (C + kGfChannelsPerCta - 1) / kGfChannelsPerCta;
+  if (k % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    dim3 grid((unsigned)((L / 4 + kGfThreads - 1) / kGfThreads), gy, B);
+    graph_feature_kernel<4><<<grid, kGfThreads, 0, stream>>>(xq, xk, idx, C, Nq, Nk, k, out);
+  } else {
+    dim3 grid((unsigned)((L + kGfThreads - 1) / kGfThreads), gy, B);
+    graph_feature_kernel<1><<<grid, kGfThreads, 0, stream>>>(xq, xk, idx, C, Nq, Nk, k, out);
+  }
   count_launch();
   return (int)cudaGetLastError();
 }
