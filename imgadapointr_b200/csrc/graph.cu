@@ -18,7 +18,7 @@ namespace iapt {
 // A thread owns kVec consecutive (q, j) positions (kVec = 4 when k % 4 == 0: one 128-bit store per channel half) and
 // kGfChannelsPerCta channels; all gathers of a thread are independent, so 8 * kVec loads are in flight per thread.
 constexpr int kGfThreads = 256;
-constexpr int kGfChannelsPerCta = 8;
+constexpr int kGfChannelsPerCta = 4;
 
 template <int kVec>
 __global__ void __launch_bounds__(kGfThreads) graph_feature_kernel(const float* __restrict__ xq,
@@ -178,23 +178,32 @@ __global__ void __launch_bounds__(256) graph_feature_grad_q_kernel(const float* 
   }
 }
 
-// grad_x_k[b,c,n] = sum_{p in inverse list of n, ascending} go[b,c,p].  One CTA per (b, c): the [Q*k] plane of go
-// is read exactly once (through L1), owner thread per n.
+// grad_x_k[b,c,n] = sum_{p in inverse list of n, ascending} go[b,c,p].  Owner thread per (b, c, n); the list is
+// walked 8 entries at a time so 8 independent gathers of go are in flight, and summed in list order.
 __global__ void __launch_bounds__(256) graph_feature_grad_k_kernel(const float* __restrict__ go,
                                                                    const int* __restrict__ start,
                                                                    const int* __restrict__ perm, int C, long long L,
                                                                    int Nk, float* __restrict__ gk) {
-  const int c = blockIdx.x, b = blockIdx.y;
+  const int c = blockIdx.y, b = blockIdx.z;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= Nk) return;
   const float* plane = go + ((size_t)b * 2 * C + c) * L;
   const int* st = start + (size_t)b * (Nk + 1);
   const int* pm = perm + (size_t)b * L;
-  float* dst = gk + ((size_t)b * C + c) * Nk;
-  for (int n = threadIdx.x; n < Nk; n += blockDim.x) {
-    const int s0 = st[n], s1 = st[n + 1];
-    float s = 0.f;
-    for (int i = s0; i < s1; ++i) s = __fadd_rn(s, __ldg(plane + __ldg(pm + i)));
-    dst[n] = s;
+  const int s0 = st[n], s1 = st[n + 1];
+  float s = 0.f;
+  for (int i0 = s0; i0 < s1; i0 += 8) {
+    int pp[8];
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) pp[e] = (i0 + e < s1) ? __ldg(pm + i0 + e) : -1;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (pp[e] >= 0) ? __ldg(plane + pp[e]) : 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (pp[e] >= 0) s = __fadd_rn(s, v[e]);
   }
+  gk[((size_t)b * C + c) * Nk + n] = s;
 }
 
 static inline int grid1d(long long total, int threads, long long cap = 148LL * 32) {
@@ -249,7 +258,7 @@ int graph_feature_grad_launch(const float* go, const long long* idx, int B, int 
     inv_scan_kernel<<<B, 1024, 0, stream>>>(start, Nk);
     dim3 gf((Nk + 8 * kInvBins - 1) / (8 * kInvBins), B);
     inv_fill_kernel<<<gf, 256, 0, stream>>>(idx, L, Nk, start, perm);
-    dim3 gg(C, B);
+    dim3 gg((Nk + 255) / 256, C, B);
     graph_feature_grad_k_kernel<<<gg, 256, 0, stream>>>(go, start, perm, C, L, Nk, gk);
     count_launch(4);
   }
