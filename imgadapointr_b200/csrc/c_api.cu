@@ -25,7 +25,8 @@ int fps_launch(const float*, int, int, int, int, int32_t*, void*, cudaStream_t);
 int gather_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
 int gather_xyz_launch(const float*, const int32_t*, int, int, int, float*, cudaStream_t);
 int gather_grad_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
-int knn_launch(const float*, const float*, int, int, int, int, int64_t*, float*, cudaStream_t);
+size_t knn_workspace_bytes(int B, int Q, int k);
+int knn_launch(const float*, const float*, int, int, int, int, int64_t*, float*, void*, cudaStream_t);
 int graph_feature_launch(const float*, const float*, const long long*, int, int, int, int, int, float*, cudaStream_t);
 int index_points_launch(const float*, const long long*, int, int, int, long long, float*, cudaStream_t);
 size_t graph_feature_grad_workspace_bytes(int B, int Nq, int Nk, int k);
@@ -191,14 +192,21 @@ int iapt_gather_xyz(const float* xyz, const int32_t* idx, int B, int N, int npoi
   return gather_xyz_launch(xyz, idx, B, N, npoint, out, (cudaStream_t)stream);
 }
 
+size_t iapt_knn_workspace_bytes(int B, int Q, int k) {
+  if (B <= 0 || Q <= 0 || k <= 0) return 0;
+  return knn_workspace_bytes(B, Q, k);
+}
+
 int iapt_knn(const float* ref, const float* query, int B, int R, int Q, int k, int64_t* idx, float* dist,
-             iapt_stream_t stream) {
+             void* workspace, size_t workspace_bytes, iapt_stream_t stream) {
   IAPT_REQUIRE(B >= 0 && R >= 1 && Q >= 0 && k >= 1);
   if (k > IAPT_KNN_MAX_K) return IAPT_EUNSUPPORTED;
   IAPT_REQUIRE(k <= R);
   if (B == 0 || Q == 0) return 0;
   IAPT_REQUIRE(ref && query && idx);
-  return knn_launch(ref, query, B, R, Q, k, idx, dist, (cudaStream_t)stream);
+  const size_t need = knn_workspace_bytes(B, Q, k);
+  if (need > 0 && (workspace == nullptr || workspace_bytes < need)) return IAPT_EWORKSPACE;
+  return knn_launch(ref, query, B, R, Q, k, idx, dist, need ? workspace : nullptr, (cudaStream_t)stream);
 }
 
 int iapt_graph_feature(const float* x_q, const float* x_k, const int64_t* idx, int B, int C, int Nq, int Nk, int k,

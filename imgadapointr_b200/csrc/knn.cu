@@ -9,6 +9,8 @@
 // candidates are inserted with a ballot-computed position and one shuffle-up.
 // Output is ascending by (distance, index); on exact distance ties the LOWEST index wins (references are scanned
 // in ascending index and only a strictly smaller distance displaces a list entry).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace iapt {
@@ -21,12 +23,18 @@ constexpr int kKnnQueriesPerCta = 32;  // queries per CTA (4 per warp), amortise
 template <int kSlots>  // list entries per lane: k <= 32 * kSlots
 __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restrict__ ref, const float* __restrict__ qry,
                                                           int R, int Q, int k, int q_blocks,
-                                                          int64_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+                                                          int64_t* __restrict__ idx_out, float* __restrict__ dist_out,
+                                                          const int* __restrict__ only_flagged) {
   __shared__ float sx[kKnnTile], sy[kKnnTile], sz[kKnnTile];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.x / q_blocks;
   const int q0 = (blockIdx.x - b * q_blocks) * kKnnQueriesPerCta;
+  if (only_flagged != nullptr) {  // second pass of the select path: only queries whose candidate buffer overflowed
+    int any = 0;
+    if (threadIdx.x < kKnnQueriesPerCta && q0 + (int)threadIdx.x < Q) any = only_flagged[(size_t)b * Q + q0 + threadIdx.x];
+    if (!__syncthreads_or(any)) return;
+  }
   const float* __restrict__ Rb = ref + (size_t)b * R * 3;
   const float* __restrict__ Qb = qry + (size_t)b * Q * 3;
   constexpr int kQPW = kKnnQueriesPerCta / kKnnWarps;
@@ -63,6 +71,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
 #pragma unroll
     for (int u = 0; u < kQPW; ++u) {
       if (q0 + warp * kQPW + u >= Q) continue;  // warp-uniform
+      if (only_flagged != nullptr && only_flagged[(size_t)b * Q + q0 + warp * kQPW + u] == 0) continue;
       for (int r0 = 0; r0 < tn; r0 += 32) {
         const int r = r0 + lane;
         float d = kInf;
@@ -112,6 +121,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
   for (int u = 0; u < kQPW; ++u) {
     const int q = q0 + warp * kQPW + u;
     if (q >= Q) continue;
+    if (only_flagged != nullptr && only_flagged[(size_t)b * Q + q] == 0) continue;
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
       const int e = s * 32 + lane;
@@ -124,14 +134,190 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
   }
 }
 
+// ---- k <= 16: thread-per-query threshold selection ------------------------------------------------------------
+// The warp-per-query kernel above spends most of its issue slots on list insertions (ncu: issue-bound, 81 %).
+// For the encoder's k = 8 / 16 calls a cheaper exact scheme: every THREAD owns one query and sweeps the references
+// (broadcast LDS.128 from a shared-memory tile) twice:
+//   sweep 1: 32 running minima, one per residue class of the reference index (mod 32) - 1 FMNMX per pair.  The k-th
+//            smallest of those 32 minima, tau0, is an upper bound on the k-th nearest distance (they belong to 32
+//            distinct references) and a tight one: ~22 references lie below it for k = 16, R = 2048.
+//   sweep 2: references with d < tau0, plus the first k with d == tau0 (ties at the threshold, e.g. zero padding), are
+//            appended in ascending index to a per-thread candidate list (u16/u32 indices in shared memory);
+//   select : a stable insertion sort by distance of the <= kSelCap candidates gives the k nearest ascending by
+//            (distance, index) - the same lowest-index tie rule.
+// A query whose candidate list overflows (adversarial clustering) is flagged and redone by knn_kernel<1>.
+constexpr int kSelThreads = 128;
+constexpr int kSelTile = 2048;  // references per smem tile (float4: 32 KB)
+constexpr int kSelCap = 64;     // candidates per query
+constexpr int kSelMaxK = 16;
+
+__device__ __forceinline__ void cmpswap(float& a, float& b) {
+  const float lo = fminf(a, b), hi = fmaxf(a, b);
+  a = lo;
+  b = hi;
+}
+
+// in-register bitonic sort of 32 floats (ascending); indices are compile-time after unrolling
+__device__ __forceinline__ void sort32(float (&v)[32]) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int j = i ^ stride;
+        if (j > i) {
+          if ((i & size) == 0)
+            cmpswap(v[i], v[j]);
+          else
+            cmpswap(v[j], v[i]);
+        }
+      }
+    }
+  }
+}
+
+struct __align__(16) SelSmem {
+  float4 ref[kSelTile];
+  unsigned short cand[kSelCap][kSelThreads];  // candidate reference indices (R <= 65536 on this path)
+  float topd[kSelMaxK][kSelThreads];
+  int topi[kSelMaxK][kSelThreads];
+};
+
+template <bool kWide>  // kWide: reference indices do not fit 16 bits -> candidates stored in global scratch instead
+__global__ void __launch_bounds__(kSelThreads) knn_select_kernel(const float* __restrict__ ref,
+                                                                 const float* __restrict__ qry, int R, int Q, int k,
+                                                                 int q_blocks, int64_t* __restrict__ idx_out,
+                                                                 float* __restrict__ dist_out, int* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char sel_raw[];
+  SelSmem& sm = *reinterpret_cast<SelSmem*>(sel_raw);
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / q_blocks;
+  const int q = (blockIdx.x - b * q_blocks) * kSelThreads + tid;
+  const bool live = q < Q;
+  const float* __restrict__ Rb = ref + (size_t)b * R * 3;
+  const float kInf = __int_as_float(0x7f800000);
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (live) {
+    const float* qp = qry + ((size_t)b * Q + q) * 3;
+    qx = __ldg(qp);
+    qy = __ldg(qp + 1);
+    qz = __ldg(qp + 2);
+  }
+
+  auto stage = [&](int t0, int tn) {
+    __syncthreads();
+    for (int r = tid; r < kSelTile; r += kSelThreads) {
+      float4 v = make_float4(kPadCoord(), kPadCoord(), kPadCoord(), 0.f);
+      if (r < tn) {
+        const float* p = Rb + 3 * (size_t)(t0 + r);
+        v = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+      }
+      sm.ref[r] = v;
+    }
+    __syncthreads();
+  };
+
+  // ---- sweep 1: residue-class minima ---------------------------------------------------------------------------
+  float mn[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) mn[i] = kInf;
+  for (int t0 = 0; t0 < R; t0 += kSelTile) {
+    const int tn = min(kSelTile, R - t0);
+    stage(t0, tn);
+    const int steps = (tn + 31) / 32;  // padded entries are 1e18 sentinels: distances ~3e36, never below a real one
+    for (int s = 0; s < steps; ++s) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float4 p = sm.ref[s * 32 + i];
+        mn[i] = fminf(mn[i], sqdist(qx, qy, qz, p.x, p.y, p.z));
+      }
+    }
+  }
+  sort32(mn);
+  float tau = mn[0];
+#pragma unroll
+  for (int i = 1; i < kSelMaxK; ++i)
+    if (i < k) tau = mn[i];  // k-th smallest class minimum (k <= 16)
+
+  // ---- sweep 2: collect candidates -----------------------------------------------------------------------------
+  int count = 0, eq_taken = 0;
+  bool overflow = false;
+  for (int t0 = 0; t0 < R; t0 += kSelTile) {
+    const int tn = min(kSelTile, R - t0);
+    if (R > kSelTile || t0 > 0) stage(t0, tn);  // single-tile clouds are still resident from sweep 1
+#pragma unroll 8
+    for (int r = 0; r < tn; ++r) {
+      const float4 p = sm.ref[r];
+      const float d = sqdist(qx, qy, qz, p.x, p.y, p.z);
+      const bool take = (d < tau) || (d == tau && eq_taken < k);
+      if (take) {
+        if (d == tau) ++eq_taken;
+        if (count < kSelCap)
+          sm.cand[count][tid] = (unsigned short)(t0 + r);
+        else
+          overflow = true;
+        ++count;
+      }
+    }
+  }
+  if (kWide) overflow = overflow || (R > 65536);
+  if (live) flags[(size_t)b * Q + q] = overflow ? 1 : 0;
+  if (!live || overflow) return;
+
+  // ---- select: stable insertion by distance (candidates arrive in ascending index) ---------------------------------
+  int have = 0;
+  for (int c = 0; c < count; ++c) {
+    const int r = sm.cand[c][tid];
+    const float* p = Rb + 3 * (size_t)r;
+    const float d = sqdist(qx, qy, qz, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+    if (have == k && !(d < sm.topd[k - 1][tid])) continue;
+    int pos = have < k ? have : k - 1;
+    while (pos > 0 && d < sm.topd[pos - 1][tid]) {
+      sm.topd[pos][tid] = sm.topd[pos - 1][tid];
+      sm.topi[pos][tid] = sm.topi[pos - 1][tid];
+      --pos;
+    }
+    sm.topd[pos][tid] = d;
+    sm.topi[pos][tid] = r;
+    if (have < k) ++have;
+  }
+  const size_t o = ((size_t)b * Q + q) * k;
+  for (int j = 0; j < k; ++j) {
+    idx_out[o + j] = (int64_t)sm.topi[j][tid];
+    if (dist_out) dist_out[o + j] = sm.topd[j][tid];
+  }
+}
+
+size_t knn_workspace_bytes(int B, int Q, int k) { return k <= kSelMaxK ? sizeof(int) * (size_t)B * Q : 0; }
+
 int knn_launch(const float* ref, const float* qry, int B, int R, int Q, int k, int64_t* idx, float* dist,
-               cudaStream_t stream) {
+               void* workspace, cudaStream_t stream) {
   const int q_blocks = (Q + kKnnQueriesPerCta - 1) / kKnnQueriesPerCta;
   const long long blocks = (long long)B * q_blocks;
+  static int force_list = -1;
+  if (force_list < 0) {
+    const char* e = std::getenv("IAPT_KNN_FORCE_LIST");
+    force_list = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (k <= kSelMaxK && R <= 65536 && workspace != nullptr && !force_list) {
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(knn_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem));
+      configured = true;
+    }
+    int* flags = static_cast<int*>(workspace);
+    const int sb = (Q + kSelThreads - 1) / kSelThreads;
+    knn_select_kernel<false><<<(unsigned)((long long)B * sb), kSelThreads, sizeof(SelSmem), stream>>>(
+        ref, qry, R, Q, k, sb, idx, dist, flags);
+    knn_kernel<1><<<(unsigned)blocks, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, flags);
+    count_launch(2);
+    return (int)cudaGetLastError();
+  }
   if (k <= 32)
-    knn_kernel<1><<<(unsigned)blocks, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist);
+    knn_kernel<1><<<(unsigned)blocks, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, nullptr);
   else
-    knn_kernel<2><<<(unsigned)blocks, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist);
+    knn_kernel<2><<<(unsigned)blocks, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, nullptr);
   count_launch();
   return (int)cudaGetLastError();
 }

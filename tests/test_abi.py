@@ -66,8 +66,9 @@ def test_version_errors_and_workspace_arithmetic():
     # argument validation happens before any CUDA call
     assert L.iapt_chamfer_forward(None, None, -1, 1, 1, None, None, None, None, None, 0, None) == -1
     assert L.iapt_chamfer_forward(None, None, 1, 4, 4, None, None, None, None, None, 0, None) == -1
-    assert L.iapt_knn(None, None, 1, 10, 10, 65, None, None, None) == -3
-    assert L.iapt_knn(None, None, 1, 10, 10, 11, None, None, None) == -1
+    assert L.iapt_knn(None, None, 1, 10, 10, 65, None, None, None, 0, None) == -3
+    assert L.iapt_knn(None, None, 1, 10, 10, 11, None, None, None, 0, None) == -1
+    assert L.iapt_knn_workspace_bytes(48, 2048, 16) == 4 * 48 * 2048 and L.iapt_knn_workspace_bytes(48, 64, 32) == 0
     assert L.iapt_fps(None, 1, 0, 4, 0, None, None, 0, None) == -1
     assert L.iapt_chamfer_forward(None, None, 0, 4, 4, None, None, None, None, None, 0, None) == 0  # empty batch
 

@@ -78,9 +78,11 @@ def test_fps_gather_knn_graph_stay_in_bounds(dev, B, N, m, k):
     Q = min(N, 37)
     qry = xyz[:, :Q].contiguous()
     kidx, kdist = Guarded(8 * B * Q * k, dev), Guarded(4 * B * Q * k, dev)
-    _lib.check(L.iapt_knn(xyz.data_ptr(), qry.data_ptr(), B, N, Q, min(k, N), kidx.ptr, kdist.ptr, st), "knn")
+    kwn = L.iapt_knn_workspace_bytes(B, Q, min(k, N))
+    kws = Guarded(max(kwn, 4), dev)
+    _lib.check(L.iapt_knn(xyz.data_ptr(), qry.data_ptr(), B, N, Q, min(k, N), kidx.ptr, kdist.ptr, kws.ptr, kwn, st), "knn")
     torch.cuda.synchronize()
-    assert all(g.intact() for g in (idx, ws, out_xyz, out, gfeat, kidx, kdist))
+    assert all(g.intact() for g in (idx, ws, out_xyz, out, gfeat, kidx, kdist, kws))
     kk = min(k, N)
     xq = torch.randn((B, C, Q), device=dev)
     gf = Guarded(4 * B * 2 * C * Q * kk, dev)
