@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
 //   select : a stable insertion sort by distance of the <= kSelCap candidates gives the k nearest ascending by
 //            (distance, index) - the same lowest-index tie rule.
 // A query whose candidate list overflows (adversarial clustering) is flagged and redone by knn_kernel<1>.
-constexpr int kSelThreads = 128;
+constexpr int kSelThreads = 256;
 constexpr int kSelTile = 2048;  // references per smem tile (float4: 32 KB)
 constexpr int kSelCap = 64;     // candidates per query
 constexpr int kSelMaxK = 16;
@@ -178,10 +178,14 @@ __device__ __forceinline__ void sort32(float (&v)[32]) {
 }
 
 struct __align__(16) SelSmem {
-  float4 ref[kSelTile];
+  union {
+    float4 ref[kSelTile];  // sweeps: the reference tile (32 KB)
+    struct {               // select phase (after a block barrier): per-thread sorted top-k
+      float topd[kSelMaxK][kSelThreads];
+      int topi[kSelMaxK][kSelThreads];
+    } top;
+  };
   unsigned short cand[kSelCap][kSelThreads];  // candidate reference indices (R <= 65536 on this path)
-  float topd[kSelMaxK][kSelThreads];
-  int topi[kSelMaxK][kSelThreads];
 };
 
 template <bool kWide>  // kWide: reference indices do not fit 16 bits -> candidates stored in global scratch instead
@@ -263,6 +267,7 @@ __global__ void __launch_bounds__(kSelThreads) knn_select_kernel(const float* __
   }
   if (kWide) overflow = overflow || (R > 65536);
   if (live) flags[(size_t)b * Q + q] = overflow ? 1 : 0;
+  __syncthreads();  // every thread is done with the reference tile: its storage becomes the top-k arrays
   if (!live || overflow) return;
 
   // ---- select: stable insertion by distance (candidates arrive in ascending index) ---------------------------------
@@ -271,21 +276,21 @@ __global__ void __launch_bounds__(kSelThreads) knn_select_kernel(const float* __
     const int r = sm.cand[c][tid];
     const float* p = Rb + 3 * (size_t)r;
     const float d = sqdist(qx, qy, qz, __ldg(p), __ldg(p + 1), __ldg(p + 2));
-    if (have == k && !(d < sm.topd[k - 1][tid])) continue;
+    if (have == k && !(d < sm.top.topd[k - 1][tid])) continue;
     int pos = have < k ? have : k - 1;
-    while (pos > 0 && d < sm.topd[pos - 1][tid]) {
-      sm.topd[pos][tid] = sm.topd[pos - 1][tid];
-      sm.topi[pos][tid] = sm.topi[pos - 1][tid];
+    while (pos > 0 && d < sm.top.topd[pos - 1][tid]) {
+      sm.top.topd[pos][tid] = sm.top.topd[pos - 1][tid];
+      sm.top.topi[pos][tid] = sm.top.topi[pos - 1][tid];
       --pos;
     }
-    sm.topd[pos][tid] = d;
-    sm.topi[pos][tid] = r;
+    sm.top.topd[pos][tid] = d;
+    sm.top.topi[pos][tid] = r;
     if (have < k) ++have;
   }
   const size_t o = ((size_t)b * Q + q) * k;
   for (int j = 0; j < k; ++j) {
-    idx_out[o + j] = (int64_t)sm.topi[j][tid];
-    if (dist_out) dist_out[o + j] = sm.topd[j][tid];
+    idx_out[o + j] = (int64_t)sm.top.topi[j][tid];
+    if (dist_out) dist_out[o + j] = sm.top.topd[j][tid];
   }
 }
 
@@ -300,7 +305,9 @@ int knn_launch(const float* ref, const float* qry, int B, int R, int Q, int k, i
     const char* e = std::getenv("IAPT_KNN_FORCE_LIST");
     force_list = (e && e[0] == '1') ? 1 : 0;
   }
-  if (k <= kSelMaxK && R <= 65536 && workspace != nullptr && !force_list) {
+  // The select path needs enough queries to fill the machine with one thread each; small calls keep the
+  // warp-per-query list kernel (32 lanes per query).
+  if (k <= kSelMaxK && R <= 65536 && workspace != nullptr && !force_list && (long long)B * Q >= 65536) {
     static bool configured = false;
     if (!configured) {
       cudaFuncSetAttribute(knn_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem));
