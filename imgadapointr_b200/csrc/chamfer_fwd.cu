@@ -35,6 +35,9 @@ constexpr int kChunk = 32;    // streamed points per row-index chunk
 #ifndef IAPT_DEFAULT_QT_LARGE
 #define IAPT_DEFAULT_QT_LARGE 16
 #endif
+#ifndef IAPT_DEFAULT_STATIC_SCHED
+#define IAPT_DEFAULT_STATIC_SCHED 0
+#endif
 #ifndef IAPT_DEFAULT_PREFETCH
 #define IAPT_DEFAULT_PREFETCH 0
 #endif
@@ -47,6 +50,7 @@ struct FwdParams {
   u64* PS;  // [B, NS] packed (dist, group id of A)
   unsigned* ticket;  // starts at 0xFFFFFFFF (same memset as the keys); item = atomicAdd(ticket, 1) + 1
   int a_tiles, s_splits, stages_per_split, total_items;
+  int static_sched;  // 1: contiguous, balanced ranges of (cloud, A tile, stage) units per CTA instead of tickets
 };
 
 template <int QT>
@@ -101,18 +105,36 @@ __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) 
   const int warp = tid >> 5;
   const float kInf = __int_as_float(0x7f800000);
 
-  for (;;) {
-    __syncthreads();  // everyone is done with smem (incl. next_item) of the previous item
-    if (tid == 0) sm.next_item = atomicAdd(p.ticket, 1u) + 1u;
-    __syncthreads();
-    const int item = (int)sm.next_item;
-    if (item >= p.total_items) break;
+  const int total_stages = (p.NS + kSStage - 1) / kSStage;
+  // static schedule: this CTA owns stage units [unit, unit_end) of the B * a_tiles * total_stages grid of units
+  const long long n_units = (long long)p.B * p.a_tiles * total_stages;
+  long long unit = n_units * blockIdx.x / gridDim.x;
+  const long long unit_end = n_units * (blockIdx.x + 1) / gridDim.x;
 
-    const int per_cloud = p.a_tiles * p.s_splits;
-    const int b = item / per_cloud;
-    const int rem = item - b * per_cloud;
-    const int at = rem / p.s_splits;
-    const int ss = rem - at * p.s_splits;
+  for (;;) {
+    int b, at, stage0, stage_end;
+    __syncthreads();  // everyone is done with smem (incl. next_item) of the previous item
+    if (p.static_sched) {
+      if (unit >= unit_end) break;
+      const long long tile = unit / total_stages;
+      stage0 = (int)(unit - tile * total_stages);
+      stage_end = (int)min((long long)total_stages, stage0 + (unit_end - unit));
+      b = (int)(tile / p.a_tiles);
+      at = (int)(tile - (long long)b * p.a_tiles);
+      unit += stage_end - stage0;
+    } else {
+      if (tid == 0) sm.next_item = atomicAdd(p.ticket, 1u) + 1u;
+      __syncthreads();
+      const int item = (int)sm.next_item;
+      if (item >= p.total_items) break;
+      const int per_cloud = p.a_tiles * p.s_splits;
+      b = item / per_cloud;
+      const int rem = item - b * per_cloud;
+      at = rem / p.s_splits;
+      const int ss = rem - at * p.s_splits;
+      stage0 = ss * p.stages_per_split;
+      stage_end = min(total_stages, stage0 + p.stages_per_split);
+    }
     const float* __restrict__ Ab = p.A + (size_t)b * p.NA * 3;
     const float* __restrict__ Sb = p.S + (size_t)b * p.NS * 3;
 
@@ -145,10 +167,6 @@ __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) 
     }
 #pragma unroll
     for (int i = 0; i < QT / 4; ++i) sm.prev[i][tid] = make_float4(kInf, kInf, kInf, kInf);
-
-    const int stage0 = ss * p.stages_per_split;
-    const int total_stages = (p.NS + kSStage - 1) / kSStage;
-    const int stage_end = min(total_stages, stage0 + p.stages_per_split);
 
     {  // prologue: first stage -> buffer 0
       float v[2][3];
@@ -519,9 +537,14 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
   const long long base_items = (long long)B * p.a_tiles;
   // Split the streamed side until there are >= 16 items per resident CTA slot (tail < ~3 %); an item never gets
   // less than one 512-point stage.
+  static long long items_per_slot = 0;
+  if (items_per_slot == 0) {
+    const char* e = std::getenv("IAPT_FWD_ITEMS_PER_SLOT");  // development knob
+    items_per_slot = (e && std::atoi(e) > 0) ? std::atoi(e) : 16;
+  }
   int splits = 1;
-  if (base_items < 16LL * slots) {
-    splits = (int)((16LL * slots + base_items - 1) / base_items);
+  if (base_items < items_per_slot * slots) {
+    splits = (int)((items_per_slot * slots + base_items - 1) / base_items);
     if (splits > total_stages) splits = total_stages;
     if (splits < 1) splits = 1;
   }
@@ -529,7 +552,15 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
   p.s_splits = (total_stages + p.stages_per_split - 1) / p.stages_per_split;
   p.total_items = (int)(base_items * p.s_splits);
 
-  const int grid = (int)((long long)p.total_items < (long long)slots ? p.total_items : slots);
+  static int static_sched = -1;
+  if (static_sched < 0) {
+    const char* e = std::getenv("IAPT_FWD_SCHED");  // development knob: "ticket" or "static"
+    static_sched = e ? (e[0] == 's' ? 1 : 0) : IAPT_DEFAULT_STATIC_SCHED;
+  }
+  p.static_sched = static_sched;
+  const long long n_units = base_items * total_stages;
+  const long long want = static_sched ? n_units : (long long)p.total_items;
+  const int grid = (int)(want < (long long)slots ? want : slots);
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (g_profile) {
     cudaEventCreate(&ev0);
