@@ -38,6 +38,9 @@ constexpr int kChunk = 32;    // streamed points per row-index chunk
 #ifndef IAPT_DEFAULT_STATIC_SCHED
 #define IAPT_DEFAULT_STATIC_SCHED 0
 #endif
+#ifndef IAPT_DEFAULT_GUIDED
+#define IAPT_DEFAULT_GUIDED 0
+#endif
 #ifndef IAPT_DEFAULT_PREFETCH
 #define IAPT_DEFAULT_PREFETCH 0
 #endif
@@ -51,6 +54,10 @@ struct FwdParams {
   unsigned* ticket;  // starts at 0xFFFFFFFF (same memset as the keys); item = atomicAdd(ticket, 1) + 1
   int a_tiles, s_splits, stages_per_split, total_items;
   int static_sched;  // 1: contiguous, balanced ranges of (cloud, A tile, stage) units per CTA instead of tickets
+  // guided schedule (n_segs > 0): every (cloud, A tile) is cut into n_segs stage ranges of DECREASING length and the
+  // tickets walk them segment-major, so the big ranges go first (few item boundaries) and one-stage ranges fill the tail
+  int n_segs;
+  unsigned char seg_start[32], seg_len[32];
 };
 
 template <int QT>
@@ -127,13 +134,23 @@ __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) 
       __syncthreads();
       const int item = (int)sm.next_item;
       if (item >= p.total_items) break;
-      const int per_cloud = p.a_tiles * p.s_splits;
-      b = item / per_cloud;
-      const int rem = item - b * per_cloud;
-      at = rem / p.s_splits;
-      const int ss = rem - at * p.s_splits;
-      stage0 = ss * p.stages_per_split;
-      stage_end = min(total_stages, stage0 + p.stages_per_split);
+      if (p.n_segs > 0) {
+        const int n_tiles = p.B * p.a_tiles;
+        const int seg = item / n_tiles;
+        const int tile = item - seg * n_tiles;
+        b = tile / p.a_tiles;
+        at = tile - b * p.a_tiles;
+        stage0 = p.seg_start[seg];
+        stage_end = stage0 + p.seg_len[seg];
+      } else {
+        const int per_cloud = p.a_tiles * p.s_splits;
+        b = item / per_cloud;
+        const int rem = item - b * per_cloud;
+        at = rem / p.s_splits;
+        const int ss = rem - at * p.s_splits;
+        stage0 = ss * p.stages_per_split;
+        stage_end = min(total_stages, stage0 + p.stages_per_split);
+      }
     }
     const float* __restrict__ Ab = p.A + (size_t)b * p.NA * 3;
     const float* __restrict__ Sb = p.S + (size_t)b * p.NS * 3;
@@ -552,6 +569,38 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
   p.s_splits = (total_stages + p.stages_per_split - 1) / p.stages_per_split;
   p.total_items = (int)(base_items * p.s_splits);
 
+  // Guided segments: used when the plain split would need many items per tile and the stage count fits the table.
+  p.n_segs = 0;
+  static int guided = -1;
+  if (guided < 0) {
+    const char* e = std::getenv("IAPT_FWD_GUIDED");  // development knob
+    guided = e ? std::atoi(e) : IAPT_DEFAULT_GUIDED;
+  }
+  if (guided && p.s_splits >= 8 && total_stages <= 255) {
+    // ones at the end: enough one-stage items for every resident CTA to balance the tail (>= 2 per slot overall)
+    int ones = (int)((2LL * slots + base_items - 1) / base_items);
+    if (ones < 2) ones = 2;
+    if (ones > 12) ones = 12;
+    if (ones > total_stages / 2) ones = total_stages / 2;
+    int rem = total_stages - ones, n = 0, pos = 0;
+    while (rem > 0 && n < 32 - ones) {
+      int len = (rem + 2) / 3;  // geometric decrease
+      if (n == 32 - ones - 1) len = rem;
+      p.seg_start[n] = (unsigned char)pos;
+      p.seg_len[n] = (unsigned char)len;
+      pos += len;
+      rem -= len;
+      ++n;
+    }
+    for (int i = 0; i < ones && n < 32; ++i, ++n, ++pos) {
+      p.seg_start[n] = (unsigned char)pos;
+      p.seg_len[n] = 1;
+    }
+    if (pos == total_stages) {  // the table covers every stage exactly once
+      p.n_segs = n;
+      p.total_items = (int)(base_items * n);
+    }
+  }
   static int static_sched = -1;
   if (static_sched < 0) {
     const char* e = std::getenv("IAPT_FWD_SCHED");  // development knob: "ticket" or "static"
