@@ -17,6 +17,9 @@ constexpr int ITER = 4096;
 // MODE 3: MODE 2 + 4 FMNMX3 per 16 packed       (ratio of the pair kernel: 1 ALU per 3 packed ... here 1:4)
 // MODE 4: MODE 2 + 6 FMNMX3 per 16 packed       (1 : 2.67)
 // MODE 5: MODE 4 + 1 REDUX + 1 LDS.128 per 16 packed
+// MODE 6: MODE 2 + 8 FMNMX (2-input)      MODE 7: MODE 2 + 8 IMNMX.U32 (min.u32)   MODE 8: MODE 2 + 4 VIMNMX3.U32
+// MODE 9: MODE 2 + 8 IADD3                MODE 10: 16 FMNMX3 only                  MODE 11: 16 VIMNMX3.U32 only
+// MODE 12: 16 FMNMX (2-input) only
 template <int MODE>
 __global__ void k(float* out, const float4* smem_src, int iters) {
   __shared__ float4 sm[64];
@@ -39,10 +42,39 @@ __global__ void k(float* out, const float4* smem_src, int iters) {
       for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int i = 0; i < 16; ++i) s[i] = fma1(s[i], s[(i + 1) & 15], s[i]);
+    } else if (MODE == 10) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s[i] = min3(s[i], s[(i + 1) & 15], s[(i + 5) & 15]);
+    } else if (MODE == 11) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        s[i] = __uint_as_float(__vimin3_u32(__float_as_uint(s[i]), __float_as_uint(s[(i + 1) & 15]), __float_as_uint(s[(i + 5) & 15])));
+    } else if (MODE == 12) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s[i] = fminf(s[i], s[(i + 1) & 15]);
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { u64 d = sub2(b[i], a[(i + 1) & 7]); a[i] = fma2(d, d, a[i]); }
-      if (MODE >= 3) {
+      if (MODE >= 6 && MODE <= 9) {
+        float lo[8], hi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(lo[i]), "=f"(hi[i]) : "l"(a[i]));
+        if (MODE == 6) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m[i] = fminf(m[i], lo[i]);
+        } else if (MODE == 7) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m[i] = __uint_as_float(min(__float_as_uint(m[i]), __float_as_uint(lo[i])));
+        } else if (MODE == 8) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            m[i] = __uint_as_float(__vimin3_u32(__float_as_uint(m[i]), __float_as_uint(lo[i]), __float_as_uint(hi[i])));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m[i] = __uint_as_float(__float_as_uint(m[i]) + __float_as_uint(lo[i]) + 3u);
+        }
+      }
+      if (MODE >= 3 && MODE <= 5) {
         float lo[8], hi[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(lo[i]), "=f"(hi[i]) : "l"(a[i]));
@@ -65,7 +97,7 @@ __global__ void k(float* out, const float4* smem_src, int iters) {
 
 template <int MODE>
 void run(const char* name, int packed_per_iter, int scalar_per_iter, int other_per_iter, float* out, float4* src) {
-  for (int threads : {128, 256, 512, 768, 1024}) {
+  for (int threads : {512, 1024}) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     k<MODE><<<148, threads>>>(out, src, 64);
     cudaEventRecord(e0);
@@ -91,6 +123,13 @@ int main() {
   run<3>("3: mode2 + 4 FMNMX3", 16, 0, 4, out, src);
   run<4>("4: mode2 + 6 FMNMX3", 16, 0, 6, out, src);
   run<5>("5: mode4 + REDUX + LDS + FMNMX3", 16, 0, 9, out, src);
+  run<6>("6: mode2 + 8 FMNMX", 16, 0, 8, out, src);
+  run<7>("7: mode2 + 8 IMNMX.U32", 16, 0, 8, out, src);
+  run<8>("8: mode2 + 4 VIMNMX3.U32", 16, 0, 4, out, src);
+  run<9>("9: mode2 + 8 IADD3", 16, 0, 8, out, src);
+  run<10>("10: 16 FMNMX3 only", 0, 0, 16, out, src);
+  run<11>("11: 16 VIMNMX3.U32 only", 0, 0, 16, out, src);
+  run<12>("12: 16 FMNMX only", 0, 0, 16, out, src);
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));
   return e != cudaSuccess;
