@@ -31,11 +31,13 @@ SIGNATURES = {
     "iapt_chamfer_forward_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "iapt_chamfer_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
                                       _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "iapt_chamfer_backward_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "iapt_chamfer_backward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
-                                       _c_int, _c_void_p, _c_void_p, _c_void_p]),
+                                       _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "iapt_chamfer_loss": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "iapt_chamfer_backward_fused": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
-                                             _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
+                                             _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
+                                             _c_size_t, _c_void_p]),
     "iapt_chamfer_reduce": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
     "iapt_fscore_counts": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p]),
     "iapt_fps_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),

@@ -47,6 +47,11 @@ def forward(xyz1: torch.Tensor, xyz2: torch.Tensor):
     return [dist1, dist2, idx1, idx2]
 
 
+def _bwd_workspace(L, B, N, M, dev):
+    n = int(L.iapt_chamfer_backward_workspace_bytes(B, N, M)) if (B > 0 and N > 0 and M > 0) else 0
+    return (torch.empty((n,), dtype=torch.uint8, device=dev) if n else None), n
+
+
 def backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
     xyz1, xyz2 = _prep(xyz1.detach(), xyz2.detach())
     B, N, _ = xyz1.shape
@@ -63,9 +68,11 @@ def backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
     with _lib.on_device(dev):
         gx1 = torch.empty_like(xyz1)
         gx2 = torch.empty_like(xyz2)
+        ws, ws_bytes = _bwd_workspace(L, B, N, M, dev)
         _lib.check(
             L.iapt_chamfer_backward(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(idx1), _lib.ptr(idx2), _lib.ptr(g1),
-                                    _lib.ptr(g2), B, N, M, _lib.ptr(gx1), _lib.ptr(gx2), _lib.stream_ptr(dev)),
+                                    _lib.ptr(g2), B, N, M, _lib.ptr(gx1), _lib.ptr(gx2), _lib.ptr(ws), ws_bytes,
+                                    _lib.stream_ptr(dev)),
             "iapt_chamfer_backward")
     return [gx1, gx2]
 
@@ -123,9 +130,11 @@ def loss_backward(xyz1, xyz2, idx1, idx2, dist1, dist2, kind: int, grad_loss):
     with _lib.on_device(dev):
         gx1 = torch.empty_like(xyz1)
         gx2 = torch.empty_like(xyz2)
+        ws, ws_bytes = _bwd_workspace(_lib.lib(), B, N, M, dev)
         _lib.check(
             _lib.lib().iapt_chamfer_backward_fused(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(idx1), _lib.ptr(idx2),
                                                    _lib.ptr(dist1), _lib.ptr(dist2), int(kind), _lib.ptr(grad_loss), B, N,
-                                                   M, _lib.ptr(gx1), _lib.ptr(gx2), _lib.stream_ptr(dev)),
+                                                   M, _lib.ptr(gx1), _lib.ptr(gx2), _lib.ptr(ws), ws_bytes,
+                                                   _lib.stream_ptr(dev)),
             "iapt_chamfer_backward_fused")
     return gx1, gx2

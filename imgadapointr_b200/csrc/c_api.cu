@@ -12,12 +12,14 @@ void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memo
 size_t chamfer_forward_workspace_bytes(int B, int N, int M);
 int chamfer_forward_launch(const float*, const float*, int, int, int, float*, float*, int32_t*, int32_t*, void*,
                            cudaStream_t);
+size_t chamfer_backward_workspace_bytes(int B, int N, int M);
 int chamfer_backward_launch(const float*, const float*, const int32_t*, const int32_t*, const float*, const float*, int,
-                            int, int, float*, float*, cudaStream_t);
+                            int, int, float*, float*, void*, cudaStream_t);
 int chamfer_metrics_launch(const float*, const float*, int, int, int, float, float*, int32_t*, cudaStream_t);
 int chamfer_loss_launch(const float*, const float*, int, int, int, int, float*, float*, cudaStream_t);
 int chamfer_backward_fused_launch(const float*, const float*, const int32_t*, const int32_t*, const float*, const float*,
-                                  int, float, float, const float*, int, int, int, int, float*, float*, cudaStream_t);
+                                  int, float, float, const float*, int, int, int, int, float*, float*, void*,
+                                  cudaStream_t);
 void profile_enable(bool on);
 int profile_collect(double* total_ms, int* launches);
 size_t fps_workspace_bytes(int B, int N, int npoint);
@@ -93,9 +95,14 @@ int iapt_chamfer_forward(const float* xyz1, const float* xyz2, int B, int N, int
   return chamfer_forward_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, workspace, st);
 }
 
+size_t iapt_chamfer_backward_workspace_bytes(int B, int N, int M) {
+  if (B <= 0 || N <= 0 || M <= 0) return 0;
+  return chamfer_backward_workspace_bytes(B, N, M);
+}
+
 int iapt_chamfer_backward(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
                           const float* grad_dist1, const float* grad_dist2, int B, int N, int M, float* grad_xyz1,
-                          float* grad_xyz2, iapt_stream_t stream) {
+                          float* grad_xyz2, void* workspace, size_t workspace_bytes, iapt_stream_t stream) {
   IAPT_REQUIRE(B >= 0 && N >= 0 && M >= 0);
   cudaStream_t st = (cudaStream_t)stream;
   if (B == 0) return 0;
@@ -106,7 +113,9 @@ int iapt_chamfer_backward(const float* xyz1, const float* xyz2, const int32_t* i
     return (int)e;
   }
   IAPT_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && grad_xyz1 && grad_xyz2);
-  return chamfer_backward_launch(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2, B, N, M, grad_xyz1, grad_xyz2, st);
+  if (workspace != nullptr && workspace_bytes < chamfer_backward_workspace_bytes(B, N, M)) return IAPT_EWORKSPACE;
+  return chamfer_backward_launch(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2, B, N, M, grad_xyz1, grad_xyz2,
+                                 workspace, st);
 }
 
 int iapt_chamfer_loss(const float* dist1, const float* dist2, int B, int N, int M, int kind, float* sums, float* loss,
@@ -118,9 +127,11 @@ int iapt_chamfer_loss(const float* dist1, const float* dist2, int B, int N, int 
 
 int iapt_chamfer_backward_fused(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
                                 const float* dist1, const float* dist2, int kind, const float* grad_loss, int B, int N,
-                                int M, float* grad_xyz1, float* grad_xyz2, iapt_stream_t stream) {
+                                int M, float* grad_xyz1, float* grad_xyz2, void* workspace, size_t workspace_bytes,
+                                iapt_stream_t stream) {
   IAPT_REQUIRE(B >= 1 && N >= 1 && M >= 1 && kind >= IAPT_LOSS_L1 && kind <= IAPT_LOSS_L1_PM);
   IAPT_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && dist1 && dist2 && grad_xyz1 && grad_xyz2);
+  if (workspace != nullptr && workspace_bytes < chamfer_backward_workspace_bytes(B, N, M)) return IAPT_EWORKSPACE;
   const float n1 = (float)B * (float)N, n2 = (float)B * (float)M;
   int mode = 1, stride = 0;
   float s1 = 0.f, s2 = 0.f;
@@ -131,7 +142,7 @@ int iapt_chamfer_backward_fused(const float* xyz1, const float* xyz2, const int3
     default: mode = 1; s1 = 0.5f / n1; s2 = 0.f; break;                           // L1_PM: mean sqrt(dist1) only
   }
   return chamfer_backward_fused_launch(xyz1, xyz2, idx1, idx2, dist1, dist2, mode, s1, s2, grad_loss, stride, B, N, M,
-                                       grad_xyz1, grad_xyz2, (cudaStream_t)stream);
+                                       grad_xyz1, grad_xyz2, workspace, (cudaStream_t)stream);
 }
 
 int iapt_chamfer_reduce(const float* dist1, const float* dist2, int B, int N, int M, float* sums,

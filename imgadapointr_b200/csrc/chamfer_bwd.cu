@@ -19,6 +19,8 @@
 // Optional fused loss mode (iapt_chamfer_backward_fused): instead of reading grad_dist arrays the kernel forms
 // g = scale / sqrt(dist) (L1) or g = scale (L2) on the fly from the saved distances - the analytic gradient of the
 // reference's sqrt/mean epilogues (extensions/chamfer_dist/__init__.py:82-84) - times the upstream scalar gradient.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace iapt {
@@ -43,9 +45,17 @@ struct BwdParams {
   float scale[2];
   const float* grad_out;    // device: upstream[side] = grad_out[side * grad_out_stride] (null = 1)
   int grad_out_stride;
+  // fan-in lists (fast path): cnt[s][b*n[s] + j] = number of side-(1-s) points whose nearest neighbour is j,
+  // list[s][(b*n[s] + j)*cap[s] + slot] = their indices in arrival order (sorted on the fly by the gather kernel).
+  // cap[s] == 0: no lists for that side, every bin is handled by the scan kernel.  Null cnt = scan everything.
+  int* cnt[2];
+  int* list[2];
+  int cap[2];
+  int* overflow_flag;       // [2]: set when some bin of side s overflowed its list
 };
 
 struct BwdSmem {
+  unsigned char over[kBwdWarps][kBins];
   float acc[kBwdWarps][kBins * 3];
   int hit_k[kBwdWarps][kHitCap];
   unsigned short hit_bin[kBwdWarps][kHitCap];
@@ -102,6 +112,22 @@ __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
   const float wY = __fmul_rn(side ? up0 : up1, scaleY);
   const unsigned lt_mask = (1u << lane) - 1u;
 
+  // With fan-in lists, this kernel only serves the bins whose list overflowed (cnt > cap): nothing to do otherwise.
+  const int* cntX = side ? p.cnt[1] : p.cnt[0];
+  const int capX = side ? p.cap[1] : p.cap[0];
+  const bool lists = cntX != nullptr && capX > 0;
+  if (lists) {
+    if (p.overflow_flag[side] == 0) return;  // warp-uniform: no bin of this side overflowed anywhere
+    bool mine = false;
+    for (int i = lane; i < kBins; i += 32) {
+      const int j = j0 + i;
+      const bool over = j < nX && cntX[(size_t)b * nX + j] > capX;
+      sm.over[warp][i] = over ? 1 : 0;
+      mine |= over;
+    }
+    if (!__any_sync(0xffffffffu, mine)) return;
+    __syncwarp();  // over[] visible to every lane
+  }
   for (int i = lane; i < kBins * 3; i += 32) a[i] = 0.f;
   __syncwarp();
 
@@ -150,7 +176,8 @@ __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const unsigned bin = (unsigned)(key[e] - j0);
-        const bool hit = (key[e] >= 0) && (bin < (unsigned)kBins) && ((int)bin + j0 < nX);
+        bool hit = (key[e] >= 0) && (bin < (unsigned)kBins) && ((int)bin + j0 < nX);
+        if (lists && hit) hit = sm.over[warp][bin] != 0;
         const unsigned mask = __ballot_sync(0xffffffffu, hit);
         if (mask != 0u) {  // warp-uniform
           if (hit) {
@@ -173,6 +200,7 @@ __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
   for (int i = lane; i < kBins; i += 32) {
     const int j = j0 + i;
     if (j >= nX) break;
+    if (lists && sm.over[warp][i] == 0) continue;  // written by the gather kernel
     float ox = 0.f, oy = 0.f, oz = 0.f;
     if (gX != nullptr) {
       const int j2 = __ldg(idxX + j);
@@ -187,10 +215,152 @@ __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdParams p) {
   }
 }
 
-static int bwd_launch_common(BwdParams& p, int B, int N, int M, cudaStream_t stream) {
+// ---- fast path: fan-in lists ------------------------------------------------------------------------------------
+// link: every point appends itself to the list of its nearest neighbour (integer atomics: the SET is deterministic, the
+// order is not - the gather kernel below restores ascending order).
+__global__ void __launch_bounds__(256) chamfer_link_kernel(BwdParams p, long long total0, long long total) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int src = t < total0 ? 0 : 1;  // the side the point belongs to; it links into side 1 - src
+    const long long u = src ? t - total0 : t;
+    const int dst = src ^ 1;
+    const int cap = dst ? p.cap[1] : p.cap[0];
+    if (cap == 0) continue;
+    const float* g = src ? p.gdist[1] : p.gdist[0];
+    if (g == nullptr) continue;  // this side contributes nothing
+    const int nS = src ? p.n[1] : p.n[0], nD = src ? p.n[0] : p.n[1];
+    const int b = (int)(u / nS);
+    const int k = (int)(u - (long long)b * nS);
+    const int j = __ldg((src ? p.idx[1] : p.idx[0]) + u);
+    int* cnt = dst ? p.cnt[1] : p.cnt[0];
+    const int slot = atomicAdd(cnt + (size_t)b * nD + j, 1);
+    if (slot < cap)
+      (dst ? p.list[1] : p.list[0])[((size_t)b * nD + j) * cap + slot] = k;
+    else
+      p.overflow_flag[dst] = 1;
+  }
+}
+
+// gather: one thread per output point: own term, then its fan-in list in ASCENDING source index (selection over the
+// <= cap unsorted entries: lists hold ~1 entry on average), so the sum order equals the scan kernel's.
+__global__ void __launch_bounds__(256) chamfer_gather_kernel(BwdParams p, long long total0, long long total) {
+  float up0 = 1.f, up1 = 1.f;
+  if (p.mode != 0 && p.grad_out != nullptr) {
+    up0 = __ldg(p.grad_out);
+    up1 = __ldg(p.grad_out + p.grad_out_stride);
+  }
+  const int mode = p.mode;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int side = t < total0 ? 0 : 1;
+    const long long u = side ? t - total0 : t;
+    const int cap = side ? p.cap[1] : p.cap[0];
+    if (cap == 0) continue;  // scan kernel owns this side
+    const int nX = side ? p.n[1] : p.n[0], nY = side ? p.n[0] : p.n[1];
+    const int b = (int)(u / nX);
+    const float* __restrict__ X = (side ? p.xyz[1] : p.xyz[0]);
+    const float* __restrict__ Y = (side ? p.xyz[0] : p.xyz[1]) + (size_t)b * nY * 3;
+    const float* gX = side ? p.gdist[1] : p.gdist[0];
+    const float* gY = side ? p.gdist[0] : p.gdist[1];
+    const int c = gY ? (side ? p.cnt[1] : p.cnt[0])[u] : 0;
+    if (c > cap) continue;  // overflowed: the scan kernel computes and writes this point
+    const float wX = __fmul_rn(side ? up1 : up0, side ? p.scale[1] : p.scale[0]);
+    const float wY = __fmul_rn(side ? up0 : up1, side ? p.scale[0] : p.scale[1]);
+    const float x0 = __ldg(X + 3 * u), x1 = __ldg(X + 3 * u + 1), x2 = __ldg(X + 3 * u + 2);
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (gX != nullptr) {
+      const int j2 = __ldg((side ? p.idx[1] : p.idx[0]) + u);
+      const float g = point_weight(mode, wX, gX + (size_t)b * nX, (int)(u - (long long)b * nX));
+      ox = __fmul_rn(g, __fsub_rn(x0, __ldg(Y + 3 * (size_t)j2 + 0)));
+      oy = __fmul_rn(g, __fsub_rn(x1, __ldg(Y + 3 * (size_t)j2 + 1)));
+      oz = __fmul_rn(g, __fsub_rn(x2, __ldg(Y + 3 * (size_t)j2 + 2)));
+    }
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    const int* lst = (side ? p.list[1] : p.list[0]) + (size_t)u * cap;
+    int prev = -1;
+    for (int r = 0; r < c; ++r) {
+      int k = 0x7fffffff;  // next larger source index
+      for (int e = 0; e < c; ++e) {
+        const int v = lst[e];
+        if (v > prev && v < k) k = v;
+      }
+      prev = k;
+      const float g = point_weight(mode, wY, gY + (size_t)b * nY, k);
+      ax = __fadd_rn(ax, __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 0), x0)));
+      ay = __fadd_rn(ay, __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 1), x1)));
+      az = __fadd_rn(az, __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 2), x2)));
+    }
+    float* out = (side ? p.grad[1] : p.grad[0]) + 3 * u;
+    out[0] = __fsub_rn(ox, ax);
+    out[1] = __fsub_rn(oy, ay);
+    out[2] = __fsub_rn(oz, az);
+  }
+}
+
+// List capacity for the side with nX bins fed by nY keys: 16 when the mean fan-in is <= 2, up to 64 for mean <= 14,
+// 0 (scan kernel only) beyond that.
+static int list_cap(int nX, int nY) {
+  const double mean = (double)nY / (double)(nX > 0 ? nX : 1);
+  if (mean <= 2.0) return 16;
+  if (mean <= 6.0) return 32;
+  if (mean <= 14.0) return 64;
+  return 0;
+}
+
+size_t chamfer_backward_workspace_bytes(int B, int N, int M) {
+  const size_t c1 = list_cap(N, M), c2 = list_cap(M, N);
+  return 256 + sizeof(int) * ((size_t)B * N * (c1 ? 1 + c1 : 0) + (size_t)B * M * (c2 ? 1 + c2 : 0));
+}
+
+static int bwd_launch_common(BwdParams& p, int B, int N, int M, void* workspace, cudaStream_t stream) {
   p.n[0] = N;
   p.n[1] = M;
   p.B = B;
+  p.cnt[0] = p.cnt[1] = nullptr;
+  p.list[0] = p.list[1] = nullptr;
+  p.cap[0] = p.cap[1] = 0;
+  p.overflow_flag = nullptr;
+  static int use_lists = -1;
+  if (use_lists < 0) {
+    const char* e = std::getenv("IAPT_BWD_LISTS");  // development knob: 0 = scan kernel only
+    use_lists = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (workspace != nullptr && use_lists) {
+    const int c1 = list_cap(N, M), c2 = list_cap(M, N);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    p.overflow_flag = reinterpret_cast<int*>(ws);
+    int* base = reinterpret_cast<int*>(ws + 256);
+    size_t zero_ints = 0;
+    if (c1) {
+      p.cnt[0] = base;
+      base += (size_t)B * N;
+      zero_ints += (size_t)B * N;
+    }
+    if (c2) {
+      p.cnt[1] = base;
+      base += (size_t)B * M;
+      zero_ints += (size_t)B * M;
+    }
+    if (c1) {
+      p.list[0] = base;
+      base += (size_t)B * N * c1;
+    }
+    if (c2) p.list[1] = base;
+    p.cap[0] = c1;
+    p.cap[1] = c2;
+    if (c1 || c2) {
+      cudaError_t err = cudaMemsetAsync(ws, 0, 256 + sizeof(int) * zero_ints, stream);
+      if (err != cudaSuccess) return (int)err;
+      const long long total0 = (long long)B * N, total = total0 + (long long)B * M;
+      long long g = (total + 255) / 256;
+      if (g > 148LL * 16) g = 148LL * 16;
+      chamfer_link_kernel<<<(unsigned)g, 256, 0, stream>>>(p, total0, total);
+      chamfer_gather_kernel<<<(unsigned)g, 256, 0, stream>>>(p, total0, total);
+      count_launch(2);
+    } else {
+      p.overflow_flag = nullptr;
+    }
+  }
   p.blocks_per_cloud[0] = (N + kBins - 1) / kBins;
   p.blocks_per_cloud[1] = (M + kBins - 1) / kBins;
   p.warps_side0 = (long long)B * p.blocks_per_cloud[0];
@@ -208,7 +378,7 @@ static int bwd_launch_common(BwdParams& p, int B, int N, int M, cudaStream_t str
 
 int chamfer_backward_launch(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
                             const float* grad_dist1, const float* grad_dist2, int B, int N, int M, float* grad_xyz1,
-                            float* grad_xyz2, cudaStream_t stream) {
+                            float* grad_xyz2, void* workspace, cudaStream_t stream) {
   BwdParams p;
   p.xyz[0] = xyz1;
   p.xyz[1] = xyz2;
@@ -222,7 +392,7 @@ int chamfer_backward_launch(const float* xyz1, const float* xyz2, const int32_t*
   p.scale[0] = p.scale[1] = 1.f;
   p.grad_out = nullptr;
   p.grad_out_stride = 0;
-  return bwd_launch_common(p, B, N, M, stream);
+  return bwd_launch_common(p, B, N, M, workspace, stream);
 }
 
 // mode 1: loss = scale1 * sum sqrt(dist1) + scale2 * sum sqrt(dist2);  mode 2: loss = scale1 * sum dist1 + scale2 * sum dist2.
@@ -230,7 +400,7 @@ int chamfer_backward_launch(const float* xyz1, const float* xyz2, const int32_t*
 int chamfer_backward_fused_launch(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
                                   const float* dist1, const float* dist2, int mode, float scale1, float scale2,
                                   const float* grad_out, int grad_out_stride, int B, int N, int M, float* grad_xyz1,
-                                  float* grad_xyz2, cudaStream_t stream) {
+                                  float* grad_xyz2, void* workspace, cudaStream_t stream) {
   BwdParams p;
   p.xyz[0] = xyz1;
   p.xyz[1] = xyz2;
@@ -245,7 +415,7 @@ int chamfer_backward_fused_launch(const float* xyz1, const float* xyz2, const in
   p.scale[1] = scale2;
   p.grad_out = grad_out;
   p.grad_out_stride = grad_out_stride;
-  return bwd_launch_common(p, B, N, M, stream);
+  return bwd_launch_common(p, B, N, M, workspace, stream);
 }
 
 }  // namespace iapt

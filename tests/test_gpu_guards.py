@@ -45,16 +45,23 @@ def test_chamfer_entry_points_stay_in_bounds(dev, B, N, M):
     torch.cuda.synchronize()
     assert all(g.intact() for g in (d1, d2, i1, i2, ws))
     gx1, gx2 = Guarded(12 * B * N, dev), Guarded(12 * B * M, dev)
+    bwn = L.iapt_chamfer_backward_workspace_bytes(B, N, M)
+    bws = Guarded(bwn, dev)
     _lib.check(L.iapt_chamfer_backward(x1.data_ptr(), x2.data_ptr(), i1.ptr, i2.ptr, d1.ptr, d2.ptr, B, N, M, gx1.ptr,
-                                       gx2.ptr, st), "bwd")
+                                       gx2.ptr, bws.ptr, bwn, st), "bwd")
+    gz1, gz2 = Guarded(12 * B * N, dev), Guarded(12 * B * M, dev)  # scan-only path (no workspace): bit-identical
+    _lib.check(L.iapt_chamfer_backward(x1.data_ptr(), x2.data_ptr(), i1.ptr, i2.ptr, d1.ptr, d2.ptr, B, N, M, gz1.ptr,
+                                       gz2.ptr, None, 0, st), "bwd-scan")
     sums, loss, cnt = Guarded(16 * B, dev), Guarded(8, dev), Guarded(8 * B, dev)
     _lib.check(L.iapt_chamfer_loss(d1.ptr, d2.ptr, B, N, M, 1, sums.ptr, loss.ptr, st), "loss")
     _lib.check(L.iapt_fscore_counts(d1.ptr, d2.ptr, B, N, M, ctypes.c_float(0.1), cnt.ptr, st), "fs")
     gy1, gy2 = Guarded(12 * B * N, dev), Guarded(12 * B * M, dev)
     _lib.check(L.iapt_chamfer_backward_fused(x1.data_ptr(), x2.data_ptr(), i1.ptr, i2.ptr, d1.ptr, d2.ptr, 1, None, B, N,
-                                             M, gy1.ptr, gy2.ptr, st), "bwdf")
+                                             M, gy1.ptr, gy2.ptr, bws.ptr, bwn, st), "bwdf")
     torch.cuda.synchronize()
-    assert all(g.intact() for g in (gx1, gx2, sums, loss, cnt, gy1, gy2, d1, d2, i1, i2))
+    assert all(g.intact() for g in (gx1, gx2, gz1, gz2, bws, sums, loss, cnt, gy1, gy2, d1, d2, i1, i2))
+    assert torch.equal(gx1.view(torch.float32, (B, N, 3)), gz1.view(torch.float32, (B, N, 3)))
+    assert torch.equal(gx2.view(torch.float32, (B, M, 3)), gz2.view(torch.float32, (B, M, 3)))
     assert torch.isfinite(gx1.view(torch.float32, (B, N, 3))).all()
 
 
