@@ -19,6 +19,7 @@
 // Optional fused loss mode (iapt_chamfer_backward_fused): instead of reading grad_dist arrays the kernel forms
 // g = scale / sqrt(dist) (L1) or g = scale (L2) on the fly from the saved distances - the analytic gradient of the
 // reference's sqrt/mean epilogues (extensions/chamfer_dist/__init__.py:82-84) - times the upstream scalar gradient.
+#include <cstdint>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -241,8 +242,15 @@ __global__ void __launch_bounds__(256) chamfer_link_kernel(BwdParams p, long lon
   }
 }
 
-// gather: one thread per output point: own term, then its fan-in list in ASCENDING source index (selection over the
-// <= cap unsorted entries: lists hold ~1 entry on average), so the sum order equals the scan kernel's.
+// gather: one thread per output point: own term, then its fan-in list in ASCENDING source index, so the sum order
+// equals the scan kernel's.  Lists of <= 8 entries (the common case: mean fan-in ~1) are pulled into registers with two
+// 128-bit loads and ordered by a 19-exchange sorting network; longer lists fall back to selection from memory.
+__device__ __forceinline__ void cswap(int& a, int& b) {
+  const int lo = min(a, b), hi = max(a, b);
+  a = lo;
+  b = hi;
+}
+
 __global__ void __launch_bounds__(256) chamfer_gather_kernel(BwdParams p, long long total0, long long total) {
   float up0 = 1.f, up1 = 1.f;
   if (p.mode != 0 && p.grad_out != nullptr) {
@@ -261,9 +269,30 @@ __global__ void __launch_bounds__(256) chamfer_gather_kernel(BwdParams p, long l
     const float* __restrict__ X = (side ? p.xyz[1] : p.xyz[0]);
     const float* __restrict__ Y = (side ? p.xyz[0] : p.xyz[1]) + (size_t)b * nY * 3;
     const float* gX = side ? p.gdist[1] : p.gdist[0];
-    const float* gY = side ? p.gdist[0] : p.gdist[1];
+    const float* gYb = side ? p.gdist[0] : p.gdist[1];
+    const float* gY = gYb ? gYb + (size_t)b * nY : nullptr;
     const int c = gY ? (side ? p.cnt[1] : p.cnt[0])[u] : 0;
     if (c > cap) continue;  // overflowed: the scan kernel computes and writes this point
+    const int* lst = (side ? p.list[1] : p.list[0]) + (size_t)u * cap;
+    int e[8];
+    if (c > 0 && c <= 8) {  // rows are 32-byte aligned (cap is a multiple of 8, base 256-byte aligned)
+      const int4 lo = *reinterpret_cast<const int4*>(lst);
+      const int4 hi = c > 4 ? *reinterpret_cast<const int4*>(lst + 4) : make_int4(0, 0, 0, 0);
+      e[0] = lo.x; e[1] = lo.y; e[2] = lo.z; e[3] = lo.w;
+      e[4] = hi.x; e[5] = hi.y; e[6] = hi.z; e[7] = hi.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i >= c) e[i] = 0x7fffffff;
+      if (c > 1) {  // 8-input sorting network (19 compare-exchanges)
+        cswap(e[0], e[1]); cswap(e[2], e[3]); cswap(e[4], e[5]); cswap(e[6], e[7]);
+        cswap(e[0], e[2]); cswap(e[1], e[3]); cswap(e[4], e[6]); cswap(e[5], e[7]);
+        cswap(e[1], e[2]); cswap(e[5], e[6]); cswap(e[0], e[4]); cswap(e[3], e[7]);
+        cswap(e[1], e[5]); cswap(e[2], e[6]);
+        cswap(e[1], e[4]); cswap(e[3], e[6]);
+        cswap(e[2], e[4]); cswap(e[3], e[5]);
+        cswap(e[3], e[4]);
+      }
+    }
     const float wX = __fmul_rn(side ? up1 : up0, side ? p.scale[1] : p.scale[0]);
     const float wY = __fmul_rn(side ? up0 : up1, side ? p.scale[0] : p.scale[1]);
     const float x0 = __ldg(X + 3 * u), x1 = __ldg(X + 3 * u + 1), x2 = __ldg(X + 3 * u + 2);
@@ -276,19 +305,41 @@ __global__ void __launch_bounds__(256) chamfer_gather_kernel(BwdParams p, long l
       oz = __fmul_rn(g, __fsub_rn(x2, __ldg(Y + 3 * (size_t)j2 + 2)));
     }
     float ax = 0.f, ay = 0.f, az = 0.f;
-    const int* lst = (side ? p.list[1] : p.list[0]) + (size_t)u * cap;
-    int prev = -1;
-    for (int r = 0; r < c; ++r) {
-      int k = 0x7fffffff;  // next larger source index
-      for (int e = 0; e < c; ++e) {
-        const int v = lst[e];
-        if (v > prev && v < k) k = v;
+    if (c <= 8) {
+      // all gathers first (independent), then the ordered sum
+      float gw[8], yx[8], yy[8], yz[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < c) {
+          const int k = e[i];
+          gw[i] = point_weight(mode, wY, gY, k);
+          yx[i] = __ldg(Y + 3 * (size_t)k + 0);
+          yy[i] = __ldg(Y + 3 * (size_t)k + 1);
+          yz[i] = __ldg(Y + 3 * (size_t)k + 2);
+        }
       }
-      prev = k;
-      const float g = point_weight(mode, wY, gY + (size_t)b * nY, k);
-      ax = __fadd_rn(ax, __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 0), x0)));
-      ay = __fadd_rn(ay, __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 1), x1)));
-      az = __fadd_rn(az, __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 2), x2)));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < c) {
+          ax = __fadd_rn(ax, __fmul_rn(gw[i], __fsub_rn(yx[i], x0)));
+          ay = __fadd_rn(ay, __fmul_rn(gw[i], __fsub_rn(yy[i], x1)));
+          az = __fadd_rn(az, __fmul_rn(gw[i], __fsub_rn(yz[i], x2)));
+        }
+      }
+    } else {
+      int prev = -1;
+      for (int r = 0; r < c; ++r) {
+        int k = 0x7fffffff;  // next larger source index
+        for (int q = 0; q < c; ++q) {
+          const int v = lst[q];
+          if (v > prev && v < k) k = v;
+        }
+        prev = k;
+        const float g = point_weight(mode, wY, gY, k);
+        ax = __fadd_rn(ax, __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 0), x0)));
+        ay = __fadd_rn(ay, __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 1), x1)));
+        az = __fadd_rn(az, __fmul_rn(g, __fsub_rn(__ldg(Y + 3 * (size_t)k + 2), x2)));
+      }
     }
     float* out = (side ? p.grad[1] : p.grad[0]) + 3 * u;
     out[0] = __fsub_rn(ox, ax);
@@ -297,11 +348,11 @@ __global__ void __launch_bounds__(256) chamfer_gather_kernel(BwdParams p, long l
   }
 }
 
-// List capacity for the side with nX bins fed by nY keys: 16 when the mean fan-in is <= 2, up to 64 for mean <= 14,
-// 0 (scan kernel only) beyond that.
+// List capacity for the side with nX bins fed by nY keys: 8 (one 32-byte sector per point) when the mean fan-in is
+// <= 2, up to 64 for mean <= 14, 0 (scan kernel only) beyond that.  Rarer, longer lists overflow to the scan kernel.
 static int list_cap(int nX, int nY) {
   const double mean = (double)nY / (double)(nX > 0 ? nX : 1);
-  if (mean <= 2.0) return 16;
+  if (mean <= 2.0) return 8;
   if (mean <= 6.0) return 32;
   if (mean <= 14.0) return 64;
   return 0;
@@ -309,7 +360,7 @@ static int list_cap(int nX, int nY) {
 
 size_t chamfer_backward_workspace_bytes(int B, int N, int M) {
   const size_t c1 = list_cap(N, M), c2 = list_cap(M, N);
-  return 256 + sizeof(int) * ((size_t)B * N * (c1 ? 1 + c1 : 0) + (size_t)B * M * (c2 ? 1 + c2 : 0));
+  return 256 + 32 + sizeof(int) * ((size_t)B * N * (c1 ? 1 + c1 : 0) + (size_t)B * M * (c2 ? 1 + c2 : 0));
 }
 
 static int bwd_launch_common(BwdParams& p, int B, int N, int M, void* workspace, cudaStream_t stream) {
@@ -341,6 +392,7 @@ static int bwd_launch_common(BwdParams& p, int B, int N, int M, void* workspace,
       base += (size_t)B * M;
       zero_ints += (size_t)B * M;
     }
+    base = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(base) + 31) & ~(uintptr_t)31);  // 32-byte rows
     if (c1) {
       p.list[0] = base;
       base += (size_t)B * N * c1;
