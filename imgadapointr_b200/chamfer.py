@@ -10,6 +10,8 @@ stream of the inputs' device.  Differences, all deliberate (SURVEY.md section 8b
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -47,8 +49,14 @@ def forward(xyz1: torch.Tensor, xyz2: torch.Tensor):
     return [dist1, dist2, idx1, idx2]
 
 
+_USE_BWD_LISTS = os.environ.get("IAPT_BWD_LISTS", "0") == "1"
+
+
 def _bwd_workspace(L, B, N, M, dev):
-    n = int(L.iapt_chamfer_backward_workspace_bytes(B, N, M)) if (B > 0 and N > 0 and M > 0) else 0
+    """Workspace of the optional fan-in-list backward path (include/iapt_b200.h); none for the default scan path."""
+    if not _USE_BWD_LISTS or B <= 0 or N <= 0 or M <= 0:
+        return None, 0
+    n = int(L.iapt_chamfer_backward_workspace_bytes(B, N, M))
     return (torch.empty((n,), dtype=torch.uint8, device=dev) if n else None), n
 
 

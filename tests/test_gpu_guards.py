@@ -30,6 +30,23 @@ class Guarded:
         return bool((self.buf[:GUARD] == PATTERN).all()) and bool((self.buf[GUARD + self.n:] == PATTERN).all())
 
 
+def _run_list_path_in_subprocess():
+    """The list backward is selected by IAPT_BWD_LISTS=1 when the library first launches a backward: run this file's
+    chamfer test in a child process with the variable set (both paths must agree bit for bit and stay in bounds)."""
+    import os, subprocess, sys
+    env = dict(os.environ, IAPT_BWD_LISTS="1", IAPT_GUARD_CHILD="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", "stay_in_bounds"],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_list_backward_path_matches_scan_path(dev):
+    import os
+    if os.environ.get("IAPT_GUARD_CHILD") == "1":
+        pytest.skip("child process")
+    _run_list_path_in_subprocess()
+
+
 @pytest.mark.parametrize("B,N,M", [(1, 1, 1), (2, 33, 7), (3, 513, 2049), (2, 4097, 300), (1, 9000, 8191)])
 def test_chamfer_entry_points_stay_in_bounds(dev, B, N, M):
     L = _lib.lib()
