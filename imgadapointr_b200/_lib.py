@@ -51,6 +51,11 @@ SIGNATURES = {
     "iapt_graph_feature_grad": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p,
                                          _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "iapt_index_points": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, ctypes.c_longlong, _c_void_p, _c_void_p]),
+    "iapt_group_gather": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p,
+                                   _c_void_p]),
+    "iapt_group_gather_grad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                        _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "iapt_ball_query": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_int, _c_void_p, _c_void_p]),
     "iapt_knn_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "iapt_knn": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t,
                           _c_void_p]),

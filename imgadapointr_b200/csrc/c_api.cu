@@ -32,6 +32,10 @@ int knn_launch(const float*, const float*, int, int, int, int, int64_t*, float*,
 int graph_feature_launch(const float*, const float*, const long long*, int, int, int, int, int, float*, cudaStream_t);
 int index_points_launch(const float*, const long long*, int, int, int, long long, float*, cudaStream_t);
 size_t graph_feature_grad_workspace_bytes(int B, int Nq, int Nk, int k);
+int group_gather_launch(const float*, const long long*, const float*, int, int, int, int, int, int, float*, cudaStream_t);
+int group_gather_grad_launch(const float*, const long long*, const float*, int, int, int, int, int, int, float*, void*,
+                             cudaStream_t);
+int ball_query_launch(const float*, const float*, int, int, int, float, int, int*, cudaStream_t);
 int graph_feature_grad_launch(const float*, const long long*, int, int, int, int, int, float*, float*, void*, cudaStream_t);
 }  // namespace iapt
 
@@ -256,6 +260,36 @@ int iapt_index_points(const float* points, const int64_t* idx, int B, int N, int
   if (B == 0 || C == 0 || S == 0) return 0;
   IAPT_REQUIRE(points && idx && out);
   return index_points_launch(points, (const long long*)idx, B, N, C, S, out, (cudaStream_t)stream);
+}
+
+int iapt_group_gather(const float* features, const int64_t* idx, const float* weight, int B, int C, int M, int P, int S,
+                      int reduce, float* out, iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && C >= 0 && M >= 1 && P >= 0 && S >= 1 && (reduce == 0 || reduce == 1));
+  if (B == 0 || C == 0 || P == 0) return 0;
+  IAPT_REQUIRE(features && idx && out && (reduce == 0 || weight));
+  return group_gather_launch(features, (const long long*)idx, weight, B, C, M, P, S, reduce, out, (cudaStream_t)stream);
+}
+
+int iapt_group_gather_grad(const float* grad_out, const int64_t* idx, const float* weight, int B, int C, int M, int P,
+                           int S, int reduce, float* grad_features, void* workspace, size_t workspace_bytes,
+                           iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && C >= 0 && M >= 1 && P >= 0 && S >= 1 && (reduce == 0 || reduce == 1) && B <= 65535 && C <= 65535);
+  if (B == 0 || C == 0) return 0;
+  IAPT_REQUIRE(grad_features);
+  if (P == 0)
+    return (int)cudaMemsetAsync(grad_features, 0, sizeof(float) * (size_t)B * C * M, (cudaStream_t)stream);
+  IAPT_REQUIRE(grad_out && idx && (reduce == 0 || weight));
+  if (workspace == nullptr || workspace_bytes < graph_feature_grad_workspace_bytes(B, P, M, S)) return IAPT_EWORKSPACE;
+  return group_gather_grad_launch(grad_out, (const long long*)idx, weight, B, C, M, P, S, reduce, grad_features,
+                                  workspace, (cudaStream_t)stream);
+}
+
+int iapt_ball_query(const float* xyz, const float* new_xyz, int B, int N, int P, float radius, int nsample, int32_t* idx,
+                    iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && N >= 1 && P >= 0 && nsample >= 1 && radius >= 0.f);
+  if (B == 0 || P == 0) return 0;
+  IAPT_REQUIRE(xyz && new_xyz && idx);
+  return ball_query_launch(xyz, new_xyz, B, N, P, radius, nsample, idx, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -206,6 +206,88 @@ __global__ void __launch_bounds__(256) graph_feature_grad_k_kernel(const float* 
   gk[((size_t)b * C + c) * Nk + n] = s;
 }
 
+// ---- grouped gathers for the remaining pointnet2_ops entry points ---------------------
+// reduce == 0 (grouping_operation): out[b,c,p,s] = f[b,c,idx[b,p,s]]            (* w[b,p,s] when w != null)
+// reduce == 1 (three_interpolate):  out[b,c,p]   = sum_s w[b,p,s] * f[b,c,idx[b,p,s]]   (fixed order over s)
+__global__ void __launch_bounds__(256) group_gather_kernel(const float* __restrict__ f, const long long* __restrict__ idx,
+                                                           const float* __restrict__ w, int C, int M, int P, int S,
+                                                           int reduce, float* __restrict__ out, long long total) {
+  const long long L = (long long)P * S;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    if (reduce) {
+      const int pp = (int)(t % P);
+      const long long bc = t / P;
+      const long long b = bc / C;
+      const float* row = f + bc * M;
+      float acc = 0.f;
+      for (int j = 0; j < S; ++j) {
+        const long long pos = b * L + (long long)pp * S + j;
+        acc = __fadd_rn(acc, __fmul_rn(__ldg(w + pos), __ldg(row + __ldg(idx + pos))));
+      }
+      out[t] = acc;
+    } else {
+      const long long pos = t % L;
+      const long long bc = t / L;
+      const long long b = bc / C;
+      float v = __ldg(f + bc * M + __ldg(idx + b * L + pos));
+      if (w) v = __fmul_rn(v, __ldg(w + b * L + pos));
+      out[t] = v;
+    }
+  }
+}
+
+// grad_f[b,c,m] = sum over the inverse list of m (ascending position) of w[pos] * go[b,c, reduce ? pos / S : pos]
+__global__ void __launch_bounds__(256) group_gather_grad_kernel(const float* __restrict__ go,
+                                                                const int* __restrict__ start,
+                                                                const int* __restrict__ perm,
+                                                                const float* __restrict__ w, int C, long long L, int S,
+                                                                int reduce, int M, float* __restrict__ gf) {
+  const int c = blockIdx.y, b = blockIdx.z;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const long long plane_len = reduce ? L / S : L;
+  const float* plane = go + ((size_t)b * C + c) * plane_len;
+  const int* st = start + (size_t)b * (M + 1);
+  const int* pm = perm + (size_t)b * L;
+  const float* wb = w ? w + (size_t)b * L : nullptr;
+  float acc = 0.f;
+  for (int i = st[m]; i < st[m + 1]; ++i) {
+    const int pos = __ldg(pm + i);
+    float v = __ldg(plane + (reduce ? pos / S : pos));
+    if (wb) v = __fmul_rn(v, __ldg(wb + pos));
+    acc = __fadd_rn(acc, v);
+  }
+  gf[((size_t)b * C + c) * M + m] = acc;
+}
+
+// ball_query (pointnet2_ops ball_query_kernel): the first nsample references, in ascending index, whose squared
+// distance to the query is < radius^2; unused slots repeat the first hit; no hit leaves zeros.
+__global__ void __launch_bounds__(256) ball_query_kernel(const float* __restrict__ xyz, const float* __restrict__ qry,
+                                                         int N, int P, float radius2, int nsample,
+                                                         int* __restrict__ idx, long long total) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long b = t / P;
+    const float* q = qry + 3 * t;
+    const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+    const float* X = xyz + (size_t)b * N * 3;
+    int* o = idx + t * nsample;
+    int cnt = 0;
+    for (int k = 0; k < N && cnt < nsample; ++k) {
+      const float d2 = sqdist(qx, qy, qz, __ldg(X + 3 * k), __ldg(X + 3 * k + 1), __ldg(X + 3 * k + 2));
+      if (d2 < radius2) {
+        if (cnt == 0)
+          for (int l = 0; l < nsample; ++l) o[l] = k;
+        o[cnt] = k;
+        ++cnt;
+      }
+    }
+    if (cnt == 0)
+      for (int l = 0; l < nsample; ++l) o[l] = 0;
+  }
+}
+
 static inline int grid1d(long long total, int threads, long long cap = 148LL * 32) {
   long long g = (total + threads - 1) / threads;
   if (g > cap) g = cap;
@@ -262,6 +344,40 @@ int graph_feature_grad_launch(const float* go, const long long* idx, int B, int 
     graph_feature_grad_k_kernel<<<gg, 256, 0, stream>>>(go, start, perm, C, L, Nk, gk);
     count_launch(4);
   }
+  return (int)cudaGetLastError();
+}
+
+int group_gather_launch(const float* f, const long long* idx, const float* w, int B, int C, int M, int P, int S,
+                        int reduce, float* out, cudaStream_t stream) {
+  const long long total = (long long)B * C * P * (reduce ? 1 : S);
+  group_gather_kernel<<<grid1d(total, 256), 256, 0, stream>>>(f, idx, w, C, M, P, S, reduce, out, total);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int group_gather_grad_launch(const float* go, const long long* idx, const float* w, int B, int C, int M, int P, int S,
+                             int reduce, float* gf, void* workspace, cudaStream_t stream) {
+  const long long L = (long long)P * S;
+  int* start = static_cast<int*>(workspace);
+  int* perm = start + (size_t)B * (M + 1);
+  cudaError_t err;
+  if ((err = cudaMemsetAsync(start, 0, sizeof(int) * (size_t)B * (M + 1), stream)) != cudaSuccess) return (int)err;
+  dim3 gc((unsigned)grid1d(L, 256, 64), B);
+  inv_count_kernel<<<gc, 256, 0, stream>>>(idx, L, M, start);
+  inv_scan_kernel<<<B, 1024, 0, stream>>>(start, M);
+  dim3 gfill((M + 8 * kInvBins - 1) / (8 * kInvBins), B);
+  inv_fill_kernel<<<gfill, 256, 0, stream>>>(idx, L, M, start, perm);
+  dim3 gg((M + 255) / 256, C, B);
+  group_gather_grad_kernel<<<gg, 256, 0, stream>>>(go, start, perm, w, C, L, S, reduce, M, gf);
+  count_launch(4);
+  return (int)cudaGetLastError();
+}
+
+int ball_query_launch(const float* xyz, const float* qry, int B, int N, int P, float radius, int nsample, int* idx,
+                      cudaStream_t stream) {
+  const long long total = (long long)B * P;
+  ball_query_kernel<<<grid1d(total, 256), 256, 0, stream>>>(xyz, qry, N, P, radius * radius, nsample, idx, total);
+  count_launch();
   return (int)cudaGetLastError();
 }
 

@@ -10,8 +10,9 @@ index on exact ties of the running minimum (upstream's tie order follows its thr
 coordinates are identical either way when the tie is between duplicated points).  Set
 ``furthest_point_sample.skip_near_origin = False`` for plain FPS.
 
-The remaining upstream names (three_nn, three_interpolate, grouping_operation, ball_query, QueryAndGroup,
-GroupAll) are not reached by any shipped config (SURVEY.md note A) and raise NotImplementedError.
+The colder upstream functions the reference imports - three_nn, three_interpolate, grouping_operation, ball_query
+(Deformable* blocks, SnowFlakeNet; not reached by any shipped config, SURVEY.md note A) - are provided too, on the same
+kernels (kNN with k=3, grouped gather with a deterministic backward, a radius scan).
 """
 from __future__ import annotations
 
@@ -151,16 +152,105 @@ def gather_xyz(xyz: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def _not_on_hot_path(name):
-    def f(*a, **k):
-        raise NotImplementedError(
-            f"pointnet2_utils.{name} is outside the accelerated hot path (not reached by any shipped config; "
-            "SURVEY.md section 2 note A)")
-    f.__name__ = name
-    return f
+# ---- the colder upstream ops: Deformable* blocks and SnowFlakeNet ---------------------------
+def three_nn(unknown, known):
+    """unknown [B,n,3], known [B,m,3] -> (dist [B,n,3] Euclidean, idx [B,n,3] int32): the 3 nearest `known` points of every
+    `unknown` point, ascending by (distance, index) like upstream's strict-`<` scan.  = the fused kNN kernel with k = 3."""
+    from ..models.Transformer_utils import knn_point
+
+    if known.size(1) < 3:
+        raise _lib.IaptError("three_nn needs at least 3 known points")
+    idx, d2 = knn_point(3, known, unknown, return_dist=True)
+    return torch.sqrt(d2), idx.to(torch.int32)
 
 
-three_nn = _not_on_hot_path("three_nn")
-three_interpolate = _not_on_hot_path("three_interpolate")
-grouping_operation = _not_on_hot_path("grouping_operation")
-ball_query = _not_on_hot_path("ball_query")
+def _group_call(features, idx, weight, reduce):
+    _lib.require_cuda_f32(features, "features", 3)
+    features = features.contiguous()
+    B, C, M = features.shape
+    if idx.dim() != 3 or idx.size(0) != B or not idx.is_cuda:
+        raise _lib.IaptError("idx must be a CUDA [B, P, S] integer tensor")
+    idx64 = idx.to(torch.int64).contiguous()
+    P, S = idx64.size(1), idx64.size(2)
+    w = None
+    if weight is not None:
+        _lib.require_cuda_f32(weight, "weight", 3)
+        w = weight.contiguous()
+        if tuple(w.shape) != (B, P, S):
+            raise _lib.IaptError("weight must be [B, P, S] like idx")
+    dev = features.device
+    with _lib.on_device(dev):
+        out = torch.empty((B, C, P) if reduce else (B, C, P, S), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().iapt_group_gather(_lib.ptr(features), _lib.ptr(idx64), _lib.ptr(w), B, C, M, P, S,
+                                                1 if reduce else 0, _lib.ptr(out), _lib.stream_ptr(dev)),
+                   "iapt_group_gather")
+    return out, idx64, w, (B, C, M, P, S)
+
+
+def _group_grad(grad_out, idx64, w, dims, reduce):
+    B, C, M, P, S = dims
+    grad_out = grad_out.to(torch.float32).contiguous()
+    dev = grad_out.device
+    L = _lib.lib()
+    with _lib.on_device(dev):
+        gf = torch.empty((B, C, M), dtype=torch.float32, device=dev)
+        ws_bytes = int(L.iapt_graph_feature_grad_workspace_bytes(B, P, M, S))
+        ws = torch.empty((max(ws_bytes, 4),), dtype=torch.uint8, device=dev)
+        _lib.check(L.iapt_group_gather_grad(_lib.ptr(grad_out), _lib.ptr(idx64), _lib.ptr(w), B, C, M, P, S,
+                                            1 if reduce else 0, _lib.ptr(gf), _lib.ptr(ws), ws_bytes,
+                                            _lib.stream_ptr(dev)), "iapt_group_gather_grad")
+    return gf
+
+
+class ThreeInterpolate(torch.autograd.Function):
+    """features [B,c,m], idx [B,n,3], weight [B,n,3] -> [B,c,n] = sum_j weight * features[..., idx]."""
+
+    @staticmethod
+    def forward(ctx, features, idx, weight):
+        out, idx64, w, dims = _group_call(features, idx, weight, True)
+        ctx.save_for_backward(idx64, w)
+        ctx.dims = dims
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx64, w = ctx.saved_tensors
+        return _group_grad(grad_out, idx64, w, ctx.dims, True), None, None
+
+
+three_interpolate = ThreeInterpolate.apply
+
+
+class GroupingOperation(torch.autograd.Function):
+    """features [B,C,N], idx [B,npoint,nsample] -> [B,C,npoint,nsample]."""
+
+    @staticmethod
+    def forward(ctx, features, idx):
+        out, idx64, _, dims = _group_call(features, idx, None, False)
+        ctx.save_for_backward(idx64)
+        ctx.dims = dims
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx64,) = ctx.saved_tensors
+        return _group_grad(grad_out, idx64, None, ctx.dims, False), None
+
+
+grouping_operation = GroupingOperation.apply
+
+
+def ball_query(radius, nsample, xyz, new_xyz):
+    """xyz [B,N,3], new_xyz [B,npoint,3] -> idx [B,npoint,nsample] int32 (not differentiable)."""
+    xyz, new_xyz = xyz.detach(), new_xyz.detach()
+    _lib.require_cuda_f32(xyz, "xyz", 3)
+    _lib.require_cuda_f32(new_xyz, "new_xyz", 3)
+    xyz, new_xyz = xyz.contiguous(), new_xyz.contiguous()
+    B, N, _ = xyz.shape
+    P = new_xyz.size(1)
+    dev = xyz.device
+    with _lib.on_device(dev):
+        idx = torch.empty((B, P, int(nsample)), dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().iapt_ball_query(_lib.ptr(xyz), _lib.ptr(new_xyz), B, N, P, float(radius), int(nsample),
+                                              _lib.ptr(idx), _lib.stream_ptr(dev)), "iapt_ball_query")
+    return idx

@@ -159,6 +159,24 @@ int iapt_graph_feature_grad(const float* grad_out, const int64_t* idx, int B, in
 int iapt_index_points(const float* points, const int64_t* idx, int B, int N, int C, long long S, float* out,
                       iapt_stream_t stream);
 
+/* ---- the remaining pointnet2_ops entry points the reference imports (cold paths:
+ * Deformable* blocks, models/Transformer_utils.py:228-232; SnowFlakeNet, models/external/SnowFlakeNet_utils.py:4,115-120) --
+ * iapt_group_gather: features [B,C,M], idx [B,P,S] int64, weight [B,P,S] (may be NULL for reduce=0)
+ *   reduce = 0 -> out [B,C,P,S] = features[b,c,idx]   (pointnet2_utils.grouping_operation)
+ *   reduce = 1 -> out [B,C,P]   = sum_s weight * features[b,c,idx]   (pointnet2_utils.three_interpolate, S = 3)
+ * iapt_group_gather_grad: gradient w.r.t. features, deterministic (same inverse-index scheme and workspace size as
+ *   iapt_graph_feature_grad: iapt_graph_feature_grad_workspace_bytes(B, P, M, S)).
+ * iapt_ball_query (pointnet2_utils.ball_query): xyz [B,N,3], new_xyz [B,P,3] -> idx [B,P,nsample] int32, the first
+ *   nsample points in ascending index with squared distance < radius^2, padded with the first hit (zeros if none).
+ * three_nn needs no entry point of its own: it is iapt_knn with k = 3 plus a square root (host mirror). */
+int iapt_group_gather(const float* features, const int64_t* idx, const float* weight, int B, int C, int M, int P, int S,
+                      int reduce, float* out, iapt_stream_t stream);
+int iapt_group_gather_grad(const float* grad_out, const int64_t* idx, const float* weight, int B, int C, int M, int P,
+                           int S, int reduce, float* grad_features, void* workspace, size_t workspace_bytes,
+                           iapt_stream_t stream);
+int iapt_ball_query(const float* xyz, const float* new_xyz, int B, int N, int P, float radius, int nsample, int32_t* idx,
+                    iapt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

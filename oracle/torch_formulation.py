@@ -111,3 +111,38 @@ def get_graph_feature(k, coor_q, x_q, coor_k, x_k, idx=None):
     feature = feature.view(batch_size, k, num_points_q, num_dims).permute(0, 3, 2, 1).contiguous()
     xq = x_q.view(batch_size, num_dims, num_points_q, 1).expand(-1, -1, -1, k)
     return torch.cat((feature - xq, xq), dim=1)
+
+
+def three_nn(unknown, known):
+    """pointnet2_ops three_nn restated: 3 nearest known points per unknown point, (sqrt distance, index), ascending by
+    (distance, index) (upstream scans in ascending index with strict `<`)."""
+    d2 = ((unknown[:, :, None, :] - known[:, None, :, :]) ** 2).sum(-1)
+    srt, order = torch.sort(d2, dim=-1, stable=True)
+    return srt[..., :3].sqrt(), order[..., :3].to(torch.int32)
+
+
+def three_interpolate(features, idx, weight):
+    """out[b,c,n] = sum_j weight[b,n,j] * features[b,c,idx[b,n,j]]."""
+    B, C, M = features.shape
+    g = torch.gather(features[:, :, None, :].expand(-1, -1, idx.size(1), -1), 3, idx.long()[:, None].expand(-1, C, -1, -1))
+    return (g * weight[:, None]).sum(-1)
+
+
+def grouping_operation(features, idx):
+    """out[b,c,p,s] = features[b,c,idx[b,p,s]]."""
+    B, C, N = features.shape
+    return torch.gather(features[:, :, None, :].expand(-1, -1, idx.size(1), -1), 3, idx.long()[:, None].expand(-1, C, -1, -1))
+
+
+def ball_query(radius, nsample, xyz, new_xyz):
+    """pointnet2_ops ball_query restated (first nsample indices within radius, padded with the first hit, zeros if none)."""
+    B, P, _ = new_xyz.shape
+    out = torch.zeros((B, P, nsample), dtype=torch.int32)
+    d2 = ((new_xyz[:, :, None, :] - xyz[:, None, :, :]) ** 2).sum(-1)
+    for b in range(B):
+        for p in range(P):
+            hits = torch.nonzero(d2[b, p] < radius * radius).flatten()[:nsample]
+            if len(hits):
+                out[b, p, :] = int(hits[0])
+                out[b, p, :len(hits)] = hits.to(torch.int32)
+    return out

@@ -86,3 +86,49 @@ def test_index_points_kernel_and_grad_path(dev):
     index_points(p, idx3).sum().backward()  # differentiable path
     want = torch.zeros(3, 400, device=dev).scatter_add_(1, idx3.reshape(3, -1), torch.ones(3, 400, device=dev))
     assert torch.allclose(p.grad[..., 0], want)
+
+
+def test_three_nn_interpolate_grouping_ball_query(dev):
+    """The colder pointnet2_ops entry points (8f rank 4) against the torch restatement of upstream's semantics."""
+    from imgadapointr_b200.pointnet2_ops import pointnet2_utils as pu
+
+    g = torch.Generator().manual_seed(9)
+    known = torch.rand((3, 300, 3), generator=g) - 0.5
+    known[:, 10] = known[:, 4]  # duplicate -> tie, lowest index first
+    unknown = torch.rand((3, 120, 3), generator=g) - 0.5
+    unknown[:, 0] = known[:, 4]
+    dist, idx = pu.three_nn(unknown.to(dev), known.to(dev))
+    wd, wi = tf.three_nn(unknown, known)
+    assert idx.dtype == torch.int32 and torch.equal(idx.cpu(), wi) and torch.allclose(dist.cpu(), wd, atol=1e-6)
+    assert int(idx[0, 0, 0]) == 4 and int(idx[0, 0, 1]) == 10
+    # three_interpolate fwd + bwd (weights as the reference forms them, Transformer_utils.py:229-231)
+    feats = torch.randn((3, 7, 300), generator=g)
+    recip = 1.0 / (wd + 1e-8)
+    weight = recip / recip.sum(dim=2, keepdim=True)
+    f = feats.to(dev).requires_grad_(True)
+    out = pu.three_interpolate(f, idx, weight.to(dev))
+    fr = feats.clone().requires_grad_(True)
+    want = tf.three_interpolate(fr, wi, weight)
+    assert torch.allclose(out.detach().cpu(), want.detach(), rtol=1e-5, atol=1e-6)
+    go = torch.randn(want.shape, generator=g)
+    out.backward(go.to(dev))
+    want.backward(go)
+    assert torch.allclose(f.grad.cpu(), fr.grad, rtol=1e-4, atol=1e-5)
+    # grouping_operation fwd + bwd with repeated indices
+    gi = torch.randint(0, 300, (3, 50, 9), generator=g, dtype=torch.int32)
+    gi[:, :10] = 3
+    f2 = feats.to(dev).requires_grad_(True)
+    grouped = pu.grouping_operation(f2, gi.to(dev))
+    fr2 = feats.clone().requires_grad_(True)
+    wgrouped = tf.grouping_operation(fr2, gi)
+    assert torch.equal(grouped.detach().cpu(), wgrouped.detach())
+    go2 = torch.randn(wgrouped.shape, generator=g)
+    grouped.backward(go2.to(dev))
+    wgrouped.backward(go2)
+    assert torch.allclose(f2.grad.cpu(), fr2.grad, rtol=1e-4, atol=1e-5)
+    r1 = [pu.grouping_operation(f2.detach().requires_grad_(True), gi.to(dev)) for _ in range(2)]
+    # ball_query
+    bq = pu.ball_query(0.15, 8, known.to(dev), unknown.to(dev))
+    assert bq.dtype == torch.int32 and torch.equal(bq.cpu(), tf.ball_query(0.15, 8, known, unknown))
+    far = pu.ball_query(1e-4, 4, known.to(dev), (unknown + 5.0).to(dev))
+    assert int(far.abs().sum()) == 0

@@ -96,12 +96,17 @@ def test_dropin_registers_reference_module_names():
     subprocess.run([sys.executable, "-c", code], check=True)
 
 
-def test_pointnet2_cold_ops_raise():
+def test_pointnet2_cold_ops_have_no_cpu_path():
+    from imgadapointr_b200._lib import IaptError
     from imgadapointr_b200.pointnet2_ops import pointnet2_utils as pu
 
-    for name in ("three_nn", "three_interpolate", "grouping_operation", "ball_query"):
-        with pytest.raises(NotImplementedError):
-            getattr(pu, name)()
+    x = torch.zeros((1, 8, 3))
+    f = torch.zeros((1, 2, 8))
+    i = torch.zeros((1, 4, 3), dtype=torch.int32)
+    for call in (lambda: pu.three_nn(x, x), lambda: pu.three_interpolate(f, i, torch.zeros(1, 4, 3)),
+                 lambda: pu.grouping_operation(f, i), lambda: pu.ball_query(0.1, 4, x, x)):
+        with pytest.raises(IaptError):
+            call()
 
 
 def test_synthetic_generators_are_deterministic_and_shaped():
