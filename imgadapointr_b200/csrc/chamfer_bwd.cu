@@ -421,10 +421,10 @@ static int bwd_launch_common(BwdParams& p, int B, int N, int M, void* workspace,
   p.warps_side0 = (long long)B * p.blocks_per_cloud[0];
   p.total_warps = p.warps_side0 + (long long)B * p.blocks_per_cloud[1];
   const long long blocks = (p.total_warps + kBwdWarps - 1) / kBwdWarps;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.pending()) {
     cudaFuncSetAttribute(chamfer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));
-    configured = true;
+    once.done();
   }
   chamfer_bwd_kernel<<<(unsigned)blocks, kBwdThreads, sizeof(BwdSmem), stream>>>(p);
   count_launch();

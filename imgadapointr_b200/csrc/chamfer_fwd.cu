@@ -499,11 +499,11 @@ static Variant pick_variant(int B, int NA, int NS, int slots) {
 
 template <int QT, bool kPrefetch>
 static cudaError_t launch_pair(const FwdParams& p, int grid, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.pending()) {
     cudaFuncSetAttribute(chamfer_pair_kernel<QT, kPrefetch>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(FwdSmem<QT>));
-    configured = true;
+    once.done();
   }
   chamfer_pair_kernel<QT, kPrefetch><<<grid, kThreads, sizeof(FwdSmem<QT>), stream>>>(p);
   return cudaGetLastError();
@@ -532,12 +532,14 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
   // one memset: keys = +inf-like all-ones, ticket = 0xFFFFFFFF (the kernel uses atomicAdd(ticket,1)+1)
   if ((err = cudaMemsetAsync(ws, 0xFF, key_bytes + 256, stream)) != cudaSuccess) return (int)err;
 
-  static int num_sms = 0;
+  static int sms_of_device[256] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int num_sms = sms_of_device[dev & 255];
   if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
+    sms_of_device[dev & 255] = num_sms;
   }
   const int slots = num_sms * 2;
   const Variant v = pick_variant(B, NA, NS, slots);

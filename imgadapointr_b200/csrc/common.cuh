@@ -20,6 +20,27 @@ typedef unsigned long long u64;
 // Host-side launch bookkeeping (c_api.cu).
 void count_launch(int n = 1);
 
+// Per-DEVICE one-time kernel configuration (cudaFuncSetAttribute is per device, and the reference runs several GPUs
+// from one process under nn.DataParallel, tools/runner.py:96).  Returns true when the caller still has to configure
+// the current device; racing threads may both configure - the call is idempotent.
+struct PerDeviceOnce {
+  unsigned long long mask[4] = {0, 0, 0, 0};  // up to 256 devices
+  // usage: if (once.pending()) { <configure>; once.done(); }   - the bit is published only AFTER configuring
+  static int dev() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 255;
+  }
+  bool pending() const {
+    const int d = dev();
+    return (__atomic_load_n(&mask[d >> 6], __ATOMIC_ACQUIRE) & (1ull << (d & 63))) == 0;
+  }
+  void done() {
+    const int d = dev();
+    __atomic_fetch_or(&mask[d >> 6], 1ull << (d & 63), __ATOMIC_RELEASE);
+  }
+};
+
 // Padding sentinel for out-of-range points.  (1e18)^2 * 3 = 3e36 < FLT_MAX, so no Inf/NaN is ever produced,
 // and any real distance (|coords| < 1e15) is smaller than a distance to a sentinel.
 __device__ __host__ constexpr float kPadCoord() { return 1.0e18f; }

@@ -177,10 +177,10 @@ size_t fps_workspace_bytes(int B, int N, int /*npoint*/) {
 template <int kT, int kPPT, bool kRegs>
 static int fps_launch_t(const float* xyz, int B, int N, int npoint, int flags, int32_t* idx, cudaStream_t stream) {
   const size_t smem = sizeof(FpsSlots) + sizeof(float) * 3 * (size_t)N;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.pending()) {
     cudaFuncSetAttribute(fps_kernel<kT, kPPT, kRegs>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    configured = true;
+    once.done();
   }
   fps_kernel<kT, kPPT, kRegs><<<B, kT, smem, stream>>>(xyz, N, npoint, flags, idx);
   count_launch();
@@ -286,10 +286,10 @@ int gather_grad_launch(const float* gout, const int32_t* idx, int B, int C, int 
   dim3 grid((N + 255) / 256, B);
   const size_t smem = sizeof(int) * (size_t)m;
   if (smem > 48 * 1024) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.pending()) {
       cudaFuncSetAttribute(gather_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      configured = true;
+      once.done();
     }
   }
   gather_grad_kernel<<<grid, 256, smem, stream>>>(gout, idx, C, N, m, gfeat);

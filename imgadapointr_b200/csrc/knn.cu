@@ -308,10 +308,10 @@ int knn_launch(const float* ref, const float* qry, int B, int R, int Q, int k, i
   // The select path needs enough queries to fill the machine with one thread each; small calls keep the
   // warp-per-query list kernel (32 lanes per query).
   if (k <= kSelMaxK && R <= 65536 && workspace != nullptr && !force_list && (long long)B * Q >= 65536) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.pending()) {
       cudaFuncSetAttribute(knn_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem));
-      configured = true;
+      once.done();
     }
     int* flags = static_cast<int*>(workspace);
     const int sb = (Q + kSelThreads - 1) / kSelThreads;
