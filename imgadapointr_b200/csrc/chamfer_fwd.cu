@@ -346,9 +346,12 @@ __global__ void __launch_bounds__(256) chamfer_resolve_kernel(const float* __res
           const u64 kj = __shfl_sync(0xffffffffu, key, j);
           const int b = __shfl_sync(0xffffffffu, bl, j);
           kd[u] = (unsigned)(kj >> 32);
-          base[u] = (int)(unsigned)kj * kChunk;
+          // a key that was never lowered (all-ones: every distance of this point was NaN - outside the contract)
+          // must not be turned into an address
+          const bool valid_key = kj != ~0ull;
+          base[u] = valid_key ? (int)(unsigned)kj * kChunk : 0;
           const int cand = base[u] + lane;
-          ok[u] = (t0 + j < totalA) && (cand < NS);
+          ok[u] = valid_key && (t0 + j < totalA) && (cand < NS);
           cx[u] = cy[u] = cz[u] = 0.f;
           if (ok[u]) {
             const float* c = S + ((size_t)b * NS + cand) * 3;
@@ -404,8 +407,9 @@ __global__ void __launch_bounds__(256) chamfer_resolve_kernel(const float* __res
           const u64 kj = __shfl_sync(0xffffffffu, key, j & 31);
           const int b = __shfl_sync(0xffffffffu, bl, j & 31);
           kd[q] = (unsigned)(kj >> 32);
-          const int cand = (int)(unsigned)kj * group + off;
-          ok[q] = (j < 32) && (u0 + j < totalS) && (cand < NA);
+          const bool valid_key = kj != ~0ull;
+          const int cand = valid_key ? (int)(unsigned)kj * group + off : 0;
+          ok[q] = valid_key && (j < 32) && (u0 + j < totalS) && (cand < NA);
           cx[q] = cy[q] = cz[q] = 0.f;
           if (ok[q]) {
             const float* c = A + ((size_t)b * NA + cand) * 3;
@@ -426,7 +430,7 @@ __global__ void __launch_bounds__(256) chamfer_resolve_kernel(const float* __res
           const int owner_sub = lane - jb;  // lane jb + s owns sub-group s of this step
           if (owner_sub >= 0 && owner_sub < per_step) {
             const unsigned mine = (hits >> (owner_sub * group)) & gmask;
-            myidx = (int)(unsigned)key * group + (mine ? (__ffs(mine) - 1) : 0);
+            myidx = (key != ~0ull) ? (int)(unsigned)key * group + (mine ? (__ffs(mine) - 1) : 0) : 0;
           }
         }
       }

@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
       const int e = s * 32 + lane;
       if (e < k) {
         const size_t o = ((size_t)b * Q + q) * k + e;
-        idx_out[o] = (int64_t)li[u][s];
+        // an unfilled slot (only possible when distances were NaN - outside the contract) must stay a valid index
+        idx_out[o] = (int64_t)(li[u][s] == 0x7fffffff ? 0 : li[u][s]);
         if (dist_out) dist_out[o] = ld[u][s];
       }
     }
@@ -289,8 +290,9 @@ __global__ void __launch_bounds__(kSelThreads) knn_select_kernel(const float* __
   }
   const size_t o = ((size_t)b * Q + q) * k;
   for (int j = 0; j < k; ++j) {
-    idx_out[o + j] = (int64_t)sm.top.topi[j][tid];
-    if (dist_out) dist_out[o + j] = sm.top.topd[j][tid];
+    const bool filled = j < have;  // fewer than k only if distances were NaN (outside the contract): stay in range
+    idx_out[o + j] = filled ? (int64_t)sm.top.topi[j][tid] : 0;
+    if (dist_out) dist_out[o + j] = filled ? sm.top.topd[j][tid] : kInf;
   }
 }
 

@@ -213,3 +213,42 @@ def test_fused_l1_zero_distance_nan_quirk(dev):
         mod(p, gt.to(dev)).backward()
         nan_sets.append(torch.isnan(p.grad).any(dim=-1).cpu())
     assert bool(nan_sets[0][0, 7]) and torch.equal(nan_sets[0], nan_sets[1])
+
+
+@pytest.mark.parametrize("scale,offset", [(1e4, 3e4), (1e-3, 0.0), (1e-19, 0.0), (1.0, -7.5)])
+def test_forward_extreme_magnitudes(dev, scale, offset):
+    """Large, tiny (products underflow to denormals / zero) and offset coordinates: still bit-identical to the oracle."""
+    x1 = synthetic.uniform(2, 600, 3) * scale + offset
+    x2 = synthetic.uniform(2, 900, 4) * scale + offset
+    _check_forward(x1.float().contiguous(), x2.float().contiguous(), dev)
+
+
+def test_forward_many_tiny_clouds(dev):
+    _check_forward(synthetic.uniform(300, 33, 5), synthetic.uniform(300, 17, 6), dev)
+
+
+def test_nan_inputs_are_memory_safe(dev):
+    """NaN / Inf coordinates are outside the parity contract but must not fault or return wild indices."""
+    from imgadapointr_b200.models.Transformer_utils import knn_point
+    from imgadapointr_b200.pointnet2_ops import pointnet2_utils
+
+    x1 = synthetic.uniform(2, 700, 7)
+    x2 = synthetic.uniform(2, 500, 8)
+    x1[0, 5] = float("nan")
+    x1[1] = float("nan")  # a whole cloud of NaNs
+    x2[0, 9, 1] = float("inf")
+    d1, d2, i1, i2 = chamfer.forward(x1.to(dev), x2.to(dev))
+    torch.cuda.synchronize()
+    assert int(i1.min()) >= 0 and int(i1.max()) < 500 and int(i2.min()) >= 0 and int(i2.max()) < 700
+    gx1, gx2 = chamfer.backward(x1.to(dev), x2.to(dev), i1, i2, torch.ones_like(d1), torch.ones_like(d2))
+    torch.cuda.synchronize()
+    for k in (8, 32):
+        ki = knn_point(k, x1.to(dev), x1.to(dev)[:, :64].contiguous())
+        assert int(ki.min()) >= 0 and int(ki.max()) < 700
+    fi = pointnet2_utils.furthest_point_sample(x1.to(dev), 32)
+    torch.cuda.synchronize()
+    assert int(fi.min()) >= 0 and int(fi.max()) < 700
+    # finite clouds in the same batch are unaffected
+    clean = chamfer.forward(x1[:1, 6:].contiguous().to(dev), x2[:1, 10:].contiguous().to(dev))
+    od = oracle.chamfer_forward(x1[:1, 6:].numpy(), x2[:1, 10:].numpy())
+    assert np.array_equal(clean[0].cpu().numpy(), od[0]) and np.array_equal(clean[2].cpu().numpy(), od[2])
