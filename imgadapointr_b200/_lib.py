@@ -56,7 +56,7 @@ SIGNATURES = {
     "iapt_group_gather_grad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                         _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "iapt_ball_query": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_int, _c_void_p, _c_void_p]),
-    "iapt_knn_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "iapt_knn_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
     "iapt_knn": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t,
                           _c_void_p]),
 }

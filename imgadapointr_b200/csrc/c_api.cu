@@ -27,7 +27,7 @@ int fps_launch(const float*, int, int, int, int, int32_t*, void*, cudaStream_t);
 int gather_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
 int gather_xyz_launch(const float*, const int32_t*, int, int, int, float*, cudaStream_t);
 int gather_grad_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
-size_t knn_workspace_bytes(int B, int Q, int k);
+size_t knn_workspace_bytes(int B, int R, int Q, int k);
 int knn_launch(const float*, const float*, int, int, int, int, int64_t*, float*, void*, cudaStream_t);
 int graph_feature_launch(const float*, const float*, const long long*, int, int, int, int, int, float*, cudaStream_t);
 int index_points_launch(const float*, const long long*, int, int, int, long long, float*, cudaStream_t);
@@ -207,9 +207,9 @@ int iapt_gather_xyz(const float* xyz, const int32_t* idx, int B, int N, int npoi
   return gather_xyz_launch(xyz, idx, B, N, npoint, out, (cudaStream_t)stream);
 }
 
-size_t iapt_knn_workspace_bytes(int B, int Q, int k) {
-  if (B <= 0 || Q <= 0 || k <= 0) return 0;
-  return knn_workspace_bytes(B, Q, k);
+size_t iapt_knn_workspace_bytes(int B, int R, int Q, int k) {
+  if (B <= 0 || R <= 0 || Q <= 0 || k <= 0) return 0;
+  return knn_workspace_bytes(B, R, Q, k);
 }
 
 int iapt_knn(const float* ref, const float* query, int B, int R, int Q, int k, int64_t* idx, float* dist,
@@ -219,7 +219,7 @@ int iapt_knn(const float* ref, const float* query, int B, int R, int Q, int k, i
   IAPT_REQUIRE(k <= R);
   if (B == 0 || Q == 0) return 0;
   IAPT_REQUIRE(ref && query && idx);
-  const size_t need = knn_workspace_bytes(B, Q, k);
+  const size_t need = knn_workspace_bytes(B, R, Q, k);
   if (need > 0 && (workspace == nullptr || workspace_bytes < need)) return IAPT_EWORKSPACE;
   return knn_launch(ref, query, B, R, Q, k, idx, dist, need ? workspace : nullptr, (cudaStream_t)stream);
 }

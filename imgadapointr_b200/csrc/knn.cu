@@ -20,11 +20,61 @@ constexpr int kKnnWarps = kKnnThreads / 32;
 constexpr int kKnnTile = 2048;         // reference points per smem tile (24 KB SoA)
 constexpr int kKnnQueriesPerCta = 32;  // queries per CTA (4 per warp), amortises the tile fill
 
+// Insert this step's candidates (one per lane: distance d, reference index my_idx; d = +inf for "none") into the
+// warp-distributed sorted list (entry s*32+lane).  Candidates are taken in lane order and only a strictly smaller
+// distance displaces an entry, so with ascending indices across lanes/steps the lowest index wins exact ties.
+template <int kSlots>
+__device__ __forceinline__ void knn_insert(float d, int my_idx, int k, float (&ld)[kSlots], int (&li)[kSlots],
+                                           float& tau) {
+  const int lane = threadIdx.x & 31;
+  unsigned mask = __ballot_sync(0xffffffffu, d < tau);
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    const float dc = __shfl_sync(0xffffffffu, d, src);
+    const int ic = __shfl_sync(0xffffffffu, my_idx, src);
+    // position = number of list entries <= dc (equal distances already listed have lower indices)
+    int pos = 0;
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) pos += __popc(__ballot_sync(0xffffffffu, ld[s] <= dc));
+    // shift entries at >= pos up by one (highest slot first), then drop the candidate in
+#pragma unroll
+    for (int s = kSlots - 1; s >= 0; --s) {
+      float up_d = __shfl_up_sync(0xffffffffu, ld[s], 1);
+      int up_i = __shfl_up_sync(0xffffffffu, li[s], 1);
+      if (s > 0) {
+        const float carry_d = __shfl_sync(0xffffffffu, ld[s - 1], 31);
+        const int carry_i = __shfl_sync(0xffffffffu, li[s - 1], 31);
+        if (lane == 0) {
+          up_d = carry_d;
+          up_i = carry_i;
+        }
+      }
+      const int e = s * 32 + lane;
+      if (e > pos) {
+        ld[s] = up_d;
+        li[s] = up_i;
+      } else if (e == pos) {
+        ld[s] = dc;
+        li[s] = ic;
+      }
+    }
+    float kth = ld[0];
+    if (kSlots > 1 && k > 32) kth = ld[kSlots - 1];
+    tau = __shfl_sync(0xffffffffu, kth, (k - 1) & 31);
+    mask &= mask - 1;
+    mask &= __ballot_sync(0xffffffffu, d < tau);
+  }
+}
+
+// r_splits > 1: blockIdx.y selects a slice of the reference range and the per-slice lists go to part_d / part_i
+// ([B*Q, r_splits, k]) for knn_merge_kernel - used when there are few queries and many references (the loss kNN:
+// Q = 64, R = 16384, k = 32, models/external/AdaPoinTr.py:201), where one warp per query cannot fill the machine.
 template <int kSlots>  // list entries per lane: k <= 32 * kSlots
 __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restrict__ ref, const float* __restrict__ qry,
                                                           int R, int Q, int k, int q_blocks,
                                                           int64_t* __restrict__ idx_out, float* __restrict__ dist_out,
-                                                          const int* __restrict__ only_flagged) {
+                                                          const int* __restrict__ only_flagged, int r_splits,
+                                                          float* __restrict__ part_d, int* __restrict__ part_i) {
   __shared__ float sx[kKnnTile], sy[kKnnTile], sz[kKnnTile];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -35,6 +85,9 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
     if (threadIdx.x < kKnnQueriesPerCta && q0 + (int)threadIdx.x < Q) any = only_flagged[(size_t)b * Q + q0 + threadIdx.x];
     if (!__syncthreads_or(any)) return;
   }
+  const int split = blockIdx.y;
+  const int per = (R + r_splits - 1) / r_splits;
+  const int r_lo = split * per, r_hi = min(R, r_lo + per);
   const float* __restrict__ Rb = ref + (size_t)b * R * 3;
   const float* __restrict__ Qb = qry + (size_t)b * Q * 3;
   constexpr int kQPW = kKnnQueriesPerCta / kKnnWarps;
@@ -59,8 +112,8 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
     tau[u] = kInf;
   }
 
-  for (int t0 = 0; t0 < R; t0 += kKnnTile) {
-    const int tn = min(kKnnTile, R - t0);
+  for (int t0 = r_lo; t0 < r_hi; t0 += kKnnTile) {
+    const int tn = min(kKnnTile, r_hi - t0);
     __syncthreads();
     for (int i = threadIdx.x; i < tn * 3; i += kKnnThreads) {
       const float v = __ldg(Rb + 3 * (size_t)t0 + i);
@@ -76,43 +129,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
         const int r = r0 + lane;
         float d = kInf;
         if (r < tn) d = sqdist(qx[u], qy[u], qz[u], sx[r], sy[r], sz[r]);
-        unsigned mask = __ballot_sync(0xffffffffu, d < tau[u]);
-        while (mask) {
-          const int src = __ffs(mask) - 1;
-          const float dc = __shfl_sync(0xffffffffu, d, src);
-          const int ic = t0 + r0 + src;
-          // position = number of list entries <= dc (equal distances already listed have lower indices)
-          int pos = 0;
-#pragma unroll
-          for (int s = 0; s < kSlots; ++s) pos += __popc(__ballot_sync(0xffffffffu, ld[u][s] <= dc));
-          // shift entries at >= pos up by one (highest slot first), then drop the candidate in
-#pragma unroll
-          for (int s = kSlots - 1; s >= 0; --s) {
-            float up_d = __shfl_up_sync(0xffffffffu, ld[u][s], 1);
-            int up_i = __shfl_up_sync(0xffffffffu, li[u][s], 1);
-            if (s > 0) {
-              const float carry_d = __shfl_sync(0xffffffffu, ld[u][s - 1], 31);
-              const int carry_i = __shfl_sync(0xffffffffu, li[u][s - 1], 31);
-              if (lane == 0) {
-                up_d = carry_d;
-                up_i = carry_i;
-              }
-            }
-            const int e = s * 32 + lane;
-            if (e > pos) {
-              ld[u][s] = up_d;
-              li[u][s] = up_i;
-            } else if (e == pos) {
-              ld[u][s] = dc;
-              li[u][s] = ic;
-            }
-          }
-          float kth = ld[u][0];
-          if (kSlots > 1 && k > 32) kth = ld[u][kSlots - 1];
-          tau[u] = __shfl_sync(0xffffffffu, kth, (k - 1) & 31);
-          mask &= mask - 1;
-          mask &= __ballot_sync(0xffffffffu, d < tau[u]);
-        }
+        knn_insert<kSlots>(d, t0 + r, k, ld[u], li[u], tau[u]);
       }
     }
   }
@@ -126,11 +143,59 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
     for (int s = 0; s < kSlots; ++s) {
       const int e = s * 32 + lane;
       if (e < k) {
-        const size_t o = ((size_t)b * Q + q) * k + e;
-        // an unfilled slot (only possible when distances were NaN - outside the contract) must stay a valid index
-        idx_out[o] = (int64_t)(li[u][s] == 0x7fffffff ? 0 : li[u][s]);
-        if (dist_out) dist_out[o] = ld[u][s];
+        if (r_splits > 1) {
+          const size_t o = (((size_t)b * Q + q) * r_splits + split) * k + e;
+          part_d[o] = ld[u][s];
+          part_i[o] = li[u][s];
+        } else {
+          const size_t o = ((size_t)b * Q + q) * k + e;
+          // an unfilled slot (only possible when distances were NaN - outside the contract) must stay a valid index
+          idx_out[o] = (int64_t)(li[u][s] == 0x7fffffff ? 0 : li[u][s]);
+          if (dist_out) dist_out[o] = ld[u][s];
+        }
       }
+    }
+  }
+}
+
+// Merge the r_splits per-slice lists of each query (each ascending by (distance, index), slices in ascending index
+// order) into the final k: the same insertion scheme over r_splits*k candidates, one warp per query.
+template <int kSlots>
+__global__ void __launch_bounds__(kKnnThreads) knn_merge_kernel(const float* __restrict__ part_d,
+                                                                const int* __restrict__ part_i, long long n_queries,
+                                                                int k, int r_splits, int64_t* __restrict__ idx_out,
+                                                                float* __restrict__ dist_out) {
+  const int lane = threadIdx.x & 31;
+  const long long q = (long long)blockIdx.x * kKnnWarps + (threadIdx.x >> 5);
+  if (q >= n_queries) return;
+  const float kInf = __int_as_float(0x7f800000);
+  float ld[kSlots];
+  int li[kSlots];
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    ld[s] = kInf;
+    li[s] = 0x7fffffff;
+  }
+  float tau = kInf;
+  const int total = r_splits * k;
+  const float* pd = part_d + (size_t)q * total;
+  const int* pi = part_i + (size_t)q * total;
+  for (int c0 = 0; c0 < total; c0 += 32) {
+    const int c = c0 + lane;
+    float d = kInf;
+    int i = 0x7fffffff;
+    if (c < total) {
+      i = __ldg(pi + c);
+      if (i != 0x7fffffff) d = __ldg(pd + c);
+    }
+    knn_insert<kSlots>(d, i, k, ld, li, tau);
+  }
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    const int e = s * 32 + lane;
+    if (e < k) {
+      idx_out[(size_t)q * k + e] = (int64_t)(li[s] == 0x7fffffff ? 0 : li[s]);
+      if (dist_out) dist_out[(size_t)q * k + e] = ld[s];
     }
   }
 }
@@ -296,38 +361,75 @@ __global__ void __launch_bounds__(kSelThreads) knn_select_kernel(const float* __
   }
 }
 
-size_t knn_workspace_bytes(int B, int Q, int k) { return k <= kSelMaxK ? sizeof(int) * (size_t)B * Q : 0; }
+// Reference-range splits for the list kernel: only when the query count cannot fill the machine on its own.
+static int knn_r_splits(int B, int R, int Q) {
+  const long long ctas = (long long)B * ((Q + kKnnQueriesPerCta - 1) / kKnnQueriesPerCta);
+  if (ctas >= 296 || R < 2 * kKnnTile) return 1;
+  long long s = (592 + ctas - 1) / ctas;          // aim at ~2 CTAs per SM
+  const long long max_s = R / 1024;               // keep >= 1024 references per slice
+  if (s > max_s) s = max_s;
+  if (s > 32) s = 32;
+  return s < 2 ? 1 : (int)s;
+}
+
+size_t knn_workspace_bytes(int B, int R, int Q, int k) {
+  size_t bytes = k <= kSelMaxK ? sizeof(int) * (size_t)B * Q : 0;
+  const int rs = knn_r_splits(B, R, Q);
+  if (rs > 1) bytes += (sizeof(float) + sizeof(int)) * (size_t)B * Q * rs * k;
+  return bytes;
+}
+
+template <int kSlots>
+static void knn_list_launch(const float* ref, const float* qry, int B, int R, int Q, int k, int64_t* idx, float* dist,
+                            const int* flags, void* split_ws, cudaStream_t stream) {
+  const int q_blocks = (Q + kKnnQueriesPerCta - 1) / kKnnQueriesPerCta;
+  const int rs = (flags == nullptr && split_ws != nullptr) ? knn_r_splits(B, R, Q) : 1;
+  dim3 grid((unsigned)((long long)B * q_blocks), rs);
+  if (rs > 1) {
+    float* pd = static_cast<float*>(split_ws);
+    int* pi = reinterpret_cast<int*>(pd + (size_t)B * Q * rs * k);
+    knn_kernel<kSlots><<<grid, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, nullptr, rs, pd, pi);
+    const long long nq = (long long)B * Q;
+    knn_merge_kernel<kSlots><<<(unsigned)((nq + kKnnWarps - 1) / kKnnWarps), kKnnThreads, 0, stream>>>(pd, pi, nq, k, rs,
+                                                                                                     idx, dist);
+    count_launch(2);
+  } else {
+    knn_kernel<kSlots><<<grid, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, flags, 1, nullptr,
+                                                         nullptr);
+    count_launch();
+  }
+}
 
 int knn_launch(const float* ref, const float* qry, int B, int R, int Q, int k, int64_t* idx, float* dist,
                void* workspace, cudaStream_t stream) {
-  const int q_blocks = (Q + kKnnQueriesPerCta - 1) / kKnnQueriesPerCta;
-  const long long blocks = (long long)B * q_blocks;
   static int force_list = -1;
   if (force_list < 0) {
     const char* e = std::getenv("IAPT_KNN_FORCE_LIST");
     force_list = (e && e[0] == '1') ? 1 : 0;
   }
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  int* flags = (k <= kSelMaxK && ws != nullptr) ? reinterpret_cast<int*>(ws) : nullptr;
+  void* split_ws = (ws != nullptr && knn_r_splits(B, R, Q) > 1) ? ws + (k <= kSelMaxK ? sizeof(int) * (size_t)B * Q : 0)
+                                                                : nullptr;
   // The select path needs enough queries to fill the machine with one thread each; small calls keep the
   // warp-per-query list kernel (32 lanes per query).
-  if (k <= kSelMaxK && R <= 65536 && workspace != nullptr && !force_list && (long long)B * Q >= 65536) {
+  if (k <= kSelMaxK && R <= 65536 && flags != nullptr && !force_list && (long long)B * Q >= 65536) {
     static PerDeviceOnce once;
     if (once.pending()) {
       cudaFuncSetAttribute(knn_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem));
       once.done();
     }
-    int* flags = static_cast<int*>(workspace);
     const int sb = (Q + kSelThreads - 1) / kSelThreads;
     knn_select_kernel<false><<<(unsigned)((long long)B * sb), kSelThreads, sizeof(SelSmem), stream>>>(
         ref, qry, R, Q, k, sb, idx, dist, flags);
-    knn_kernel<1><<<(unsigned)blocks, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, flags);
-    count_launch(2);
+    count_launch();
+    knn_list_launch<1>(ref, qry, B, R, Q, k, idx, dist, flags, nullptr, stream);
     return (int)cudaGetLastError();
   }
   if (k <= 32)
-    knn_kernel<1><<<(unsigned)blocks, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, nullptr);
+    knn_list_launch<1>(ref, qry, B, R, Q, k, idx, dist, nullptr, split_ws, stream);
   else
-    knn_kernel<2><<<(unsigned)blocks, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, nullptr);
-  count_launch();
+    knn_list_launch<2>(ref, qry, B, R, Q, k, idx, dist, nullptr, split_ws, stream);
   return (int)cudaGetLastError();
 }
 

@@ -38,7 +38,7 @@ def knn_point(nsample, xyz, new_xyz, return_dist=False):
     with _lib.on_device(dev):
         idx = torch.empty((B, Q, k), dtype=torch.int64, device=dev)
         dist = torch.empty((B, Q, k), dtype=torch.float32, device=dev) if return_dist else None
-        ws_bytes = 4 * B * Q if k <= 16 else 0  # == iapt_knn_workspace_bytes (checked in tests/test_abi.py)
+        ws_bytes = int(_lib.lib().iapt_knn_workspace_bytes(B, R, Q, k))
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
         _lib.check(_lib.lib().iapt_knn(_lib.ptr(xyz), _lib.ptr(new_xyz), B, R, Q, k, _lib.ptr(idx), _lib.ptr(dist),
                                        _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)), "iapt_knn")

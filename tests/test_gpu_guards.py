@@ -102,7 +102,7 @@ def test_fps_gather_knn_graph_stay_in_bounds(dev, B, N, m, k):
     Q = min(N, 37)
     qry = xyz[:, :Q].contiguous()
     kidx, kdist = Guarded(8 * B * Q * k, dev), Guarded(4 * B * Q * k, dev)
-    kwn = L.iapt_knn_workspace_bytes(B, Q, min(k, N))
+    kwn = L.iapt_knn_workspace_bytes(B, N, Q, min(k, N))
     kws = Guarded(max(kwn, 4), dev)
     _lib.check(L.iapt_knn(xyz.data_ptr(), qry.data_ptr(), B, N, Q, min(k, N), kidx.ptr, kdist.ptr, kws.ptr, kwn, st), "knn")
     torch.cuda.synchronize()
