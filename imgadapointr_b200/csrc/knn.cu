@@ -69,7 +69,7 @@ __device__ __forceinline__ void knn_insert(float d, int my_idx, int k, float (&l
 // r_splits > 1: blockIdx.y selects a slice of the reference range and the per-slice lists go to part_d / part_i
 // ([B*Q, r_splits, k]) for knn_merge_kernel - used when there are few queries and many references (the loss kNN:
 // Q = 64, R = 16384, k = 32, models/external/AdaPoinTr.py:201), where one warp per query cannot fill the machine.
-template <int kSlots>  // list entries per lane: k <= 32 * kSlots
+template <int kSlots, int kQPW>  // list entries per lane: k <= 32 * kSlots; kQPW queries per warp (processed in turn)
 __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restrict__ ref, const float* __restrict__ qry,
                                                           int R, int Q, int k, int q_blocks,
                                                           int64_t* __restrict__ idx_out, float* __restrict__ dist_out,
@@ -79,10 +79,10 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.x / q_blocks;
-  const int q0 = (blockIdx.x - b * q_blocks) * kKnnQueriesPerCta;
+  const int q0 = (blockIdx.x - b * q_blocks) * (kKnnWarps * kQPW);
   if (only_flagged != nullptr) {  // second pass of the select path: only queries whose candidate buffer overflowed
     int any = 0;
-    if (threadIdx.x < kKnnQueriesPerCta && q0 + (int)threadIdx.x < Q) any = only_flagged[(size_t)b * Q + q0 + threadIdx.x];
+    if (threadIdx.x < (kKnnWarps * kQPW) && q0 + (int)threadIdx.x < Q) any = only_flagged[(size_t)b * Q + q0 + threadIdx.x];
     if (!__syncthreads_or(any)) return;
   }
   const int split = blockIdx.y;
@@ -90,7 +90,6 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
   const int r_lo = split * per, r_hi = min(R, r_lo + per);
   const float* __restrict__ Rb = ref + (size_t)b * R * 3;
   const float* __restrict__ Qb = qry + (size_t)b * Q * 3;
-  constexpr int kQPW = kKnnQueriesPerCta / kKnnWarps;
   const float kInf = __int_as_float(0x7f800000);
 
   float qx[kQPW], qy[kQPW], qz[kQPW];
@@ -361,11 +360,13 @@ __global__ void __launch_bounds__(kSelThreads) knn_select_kernel(const float* __
   }
 }
 
-// Reference-range splits for the list kernel: only when the query count cannot fill the machine on its own.
+// Reference-range splits for the list kernel: only when the query count cannot fill the machine on its own.  In that
+// mode a warp owns ONE query (8 per CTA) instead of four in turn.
 static int knn_r_splits(int B, int R, int Q) {
-  const long long ctas = (long long)B * ((Q + kKnnQueriesPerCta - 1) / kKnnQueriesPerCta);
-  if (ctas >= 296 || R < 2 * kKnnTile) return 1;
-  long long s = (592 + ctas - 1) / ctas;          // aim at ~2 CTAs per SM
+  const long long ctas4 = (long long)B * ((Q + kKnnQueriesPerCta - 1) / kKnnQueriesPerCta);
+  if (ctas4 >= 296 || R < 2 * kKnnTile) return 1;
+  const long long ctas = (long long)B * ((Q + kKnnWarps - 1) / kKnnWarps);
+  long long s = (1184 + ctas - 1) / ctas;         // aim at ~8 CTAs (64 warps) per SM
   const long long max_s = R / 1024;               // keep >= 1024 references per slice
   if (s > max_s) s = max_s;
   if (s > 32) s = 32;
@@ -382,20 +383,22 @@ size_t knn_workspace_bytes(int B, int R, int Q, int k) {
 template <int kSlots>
 static void knn_list_launch(const float* ref, const float* qry, int B, int R, int Q, int k, int64_t* idx, float* dist,
                             const int* flags, void* split_ws, cudaStream_t stream) {
-  const int q_blocks = (Q + kKnnQueriesPerCta - 1) / kKnnQueriesPerCta;
   const int rs = (flags == nullptr && split_ws != nullptr) ? knn_r_splits(B, R, Q) : 1;
-  dim3 grid((unsigned)((long long)B * q_blocks), rs);
   if (rs > 1) {
+    const int q_blocks = (Q + kKnnWarps - 1) / kKnnWarps;
+    dim3 grid((unsigned)((long long)B * q_blocks), rs);
     float* pd = static_cast<float*>(split_ws);
     int* pi = reinterpret_cast<int*>(pd + (size_t)B * Q * rs * k);
-    knn_kernel<kSlots><<<grid, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, nullptr, rs, pd, pi);
+    knn_kernel<kSlots, 1><<<grid, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, nullptr, rs, pd, pi);
     const long long nq = (long long)B * Q;
     knn_merge_kernel<kSlots><<<(unsigned)((nq + kKnnWarps - 1) / kKnnWarps), kKnnThreads, 0, stream>>>(pd, pi, nq, k, rs,
                                                                                                      idx, dist);
     count_launch(2);
   } else {
-    knn_kernel<kSlots><<<grid, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, flags, 1, nullptr,
-                                                         nullptr);
+    const int q_blocks = (Q + kKnnQueriesPerCta - 1) / kKnnQueriesPerCta;
+    dim3 grid((unsigned)((long long)B * q_blocks), 1);
+    knn_kernel<kSlots, 4><<<grid, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, flags, 1, nullptr,
+                                                            nullptr);
     count_launch();
   }
 }
