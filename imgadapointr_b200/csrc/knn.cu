@@ -366,7 +366,12 @@ static int knn_r_splits(int B, int R, int Q) {
   const long long ctas4 = (long long)B * ((Q + kKnnQueriesPerCta - 1) / kKnnQueriesPerCta);
   if (ctas4 >= 296 || R < 2 * kKnnTile) return 1;
   const long long ctas = (long long)B * ((Q + kKnnWarps - 1) / kKnnWarps);
-  long long s = (1184 + ctas - 1) / ctas;         // aim at ~8 CTAs (64 warps) per SM
+  static long long target = 0;
+  if (target == 0) {
+    const char* e = std::getenv("IAPT_KNN_SPLIT_TARGET");  // development knob: total CTAs to aim for
+    target = (e && std::atoi(e) > 0) ? std::atoi(e) : 600;
+  }
+  long long s = (target + ctas - 1) / ctas;       // default: ~4 CTAs (32 warps) per SM; more slices only add merge work
   const long long max_s = R / 1024;               // keep >= 1024 references per slice
   if (s > max_s) s = max_s;
   if (s > 32) s = 32;
@@ -394,6 +399,13 @@ static void knn_list_launch(const float* ref, const float* qry, int B, int R, in
     knn_merge_kernel<kSlots><<<(unsigned)((nq + kKnnWarps - 1) / kKnnWarps), kKnnThreads, 0, stream>>>(pd, pi, nq, k, rs,
                                                                                                      idx, dist);
     count_launch(2);
+  } else if (flags == nullptr && (long long)B * ((Q + kKnnQueriesPerCta - 1) / kKnnQueriesPerCta) < 296) {
+    // few queries: one query per warp (4x the CTAs) instead of four in turn
+    const int q_blocks = (Q + kKnnWarps - 1) / kKnnWarps;
+    dim3 grid((unsigned)((long long)B * q_blocks), 1);
+    knn_kernel<kSlots, 1><<<grid, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, nullptr, 1, nullptr,
+                                                            nullptr);
+    count_launch();
   } else {
     const int q_blocks = (Q + kKnnQueriesPerCta - 1) / kKnnQueriesPerCta;
     dim3 grid((unsigned)((long long)B * q_blocks), 1);
