@@ -32,21 +32,6 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kSStage = 512;  // streamed points per smem stage
 constexpr int kChunk = 32;    // streamed points per row-index chunk
-#ifndef IAPT_DEFAULT_QT_LARGE
-#define IAPT_DEFAULT_QT_LARGE 16
-#endif
-#ifndef IAPT_DEFAULT_STATIC_SCHED
-#define IAPT_DEFAULT_STATIC_SCHED 0
-#endif
-#ifndef IAPT_DEFAULT_GUIDED
-#define IAPT_DEFAULT_GUIDED 0
-#endif
-#ifndef IAPT_MIN3
-#define IAPT_MIN3 fmin3  // fmin3 (FMNMX3) or umin3 (VIMNMX3.U32 on the bit patterns): measured equal (3.088 ms)
-#endif
-#ifndef IAPT_DEFAULT_PREFETCH
-#define IAPT_DEFAULT_PREFETCH 0
-#endif
 
 struct FwdParams {
   const float* A;  // [B, NA, 3] register side
@@ -56,17 +41,12 @@ struct FwdParams {
   u64* PS;  // [B, NS] packed (dist, group id of A)
   unsigned* ticket;  // starts at 0xFFFFFFFF (same memset as the keys); item = atomicAdd(ticket, 1) + 1
   int a_tiles, s_splits, stages_per_split, total_items;
-  int static_sched;  // 1: contiguous, balanced ranges of (cloud, A tile, stage) units per CTA instead of tickets
-  // guided schedule (n_segs > 0): every (cloud, A tile) is cut into n_segs stage ranges of DECREASING length and the
-  // tickets walk them segment-major, so the big ranges go first (few item boundaries) and one-stage ranges fill the tail
-  int n_segs;
-  unsigned char seg_start[32], seg_len[32];
 };
 
 template <int QT>
 struct __align__(16) FwdSmem {
-  ulonglong2 sxy[2][kSStage + 2];   // (x,x),(y,y)      (+2: the register prefetch reads one pair past the stage)
-  ulonglong2 szz[2][kSStage / 2 + 1];  // (z,z) of two consecutive points
+  ulonglong2 sxy[2][kSStage];       // (x,x),(y,y)
+  ulonglong2 szz[2][kSStage / 2];   // (z,z) of two consecutive points
   uint4 col[kWarps][kSStage / 2];   // per warp, per streamed point pair: (min bits, ballot) x2
   float4 prev[QT / 4][kThreads];    // running minima at the last chunk boundary
   unsigned bestc[QT][kThreads];     // first chunk in which the running minimum strictly decreased
@@ -103,8 +83,8 @@ __device__ __forceinline__ void stage_fill_store(FwdSmem<QT>& sm, int buf, int t
   sm.szz[buf][tid] = zz;
 }
 
-// QT: A-side points per thread (8 or 16).  kPrefetch: keep the NEXT pair of streamed points in registers.
-template <int QT, bool kPrefetch>
+// QT: A-side points per thread (8 or 16).
+template <int QT>
 __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdSmem<QT>& sm = *reinterpret_cast<FwdSmem<QT>*>(smem_raw);
@@ -116,45 +96,20 @@ __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) 
   const float kInf = __int_as_float(0x7f800000);
 
   const int total_stages = (p.NS + kSStage - 1) / kSStage;
-  // static schedule: this CTA owns stage units [unit, unit_end) of the B * a_tiles * total_stages grid of units
-  const long long n_units = (long long)p.B * p.a_tiles * total_stages;
-  long long unit = n_units * blockIdx.x / gridDim.x;
-  const long long unit_end = n_units * (blockIdx.x + 1) / gridDim.x;
 
   for (;;) {
-    int b, at, stage0, stage_end;
     __syncthreads();  // everyone is done with smem (incl. next_item) of the previous item
-    if (p.static_sched) {
-      if (unit >= unit_end) break;
-      const long long tile = unit / total_stages;
-      stage0 = (int)(unit - tile * total_stages);
-      stage_end = (int)min((long long)total_stages, stage0 + (unit_end - unit));
-      b = (int)(tile / p.a_tiles);
-      at = (int)(tile - (long long)b * p.a_tiles);
-      unit += stage_end - stage0;
-    } else {
-      if (tid == 0) sm.next_item = atomicAdd(p.ticket, 1u) + 1u;
-      __syncthreads();
-      const int item = (int)sm.next_item;
-      if (item >= p.total_items) break;
-      if (p.n_segs > 0) {
-        const int n_tiles = p.B * p.a_tiles;
-        const int seg = item / n_tiles;
-        const int tile = item - seg * n_tiles;
-        b = tile / p.a_tiles;
-        at = tile - b * p.a_tiles;
-        stage0 = p.seg_start[seg];
-        stage_end = stage0 + p.seg_len[seg];
-      } else {
-        const int per_cloud = p.a_tiles * p.s_splits;
-        b = item / per_cloud;
-        const int rem = item - b * per_cloud;
-        at = rem / p.s_splits;
-        const int ss = rem - at * p.s_splits;
-        stage0 = ss * p.stages_per_split;
-        stage_end = min(total_stages, stage0 + p.stages_per_split);
-      }
-    }
+    if (tid == 0) sm.next_item = atomicAdd(p.ticket, 1u) + 1u;
+    __syncthreads();
+    const int item = (int)sm.next_item;
+    if (item >= p.total_items) break;
+    const int per_cloud = p.a_tiles * p.s_splits;
+    const int b = item / per_cloud;
+    const int rem = item - b * per_cloud;
+    const int at = rem / p.s_splits;
+    const int ss = rem - at * p.s_splits;
+    const int stage0 = ss * p.stages_per_split;
+    const int stage_end = min(total_stages, stage0 + p.stages_per_split);
     const float* __restrict__ Ab = p.A + (size_t)b * p.NA * 3;
     const float* __restrict__ Sb = p.S + (size_t)b * p.NS * 3;
 
@@ -208,24 +163,13 @@ __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) 
       const ulonglong2* __restrict__ sxy = sm.sxy[buf];
       const ulonglong2* __restrict__ szz = sm.szz[buf];
 
-      ulonglong2 xy0 = sxy[0], xy1 = sxy[1], zz = szz[0];
       for (int c = 0; c < n_chunks; ++c) {
 #pragma unroll 4
         for (int rr = 0; rr < kChunk; rr += 2) {
           const int r = c * kChunk + rr;
-          ulonglong2 cxy0, cxy1, czz;
-          if (kPrefetch) {
-            cxy0 = xy0;
-            cxy1 = xy1;
-            czz = zz;
-            xy0 = sxy[r + 2];  // next pair (the arrays are padded, the last prefetch is never used)
-            xy1 = sxy[r + 3];
-            zz = szz[(r >> 1) + 1];
-          } else {
-            cxy0 = sxy[r];
-            cxy1 = sxy[r + 1];
-            czz = szz[r >> 1];
-          }
+          const ulonglong2 cxy0 = sxy[r];
+          const ulonglong2 cxy1 = sxy[r + 1];
+          const ulonglong2 czz = szz[r >> 1];
           float c0 = kInf, c1 = kInf;
 #pragma unroll
           for (int i = 0; i < kPairs; ++i) {
@@ -234,10 +178,10 @@ __global__ void __launch_bounds__(kThreads, 2) chamfer_pair_kernel(FwdParams p) 
             float dl, dh, el, eh;
             unpack2(d, dl, dh);
             unpack2(e, el, eh);
-            m[2 * i] = IAPT_MIN3(m[2 * i], dl, el);
-            m[2 * i + 1] = IAPT_MIN3(m[2 * i + 1], dh, eh);
-            c0 = IAPT_MIN3(c0, dl, dh);
-            c1 = IAPT_MIN3(c1, el, eh);
+            m[2 * i] = fmin3(m[2 * i], dl, el);
+            m[2 * i + 1] = fmin3(m[2 * i + 1], dh, eh);
+            c0 = fmin3(c0, dl, dh);
+            c1 = fmin3(c1, el, eh);
           }
           const unsigned u0 = __float_as_uint(c0), u1 = __float_as_uint(c1);
           const unsigned w0 = redux_min_u32(u0);
@@ -476,40 +420,35 @@ size_t chamfer_forward_workspace_bytes(int B, int N, int M) {
   return sizeof(u64) * ((size_t)B * N + (size_t)B * M) + 256;
 }
 
-// Variant selection.  Default: QT=16 when the register side is large enough to fill 4096-point tiles, else QT=8.
-// IAPT_FWD_VARIANT (development knob, read once): "8", "8p", "16", "16p" force a variant (p = register prefetch).
-struct Variant {
-  int qt;
-  bool prefetch;
-};
-
-static Variant pick_variant(int B, int NA, int NS, int slots) {
+// A-side points per thread.  QT=16 halves the per-pair LDS/REDUX overhead but makes 4096-point tiles: it is used only
+// when even one-stage items of that size would still oversubscribe the persistent grid 4x (large batches); otherwise
+// QT=8 (2048-point tiles).  IAPT_FWD_VARIANT=8|16 (development knob, read once) forces one.
+// Measured at B=48 x 16384^2 (all parity-green): QT=8 3.22 ms, QT=16 3.09 ms; also tried and dropped for no gain:
+// register prefetch of the next streamed pair, VIMNMX3 integer minima, a static contiguous schedule (3.17 ms) and
+// guided decreasing-size tickets (3.09 ms) - see DESIGN.md section 3.1.
+static int pick_qt(int B, int NA, int NS, int slots) {
   static int forced = -1;
   if (forced < 0) {
     forced = 0;
     if (const char* e = std::getenv("IAPT_FWD_VARIANT")) {
       const int q = std::atoi(e);
-      if (q == 8 || q == 16) forced = q | ((e[0] && (e[1] == 'p' || (e[1] && e[2] == 'p'))) ? 0x100 : 0);
+      if (q == 8 || q == 16) forced = q;
     }
   }
-  if (forced > 0) return Variant{forced & 0xff, (forced & 0x100) != 0};
-  // QT=16 halves the per-pair LDS/REDUX overhead but makes 4096-point tiles: use it only when even one-stage items
-  // of that size would still oversubscribe the persistent grid 4x (large batches); otherwise QT=8 (2048-point tiles).
+  if (forced > 0) return forced;
   const long long tiles16 = (NA + kThreads * 16 - 1) / (kThreads * 16);
   const long long stages = (NS + kSStage - 1) / kSStage;
-  const bool big = NA >= 4096 && (long long)B * tiles16 * stages >= 4LL * slots;
-  return Variant{big ? IAPT_DEFAULT_QT_LARGE : 8, IAPT_DEFAULT_PREFETCH != 0};
+  return (NA >= 4096 && (long long)B * tiles16 * stages >= 4LL * slots) ? 16 : 8;
 }
 
-template <int QT, bool kPrefetch>
+template <int QT>
 static cudaError_t launch_pair(const FwdParams& p, int grid, cudaStream_t stream) {
   static PerDeviceOnce once;
   if (once.pending()) {
-    cudaFuncSetAttribute(chamfer_pair_kernel<QT, kPrefetch>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(FwdSmem<QT>));
+    cudaFuncSetAttribute(chamfer_pair_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem<QT>));
     once.done();
   }
-  chamfer_pair_kernel<QT, kPrefetch><<<grid, kThreads, sizeof(FwdSmem<QT>), stream>>>(p);
+  chamfer_pair_kernel<QT><<<grid, kThreads, sizeof(FwdSmem<QT>), stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -546,8 +485,8 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
     sms_of_device[dev & 255] = num_sms;
   }
   const int slots = num_sms * 2;
-  const Variant v = pick_variant(B, NA, NS, slots);
-  const int a_tile = kThreads * v.qt;
+  const int qt = pick_qt(B, NA, NS, slots);
+  const int a_tile = kThreads * qt;
 
   FwdParams p;
   p.A = A;
@@ -563,11 +502,7 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
   const long long base_items = (long long)B * p.a_tiles;
   // Split the streamed side until there are >= 16 items per resident CTA slot (tail < ~3 %); an item never gets
   // less than one 512-point stage.
-  static long long items_per_slot = 0;
-  if (items_per_slot == 0) {
-    const char* e = std::getenv("IAPT_FWD_ITEMS_PER_SLOT");  // development knob
-    items_per_slot = (e && std::atoi(e) > 0) ? std::atoi(e) : 16;
-  }
+  const long long items_per_slot = 16;  // measured: 8 -> 3.20 ms, 16 -> 3.09 ms, 32/64 -> 3.23 ms at B=48 x 16384^2
   int splits = 1;
   if (base_items < items_per_slot * slots) {
     splits = (int)((items_per_slot * slots + base_items - 1) / base_items);
@@ -578,57 +513,14 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
   p.s_splits = (total_stages + p.stages_per_split - 1) / p.stages_per_split;
   p.total_items = (int)(base_items * p.s_splits);
 
-  // Guided segments: used when the plain split would need many items per tile and the stage count fits the table.
-  p.n_segs = 0;
-  static int guided = -1;
-  if (guided < 0) {
-    const char* e = std::getenv("IAPT_FWD_GUIDED");  // development knob
-    guided = e ? std::atoi(e) : IAPT_DEFAULT_GUIDED;
-  }
-  if (guided && p.s_splits >= 8 && total_stages <= 255) {
-    // ones at the end: enough one-stage items for every resident CTA to balance the tail (>= 2 per slot overall)
-    int ones = (int)((2LL * slots + base_items - 1) / base_items);
-    if (ones < 2) ones = 2;
-    if (ones > 12) ones = 12;
-    if (ones > total_stages / 2) ones = total_stages / 2;
-    int rem = total_stages - ones, n = 0, pos = 0;
-    while (rem > 0 && n < 32 - ones) {
-      int len = (rem + 2) / 3;  // geometric decrease
-      if (n == 32 - ones - 1) len = rem;
-      p.seg_start[n] = (unsigned char)pos;
-      p.seg_len[n] = (unsigned char)len;
-      pos += len;
-      rem -= len;
-      ++n;
-    }
-    for (int i = 0; i < ones && n < 32; ++i, ++n, ++pos) {
-      p.seg_start[n] = (unsigned char)pos;
-      p.seg_len[n] = 1;
-    }
-    if (pos == total_stages) {  // the table covers every stage exactly once
-      p.n_segs = n;
-      p.total_items = (int)(base_items * n);
-    }
-  }
-  static int static_sched = -1;
-  if (static_sched < 0) {
-    const char* e = std::getenv("IAPT_FWD_SCHED");  // development knob: "ticket" or "static"
-    static_sched = e ? (e[0] == 's' ? 1 : 0) : IAPT_DEFAULT_STATIC_SCHED;
-  }
-  p.static_sched = static_sched;
-  const long long n_units = base_items * total_stages;
-  const long long want = static_sched ? n_units : (long long)p.total_items;
-  const int grid = (int)(want < (long long)slots ? want : slots);
+  const int grid = (int)((long long)p.total_items < (long long)slots ? p.total_items : slots);
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (g_profile) {
     cudaEventCreate(&ev0);
     cudaEventCreate(&ev1);
     cudaEventRecord(ev0, stream);
   }
-  if (v.qt == 16)
-    err = v.prefetch ? launch_pair<16, true>(p, grid, stream) : launch_pair<16, false>(p, grid, stream);
-  else
-    err = v.prefetch ? launch_pair<8, true>(p, grid, stream) : launch_pair<8, false>(p, grid, stream);
+  err = qt == 16 ? launch_pair<16>(p, grid, stream) : launch_pair<8>(p, grid, stream);
   count_launch();
   if (g_profile) {
     cudaEventRecord(ev1, stream);
@@ -640,7 +532,7 @@ int chamfer_forward_launch(const float* xyz1, const float* xyz2, int B, int N, i
   long long rblocks = (pts / 32 + 7) / 8;  // one warp per 32 points
   if (rblocks > num_sms * 16LL) rblocks = num_sms * 16LL;
   if (rblocks < 1) rblocks = 1;
-  chamfer_resolve_kernel<<<(int)rblocks, 256, 0, stream>>>(A, S, B, NA, NS, v.qt, PA, PS, distA, idxA, distS, idxS);
+  chamfer_resolve_kernel<<<(int)rblocks, 256, 0, stream>>>(A, S, B, NA, NS, qt, PA, PS, distA, idxA, distS, idxS);
   count_launch();
   return (int)cudaGetLastError();
 }

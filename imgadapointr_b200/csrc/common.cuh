@@ -97,13 +97,6 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
   return r;
 }
 
-// Same fold on the BIT PATTERNS (VIMNMX3.U32).  Squared distances are >= +0 and the +inf / 1e36 sentinels are positive,
-// so unsigned integer order == float order; measured ~12 % cheaper in issue slots than FMNMX3 next to packed FP ops
-// (scripts/microbench/pipe_mix.cu, modes 3 vs 8).
-__device__ __forceinline__ float umin3(float a, float b, float c) {
-  return __uint_as_float(__vimin3_u32(__float_as_uint(a), __float_as_uint(b), __float_as_uint(c)));
-}
-
 // Warp-wide reductions in ONE instruction (REDUX).  Distances are >= +0 so their bit patterns order like uints.
 __device__ __forceinline__ unsigned redux_min_u32(unsigned v) {
   unsigned r;

@@ -195,16 +195,7 @@ int fps_launch(const float* xyz, int B, int N, int npoint, int flags, int32_t* i
   if (N <= 256) return fps_launch_t<256, 1, true>(xyz, B, N, npoint, flags, idx, stream);
   if (N <= 512) return fps_launch_t<256, 2, true>(xyz, B, N, npoint, flags, idx, stream);
   if (N <= 1024) return fps_launch_t<512, 2, true>(xyz, B, N, npoint, flags, idx, stream);
-  if (N <= 2048) {
-    static int variant = -1;
-    if (variant < 0) {
-      const char* e = std::getenv("IAPT_FPS_VARIANT");  // development knob: threads per cloud for N <= 2048
-      variant = e ? std::atoi(e) : 512;
-    }
-    if (variant == 256) return fps_launch_t<256, 8, true>(xyz, B, N, npoint, flags, idx, stream);
-    if (variant == 1024) return fps_launch_t<1024, 2, true>(xyz, B, N, npoint, flags, idx, stream);
-    return fps_launch_t<512, 4, true>(xyz, B, N, npoint, flags, idx, stream);
-  }
+  if (N <= 2048) return fps_launch_t<512, 4, true>(xyz, B, N, npoint, flags, idx, stream);  // 256x8: 0.184, 1024x2: 0.167, 512x4: 0.160 ms
   if (N <= 4096) return fps_launch_t<512, 8, true>(xyz, B, N, npoint, flags, idx, stream);
   if (N <= 8192) return fps_launch_t<1024, 8, true>(xyz, B, N, npoint, flags, idx, stream);
   if (N <= kFpsMaxSmemPoints) return fps_launch_t<1024, 18, false>(xyz, B, N, npoint, flags, idx, stream);

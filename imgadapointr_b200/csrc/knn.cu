@@ -253,7 +253,6 @@ struct __align__(16) SelSmem {
   unsigned short cand[kSelCap][kSelThreads];  // candidate reference indices (R <= 65536 on this path)
 };
 
-template <bool kWide>  // kWide: reference indices do not fit 16 bits -> candidates stored in global scratch instead
 __global__ void __launch_bounds__(kSelThreads) knn_select_kernel(const float* __restrict__ ref,
                                                                  const float* __restrict__ qry, int R, int Q, int k,
                                                                  int q_blocks, int64_t* __restrict__ idx_out,
@@ -330,7 +329,6 @@ __global__ void __launch_bounds__(kSelThreads) knn_select_kernel(const float* __
       }
     }
   }
-  if (kWide) overflow = overflow || (R > 65536);
   if (live) flags[(size_t)b * Q + q] = overflow ? 1 : 0;
   __syncthreads();  // every thread is done with the reference tile: its storage becomes the top-k arrays
   if (!live || overflow) return;
@@ -431,11 +429,11 @@ int knn_launch(const float* ref, const float* qry, int B, int R, int Q, int k, i
   if (k <= kSelMaxK && R <= 65536 && flags != nullptr && !force_list && (long long)B * Q >= 65536) {
     static PerDeviceOnce once;
     if (once.pending()) {
-      cudaFuncSetAttribute(knn_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem));
+      cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem));
       once.done();
     }
     const int sb = (Q + kSelThreads - 1) / kSelThreads;
-    knn_select_kernel<false><<<(unsigned)((long long)B * sb), kSelThreads, sizeof(SelSmem), stream>>>(
+    knn_select_kernel<<<(unsigned)((long long)B * sb), kSelThreads, sizeof(SelSmem), stream>>>(
         ref, qry, R, Q, k, sb, idx, dist, flags);
     count_launch();
     knn_list_launch<1>(ref, qry, B, R, Q, k, idx, dist, flags, nullptr, stream);
