@@ -24,6 +24,15 @@ l1c = ChamferDistanceL1(); l1c.fused = False
 def fb2():
     p = x.detach().requires_grad_(True); l1c(p, y).backward()
 print("L1 composed fwd+bwd us/call", t(fb2))
+from imgadapointr_b200.graphs import GraphedChamferLoss
+gl = GraphedChamferLoss("L1")
+def fb3():
+    p = x.detach().requires_grad_(True); gl(p, y).backward()
+print("L1 graphed fwd+bwd us/call", t(fb3))
+gt16 = torch.rand(1, 16384, 3, device=dev); part = torch.rand(1, 2048, 3, device=dev)
+def c1(mod):
+    p = part.detach().requires_grad_(True); mod(p, gt16).backward()
+print("C1 (2048 x 16384) fused us/call", t(lambda: c1(l1), 100), " graphed us/call", t(lambda: c1(gl), 100))
 print("knn us/call", t(lambda: knn_point(8, x, y)))
 print("fps us/call", t(lambda: pointnet2_utils.furthest_point_sample(x, 16)))
 print("torch.empty us/call", t(lambda: torch.empty((1, 64), device=dev)))

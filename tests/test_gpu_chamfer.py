@@ -252,3 +252,29 @@ def test_nan_inputs_are_memory_safe(dev):
     clean = chamfer.forward(x1[:1, 6:].contiguous().to(dev), x2[:1, 10:].contiguous().to(dev))
     od = oracle.chamfer_forward(x1[:1, 6:].numpy(), x2[:1, 10:].numpy())
     assert np.array_equal(clean[0].cpu().numpy(), od[0]) and np.array_equal(clean[2].cpu().numpy(), od[2])
+
+
+@pytest.mark.parametrize("kind,cls", [("L1", ChamferDistanceL1), ("L2", ChamferDistanceL2),
+                                      ("L2_split", ChamferDistanceL2_split), ("L1_PM", ChamferDistanceL1_PM)])
+def test_graphed_loss_replay_is_bit_identical(dev, kind, cls):
+    """CUDA-graph replay of the fused loss step (imgadapointr_b200.graphs): same kernels -> same bits, for several calls
+    with different data through the same captured graph."""
+    from imgadapointr_b200.graphs import GraphedChamferLoss
+
+    graphed = GraphedChamferLoss(kind)
+    for seed in (1, 2, 3):
+        pred, gt = synthetic.pcn_pair(2, 2048, 100 + seed)
+        gt = gt[:, :1500].contiguous()
+        outs = []
+        for mod in (graphed, cls()):
+            p = pred.to(dev).requires_grad_(True)
+            g = gt.to(dev).requires_grad_(True)
+            out = mod(p, g)
+            out = torch.stack(list(out)) if isinstance(out, tuple) else out.reshape(1)
+            w = torch.tensor([0.7, -1.3], device=dev)[: out.numel()]
+            (out * w).sum().backward()
+            outs.append((out.detach().clone(), p.grad.clone(), g.grad.clone() if g.grad is not None else None))
+        assert torch.equal(outs[0][0], outs[1][0])
+        assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-6, atol=0)
+        if outs[1][2] is not None:
+            assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-6, atol=0)
