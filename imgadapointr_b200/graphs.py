@@ -22,6 +22,9 @@ class _Captured:
         self.x2 = torch.zeros((B, M, 3), dtype=torch.float32, device=dev)
         n_out = 2 if kind == chamfer.LOSS_L2_SPLIT else 1
         self.unit = torch.ones((n_out,), dtype=torch.float32, device=dev)  # upstream gradient 1 (scaled in backward)
+        # unit upstream gradients of the two L2_split outputs (created BEFORE capture: no host copies inside a graph)
+        self.e0 = torch.tensor([1.0, 0.0], dtype=torch.float32, device=dev)
+        self.e1 = torch.tensor([0.0, 1.0], dtype=torch.float32, device=dev)
         self.kind = kind
         self.x1.uniform_(-0.5, 0.5)
         self.x2.uniform_(-0.5, 0.5)
@@ -40,10 +43,8 @@ class _Captured:
         self.loss, _ = chamfer.loss_forward(d1, d2, self.kind)
         if self.kind == chamfer.LOSS_L2_SPLIT:
             # the two outputs have independent upstream gradients: keep the per-output gradients separately
-            e0 = torch.tensor([1.0, 0.0], device=self.x1.device)
-            e1 = torch.tensor([0.0, 1.0], device=self.x1.device)
-            self.g1a, self.g2a = chamfer.loss_backward(self.x1, self.x2, i1, i2, d1, d2, self.kind, e0)
-            self.g1b, self.g2b = chamfer.loss_backward(self.x1, self.x2, i1, i2, d1, d2, self.kind, e1)
+            self.g1a, self.g2a = chamfer.loss_backward(self.x1, self.x2, i1, i2, d1, d2, self.kind, self.e0)
+            self.g1b, self.g2b = chamfer.loss_backward(self.x1, self.x2, i1, i2, d1, d2, self.kind, self.e1)
         else:
             self.g1, self.g2 = chamfer.loss_backward(self.x1, self.x2, i1, i2, d1, d2, self.kind, self.unit)
 
