@@ -49,11 +49,11 @@ def forward(xyz1: torch.Tensor, xyz2: torch.Tensor):
     return [dist1, dist2, idx1, idx2]
 
 
-_USE_BWD_LISTS = os.environ.get("IAPT_BWD_LISTS", "0") == "1"
+_USE_BWD_LISTS = os.environ.get("IAPT_BWD_LISTS", "1") != "0"
 
 
 def _bwd_workspace(L, B, N, M, dev):
-    """Workspace of the optional fan-in-list backward path (include/iapt_b200.h); none for the default scan path."""
+    """Workspace of the fan-in-list backward path (include/iapt_b200.h); none when IAPT_BWD_LISTS=0 (scan kernel only)."""
     if not _USE_BWD_LISTS or B <= 0 or N <= 0 or M <= 0:
         return None, 0
     n = int(L.iapt_chamfer_backward_workspace_bytes(B, N, M))

@@ -31,16 +31,17 @@ class Guarded:
 
 
 def _run_list_path_in_subprocess():
-    """The list backward is selected by IAPT_BWD_LISTS=1 when the library first launches a backward: run this file's
-    chamfer test in a child process with the variable set (both paths must agree bit for bit and stay in bounds)."""
+    """The backward path is fixed when the library first launches a backward (IAPT_BWD_LISTS): run this file's chamfer
+    test in a child process with the scan-only setting too (in-process the default list path is compared with the
+    scan path bit for bit; the child covers the scan-only configuration end to end)."""
     import os, subprocess, sys
-    env = dict(os.environ, IAPT_BWD_LISTS="1", IAPT_GUARD_CHILD="1")
+    env = dict(os.environ, IAPT_BWD_LISTS="0", IAPT_GUARD_CHILD="1")
     out = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", "stay_in_bounds"],
                          env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
 
 
-def test_list_backward_path_matches_scan_path(dev):
+def test_scan_only_backward_configuration(dev):
     import os
     if os.environ.get("IAPT_GUARD_CHILD") == "1":
         pytest.skip("child process")
