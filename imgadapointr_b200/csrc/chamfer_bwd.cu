@@ -409,8 +409,8 @@ static int bwd_launch_common(BwdParams& p, int B, int N, int M, void* workspace,
       cudaError_t err = cudaMemsetAsync(ws, 0, 256 + sizeof(int) * zero_ints, stream);
       if (err != cudaSuccess) return (int)err;
       const long long total0 = (long long)B * N, total = total0 + (long long)B * M;
-      long long g = (total + 255) / 256;
-      if (g > 148LL * 16) g = 148LL * 16;
+      long long g = (total + 255) / 256;  // one point per thread: both kernels are bound by dependent L2 round trips
+      if (g > (1LL << 20)) g = 1LL << 20;
       chamfer_link_kernel<<<(unsigned)g, 256, 0, stream>>>(p, total0, total);
       chamfer_gather_kernel<<<(unsigned)g, 256, 0, stream>>>(p, total0, total);
       count_launch(2);
