@@ -10,6 +10,8 @@
 // instructions (max of the value bits, then min index among the lanes holding it), one shared-memory slot per
 // warp (double-buffered by round parity), and every warp redundantly folds the <= 32 slots with two more REDUX.
 // Tie rule: LOWEST index among equal maxima (documented in include/iapt_b200.h and DESIGN.md).
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -21,6 +23,7 @@ constexpr int kFpsMaxSmemPoints = 18432;  // 12 B per point SoA -> 216 KB
 struct FpsSlots {
   int val[2][32];
   int idx[2][32];
+  float cx[2][32], cy[2][32], cz[2][32];  // cluster kernel: coordinates of each warp's candidate
 };
 
 // kRegs: points cached in registers (N <= kT * kPPT); otherwise re-read from shared memory each round.
@@ -121,6 +124,145 @@ __global__ void __launch_bounds__(kT) fps_kernel(const float* __restrict__ xyz, 
   }
 }
 
+// ---- thread-block-cluster FPS for large clouds ------------------------------------------------------------------
+// One CTA per cloud leaves 100 of 148 SMs idle at B = 48 and makes a round cost N/128 lane-cycles.  For N >= 8192 a
+// cluster of kC CTAs shares one cloud: every CTA keeps N/kC points and their running minima in registers, finds its
+// local argmax exactly as above, then warp 0 pushes one record {value bits, index, x, y, z} into the exchange slot of
+// EVERY CTA of the cluster through distributed shared memory; after one cluster barrier each CTA folds the kC records
+// (max value, min index) and already holds the winner's coordinates for the next round - no remote read on the
+// critical path.  The exchange buffer is double-buffered by round parity (a CTA may run one round ahead).
+struct FpsRecord {
+  int val, idx;
+  float x, y, z;
+  int pad[3];
+};
+
+template <int kT, int kPPT, int kC>
+__global__ void __launch_bounds__(kT) fps_cluster_kernel(const float* __restrict__ xyz, int N, int npoint, int flags,
+                                                         int32_t* __restrict__ idx_out) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FpsSlots* slots = reinterpret_cast<FpsSlots*>(smem_raw);
+  FpsRecord* xchg = reinterpret_cast<FpsRecord*>(smem_raw + sizeof(FpsSlots));  // [2][kC]
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / kC;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kNW = kT / 32;
+  const int chunk = (N + kC - 1) / kC;  // points [rank*chunk, ...) belong to this CTA
+  const int base = rank * chunk;
+  const float* __restrict__ P = xyz + (size_t)b * N * 3;
+  int32_t* __restrict__ out = idx_out + (size_t)b * npoint;
+
+  float px[kPPT], py[kPPT], pz[kPPT], tmp[kPPT];
+#pragma unroll
+  for (int i = 0; i < kPPT; ++i) {
+    const int local = tid + i * kT;
+    const int k = base + local;
+    bool ok = local < chunk && k < N;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (ok) {
+      x = __ldg(P + 3 * (size_t)k);
+      y = __ldg(P + 3 * (size_t)k + 1);
+      z = __ldg(P + 3 * (size_t)k + 2);
+      if (flags & 1) {
+        const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+        ok = !((double)mag <= 1e-3);
+      }
+    }
+    px[i] = x;
+    py[i] = y;
+    pz[i] = z;
+    tmp[i] = ok ? 1e10f : -1.f;
+  }
+  float ox = __ldg(P), oy = __ldg(P + 1), oz = __ldg(P + 2);  // round 0 selects index 0
+  if (rank == 0 && tid == 0) out[0] = 0;
+  cluster.sync();  // every CTA of the cluster is resident before the first remote store
+
+  for (int j = 1; j < npoint; ++j) {
+    float best = -1.f;
+    int besti = 0;
+    float bx = 0.f, by = 0.f, bz = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPPT; ++i) {
+      const float d = sqdist(ox, oy, oz, px[i], py[i], pz[i]);
+      const float t = fminf(tmp[i], d);
+      tmp[i] = t;
+      if (t > best) {
+        best = t;
+        besti = base + tid + i * kT;
+        bx = px[i];
+        by = py[i];
+        bz = pz[i];
+      }
+    }
+    const int vb = __float_as_int(best);
+    const int vmax = redux_max_s32(vb);
+    const int imin = redux_min_s32(vb == vmax ? besti : 0x7fffffff);
+    const int par = j & 1;
+    // the lane that owns the warp's winner publishes its coordinates with it
+    if (vb == vmax && besti == imin) {
+      slots->val[par][warp] = vmax;
+      slots->idx[par][warp] = imin;
+      reinterpret_cast<float*>(slots->cx[par])[warp] = bx;
+      reinterpret_cast<float*>(slots->cy[par])[warp] = by;
+      reinterpret_cast<float*>(slots->cz[par])[warp] = bz;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int v = (lane < kNW) ? slots->val[par][lane] : (int)0x80000000;
+      const int ii = (lane < kNW) ? slots->idx[par][lane] : 0x7fffffff;
+      const int gmax = redux_max_s32(v);
+      const int gidx = redux_min_s32(v == gmax ? ii : 0x7fffffff);
+      // lane holding the CTA winner pushes the record to every CTA of the cluster (DSMEM stores)
+      if (lane < kNW && v == gmax && ii == gidx) {
+        FpsRecord r;
+        r.val = gmax;
+        r.idx = gidx;
+        r.x = slots->cx[par][lane];
+        r.y = slots->cy[par][lane];
+        r.z = slots->cz[par][lane];
+#pragma unroll
+        for (int c = 0; c < kC; ++c) {
+          FpsRecord* dst = cluster.map_shared_rank(xchg, c) + par * kC + rank;
+          dst->val = r.val;
+          dst->idx = r.idx;
+          dst->x = r.x;
+          dst->y = r.y;
+          dst->z = r.z;
+        }
+      }
+    }
+    cluster.sync();  // records of all kC CTAs have landed (release/acquire at cluster scope)
+    {
+      const FpsRecord* rec = xchg + par * kC;
+      int v = (int)0x80000000, ii = 0x7fffffff;
+      if (lane < kC) {
+        v = rec[lane].val;
+        ii = rec[lane].idx;
+      }
+      const int gmax = redux_max_s32(v);
+      const int old = redux_min_s32(v == gmax ? ii : 0x7fffffff);
+      // coordinates of the winner: the record whose (val, idx) won
+      int src = 0;
+#pragma unroll
+      for (int c = 0; c < kC; ++c)
+        if (rec[c].val == gmax && rec[c].idx == old) src = c;
+      if (gmax < 0) {  // nothing eligible anywhere: upstream selects index 0
+        ox = __ldg(P);
+        oy = __ldg(P + 1);
+        oz = __ldg(P + 2);
+      } else {
+        ox = rec[src].x;
+        oy = rec[src].y;
+        oz = rec[src].z;
+      }
+      if (rank == 0 && tid == 0) out[j] = gmax < 0 ? 0 : old;
+    }
+  }
+  cluster.sync();  // no CTA exits while a peer may still write into its shared memory
+}
+
 // Generic fallback for clouds too large for shared memory: points from global (L2), running min in a workspace.
 __global__ void __launch_bounds__(1024) fps_generic_kernel(const float* __restrict__ xyz, int N, int npoint, int flags,
                                                            float* __restrict__ temp_all,
@@ -189,8 +331,66 @@ static int fps_launch_t(const float* xyz, int B, int N, int npoint, int flags, i
   return (int)cudaGetLastError();
 }
 
+template <int kT, int kPPT, int kC>
+static int fps_cluster_launch_t(const float* xyz, int B, int N, int npoint, int flags, int32_t* idx,
+                                cudaStream_t stream) {
+  const size_t smem = sizeof(FpsSlots) + sizeof(FpsRecord) * 2 * kC;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)B * kC, 1, 1);
+  cfg.blockDim = dim3(kT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, fps_cluster_kernel<kT, kPPT, kC>, xyz, N, npoint, flags, idx);
+  count_launch();
+  return (int)(err != cudaSuccess ? err : cudaGetLastError());
+}
+
+// Cluster width for a large cloud: the widest power of two that keeps all B clusters resident at once (one CTA per SM)
+// and leaves every CTA at least 2048 points; 1 = use the single-CTA kernels.
+static int fps_cluster_width(int B, int N) {
+  static int sms_of_device[256] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int sms = sms_of_device[dev & 255];
+  if (sms == 0) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    sms_of_device[dev & 255] = sms;
+  }
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = std::getenv("IAPT_FPS_CLUSTER");  // development knob: 0 disables the cluster kernels
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled || N < 8192) return 1;
+  int c = 8;
+  while (c > 1 && ((long long)B * c > sms || N / c < 2048)) c >>= 1;
+  return c;
+}
+
 int fps_launch(const float* xyz, int B, int N, int npoint, int flags, int32_t* idx, void* workspace,
                cudaStream_t stream) {
+  const int cw = fps_cluster_width(B, N);
+  if (cw > 1) {
+    const int per = (N + cw - 1) / cw;  // points per CTA: registers hold up to 1024 x 8
+    if (per <= 8192) {
+      if (per <= 4096) {
+        if (cw == 2) return fps_cluster_launch_t<512, 8, 2>(xyz, B, N, npoint, flags, idx, stream);
+        if (cw == 4) return fps_cluster_launch_t<512, 8, 4>(xyz, B, N, npoint, flags, idx, stream);
+        return fps_cluster_launch_t<512, 8, 8>(xyz, B, N, npoint, flags, idx, stream);
+      }
+      if (cw == 2) return fps_cluster_launch_t<1024, 8, 2>(xyz, B, N, npoint, flags, idx, stream);
+      if (cw == 4) return fps_cluster_launch_t<1024, 8, 4>(xyz, B, N, npoint, flags, idx, stream);
+      return fps_cluster_launch_t<1024, 8, 8>(xyz, B, N, npoint, flags, idx, stream);
+    }
+  }
   if (N <= 128) return fps_launch_t<128, 1, true>(xyz, B, N, npoint, flags, idx, stream);
   if (N <= 256) return fps_launch_t<256, 1, true>(xyz, B, N, npoint, flags, idx, stream);
   if (N <= 512) return fps_launch_t<256, 2, true>(xyz, B, N, npoint, flags, idx, stream);
