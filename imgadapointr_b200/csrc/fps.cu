@@ -130,12 +130,25 @@ __global__ void __launch_bounds__(kT) fps_kernel(const float* __restrict__ xyz, 
 // local argmax exactly as above, then warp 0 pushes one record {value bits, index, x, y, z} into the exchange slot of
 // EVERY CTA of the cluster through distributed shared memory; after one cluster barrier each CTA folds the kC records
 // (max value, min index) and already holds the winner's coordinates for the next round - no remote read on the
-// critical path.  The exchange buffer is double-buffered by round parity (a CTA may run one round ahead).
+// critical path.  No cluster barrier inside the loop: a record carries its round number as a tag written with
+// st.release.cluster after the payload, and the receivers poll their OWN shared memory with ld.acquire.cluster (the
+// CTAs of a cluster are co-scheduled, so spinning cannot deadlock).  Two buffers by round parity suffice: a peer can
+// only be writing round j+2 after it consumed this CTA's round j+1 record, which is sent after round j was read.
 struct FpsRecord {
   int val, idx;
   float x, y, z;
-  int pad[3];
+  int tag;  // round number, written last (release)
+  int pad[2];
 };
+
+__device__ __forceinline__ void st_release_cluster(int* p, int v) {
+  asm volatile("st.release.cluster.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cluster(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cluster.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 template <int kT, int kPPT, int kC>
 __global__ void __launch_bounds__(kT) fps_cluster_kernel(const float* __restrict__ xyz, int N, int npoint, int flags,
@@ -177,7 +190,8 @@ __global__ void __launch_bounds__(kT) fps_cluster_kernel(const float* __restrict
   }
   float ox = __ldg(P), oy = __ldg(P + 1), oz = __ldg(P + 2);  // round 0 selects index 0
   if (rank == 0 && tid == 0) out[0] = 0;
-  cluster.sync();  // every CTA of the cluster is resident before the first remote store
+  if (tid < 2 * kC) xchg[tid].tag = 0;  // rounds are numbered from 1
+  cluster.sync();  // tags initialised and every CTA of the cluster resident before the first remote store
 
   for (int j = 1; j < npoint; ++j) {
     float best = -1.f;
@@ -222,25 +236,33 @@ __global__ void __launch_bounds__(kT) fps_cluster_kernel(const float* __restrict
         r.x = slots->cx[par][lane];
         r.y = slots->cy[par][lane];
         r.z = slots->cz[par][lane];
+        bool sent = false;  // several lanes can hold identical records only in the nothing-eligible case: send once
+        const unsigned holders = __activemask();
+        if (lane == __ffs(holders) - 1) sent = true;
+        if (sent) {
 #pragma unroll
-        for (int c = 0; c < kC; ++c) {
-          FpsRecord* dst = cluster.map_shared_rank(xchg, c) + par * kC + rank;
-          dst->val = r.val;
-          dst->idx = r.idx;
-          dst->x = r.x;
-          dst->y = r.y;
-          dst->z = r.z;
+          for (int c = 0; c < kC; ++c) {
+            FpsRecord* dst = cluster.map_shared_rank(xchg, c) + par * kC + rank;
+            dst->val = r.val;
+            dst->idx = r.idx;
+            dst->x = r.x;
+            dst->y = r.y;
+            dst->z = r.z;
+            st_release_cluster(&dst->tag, j);  // payload first, tag last
+          }
         }
       }
     }
-    cluster.sync();  // records of all kC CTAs have landed (release/acquire at cluster scope)
     {
-      const FpsRecord* rec = xchg + par * kC;
+      FpsRecord* rec = xchg + par * kC;
       int v = (int)0x80000000, ii = 0x7fffffff;
       if (lane < kC) {
+        while (ld_acquire_cluster(&rec[lane].tag) != j) {
+        }
         v = rec[lane].val;
         ii = rec[lane].idx;
       }
+      __syncwarp();
       const int gmax = redux_max_s32(v);
       const int old = redux_min_s32(v == gmax ? ii : 0x7fffffff);
       // coordinates of the winner: the record whose (val, idx) won
