@@ -24,6 +24,8 @@ struct FpsSlots {
   int val[2][32];
   int idx[2][32];
   float cx[2][32], cy[2][32], cz[2][32];  // cluster kernel: coordinates of each warp's candidate
+  int win_idx[2], win_ok[2];              // cluster kernel: the round's winner, published by warp 0
+  float win_xyz[2][3];
 };
 
 // kRegs: points cached in registers (N <= kT * kPPT); otherwise re-read from shared memory each round.
@@ -144,11 +146,12 @@ struct FpsRecord {
 __device__ __forceinline__ void st_release_cluster(int* p, int v) {
   asm volatile("st.release.cluster.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ int ld_acquire_cluster(const int* p) {
+__device__ __forceinline__ int ld_relaxed_cluster(const int* p) {
   int v;
-  asm volatile("ld.acquire.cluster.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.cluster.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acquire_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 
 template <int kT, int kPPT, int kC>
 __global__ void __launch_bounds__(kT) fps_cluster_kernel(const float* __restrict__ xyz, int N, int npoint, int flags,
@@ -253,34 +256,42 @@ __global__ void __launch_bounds__(kT) fps_cluster_kernel(const float* __restrict
         }
       }
     }
-    {
+    // Only warp 0 waits for the kC records (relaxed polling of its own shared memory, one acquire fence at the end),
+    // folds them and publishes the winner to the rest of the CTA through shared memory + one block barrier.
+    if (warp == 0) {
       FpsRecord* rec = xchg + par * kC;
       int v = (int)0x80000000, ii = 0x7fffffff;
       if (lane < kC) {
-        while (ld_acquire_cluster(&rec[lane].tag) != j) {
+        while (ld_relaxed_cluster(&rec[lane].tag) != j) {
         }
+      }
+      __syncwarp();
+      fence_acquire_cluster();
+      if (lane < kC) {
         v = rec[lane].val;
         ii = rec[lane].idx;
       }
-      __syncwarp();
       const int gmax = redux_max_s32(v);
       const int old = redux_min_s32(v == gmax ? ii : 0x7fffffff);
-      // coordinates of the winner: the record whose (val, idx) won
-      int src = 0;
-#pragma unroll
-      for (int c = 0; c < kC; ++c)
-        if (rec[c].val == gmax && rec[c].idx == old) src = c;
-      if (gmax < 0) {  // nothing eligible anywhere: upstream selects index 0
-        ox = __ldg(P);
-        oy = __ldg(P + 1);
-        oz = __ldg(P + 2);
-      } else {
-        ox = rec[src].x;
-        oy = rec[src].y;
-        oz = rec[src].z;
+      if (lane < kC && v == gmax && ii == old) {  // (identical records only in the nothing-eligible case)
+        slots->win_idx[par] = gmax < 0 ? 0 : old;
+        slots->win_ok[par] = gmax < 0 ? 0 : 1;
+        slots->win_xyz[par][0] = rec[lane].x;
+        slots->win_xyz[par][1] = rec[lane].y;
+        slots->win_xyz[par][2] = rec[lane].z;
       }
-      if (rank == 0 && tid == 0) out[j] = gmax < 0 ? 0 : old;
     }
+    __syncthreads();
+    if (slots->win_ok[par]) {
+      ox = slots->win_xyz[par][0];
+      oy = slots->win_xyz[par][1];
+      oz = slots->win_xyz[par][2];
+    } else {  // nothing eligible anywhere: upstream selects index 0
+      ox = __ldg(P);
+      oy = __ldg(P + 1);
+      oz = __ldg(P + 2);
+    }
+    if (rank == 0 && tid == 0) out[j] = slots->win_idx[par];
   }
   cluster.sync();  // no CTA exits while a peer may still write into its shared memory
 }
