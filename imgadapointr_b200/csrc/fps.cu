@@ -24,8 +24,6 @@ struct FpsSlots {
   int val[2][32];
   int idx[2][32];
   float cx[2][32], cy[2][32], cz[2][32];  // cluster kernel: coordinates of each warp's candidate
-  int win_idx[2], win_ok[2];              // cluster kernel: the round's winner, published by warp 0
-  float win_xyz[2][3];
 };
 
 // kRegs: points cached in registers (N <= kT * kPPT); otherwise re-read from shared memory each round.
@@ -132,26 +130,12 @@ __global__ void __launch_bounds__(kT) fps_kernel(const float* __restrict__ xyz, 
 // local argmax exactly as above, then warp 0 pushes one record {value bits, index, x, y, z} into the exchange slot of
 // EVERY CTA of the cluster through distributed shared memory; after one cluster barrier each CTA folds the kC records
 // (max value, min index) and already holds the winner's coordinates for the next round - no remote read on the
-// critical path.  No cluster barrier inside the loop: a record carries its round number as a tag written with
-// st.release.cluster after the payload, and the receivers poll their OWN shared memory with ld.acquire.cluster (the
-// CTAs of a cluster are co-scheduled, so spinning cannot deadlock).  Two buffers by round parity suffice: a peer can
-// only be writing round j+2 after it consumed this CTA's round j+1 record, which is sent after round j was read.
+// critical path.  The exchange buffer is double-buffered by round parity (a CTA may run one round ahead).
 struct FpsRecord {
   int val, idx;
   float x, y, z;
-  int tag;  // round number, written last (release)
-  int pad[2];
+  int pad[3];
 };
-
-__device__ __forceinline__ void st_release_cluster(int* p, int v) {
-  asm volatile("st.release.cluster.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_relaxed_cluster(const int* p) {
-  int v;
-  asm volatile("ld.relaxed.cluster.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_acquire_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 
 template <int kT, int kPPT, int kC>
 __global__ void __launch_bounds__(kT) fps_cluster_kernel(const float* __restrict__ xyz, int N, int npoint, int flags,
@@ -193,8 +177,7 @@ __global__ void __launch_bounds__(kT) fps_cluster_kernel(const float* __restrict
   }
   float ox = __ldg(P), oy = __ldg(P + 1), oz = __ldg(P + 2);  // round 0 selects index 0
   if (rank == 0 && tid == 0) out[0] = 0;
-  if (tid < 2 * kC) xchg[tid].tag = 0;  // rounds are numbered from 1
-  cluster.sync();  // tags initialised and every CTA of the cluster resident before the first remote store
+  cluster.sync();  // every CTA of the cluster is resident before the first remote store
 
   for (int j = 1; j < npoint; ++j) {
     float best = -1.f;
@@ -239,59 +222,43 @@ __global__ void __launch_bounds__(kT) fps_cluster_kernel(const float* __restrict
         r.x = slots->cx[par][lane];
         r.y = slots->cy[par][lane];
         r.z = slots->cz[par][lane];
-        bool sent = false;  // several lanes can hold identical records only in the nothing-eligible case: send once
-        const unsigned holders = __activemask();
-        if (lane == __ffs(holders) - 1) sent = true;
-        if (sent) {
 #pragma unroll
-          for (int c = 0; c < kC; ++c) {
-            FpsRecord* dst = cluster.map_shared_rank(xchg, c) + par * kC + rank;
-            dst->val = r.val;
-            dst->idx = r.idx;
-            dst->x = r.x;
-            dst->y = r.y;
-            dst->z = r.z;
-            st_release_cluster(&dst->tag, j);  // payload first, tag last
-          }
+        for (int c = 0; c < kC; ++c) {
+          FpsRecord* dst = cluster.map_shared_rank(xchg, c) + par * kC + rank;
+          dst->val = r.val;
+          dst->idx = r.idx;
+          dst->x = r.x;
+          dst->y = r.y;
+          dst->z = r.z;
         }
       }
     }
-    // Only warp 0 waits for the kC records (relaxed polling of its own shared memory, one acquire fence at the end),
-    // folds them and publishes the winner to the rest of the CTA through shared memory + one block barrier.
-    if (warp == 0) {
-      FpsRecord* rec = xchg + par * kC;
+    cluster.sync();  // records of all kC CTAs have landed (release/acquire at cluster scope)
+    {
+      const FpsRecord* rec = xchg + par * kC;
       int v = (int)0x80000000, ii = 0x7fffffff;
-      if (lane < kC) {
-        while (ld_relaxed_cluster(&rec[lane].tag) != j) {
-        }
-      }
-      __syncwarp();
-      fence_acquire_cluster();
       if (lane < kC) {
         v = rec[lane].val;
         ii = rec[lane].idx;
       }
       const int gmax = redux_max_s32(v);
       const int old = redux_min_s32(v == gmax ? ii : 0x7fffffff);
-      if (lane < kC && v == gmax && ii == old) {  // (identical records only in the nothing-eligible case)
-        slots->win_idx[par] = gmax < 0 ? 0 : old;
-        slots->win_ok[par] = gmax < 0 ? 0 : 1;
-        slots->win_xyz[par][0] = rec[lane].x;
-        slots->win_xyz[par][1] = rec[lane].y;
-        slots->win_xyz[par][2] = rec[lane].z;
+      // coordinates of the winner: the record whose (val, idx) won
+      int src = 0;
+#pragma unroll
+      for (int c = 0; c < kC; ++c)
+        if (rec[c].val == gmax && rec[c].idx == old) src = c;
+      if (gmax < 0) {  // nothing eligible anywhere: upstream selects index 0
+        ox = __ldg(P);
+        oy = __ldg(P + 1);
+        oz = __ldg(P + 2);
+      } else {
+        ox = rec[src].x;
+        oy = rec[src].y;
+        oz = rec[src].z;
       }
+      if (rank == 0 && tid == 0) out[j] = gmax < 0 ? 0 : old;
     }
-    __syncthreads();
-    if (slots->win_ok[par]) {
-      ox = slots->win_xyz[par][0];
-      oy = slots->win_xyz[par][1];
-      oz = slots->win_xyz[par][2];
-    } else {  // nothing eligible anywhere: upstream selects index 0
-      ox = __ldg(P);
-      oy = __ldg(P + 1);
-      oz = __ldg(P + 2);
-    }
-    if (rank == 0 && tid == 0) out[j] = slots->win_idx[par];
   }
   cluster.sync();  // no CTA exits while a peer may still write into its shared memory
 }
@@ -402,7 +369,11 @@ static int fps_cluster_width(int B, int N) {
     const char* e = std::getenv("IAPT_FPS_CLUSTER");  // development knob: 0 disables the cluster kernels
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
-  if (!enabled || N < 8192) return 1;
+  // Measured (profiles/r01d_fps_sizes.txt): a round costs ~0.12 + 0.075 us per 1024 points per CTA, plus ~0.55 us for
+  // the cluster exchange (remote stores + barrier.cluster).  A single CTA holds up to 8192 points in registers
+  // (0.73 us/round), so clusters pay off only beyond that - where one CTA would fall back to shared / global memory.
+  // (A barrier-free variant - tagged records, st.release.cluster + polling - was measured SLOWER: 1.8 vs 1.44 us/round.)
+  if (!enabled || N <= 8192) return 1;
   int c = 8;
   while (c > 1 && ((long long)B * c > sms || N / c < 2048)) c >>= 1;
   return c;
