@@ -6,6 +6,8 @@
 
   C1  one PCN-shaped cloud pair (2048 partial / 16384 gt): Chamfer-L1/L2 + FPS 2048->512 + kNN k=16, beside the
       PyTorch CPU formulation on the host cores
+  C2  (extra) the whole AdaPoinTr get_loss geometry at B=48: kNN k=32 + index_points + three Chamfer-L1 fwd+bwd, beside
+      the reference's own CUDA extension driven the reference's way on the same GPU
   C3  AdaPoinTr encoder geometry at B=48: FPS 2048->512 + DGCNN kNN k=16 (4 shapes) + transformer kNN k=8 (3 shapes),
       beside the reference formulation (square_distance + topk) run on the same GPU
   C4  PCN test-set metric sweep: 1200 synthetic clouds (8 categories x 150), CD-L1 / CD-L2 / F-Score@1% per cloud from
@@ -165,6 +167,71 @@ def config3(dev, B=48):
     return out
 
 
+def config2_get_loss(dev, B=48):
+    """The whole geometry of one AdaPoinTr training loss (models/external/AdaPoinTr.py:193-216) at the PCN shapes:
+    kNN(k=32, gt[B,16384], denoised_coarse[B,64]) + index_points + ChamferDistanceL1 on (2048 x 2048), (512 x 16384) and
+    (16384 x 16384), forward + backward.  'reference' = the reference's CUDA extension (oracle/_ref, if present) driven
+    by its own ChamferFunction/ChamferDistanceL1 logic + the torch formulation of knn_point / index_points."""
+    import glob
+    import importlib.util
+
+    from imgadapointr_b200.models.Transformer_utils import index_points
+    from oracle import torch_formulation as tf
+
+    pred_fine, gt = synthetic.pcn_pair(B, 16384, 202)
+    pred_fine, gt = pred_fine.to(dev), gt.to(dev)
+    pred_coarse = misc.fps(gt, 512) + 0.01
+    denoised_coarse = gt[:, :64].contiguous() + 0.005
+    denoised_fine = (gt[:, :2048] + 0.003).contiguous()
+    leaves = [pred_coarse, denoised_fine, pred_fine]
+    l1 = ChamferDistanceL1()
+
+    def ours():
+        xs = [t.detach().requires_grad_(True) for t in leaves]
+        idx = knn_point(32, gt, denoised_coarse)
+        target = index_points(gt, idx).reshape(B, -1, 3)
+        loss = l1(xs[1], target) * 0.5 + l1(xs[0], gt) + l1(xs[2], gt)
+        loss.backward()
+        return loss
+
+    out = {"B": B, "ours_ms": gpu_time(ours, warm=2, iters=5)}
+    so = glob.glob(os.path.join(ROOT, "oracle", "_ref", "chamfer*.so"))
+    if so:
+        spec = importlib.util.spec_from_file_location("chamfer", so[0])
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+
+        class RefFn(torch.autograd.Function):  # extensions/chamfer_dist/__init__.py:13-25
+            @staticmethod
+            def forward(ctx, a, b):
+                d1, d2, i1, i2 = ref.forward(a, b)
+                ctx.save_for_backward(a, b, i1, i2)
+                return d1, d2
+
+            @staticmethod
+            def backward(ctx, g1, g2):
+                a, b, i1, i2 = ctx.saved_tensors
+                ga, gb = ref.backward(a, b, i1, i2, g1.contiguous(), g2.contiguous())
+                return ga, gb
+
+        def ref_l1(a, b):  # ChamferDistanceL1.forward, __init__.py:71-84
+            d1, d2 = RefFn.apply(a, b)
+            return (torch.mean(torch.sqrt(d1)) + torch.mean(torch.sqrt(d2))) / 2
+
+        def reference():
+            xs = [t.detach().requires_grad_(True) for t in leaves]
+            idx = tf.knn_point(32, gt, denoised_coarse)
+            bi = torch.arange(B, device=dev).view(B, 1, 1).expand_as(idx)
+            target = gt[bi, idx, :].reshape(B, -1, 3)
+            loss = ref_l1(xs[1], target.contiguous()) * 0.5 + ref_l1(xs[0], gt) + ref_l1(xs[2], gt)
+            loss.backward()
+            return loss
+
+        out["reference_cuda_ext_ms"] = gpu_time(reference, warm=2, iters=5)
+        out["loss_ours_vs_reference"] = [float(ours().detach()), float(reference().detach())]
+    return out
+
+
 def config4(dev, rank, world, n_per_cat=150, n_cat=8, chunk=25):
     total = n_per_cat * n_cat
     b, e = dist_utils.shard_range(total, rank, world)
@@ -233,7 +300,7 @@ def config5(dev, rank, world):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="1,3,4,5")
+    ap.add_argument("--configs", default="1,2,3,4,5")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "extra.json"))
     ap.add_argument("--c4-per-cat", type=int, default=150)
     args = ap.parse_args()
@@ -248,6 +315,8 @@ def main():
     res = {"world": world, "gpu": torch.cuda.get_device_name(dev), "host_cores": os.cpu_count()}
     if 1 in want and rank == 0:
         res["config1"] = config1(dev)
+    if 2 in want and rank == 0:
+        res["config2_get_loss"] = config2_get_loss(dev)
     if 3 in want and rank == 0:
         res["config3"] = config3(dev)
     if world > 1:
