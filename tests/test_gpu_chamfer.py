@@ -279,3 +279,24 @@ def test_graphed_loss_replay_matches_fused_path(dev, kind, cls):
         for a, b in ((outs[0][1], outs[1][1]), (outs[0][2], outs[1][2])):
             if b is not None:
                 assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max())
+
+
+def test_forward_backward_random_shapes(dev):
+    """40 seeded random (B, N, M) shapes - ragged sizes around the tile (2048/4096), stage (512) and chunk (32)
+    boundaries - forward bit-exact, backward within 1e-5 of the oracle."""
+    rng = np.random.default_rng(12345)
+    edges = [1, 2, 31, 32, 33, 255, 256, 257, 511, 512, 513, 1023, 1025, 2047, 2048, 2049, 4095, 4097]
+    for trial in range(40):
+        B = int(rng.integers(1, 5))
+        N = int(rng.choice(edges)) if rng.random() < 0.6 else int(rng.integers(1, 5000))
+        M = int(rng.choice(edges)) if rng.random() < 0.6 else int(rng.integers(1, 5000))
+        x1 = synthetic.uniform(B, N, 1000 + trial)
+        x2 = synthetic.uniform(B, M, 2000 + trial)
+        if trial % 4 == 0:  # duplicates -> exact ties
+            x2[:, M // 2:] = x2[:, : M - M // 2]
+        d1, d2, i1, i2 = _check_forward(x1, x2, dev)
+        g1 = torch.randn((B, N), generator=torch.Generator().manual_seed(trial))
+        g2 = torch.randn((B, M), generator=torch.Generator().manual_seed(trial + 1))
+        gx1, gx2 = chamfer.backward(x1.to(dev), x2.to(dev), i1, i2, g1.to(dev), g2.to(dev))
+        o1, o2 = _oracle_grads(x1.numpy(), x2.numpy(), g1.numpy(), g2.numpy())
+        assert _rel(gx1.cpu().numpy(), o1) < GRAD_RTOL and _rel(gx2.cpu().numpy(), o2) < GRAD_RTOL, (B, N, M)
