@@ -293,7 +293,7 @@ def test_forward_backward_random_shapes(dev):
         x1 = synthetic.uniform(B, N, 1000 + trial)
         x2 = synthetic.uniform(B, M, 2000 + trial)
         if trial % 4 == 0:  # duplicates -> exact ties
-            x2[:, M // 2:] = x2[:, : M - M // 2]
+            x2[:, M // 2:] = x2[:, : M - M // 2].clone()
         d1, d2, i1, i2 = _check_forward(x1, x2, dev)
         g1 = torch.randn((B, N), generator=torch.Generator().manual_seed(trial))
         g2 = torch.randn((B, M), generator=torch.Generator().manual_seed(trial + 1))
