@@ -42,6 +42,12 @@ __global__ void k(float* out, const float4* smem_src, int iters) {
       for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int i = 0; i < 16; ++i) s[i] = fma1(s[i], s[(i + 1) & 15], s[i]);
+    } else if (MODE == 13 || MODE == 14) {
+      // packed ops + independent SCALAR FMAs: do the scalar ones ride on the other FMA pipe for free?
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { u64 d = sub2(b[i], a[(i + 1) & 7]); a[i] = fma2(d, d, a[i]); }
+#pragma unroll
+      for (int i = 0; i < (MODE == 13 ? 8 : 16); ++i) s[i] = fma1(s[i], s[(i + 1) & 15], s[i]);
     } else if (MODE == 10) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) s[i] = min3(s[i], s[(i + 1) & 15], s[(i + 5) & 15]);
@@ -127,6 +133,8 @@ int main() {
   run<7>("7: mode2 + 8 IMNMX.U32", 16, 0, 8, out, src);
   run<8>("8: mode2 + 4 VIMNMX3.U32", 16, 0, 4, out, src);
   run<9>("9: mode2 + 8 IADD3", 16, 0, 8, out, src);
+  run<13>("13: mode2 + 8 scalar FFMA", 16, 8, 0, out, src);
+  run<14>("14: mode2 + 16 scalar FFMA", 16, 16, 0, out, src);
   run<10>("10: 16 FMNMX3 only", 0, 0, 16, out, src);
   run<11>("11: 16 VIMNMX3.U32 only", 0, 0, 16, out, src);
   run<12>("12: 16 FMNMX only", 0, 0, 16, out, src);
