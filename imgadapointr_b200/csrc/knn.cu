@@ -66,6 +66,27 @@ __device__ __forceinline__ void knn_insert(float d, int my_idx, int k, float (&l
   }
 }
 
+// Sort one (distance, index) pair per lane ascending across the warp (bitonic network, 15 exchange stages): the list
+// of an empty query is seeded with its first 32 references in ~120 instructions instead of 32 serial insertions.
+__device__ __forceinline__ void warp_sort_pairs(float& d, int& i) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, d, stride);
+      const int oi = __shfl_xor_sync(0xffffffffu, i, stride);
+      const bool up = (lane & size) == 0;        // ascending block
+      const bool lower = (lane & stride) == 0;   // this lane is the lower position of its pair
+      const bool other_less = (od < d) || (od == d && oi < i);  // indices are distinct: never equal
+      if ((up == lower) ? other_less : !other_less) {
+        d = od;
+        i = oi;
+      }
+    }
+  }
+}
+
 // r_splits > 1: blockIdx.y selects a slice of the reference range and the per-slice lists go to part_d / part_i
 // ([B*Q, r_splits, k]) for knn_merge_kernel - used when there are few queries and many references (the loss kNN:
 // Q = 64, R = 16384, k = 32, models/external/AdaPoinTr.py:201), where one warp per query cannot fill the machine.
@@ -124,7 +145,20 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
     for (int u = 0; u < kQPW; ++u) {
       if (q0 + warp * kQPW + u >= Q) continue;  // warp-uniform
       if (only_flagged != nullptr && only_flagged[(size_t)b * Q + q0 + warp * kQPW + u] == 0) continue;
-      for (int r0 = 0; r0 < tn; r0 += 32) {
+      int r_first = 0;
+      if (t0 == r_lo) {  // empty list: seed it with the first 32 references by one warp sort
+        float d = kInf;
+        int i = t0 + lane;
+        if (lane < tn) d = sqdist(qx[u], qy[u], qz[u], sx[lane], sy[lane], sz[lane]);
+        warp_sort_pairs(d, i);
+        ld[u][0] = d;
+        li[u][0] = (d < kInf) ? i : 0x7fffffff;
+        float kth = ld[u][0];
+        if (kSlots > 1 && k > 32) kth = ld[u][kSlots - 1];
+        tau[u] = __shfl_sync(0xffffffffu, kth, (k - 1) & 31);
+        r_first = 32;
+      }
+      for (int r0 = r_first; r0 < tn; r0 += 32) {
         const int r = r0 + lane;
         float d = kInf;
         if (r < tn) d = sqdist(qx[u], qy[u], qz[u], sx[r], sy[r], sz[r]);
