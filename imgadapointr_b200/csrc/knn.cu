@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
                                                           int64_t* __restrict__ idx_out, float* __restrict__ dist_out,
                                                           const int* __restrict__ only_flagged, int r_splits,
                                                           float* __restrict__ part_d, int* __restrict__ part_i) {
-  __shared__ float sx[kKnnTile], sy[kKnnTile], sz[kKnnTile];
+  __shared__ float4 sp[kKnnTile];  // one broadcast-free LDS.128 per reference
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.x / q_blocks;
@@ -135,10 +135,9 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
   for (int t0 = r_lo; t0 < r_hi; t0 += kKnnTile) {
     const int tn = min(kKnnTile, r_hi - t0);
     __syncthreads();
-    for (int i = threadIdx.x; i < tn * 3; i += kKnnThreads) {
-      const float v = __ldg(Rb + 3 * (size_t)t0 + i);
-      const int r = i / 3, c = i - 3 * r;
-      (c == 0 ? sx : (c == 1 ? sy : sz))[r] = v;
+    for (int r = threadIdx.x; r < tn; r += kKnnThreads) {
+      const float* p = Rb + 3 * (size_t)(t0 + r);
+      sp[r] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
     }
     __syncthreads();
 #pragma unroll
@@ -149,7 +148,10 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
       if (t0 == r_lo) {  // empty list: seed it with the first 32 references by one warp sort
         float d = kInf;
         int i = t0 + lane;
-        if (lane < tn) d = sqdist(qx[u], qy[u], qz[u], sx[lane], sy[lane], sz[lane]);
+        if (lane < tn) {
+          const float4 p = sp[lane];
+          d = sqdist(qx[u], qy[u], qz[u], p.x, p.y, p.z);
+        }
         warp_sort_pairs(d, i);
         ld[u][0] = d;
         li[u][0] = (d < kInf) ? i : 0x7fffffff;
@@ -161,7 +163,10 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
       for (int r0 = r_first; r0 < tn; r0 += 32) {
         const int r = r0 + lane;
         float d = kInf;
-        if (r < tn) d = sqdist(qx[u], qy[u], qz[u], sx[r], sy[r], sz[r]);
+        if (r < tn) {
+          const float4 p = sp[r];
+          d = sqdist(qx[u], qy[u], qz[u], p.x, p.y, p.z);
+        }
         knn_insert<kSlots>(d, t0 + r, k, ld[u], li[u], tau[u]);
       }
     }
