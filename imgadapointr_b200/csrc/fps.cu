@@ -18,7 +18,7 @@
 
 namespace iapt {
 
-constexpr int kFpsMaxSmemPoints = 18432;  // 12 B per point SoA -> 216 KB
+constexpr int kFpsMaxSmemPoints = 14000;  // 16 B per point (float4) -> 224 KB
 
 struct FpsSlots {
   int val[2][32];
@@ -27,14 +27,14 @@ struct FpsSlots {
 };
 
 // kRegs: points cached in registers (N <= kT * kPPT); otherwise re-read from shared memory each round.
+// Shared memory: the cloud as float4 (one LDS.128 fetches the selected point's coordinates) and one int2
+// (value bits, index) slot per warp, double-buffered by round parity.
 template <int kT, int kPPT, bool kRegs>
 __global__ void __launch_bounds__(kT) fps_kernel(const float* __restrict__ xyz, int N, int npoint, int flags,
                                                  int32_t* __restrict__ idx_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FpsSlots* slots = reinterpret_cast<FpsSlots*>(smem_raw);
-  float* sx = reinterpret_cast<float*>(smem_raw + sizeof(FpsSlots));
-  float* sy = sx + N;
-  float* sz = sy + N;
+  int2* wslot = reinterpret_cast<int2*>(smem_raw);          // [2][32]
+  float4* sp = reinterpret_cast<float4*>(smem_raw + 512);   // [N]
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
@@ -44,11 +44,9 @@ __global__ void __launch_bounds__(kT) fps_kernel(const float* __restrict__ xyz, 
   const float* __restrict__ P = xyz + (size_t)b * N * 3;
   int32_t* __restrict__ out = idx_out + (size_t)b * npoint;
 
-  // coalesced fill of the SoA copy
-  for (int i = tid; i < N * 3; i += kT) {
-    const float v = __ldg(P + i);
-    const int k = i / 3, c = i - 3 * k;
-    (c == 0 ? sx : (c == 1 ? sy : sz))[k] = v;
+  for (int k = tid; k < N; k += kT) {
+    const float* p = P + 3 * (size_t)k;
+    sp[k] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
   }
   __syncthreads();
 
@@ -60,9 +58,10 @@ __global__ void __launch_bounds__(kT) fps_kernel(const float* __restrict__ xyz, 
     float x = 0.f, y = 0.f, z = 0.f;
     bool ok = k < N;
     if (ok) {
-      x = sx[k];
-      y = sy[k];
-      z = sz[k];
+      const float4 p = sp[k];
+      x = p.x;
+      y = p.y;
+      z = p.z;
       if (flags & 1) {
         // upstream: `if (mag <= 1e-3) continue;` - float magnitude against the DOUBLE literal
         const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
@@ -81,7 +80,7 @@ __global__ void __launch_bounds__(kT) fps_kernel(const float* __restrict__ xyz, 
   if (tid == 0) out[0] = 0;
 
   for (int j = 1; j < npoint; ++j) {
-    const float ox = sx[old], oy = sy[old], oz = sz[old];
+    const float4 o = sp[old];
     float best = -1.f;
     int besti = 0;
 #pragma unroll
@@ -93,12 +92,12 @@ __global__ void __launch_bounds__(kT) fps_kernel(const float* __restrict__ xyz, 
         y = py[i];
         z = pz[i];
       } else {
-        const int kk = k < N ? k : 0;
-        x = sx[kk];
-        y = sy[kk];
-        z = sz[kk];
+        const float4 p = sp[k < N ? k : 0];
+        x = p.x;
+        y = p.y;
+        z = p.z;
       }
-      const float d = sqdist(ox, oy, oz, x, y, z);
+      const float d = sqdist(o.x, o.y, o.z, x, y, z);
       const float t = fminf(tmp[i], d);  // stays -1 for ineligible points (d >= 0)
       tmp[i] = t;
       if (t > best) {  // ascending k inside a thread + strict '>' keeps the thread's lowest index
@@ -110,16 +109,13 @@ __global__ void __launch_bounds__(kT) fps_kernel(const float* __restrict__ xyz, 
     const int vb = __float_as_int(best);
     const int vmax = redux_max_s32(vb);
     const int imin = redux_min_s32(vb == vmax ? besti : 0x7fffffff);
-    const int par = j & 1;
-    if (lane == 0) {
-      slots->val[par][warp] = vmax;
-      slots->idx[par][warp] = imin;
-    }
+    const int par = (j & 1) * 32;
+    if (lane == 0) wslot[par + warp] = make_int2(vmax, imin);
     __syncthreads();
-    int v = (lane < kNW) ? slots->val[par][lane] : (int)0x80000000;
-    int ii = (lane < kNW) ? slots->idx[par][lane] : 0x7fffffff;
-    const int gmax = redux_max_s32(v);
-    old = redux_min_s32(v == gmax ? ii : 0x7fffffff);
+    int2 s = make_int2((int)0x80000000, 0x7fffffff);
+    if (lane < kNW) s = wslot[par + lane];
+    const int gmax = redux_max_s32(s.x);
+    old = redux_min_s32(s.x == gmax ? s.y : 0x7fffffff);
     if (tid == 0) out[j] = old;
   }
 }
@@ -320,7 +316,7 @@ size_t fps_workspace_bytes(int B, int N, int /*npoint*/) {
 
 template <int kT, int kPPT, bool kRegs>
 static int fps_launch_t(const float* xyz, int B, int N, int npoint, int flags, int32_t* idx, cudaStream_t stream) {
-  const size_t smem = sizeof(FpsSlots) + sizeof(float) * 3 * (size_t)N;
+  const size_t smem = 512 + sizeof(float4) * (size_t)N;
   static PerDeviceOnce once;
   if (once.pending()) {
     cudaFuncSetAttribute(fps_kernel<kT, kPPT, kRegs>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -402,7 +398,7 @@ int fps_launch(const float* xyz, int B, int N, int npoint, int flags, int32_t* i
   if (N <= 2048) return fps_launch_t<512, 4, true>(xyz, B, N, npoint, flags, idx, stream);  // 256x8: 0.184, 1024x2: 0.167, 512x4: 0.160 ms
   if (N <= 4096) return fps_launch_t<512, 8, true>(xyz, B, N, npoint, flags, idx, stream);
   if (N <= 8192) return fps_launch_t<1024, 8, true>(xyz, B, N, npoint, flags, idx, stream);
-  if (N <= kFpsMaxSmemPoints) return fps_launch_t<1024, 18, false>(xyz, B, N, npoint, flags, idx, stream);
+  if (N <= kFpsMaxSmemPoints) return fps_launch_t<1024, 14, false>(xyz, B, N, npoint, flags, idx, stream);
   fps_generic_kernel<<<B, 1024, 0, stream>>>(xyz, N, npoint, flags, static_cast<float*>(workspace), idx);
   count_launch();
   return (int)cudaGetLastError();
