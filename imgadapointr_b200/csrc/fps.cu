@@ -348,8 +348,8 @@ static int fps_cluster_launch_t(const float* xyz, int B, int N, int npoint, int 
   return (int)(err != cudaSuccess ? err : cudaGetLastError());
 }
 
-// Cluster width for a large cloud: the widest power of two that keeps all B clusters resident at once (one CTA per SM)
-// and leaves every CTA at least 2048 points; 1 = use the single-CTA kernels.
+// Cluster width for a large cloud: the widest of {8,6,4,3,2} that keeps all B clusters resident at once (one CTA per
+// SM) and leaves every CTA at least 2048 points; 1 = use the single-CTA kernels.
 static int fps_cluster_width(int B, int N) {
   static int sms_of_device[256] = {0};
   int dev = 0;
@@ -370,9 +370,10 @@ static int fps_cluster_width(int B, int N) {
   // (0.73 us/round), so clusters pay off only beyond that - where one CTA would fall back to shared / global memory.
   // (A barrier-free variant - tagged records, st.release.cluster + polling - was measured SLOWER: 1.8 vs 1.44 us/round.)
   if (!enabled || N <= 8192) return 1;
-  int c = 8;
-  while (c > 1 && ((long long)B * c > sms || N / c < 2048)) c >>= 1;
-  return c;
+  const int widths[] = {8, 6, 4, 3, 2};  // widest cluster that keeps every cluster resident (one CTA per SM)
+  for (int c : widths)
+    if ((long long)B * c <= sms && N / c >= 2048) return c;
+  return 1;
 }
 
 int fps_launch(const float* xyz, int B, int N, int npoint, int flags, int32_t* idx, void* workspace,
@@ -381,14 +382,16 @@ int fps_launch(const float* xyz, int B, int N, int npoint, int flags, int32_t* i
   if (cw > 1) {
     const int per = (N + cw - 1) / cw;  // points per CTA: registers hold up to 1024 x 8
     if (per <= 8192) {
-      if (per <= 4096) {
-        if (cw == 2) return fps_cluster_launch_t<512, 8, 2>(xyz, B, N, npoint, flags, idx, stream);
-        if (cw == 4) return fps_cluster_launch_t<512, 8, 4>(xyz, B, N, npoint, flags, idx, stream);
-        return fps_cluster_launch_t<512, 8, 8>(xyz, B, N, npoint, flags, idx, stream);
-      }
-      if (cw == 2) return fps_cluster_launch_t<1024, 8, 2>(xyz, B, N, npoint, flags, idx, stream);
-      if (cw == 4) return fps_cluster_launch_t<1024, 8, 4>(xyz, B, N, npoint, flags, idx, stream);
-      return fps_cluster_launch_t<1024, 8, 8>(xyz, B, N, npoint, flags, idx, stream);
+#define IAPT_FPS_CLUSTER_CASE(C)                                                                          \
+  if (cw == C)                                                                                            \
+    return per <= 4096 ? fps_cluster_launch_t<512, 8, C>(xyz, B, N, npoint, flags, idx, stream)          \
+                       : fps_cluster_launch_t<1024, 8, C>(xyz, B, N, npoint, flags, idx, stream);
+      IAPT_FPS_CLUSTER_CASE(2)
+      IAPT_FPS_CLUSTER_CASE(3)
+      IAPT_FPS_CLUSTER_CASE(4)
+      IAPT_FPS_CLUSTER_CASE(6)
+      IAPT_FPS_CLUSTER_CASE(8)
+#undef IAPT_FPS_CLUSTER_CASE
     }
   }
   if (N <= 128) return fps_launch_t<128, 1, true>(xyz, B, N, npoint, flags, idx, stream);

@@ -16,7 +16,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
 @pytest.mark.parametrize("B,N,m", [(2, 7, 7), (3, 100, 33), (2, 129, 64), (2, 300, 300), (4, 1000, 256), (2, 2048, 512),
-                                   (2, 3000, 100), (1, 5000, 64), (1, 16384, 2048), (1, 20000, 50), (30, 16384, 40),
+                                   (2, 3000, 100), (1, 5000, 64), (1, 16384, 2048), (1, 20000, 50), (30, 16384, 40), (48, 16384, 24), (24, 16390, 24),
                                    (80, 9000, 20), (76, 15000, 12)])
 def test_fps_matches_oracle(dev, B, N, m):
     """Covers every kernel tier: registers (N <= 8192), thread-block clusters of 8/4/2 CTAs (N > 8192 while all clusters
