@@ -348,8 +348,8 @@ static int fps_cluster_launch_t(const float* xyz, int B, int N, int npoint, int 
   return (int)(err != cudaSuccess ? err : cudaGetLastError());
 }
 
-// Cluster width for a large cloud: the widest of {8,6,4,3,2} that keeps all B clusters resident at once (one CTA per
-// SM) and leaves every CTA at least 2048 points; 1 = use the single-CTA kernels.
+// Cluster width for a large cloud: the widest of {8,4,2} that keeps all B clusters resident at once (one CTA per SM)
+// and leaves every CTA at least 2048 points; 1 = use the single-CTA kernels.
 static int fps_cluster_width(int B, int N) {
   static int sms_of_device[256] = {0};
   int dev = 0;
@@ -370,7 +370,10 @@ static int fps_cluster_width(int B, int N) {
   // (0.73 us/round), so clusters pay off only beyond that - where one CTA would fall back to shared / global memory.
   // (A barrier-free variant - tagged records, st.release.cluster + polling - was measured SLOWER: 1.8 vs 1.44 us/round.)
   if (!enabled || N <= 8192) return 1;
-  const int widths[] = {8, 6, 4, 3, 2};  // widest cluster that keeps every cluster resident (one CTA per SM)
+  // Widest power-of-two cluster that keeps every cluster resident (one CTA per SM).  Widths 3 and 6 were tried for
+  // B=48 x 16384 (144 of 148 SMs): clusters live inside a GPC (16/18/20 SMs), they did not all fit at once and the
+  // kernel ran in two waves (6.0 ms vs 2.9 ms with width 2).
+  const int widths[] = {8, 4, 2};
   for (int c : widths)
     if ((long long)B * c <= sms && N / c >= 2048) return c;
   return 1;
@@ -387,9 +390,7 @@ int fps_launch(const float* xyz, int B, int N, int npoint, int flags, int32_t* i
     return per <= 4096 ? fps_cluster_launch_t<512, 8, C>(xyz, B, N, npoint, flags, idx, stream)          \
                        : fps_cluster_launch_t<1024, 8, C>(xyz, B, N, npoint, flags, idx, stream);
       IAPT_FPS_CLUSTER_CASE(2)
-      IAPT_FPS_CLUSTER_CASE(3)
       IAPT_FPS_CLUSTER_CASE(4)
-      IAPT_FPS_CLUSTER_CASE(6)
       IAPT_FPS_CLUSTER_CASE(8)
 #undef IAPT_FPS_CLUSTER_CASE
     }
