@@ -61,8 +61,10 @@ def patch_reference_modules() -> list:
         root = name.split(".")[0]
         if root not in ("models", "utils", "tools", "extensions", "datasets"):
             continue
+        from .models import SnowFlakeNet_utils as sf
+
         for attr, new in (("knn_point", tu.knn_point), ("index_points", tu.index_points), ("fps", misc.fps),
-                          ("Metrics", m.Metrics)):
+                          ("Metrics", m.Metrics), ("query_knn", sf.query_knn)):
             old = getattr(mod, attr, None)
             if old is not None and old is not new and callable(old):
                 if attr == "fps" and not name.endswith("misc") and getattr(old, "__module__", "") != "utils.misc":

@@ -170,3 +170,17 @@ def test_fps_prefix_reuse_is_exact_and_safe(dev):
     clone = xyz.clone()
     fps(clone, 32)
     assert fps.prefix_hits == h0 + 1  # a different tensor object never hits
+
+
+def test_snowflake_query_knn(dev):
+    """models/external/SnowFlakeNet_utils.py:284-289 (argsort of the distance matrix) vs the fused kernel."""
+    from imgadapointr_b200.models.SnowFlakeNet_utils import query_knn
+
+    xyz = synthetic.uniform(2, 700, 91).to(dev)
+    q = xyz[:, :128].contiguous()
+    for include_self in (True, False):
+        got = query_knn(16, xyz, q, include_self=include_self)
+        pad = 0 if include_self else 1
+        D = oracle.torch_formulation.square_distance(q.double(), xyz.double())
+        want = torch.argsort(D, dim=-1)[:, :, pad:16 + pad].int()
+        assert got.dtype == torch.int32 and torch.equal(got, want)
