@@ -251,6 +251,10 @@ def main():
 
     import torch.distributed as dist
 
+    if local_rank == 0:
+        import __graft_entry__
+
+        __graft_entry__.ensure_built()  # no-op when the in-tree libraries are present
     from imgadapointr_b200 import _lib, chamfer
     from imgadapointr_b200.extensions.chamfer_dist import ChamferDistanceL1
     from imgadapointr_b200.utils import dist_utils, synthetic

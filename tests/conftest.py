@@ -28,7 +28,11 @@ def dev():
 
 @pytest.fixture(scope="session", autouse=True)
 def _built():
-    """Build the oracle (gcc, ~1 s).  The CUDA library must already exist (built by __graft_entry__.build())."""
+    """Build the oracle (gcc, ~1 s).  The CUDA library is built by __graft_entry__.build(); if a checkout arrives
+    without the git-ignored artefacts it is rebuilt here once (nvcc cross-compiles without a GPU)."""
+    import __graft_entry__
+
+    __graft_entry__.ensure_built()
     import oracle
 
     oracle.build()
