@@ -255,6 +255,11 @@ def main():
         import __graft_entry__
 
         __graft_entry__.ensure_built()  # no-op when the in-tree libraries are present
+    else:  # other local ranks wait for rank 0's (normally instantaneous) check / build
+        lib_path = os.path.join(ROOT, "imgadapointr_b200", "libiapt_b200.so")
+        t_wait = time.time()
+        while not os.path.exists(lib_path) and time.time() - t_wait < 600:
+            time.sleep(1.0)
     from imgadapointr_b200 import _lib, chamfer
     from imgadapointr_b200.extensions.chamfer_dist import ChamferDistanceL1
     from imgadapointr_b200.utils import dist_utils, synthetic
