@@ -198,6 +198,72 @@ def run_reference(args, rank):
     }))
 
 
+def _event_ms(fn, warm=3, iters=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def secondary_gpu(dev, B=B_PER_GPU):
+    """FPS 2048->512, kNN k=16 (2048 x 2048) and the whole encoder geometry sequence (2 FPS + 7 kNN calls,
+    models/base_blocks.py:606-621,331,361-364) on zero-padded PCN-shaped partial clouds, clouds/s."""
+    from imgadapointr_b200.models.Transformer_utils import knn_point
+    from imgadapointr_b200.pointnet2_ops import pointnet2_utils
+    from imgadapointr_b200.utils import misc, synthetic
+
+    fps = pointnet2_utils.furthest_point_sample
+    fps.reuse_prefix = False  # time real launches, not the prefix cache
+    try:
+        gt = synthetic.pcn_gt(B, N_PTS, seed=303)
+        xyz = synthetic.pcn_partial(gt, 2048, seed=304).to(dev)
+        c512 = misc.fps(xyz, 512)
+        c256 = misc.fps(c512, 256)
+        clouds = {2048: xyz, 512: c512, 256: c256}
+        shapes = [(16, 2048, 2048), (16, 2048, 512), (16, 512, 512), (16, 512, 256), (8, 256, 256), (8, 512, 512), (8, 256, 512)]
+
+        def sequence():
+            fps(xyz, 512)
+            fps(c512, 256)
+            for (k, R, Q) in shapes:
+                knn_point(k, clouds[R], clouds[Q])
+
+        t_fps = _event_ms(lambda: fps(xyz, 512))
+        t_knn = _event_ms(lambda: knn_point(16, xyz, xyz))
+        t_seq = _event_ms(sequence)
+    finally:
+        fps.reuse_prefix = True
+    return {"unit": "clouds/s", "batch": B,
+            "fps_2048_to_512": B / (t_fps * 1e-3), "knn_k16_2048x2048": B / (t_knn * 1e-3),
+            "encoder_geometry_sequence": B / (t_seq * 1e-3),
+            "ms": {"fps": t_fps, "knn": t_knn, "sequence": t_seq}}
+
+
+def secondary_cpu(threads, n_clouds=4):
+    """The same two ops in the reference's PyTorch CPU formulation (square_distance + topk, Python-loop FPS)."""
+    from imgadapointr_b200.utils import synthetic
+    from oracle import torch_formulation as tf
+
+    torch.set_num_threads(threads)
+    gt = synthetic.pcn_gt(n_clouds, N_PTS, seed=303)
+    xyz = synthetic.pcn_partial(gt, 2048, seed=304)
+    t0 = time.perf_counter()
+    tf.fps_loop(xyz, 512)
+    t_fps = time.perf_counter() - t0
+    tf.knn_point(16, xyz, xyz)
+    t0 = time.perf_counter()
+    tf.knn_point(16, xyz, xyz)
+    t_knn = time.perf_counter() - t0
+    return {"unit": "clouds/s", "sample": f"{n_clouds} clouds", "fps_2048_to_512": n_clouds / t_fps,
+            "knn_k16_2048x2048": n_clouds / t_knn}
+
+
 def time_ref_cuda_kernel(pred, gt, iters=3):
     """The reference's own CUDA extension (oracle/_ref, built unmodified for sm_100a) on the same inputs: the
     'kernel to beat'.  Returns ms per fwd+bwd or None if the .so is absent."""
@@ -433,6 +499,9 @@ def main():
         "loss": float(loss.detach()),
     }
 
+    # ---- secondary metrics of BASELINE.json ("FPS/kNN clouds/s"): config 3 shapes, B = 48, rank 0's GPU --------------
+    out["secondary"] = secondary_gpu(dev)
+
     ref_ms = time_ref_cuda_kernel(dev_sets[0][0], dev_sets[0][1])
     if ref_ms is not None:
         out["ref_cuda_kernel"] = {"ms_per_step": ref_ms, "value": B * N * M / (ref_ms * 1e-3), "unit": UNIT,
@@ -447,7 +516,8 @@ def main():
         v, secs = cpu_chamfer_l1_fwd_bwd_rate(n_clouds, threads)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": f"{n_clouds} of the {B} clouds ({N}x{M} each), torch.cdist+min+autograd fwd+bwd, "
-                                         f"{secs:.1f} s"}
+                                         f"{secs:.1f} s",
+                               "secondary": secondary_cpu(threads)}
     print(json.dumps(out))
 
 
