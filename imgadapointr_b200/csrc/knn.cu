@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(kKnnThreads) knn_merge_kernel(const float* __r
 //   sweep 1: 32 running minima, one per residue class of the reference index (mod 32) - 1 FMNMX per pair.  The k-th
 //            smallest of those 32 minima, tau0, is an upper bound on the k-th nearest distance (they belong to 32
 //            distinct references) and a tight one: ~22 references lie below it for k = 16, R = 2048.
-//   sweep 2: references with d < tau0, plus the first k with d == tau0 (ties at the threshold, e.g. zero padding), are
-//            appended in ascending index to a per-thread candidate list (u16/u32 indices in shared memory);
+//   sweep 2: references with d <= tau0 are appended in ascending index to a per-thread candidate list (u16 indices in
+//            shared memory) - a bit mask per 32 references, expanded once per chunk, keeps the inner loop branch-free;
 //   select : a stable insertion sort by distance of the <= kSelCap candidates gives the k nearest ascending by
 //            (distance, index) - the same lowest-index tie rule.
 // A query whose candidate list overflows (adversarial clustering) is flagged and redone by knn_kernel<1>.
@@ -348,36 +348,63 @@ __global__ void __launch_bounds__(kSelThreads) knn_select_kernel(const float* __
     if (i < k) tau = mn[i];  // k-th smallest class minimum (k <= 16)
 
   // ---- sweep 2: collect candidates -----------------------------------------------------------------------------
+  // Branch-free inner loop: 32 references set bits of a per-thread mask (FSETP + SEL), so the loads and the FP chains
+  // of neighbouring references overlap; the set bits are appended to the candidate list once per 32-reference chunk.
+  // Of the references exactly AT the threshold only the first k (ascending index) are kept - zero-padded clouds hold
+  // hundreds of them; a query with more than kSelCap candidates goes to the list kernel.
   int count = 0, eq_taken = 0;
-  bool overflow = false;
+  float thr = tau;  // inclusive threshold of the sweep
   for (int t0 = 0; t0 < R; t0 += kSelTile) {
     const int tn = min(kSelTile, R - t0);
     if (R > kSelTile || t0 > 0) stage(t0, tn);  // single-tile clouds are still resident from sweep 1
-#pragma unroll 8
-    for (int r = 0; r < tn; ++r) {
-      const float4 p = sm.ref[r];
-      const float d = sqdist(qx, qy, qz, p.x, p.y, p.z);
-      const bool take = (d < tau) || (d == tau && eq_taken < k);
-      if (take) {
-        if (d == tau) ++eq_taken;
-        if (count < kSelCap)
-          sm.cand[count][tid] = (unsigned short)(t0 + r);
-        else
-          overflow = true;
+    const int steps = (tn + 31) / 32;           // sentinel padding: d ~ 3e36 > tau
+    for (int s = 0; s < steps; ++s) {
+      unsigned m = 0u;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float4 p = sm.ref[s * 32 + i];
+        if (sqdist(qx, qy, qz, p.x, p.y, p.z) <= thr) m |= 1u << i;
+      }
+      while (m) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1u;
+        const float4 p = sm.ref[s * 32 + i];
+        if (sqdist(qx, qy, qz, p.x, p.y, p.z) == tau) {
+          if (++eq_taken > k) continue;
+          if (eq_taken == k) thr = tau > 0.f ? __uint_as_float(__float_as_uint(tau) - 1u) : -1.f;  // now strictly below
+        }
+        if (count < kSelCap) sm.cand[count][tid] = (unsigned short)(t0 + s * 32 + i);
         ++count;
       }
     }
   }
+  const bool overflow = count > kSelCap;
   if (live) flags[(size_t)b * Q + q] = overflow ? 1 : 0;
   __syncthreads();  // every thread is done with the reference tile: its storage becomes the top-k arrays
   if (!live || overflow) return;
 
   // ---- select: stable insertion by distance (candidates arrive in ascending index) ---------------------------------
+  // The next candidate's coordinates are fetched while the current one is inserted.
   int have = 0;
+  float nx = 0.f, ny = 0.f, nz = 0.f;
+  int nr = 0;
+  if (count > 0) {
+    nr = sm.cand[0][tid];
+    const float* p = Rb + 3 * (size_t)nr;
+    nx = __ldg(p);
+    ny = __ldg(p + 1);
+    nz = __ldg(p + 2);
+  }
   for (int c = 0; c < count; ++c) {
-    const int r = sm.cand[c][tid];
-    const float* p = Rb + 3 * (size_t)r;
-    const float d = sqdist(qx, qy, qz, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+    const int r = nr;
+    const float d = sqdist(qx, qy, qz, nx, ny, nz);
+    if (c + 1 < count) {
+      nr = sm.cand[c + 1][tid];
+      const float* p = Rb + 3 * (size_t)nr;
+      nx = __ldg(p);
+      ny = __ldg(p + 1);
+      nz = __ldg(p + 2);
+    }
     if (have == k && !(d < sm.top.topd[k - 1][tid])) continue;
     int pos = have < k ? have : k - 1;
     while (pos > 0 && d < sm.top.topd[pos - 1][tid]) {

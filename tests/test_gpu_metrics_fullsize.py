@@ -114,8 +114,10 @@ def test_fullsize_encoder_geometry(dev):
     tie = dist[..., 1:] == dist[..., :-1]
     assert bool((idx[..., 1:][tie] > idx[..., :-1][tie]).all())  # ascending index inside exact ties
     assert float(dist[..., 0].max()) == 0.0  # every point is its own (or a duplicate's) nearest neighbour
-    oi, od = oracle.knn(16, xyz[:4].numpy(), xyz[:4].numpy())
-    assert np.array_equal(idx[:4].cpu().numpy(), oi) and np.array_equal(dist[:4].cpu().numpy(), od)
+    oi, od = oracle.knn(16, xyz.numpy(), xyz.numpy())  # all 48 clouds: the select path and its tie handling, bit for bit
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(dist.cpu().numpy(), od)
+    i8 = knn_point(8, x, x)
+    assert np.array_equal(i8.cpu().numpy(), oi[..., :8])  # k = 8 is a prefix of k = 16 under the (distance, index) order
     # the reference formulation on the GPU picks the same neighbour sets wherever its FP32 expansion cannot flip a tie
     D = -2 * torch.matmul(x, x.transpose(1, 2)) + (x ** 2).sum(-1)[:, :, None] + (x ** 2).sum(-1)[:, None, :]
     ref = torch.topk(D, 16, dim=-1, largest=False, sorted=False).indices
