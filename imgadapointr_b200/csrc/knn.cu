@@ -241,19 +241,30 @@ __global__ void __launch_bounds__(kKnnThreads) knn_merge_kernel(const float* __r
 // ---- k <= 16: thread-per-query threshold selection ------------------------------------------------------------
 // The warp-per-query kernel above spends most of its issue slots on list insertions (ncu: issue-bound, 81 %).
 // For the encoder's k = 8 / 16 calls a cheaper exact scheme: every THREAD owns one query and sweeps the references
-// (broadcast LDS.128 from a shared-memory tile) twice:
-//   sweep 1: 32 running minima, one per residue class of the reference index (mod 32) - 1 FMNMX per pair.  The k-th
-//            smallest of those 32 minima, tau0, is an upper bound on the k-th nearest distance (they belong to 32
-//            distinct references) and a tight one: ~22 references lie below it for k = 16, R = 2048.
-//   sweep 2: references with d <= tau0 are appended in ascending index to a per-thread candidate list (u16 indices in
-//            shared memory) - a bit mask per 32 references, expanded once per chunk, keeps the inner loop branch-free;
-//   select : a stable insertion sort by distance of the <= kSelCap candidates gives the k nearest ascending by
-//            (distance, index) - the same lowest-index tie rule.
+// (warp-uniform LDS.128 from a shared-memory tile) twice:
+//   sweep 1: 32 running minima over 32 classes of distinct references - 1 FMNMX per pair.  The k-th smallest of the
+//            32 minima, tau, is an upper bound on the k-th nearest distance.  Only every kStride-th group of four
+//            references is looked at: any distinct references bound the k-th distance, half the sweep is saved and the
+//            candidate list grows from ~22 to ~44 entries (k = 16);
+//   sweep 2: references with d <= tau set bits of a per-thread mask (FSETP + SEL, branch-free so loads and FP chains
+//            overlap); once per 32 references the set bits are appended, in ascending index, to a per-thread candidate
+//            list (u16 indices in shared memory);
+//   select : a branch-free stable insert of the candidates into a register-resident sorted list gives the k nearest
+//            ascending by (distance, index) - the same lowest-index tie rule.
+// Layout choices, each from a measurement (profiles/r01f_*, scripts/microbench/lds_bcast.cu):
+//  * a warp-uniform LDS costs ~3.3 issue cycles whatever its width, so the tile is a RAW copy of the [R,3] rows and
+//    four references come out of three LDS.128 (0.75 loads per pair instead of 1);
+//  * a warp is the unit of work (32 queries, its own tile, __syncwarp only): 48 x 2048 queries are 3072 warps = 20.8 per
+//    SM, so every SM gets 20 or 21 of them (256-thread CTAs gave 2 or 3 per SM: 14 % of the machine idle);
+//  * calls with few queries put kSplit warps on the same 32 queries, each sweeping a slice of the references: the
+//    slices' class minima are combined through shared memory after sweep 1 (one tau per query, as without slices) and
+//    warp 0 selects from the slices' candidate lists in slice order.
 // A query whose candidate list overflows (adversarial clustering) is flagged and redone by knn_kernel<1>.
-constexpr int kSelThreads = 256;
-constexpr int kSelTile = 2048;  // references per smem tile (float4: 32 KB)
-constexpr int kSelCap = 64;     // candidates per query
 constexpr int kSelMaxK = 16;
+constexpr int kS2Tile = 128;                  // references per tile: 96 float4 = the rows' 384 floats verbatim
+constexpr int kS2Vec = kS2Tile * 3 / 4;       // float4 per tile
+constexpr int kS2Cap = 112;                   // candidates per query (and slice)
+constexpr int kS2TieCheckFrom = 80;           // candidates appended before ties at the threshold start to be counted
 
 __device__ __forceinline__ void cmpswap(float& a, float& b) {
   const float lo = fminf(a, b), hi = fmaxf(a, b);
@@ -281,29 +292,46 @@ __device__ __forceinline__ void sort32(float (&v)[32]) {
   }
 }
 
-struct __align__(16) SelSmem {
+struct __align__(16) S2Smem {
+  float4 tile[kS2Vec];
   union {
-    float4 ref[kSelTile];  // sweeps: the reference tile (32 KB)
-    struct {               // select phase (after a block barrier): per-thread sorted top-k
-      float topd[kSelMaxK][kSelThreads];
-      int topi[kSelMaxK][kSelThreads];
-    } top;
+    unsigned short cand[kS2Cap][32];  // sweep 2 -> select
+    float minima[32][32];             // kSplit > 1: this slice's class minima, exchanged after sweep 1
   };
-  unsigned short cand[kSelCap][kSelThreads];  // candidate reference indices (R <= 65536 on this path)
 };
 
-__global__ void __launch_bounds__(kSelThreads) knn_select_kernel(const float* __restrict__ ref,
-                                                                 const float* __restrict__ qry, int R, int Q, int k,
-                                                                 int q_blocks, int64_t* __restrict__ idx_out,
-                                                                 float* __restrict__ dist_out, int* __restrict__ flags) {
-  extern __shared__ __align__(16) unsigned char sel_raw[];
-  SelSmem& sm = *reinterpret_cast<SelSmem*>(sel_raw);
-  const int tid = threadIdx.x;
+// new[j] = (d < old[j-1]) ? old[j-1] : (d < old[j]) ? d : old[j]; strict '<' puts d after equal, earlier entries
+template <int kK>
+__device__ __forceinline__ void sorted_insert(float d, int r, float (&td)[kK], int (&ti)[kK]) {
+#pragma unroll
+  for (int j = kK - 1; j >= 0; --j) {
+    const bool here = d < td[j];
+    const bool up = j > 0 && d < td[j > 0 ? j - 1 : 0];
+    td[j] = up ? td[j > 0 ? j - 1 : 0] : (here ? d : td[j]);
+    ti[j] = up ? ti[j > 0 ? j - 1 : 0] : (here ? r : ti[j]);
+  }
+}
+
+template <int kStride, int kK, int kSplit>
+__global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
+    knn_select_kernel(const float* __restrict__ ref, const float* __restrict__ qry, int R, int Q, int k, int q_blocks,
+                      int aligned, int64_t* __restrict__ idx_out, float* __restrict__ dist_out,
+                      int* __restrict__ flags) {
+  __shared__ S2Smem smem[kSplit];
+  __shared__ int counts[kSplit][32];
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;  // slice of the references this warp sweeps
+  S2Smem& sm = smem[w];
   const int b = blockIdx.x / q_blocks;
-  const int q = (blockIdx.x - b * q_blocks) * kSelThreads + tid;
+  const int q = (blockIdx.x - b * q_blocks) * 32 + lane;
   const bool live = q < Q;
   const float* __restrict__ Rb = ref + (size_t)b * R * 3;
   const float kInf = __int_as_float(0x7f800000);
+  // slice [lo, hi): whole tiles, so slice starts stay 16-byte aligned whenever the cloud is
+  const int per = ((R + kSplit - 1) / kSplit + kS2Tile - 1) / kS2Tile * kS2Tile;
+  const int lo = min(R, w * per), hi = min(R, lo + per);
+  const int fl0 = 3 * lo, nfl = 3 * hi;  // float range of the slice inside the cloud
+  const int n_tiles = (hi - lo + kS2Tile - 1) / kS2Tile;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   if (live) {
     const float* qp = qry + ((size_t)b * Q + q) * 3;
@@ -312,115 +340,172 @@ __global__ void __launch_bounds__(kSelThreads) knn_select_kernel(const float* __
     qz = __ldg(qp + 2);
   }
 
-  auto stage = [&](int t0, int tn) {
-    __syncthreads();
-    for (int r = tid; r < kSelTile; r += kSelThreads) {
-      float4 v = make_float4(kPadCoord(), kPadCoord(), kPadCoord(), 0.f);
-      if (r < tn) {
-        const float* p = Rb + 3 * (size_t)(t0 + r);
-        v = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+  // Tile t -> three float4 per lane, fetched one tile ahead of its use.  The loads are unconditional (addresses
+  // clamped into the slice); publish() swaps in the sentinels for floats past its end.
+  auto fetch = [&](int t, float4 (&v)[3]) {
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      const int f0 = fl0 + (t * kS2Vec + e * 32 + lane) * 4;
+      if (aligned) {
+        v[e] = __ldg(reinterpret_cast<const float4*>(Rb + min(f0, nfl - 4)));
+      } else {
+        v[e].x = __ldg(Rb + min(f0 + 0, nfl - 1));
+        v[e].y = __ldg(Rb + min(f0 + 1, nfl - 1));
+        v[e].z = __ldg(Rb + min(f0 + 2, nfl - 1));
+        v[e].w = __ldg(Rb + min(f0 + 3, nfl - 1));
       }
-      sm.ref[r] = v;
     }
-    __syncthreads();
+  };
+  auto publish = [&](int t, const float4 (&v)[3]) {
+    __syncwarp();  // every lane is done with the previous tile
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      const int f0 = fl0 + (t * kS2Vec + e * 32 + lane) * 4;
+      float4 wv = v[e];
+      if (f0 + 0 >= nfl) wv.x = kPadCoord();
+      if (f0 + 1 >= nfl) wv.y = kPadCoord();
+      if (f0 + 2 >= nfl) wv.z = kPadCoord();
+      if (f0 + 3 >= nfl) wv.w = kPadCoord();
+      sm.tile[e * 32 + lane] = wv;
+    }
+    __syncwarp();
   };
 
-  // ---- sweep 1: residue-class minima ---------------------------------------------------------------------------
+  // ---- sweep 1: 32 class minima over the sampled references ---------------------------------------------------
   float mn[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) mn[i] = kInf;
-  for (int t0 = 0; t0 < R; t0 += kSelTile) {
-    const int tn = min(kSelTile, R - t0);
-    stage(t0, tn);
-    const int steps = (tn + 31) / 32;  // padded entries are 1e18 sentinels: distances ~3e36, never below a real one
-    for (int s = 0; s < steps; ++s) {
+  float4 nx[3];
+  if (n_tiles > 0) fetch(0, nx);
+  for (int t = 0; t < n_tiles; ++t) {
+    publish(t, nx);
+    if (t + 1 < n_tiles) fetch(t + 1, nx);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float4 p = sm.ref[s * 32 + i];
-        mn[i] = fminf(mn[i], sqdist(qx, qy, qz, p.x, p.y, p.z));
+    for (int g0 = 0; g0 < kS2Tile / 4; g0 += 8 * kStride) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4* G = &sm.tile[3 * (g0 + j * kStride)];
+        const float4 A = G[0], Bv = G[1], C = G[2];
+        mn[4 * j + 0] = fminf(mn[4 * j + 0], sqdist(qx, qy, qz, A.x, A.y, A.z));
+        mn[4 * j + 1] = fminf(mn[4 * j + 1], sqdist(qx, qy, qz, A.w, Bv.x, Bv.y));
+        mn[4 * j + 2] = fminf(mn[4 * j + 2], sqdist(qx, qy, qz, Bv.z, Bv.w, C.x));
+        mn[4 * j + 3] = fminf(mn[4 * j + 3], sqdist(qx, qy, qz, C.y, C.z, C.w));
       }
     }
+  }
+  if (kSplit > 1) {
+    // the slices' minima of a class belong to different references: their minimum is the class minimum of the cloud
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sm.minima[i][lane] = mn[i];
+    __syncthreads();
+#pragma unroll
+    for (int o = 1; o < kSplit; ++o) {
+      const S2Smem& other = smem[(w + o) % kSplit];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mn[i] = fminf(mn[i], other.minima[i][lane]);
+    }
+    __syncthreads();  // minima[] aliases cand[]
   }
   sort32(mn);
   float tau = mn[0];
 #pragma unroll
-  for (int i = 1; i < kSelMaxK; ++i)
-    if (i < k) tau = mn[i];  // k-th smallest class minimum (k <= 16)
+  for (int i = 1; i < kK; ++i)
+    if (i < k) tau = mn[i];
 
-  // ---- sweep 2: collect candidates -----------------------------------------------------------------------------
-  // Branch-free inner loop: 32 references set bits of a per-thread mask (FSETP + SEL), so the loads and the FP chains
-  // of neighbouring references overlap; the set bits are appended to the candidate list once per 32-reference chunk.
-  // Of the references exactly AT the threshold only the first k (ascending index) are kept - zero-padded clouds hold
-  // hundreds of them; a query with more than kSelCap candidates goes to the list kernel.
+  // ---- sweep 2: candidates (d <= thr) ------------------------------------------------------------------------------
+  // References exactly AT tau (hundreds in a zero-padded cloud) are all taken until the list holds kS2TieCheckFrom
+  // entries - the lowest-index ones are among them - then counted, and after k more the threshold drops just below
+  // tau.  Typical queries (~44 candidates) never pay for the check.
   int count = 0, eq_taken = 0;
-  float thr = tau;  // inclusive threshold of the sweep
-  for (int t0 = 0; t0 < R; t0 += kSelTile) {
-    const int tn = min(kSelTile, R - t0);
-    if (R > kSelTile || t0 > 0) stage(t0, tn);  // single-tile clouds are still resident from sweep 1
-    const int steps = (tn + 31) / 32;           // sentinel padding: d ~ 3e36 > tau
-    for (int s = 0; s < steps; ++s) {
+  float thr = tau;
+  const float* tf = reinterpret_cast<const float*>(sm.tile);
+  if (n_tiles > 0) fetch(0, nx);
+  for (int t = 0; t < n_tiles; ++t) {
+    publish(t, nx);
+    if (t + 1 < n_tiles) fetch(t + 1, nx);
+#pragma unroll 1
+    for (int c = 0; c < kS2Tile / 32; ++c) {
       unsigned m = 0u;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float4 p = sm.ref[s * 32 + i];
-        if (sqdist(qx, qy, qz, p.x, p.y, p.z) <= thr) m |= 1u << i;
+      for (int j = 0; j < 8; ++j) {
+        const float4* G = &sm.tile[3 * (c * 8 + j)];
+        const float4 A = G[0], Bv = G[1], C = G[2];
+        if (sqdist(qx, qy, qz, A.x, A.y, A.z) <= thr) m |= 1u << (4 * j + 0);
+        if (sqdist(qx, qy, qz, A.w, Bv.x, Bv.y) <= thr) m |= 1u << (4 * j + 1);
+        if (sqdist(qx, qy, qz, Bv.z, Bv.w, C.x) <= thr) m |= 1u << (4 * j + 2);
+        if (sqdist(qx, qy, qz, C.y, C.z, C.w) <= thr) m |= 1u << (4 * j + 3);
       }
       while (m) {
         const int i = __ffs(m) - 1;
         m &= m - 1u;
-        const float4 p = sm.ref[s * 32 + i];
-        if (sqdist(qx, qy, qz, p.x, p.y, p.z) == tau) {
-          if (++eq_taken > k) continue;
-          if (eq_taken == k) thr = tau > 0.f ? __uint_as_float(__float_as_uint(tau) - 1u) : -1.f;  // now strictly below
+        const int r = lo + t * kS2Tile + c * 32 + i;
+        if (r >= hi) continue;  // sentinel (only reachable when tau itself is a sentinel distance or +inf)
+        if (count >= kS2TieCheckFrom) {
+          const float* p = tf + 3 * (c * 32 + i);
+          if (sqdist(qx, qy, qz, p[0], p[1], p[2]) == tau) {
+            if (++eq_taken > k) continue;
+            if (eq_taken == k) thr = tau > 0.f ? __uint_as_float(__float_as_uint(tau) - 1u) : -1.f;
+          }
         }
-        if (count < kSelCap) sm.cand[count][tid] = (unsigned short)(t0 + s * 32 + i);
+        if (count < kS2Cap) sm.cand[count][lane] = (unsigned short)r;
         ++count;
       }
     }
   }
-  const bool overflow = count > kSelCap;
-  if (live) flags[(size_t)b * Q + q] = overflow ? 1 : 0;
-  __syncthreads();  // every thread is done with the reference tile: its storage becomes the top-k arrays
-  if (!live || overflow) return;
-
-  // ---- select: stable insertion by distance (candidates arrive in ascending index) ---------------------------------
-  // The next candidate's coordinates are fetched while the current one is inserted.
-  int have = 0;
-  float nx = 0.f, ny = 0.f, nz = 0.f;
-  int nr = 0;
-  if (count > 0) {
-    nr = sm.cand[0][tid];
-    const float* p = Rb + 3 * (size_t)nr;
-    nx = __ldg(p);
-    ny = __ldg(p + 1);
-    nz = __ldg(p + 2);
+  bool overflow = count > kS2Cap;
+  if (kSplit > 1) {  // warp 0 selects from every slice's candidates, in slice (= ascending index) order
+    counts[w][lane] = count;
+    __syncthreads();
+    if (w != 0) return;
+#pragma unroll
+    for (int o = 1; o < kSplit; ++o) overflow |= counts[o][lane] > kS2Cap;
   }
-  for (int c = 0; c < count; ++c) {
-    const int r = nr;
-    const float d = sqdist(qx, qy, qz, nx, ny, nz);
-    if (c + 1 < count) {
-      nr = sm.cand[c + 1][tid];
-      const float* p = Rb + 3 * (size_t)nr;
-      nx = __ldg(p);
-      ny = __ldg(p + 1);
-      nz = __ldg(p + 2);
+  if (!live) return;
+  flags[(size_t)b * Q + q] = overflow ? 1 : 0;
+  if (overflow) return;
+
+  // ---- select: stable insert into a register-resident sorted list ---------------------------------------------------
+  float td[kK];
+  int ti[kK];
+#pragma unroll
+  for (int j = 0; j < kK; ++j) {
+    td[j] = kInf;
+    ti[j] = 0;
+  }
+#pragma unroll 1
+  for (int o = 0; o < kSplit; ++o) {
+    const S2Smem& src = smem[o];
+    const int n = kSplit > 1 ? counts[o][lane] : count;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    int cr = 0;
+    if (n > 0) {
+      cr = src.cand[0][lane];
+      const float* p = Rb + 3 * (size_t)cr;
+      cx = __ldg(p);
+      cy = __ldg(p + 1);
+      cz = __ldg(p + 2);
     }
-    if (have == k && !(d < sm.top.topd[k - 1][tid])) continue;
-    int pos = have < k ? have : k - 1;
-    while (pos > 0 && d < sm.top.topd[pos - 1][tid]) {
-      sm.top.topd[pos][tid] = sm.top.topd[pos - 1][tid];
-      sm.top.topi[pos][tid] = sm.top.topi[pos - 1][tid];
-      --pos;
+    for (int c = 0; c < n; ++c) {
+      const int r = cr;
+      const float d = sqdist(qx, qy, qz, cx, cy, cz);
+      if (c + 1 < n) {  // the next candidate's coordinates travel while this one is inserted
+        cr = src.cand[c + 1][lane];
+        const float* p = Rb + 3 * (size_t)cr;
+        cx = __ldg(p);
+        cy = __ldg(p + 1);
+        cz = __ldg(p + 2);
+      }
+      sorted_insert<kK>(d, r, td, ti);
     }
-    sm.top.topd[pos][tid] = d;
-    sm.top.topi[pos][tid] = r;
-    if (have < k) ++have;
   }
   const size_t o = ((size_t)b * Q + q) * k;
-  for (int j = 0; j < k; ++j) {
-    const bool filled = j < have;  // fewer than k only if distances were NaN (outside the contract): stay in range
-    idx_out[o + j] = filled ? (int64_t)sm.top.topi[j][tid] : 0;
-    if (dist_out) dist_out[o + j] = filled ? sm.top.topd[j][tid] : kInf;
+#pragma unroll
+  for (int j = 0; j < kK; ++j) {
+    if (j < k) {
+      // fewer than k entries only if distances were NaN (outside the contract): index 0 keeps consumers in range
+      idx_out[o + j] = (int64_t)ti[j];
+      if (dist_out) dist_out[o + j] = td[j];
+    }
   }
 }
 
@@ -442,18 +527,42 @@ static int knn_r_splits(int B, int R, int Q) {
   return s < 2 ? 1 : (int)s;
 }
 
+// Which kernel a call takes, shared by the workspace query and the launcher.
+struct KnnPlan {
+  bool select;  // thread-per-query selection (k <= 16) vs warp-per-query list
+  int splits;   // select: warps per 32 queries; list: reference slices merged by knn_merge_kernel
+};
+
+static long long env_ll(const char* name, long long fallback) {
+  const char* e = std::getenv(name);
+  return (e && std::atoll(e) > 0) ? std::atoll(e) : fallback;
+}
+
+static KnnPlan knn_plan(int B, int R, int Q, int k) {
+  static const bool force_list = env_ll("IAPT_KNN_FORCE_LIST", 0) == 1;             // development knobs
+  static const long long min_warps = env_ll("IAPT_KNN_SELECT_MIN_WARPS", 256);
+  static const long long want_warps = env_ll("IAPT_KNN_SELECT_WANT_WARPS", 2048);
+  static const long long force_split = env_ll("IAPT_KNN_SELECT_SPLIT", 0);
+  const long long warps = (long long)B * ((Q + 31) / 32);
+  if (k <= kSelMaxK && R >= 64 && R <= 65536 && !force_list && warps >= min_warps) {
+    int s = 1;
+    while (s < 4 && warps * s < want_warps && R / (2 * s) >= 512) s *= 2;  // slices shorter than 512 do not pay
+    if (force_split == 1 || force_split == 2 || force_split == 4) s = (int)force_split;
+    return {true, s};
+  }
+  return {false, knn_r_splits(B, R, Q)};
+}
+
 size_t knn_workspace_bytes(int B, int R, int Q, int k) {
-  size_t bytes = k <= kSelMaxK ? sizeof(int) * (size_t)B * Q : 0;
-  const int rs = knn_r_splits(B, R, Q);
-  if (rs > 1) bytes += (sizeof(float) + sizeof(int)) * (size_t)B * Q * rs * k;
-  return bytes;
+  const KnnPlan plan = knn_plan(B, R, Q, k);
+  if (plan.select) return sizeof(int) * (size_t)B * Q;  // overflow flags
+  return plan.splits > 1 ? (sizeof(float) + sizeof(int)) * (size_t)B * Q * plan.splits * k : 0;
 }
 
 template <int kSlots>
 static void knn_list_launch(const float* ref, const float* qry, int B, int R, int Q, int k, int64_t* idx, float* dist,
-                            const int* flags, void* split_ws, cudaStream_t stream) {
-  const int rs = (flags == nullptr && split_ws != nullptr) ? knn_r_splits(B, R, Q) : 1;
-  if (rs > 1) {
+                            const int* flags, void* split_ws, int rs, cudaStream_t stream) {
+  if (rs > 1 && flags == nullptr && split_ws != nullptr) {
     const int q_blocks = (Q + kKnnWarps - 1) / kKnnWarps;
     dim3 grid((unsigned)((long long)B * q_blocks), rs);
     float* pd = static_cast<float*>(split_ws);
@@ -479,36 +588,46 @@ static void knn_list_launch(const float* ref, const float* qry, int B, int R, in
   }
 }
 
+template <int kStride, int kK, int kSplit>
+static void knn_select_launch(const float* ref, const float* qry, int B, int R, int Q, int k, int64_t* idx, float* dist,
+                              int* flags, cudaStream_t stream) {
+  const int qb = (Q + 31) / 32;
+  const int aligned = (reinterpret_cast<uintptr_t>(ref) % 16 == 0 && R % 4 == 0) ? 1 : 0;
+  knn_select_kernel<kStride, kK, kSplit><<<(unsigned)((long long)B * qb), 32 * kSplit, 0, stream>>>(
+      ref, qry, R, Q, k, qb, aligned, idx, dist, flags);
+}
+
+template <int kK>
+static void knn_select_dispatch(const float* ref, const float* qry, int B, int R, int Q, int k, int splits, int64_t* idx,
+                                float* dist, int* flags, cudaStream_t stream) {
+  if (splits == 4)
+    knn_select_launch<1, kK, 4>(ref, qry, B, R, Q, k, idx, dist, flags, stream);
+  else if (splits == 2)
+    knn_select_launch<1, kK, 2>(ref, qry, B, R, Q, k, idx, dist, flags, stream);
+  else if (R >= 1024)  // sampled sweep 1 only where the slice is long enough to pay for the extra candidates
+    knn_select_launch<2, kK, 1>(ref, qry, B, R, Q, k, idx, dist, flags, stream);
+  else
+    knn_select_launch<1, kK, 1>(ref, qry, B, R, Q, k, idx, dist, flags, stream);
+}
+
 int knn_launch(const float* ref, const float* qry, int B, int R, int Q, int k, int64_t* idx, float* dist,
                void* workspace, cudaStream_t stream) {
-  static int force_list = -1;
-  if (force_list < 0) {
-    const char* e = std::getenv("IAPT_KNN_FORCE_LIST");
-    force_list = (e && e[0] == '1') ? 1 : 0;
-  }
-  unsigned char* ws = static_cast<unsigned char*>(workspace);
-  int* flags = (k <= kSelMaxK && ws != nullptr) ? reinterpret_cast<int*>(ws) : nullptr;
-  void* split_ws = (ws != nullptr && knn_r_splits(B, R, Q) > 1) ? ws + (k <= kSelMaxK ? sizeof(int) * (size_t)B * Q : 0)
-                                                                : nullptr;
-  // The select path needs enough queries to fill the machine with one thread each; small calls keep the
-  // warp-per-query list kernel (32 lanes per query).
-  if (k <= kSelMaxK && R <= 65536 && flags != nullptr && !force_list && (long long)B * Q >= 65536) {
-    static PerDeviceOnce once;
-    if (once.pending()) {
-      cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem));
-      once.done();
-    }
-    const int sb = (Q + kSelThreads - 1) / kSelThreads;
-    knn_select_kernel<<<(unsigned)((long long)B * sb), kSelThreads, sizeof(SelSmem), stream>>>(
-        ref, qry, R, Q, k, sb, idx, dist, flags);
+  const KnnPlan plan = knn_plan(B, R, Q, k);
+  if (plan.select && workspace != nullptr) {
+    int* flags = static_cast<int*>(workspace);
+    if (k <= 8)
+      knn_select_dispatch<8>(ref, qry, B, R, Q, k, plan.splits, idx, dist, flags, stream);
+    else
+      knn_select_dispatch<16>(ref, qry, B, R, Q, k, plan.splits, idx, dist, flags, stream);
     count_launch();
-    knn_list_launch<1>(ref, qry, B, R, Q, k, idx, dist, flags, nullptr, stream);
+    knn_list_launch<1>(ref, qry, B, R, Q, k, idx, dist, flags, nullptr, 1, stream);  // flagged queries only
     return (int)cudaGetLastError();
   }
+  const int rs = (plan.select || workspace == nullptr) ? 1 : plan.splits;
   if (k <= 32)
-    knn_list_launch<1>(ref, qry, B, R, Q, k, idx, dist, nullptr, split_ws, stream);
+    knn_list_launch<1>(ref, qry, B, R, Q, k, idx, dist, nullptr, workspace, rs, stream);
   else
-    knn_list_launch<2>(ref, qry, B, R, Q, k, idx, dist, nullptr, split_ws, stream);
+    knn_list_launch<2>(ref, qry, B, R, Q, k, idx, dist, nullptr, workspace, rs, stream);
   return (int)cudaGetLastError();
 }
 

@@ -103,6 +103,30 @@ def test_knn_matches_oracle_config3_shapes(dev, R, Q, k):
     _knn_check(xyz, new_xyz, k, dev)
 
 
+@pytest.mark.parametrize("B,R,Q,k,kind", [
+    (16, 2048, 512, 16, "uniform"),   # select path, 4 warps per 32 queries, each a 512-reference slice
+    (16, 512, 512, 16, "grid"),       # 4 slices of one tile each, heavy exact ties
+    (32, 512, 256, 16, "zeros"),      # zero-padded tail: hundreds of references tie at the threshold
+    (32, 256, 256, 8, "uniform"),     # k = 8 instantiation, 2 slices
+    (16, 256, 512, 8, "grid"),
+    (16, 1001, 600, 16, "zeros"),     # R not a multiple of 4 (scalar staging), ragged last tile and query block
+    (9, 1500, 1000, 13, "grid"),      # k between the template sizes, last slice shorter than the others
+    (64, 2048, 1024, 16, "zeros"),    # one warp per 32 queries, sampled first sweep
+    (300, 64, 32, 16, "uniform"),     # smallest reference count the select path takes
+])
+def test_knn_select_path_slices_and_ties(dev, B, R, Q, k, kind):
+    """Batches large enough (B*ceil(Q/32) >= 256 warps) for the thread-per-query select kernel, bit for bit against
+    the oracle: every slice count, both k instantiations, unaligned clouds, zero padding and exact-tie grids."""
+    if kind == "uniform":
+        xyz = synthetic.uniform(B, R, 900 + R)
+    elif kind == "grid":
+        xyz = synthetic.grid(B, R, 901 + R, bits=3, dup_frac=0.2)
+    else:
+        xyz = synthetic.grid(B, R, 902 + R, bits=10, zero_frac=0.4)
+    new_xyz = xyz[:, :Q].contiguous() if Q <= R and kind != "uniform" else synthetic.uniform(B, Q, 903 + Q)
+    _knn_check(xyz, new_xyz, k, dev)
+
+
 def test_knn_zero_padded_and_grid_ties(dev):
     gt = synthetic.pcn_gt(2, 4096, 303)
     xyz = synthetic.pcn_partial(gt, 2048, 305)
