@@ -18,7 +18,6 @@ namespace iapt {
 constexpr int kKnnThreads = 256;
 constexpr int kKnnWarps = kKnnThreads / 32;
 constexpr int kKnnTile = 2048;         // reference points per smem tile (24 KB SoA)
-constexpr int kKnnQueriesPerCta = 32;  // queries per CTA (4 per warp), amortises the tile fill
 
 // Insert this step's candidates (one per lane: distance d, reference index my_idx; d = +inf for "none") into the
 // warp-distributed sorted list (entry s*32+lane).  Candidates are taken in lane order and only a strictly smaller
@@ -90,47 +89,36 @@ __device__ __forceinline__ void warp_sort_pairs(float& d, int& i) {
 // r_splits > 1: blockIdx.y selects a slice of the reference range and the per-slice lists go to part_d / part_i
 // ([B*Q, r_splits, k]) for knn_merge_kernel - used when there are few queries and many references (the loss kNN:
 // Q = 64, R = 16384, k = 32, models/external/AdaPoinTr.py:201), where one warp per query cannot fill the machine.
-template <int kSlots, int kQPW>  // list entries per lane: k <= 32 * kSlots; kQPW queries per warp (processed in turn)
+template <int kSlots>  // list entries per lane: k <= 32 * kSlots
 __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restrict__ ref, const float* __restrict__ qry,
                                                           int R, int Q, int k, int q_blocks,
                                                           int64_t* __restrict__ idx_out, float* __restrict__ dist_out,
-                                                          const int* __restrict__ only_flagged, int r_splits,
-                                                          float* __restrict__ part_d, int* __restrict__ part_i) {
+                                                          int r_splits, float* __restrict__ part_d,
+                                                          int* __restrict__ part_i) {
   __shared__ float4 sp[kKnnTile];  // one broadcast-free LDS.128 per reference
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.x / q_blocks;
-  const int q0 = (blockIdx.x - b * q_blocks) * (kKnnWarps * kQPW);
-  if (only_flagged != nullptr) {  // second pass of the select path: only queries whose candidate buffer overflowed
-    int any = 0;
-    if (threadIdx.x < (kKnnWarps * kQPW) && q0 + (int)threadIdx.x < Q) any = only_flagged[(size_t)b * Q + q0 + threadIdx.x];
-    if (!__syncthreads_or(any)) return;
-  }
-  const int split = blockIdx.y;
+  const int q = (blockIdx.x - b * q_blocks) * kKnnWarps + warp;  // one query per warp (measured 10-15 % faster than
+  const int split = blockIdx.y;                                   // four in turn on every encoder shape)
   const int per = (R + r_splits - 1) / r_splits;
   const int r_lo = split * per, r_hi = min(R, r_lo + per);
   const float* __restrict__ Rb = ref + (size_t)b * R * 3;
   const float* __restrict__ Qb = qry + (size_t)b * Q * 3;
   const float kInf = __int_as_float(0x7f800000);
 
-  float qx[kQPW], qy[kQPW], qz[kQPW];
-  float ld[kQPW][kSlots];  // sorted list: entry (s*32 + lane)
-  int li[kQPW][kSlots];
-  float tau[kQPW];
+  const int qq = q < Q ? q : 0;
+  const float qx = __ldg(Qb + 3 * (size_t)qq + 0);
+  const float qy = __ldg(Qb + 3 * (size_t)qq + 1);
+  const float qz = __ldg(Qb + 3 * (size_t)qq + 2);
+  float ld[kSlots];  // sorted list: entry (s*32 + lane)
+  int li[kSlots];
 #pragma unroll
-  for (int u = 0; u < kQPW; ++u) {
-    const int q = q0 + warp * kQPW + u;
-    const int qq = q < Q ? q : 0;
-    qx[u] = __ldg(Qb + 3 * (size_t)qq + 0);
-    qy[u] = __ldg(Qb + 3 * (size_t)qq + 1);
-    qz[u] = __ldg(Qb + 3 * (size_t)qq + 2);
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) {
-      ld[u][s] = kInf;
-      li[u][s] = 0x7fffffff;
-    }
-    tau[u] = kInf;
+  for (int s = 0; s < kSlots; ++s) {
+    ld[s] = kInf;
+    li[s] = 0x7fffffff;
   }
+  float tau = kInf;
 
   for (int t0 = r_lo; t0 < r_hi; t0 += kKnnTile) {
     const int tn = min(kKnnTile, r_hi - t0);
@@ -140,57 +128,48 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
       sp[r] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
     }
     __syncthreads();
-#pragma unroll
-    for (int u = 0; u < kQPW; ++u) {
-      if (q0 + warp * kQPW + u >= Q) continue;  // warp-uniform
-      if (only_flagged != nullptr && only_flagged[(size_t)b * Q + q0 + warp * kQPW + u] == 0) continue;
-      int r_first = 0;
-      if (t0 == r_lo) {  // empty list: seed it with the first 32 references by one warp sort
-        float d = kInf;
-        int i = t0 + lane;
-        if (lane < tn) {
-          const float4 p = sp[lane];
-          d = sqdist(qx[u], qy[u], qz[u], p.x, p.y, p.z);
-        }
-        warp_sort_pairs(d, i);
-        ld[u][0] = d;
-        li[u][0] = (d < kInf) ? i : 0x7fffffff;
-        float kth = ld[u][0];
-        if (kSlots > 1 && k > 32) kth = ld[u][kSlots - 1];
-        tau[u] = __shfl_sync(0xffffffffu, kth, (k - 1) & 31);
-        r_first = 32;
+    if (q >= Q) continue;  // warp-uniform
+    int r_first = 0;
+    if (t0 == r_lo) {  // empty list: seed it with the first 32 references by one warp sort
+      float d = kInf;
+      int i = t0 + lane;
+      if (lane < tn) {
+        const float4 p = sp[lane];
+        d = sqdist(qx, qy, qz, p.x, p.y, p.z);
       }
-      for (int r0 = r_first; r0 < tn; r0 += 32) {
-        const int r = r0 + lane;
-        float d = kInf;
-        if (r < tn) {
-          const float4 p = sp[r];
-          d = sqdist(qx[u], qy[u], qz[u], p.x, p.y, p.z);
-        }
-        knn_insert<kSlots>(d, t0 + r, k, ld[u], li[u], tau[u]);
+      warp_sort_pairs(d, i);
+      ld[0] = d;
+      li[0] = (d < kInf) ? i : 0x7fffffff;
+      float kth = ld[0];
+      if (kSlots > 1 && k > 32) kth = ld[kSlots - 1];
+      tau = __shfl_sync(0xffffffffu, kth, (k - 1) & 31);
+      r_first = 32;
+    }
+    for (int r0 = r_first; r0 < tn; r0 += 32) {
+      const int r = r0 + lane;
+      float d = kInf;
+      if (r < tn) {
+        const float4 p = sp[r];
+        d = sqdist(qx, qy, qz, p.x, p.y, p.z);
       }
+      knn_insert<kSlots>(d, t0 + r, k, ld, li, tau);
     }
   }
 
+  if (q >= Q) return;
 #pragma unroll
-  for (int u = 0; u < kQPW; ++u) {
-    const int q = q0 + warp * kQPW + u;
-    if (q >= Q) continue;
-    if (only_flagged != nullptr && only_flagged[(size_t)b * Q + q] == 0) continue;
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) {
-      const int e = s * 32 + lane;
-      if (e < k) {
-        if (r_splits > 1) {
-          const size_t o = (((size_t)b * Q + q) * r_splits + split) * k + e;
-          part_d[o] = ld[u][s];
-          part_i[o] = li[u][s];
-        } else {
-          const size_t o = ((size_t)b * Q + q) * k + e;
-          // an unfilled slot (only possible when distances were NaN - outside the contract) must stay a valid index
-          idx_out[o] = (int64_t)(li[u][s] == 0x7fffffff ? 0 : li[u][s]);
-          if (dist_out) dist_out[o] = ld[u][s];
-        }
+  for (int s = 0; s < kSlots; ++s) {
+    const int e = s * 32 + lane;
+    if (e < k) {
+      if (r_splits > 1) {
+        const size_t o = (((size_t)b * Q + q) * r_splits + split) * k + e;
+        part_d[o] = ld[s];
+        part_i[o] = li[s];
+      } else {
+        const size_t o = ((size_t)b * Q + q) * k + e;
+        // an unfilled slot (only possible when distances were NaN - outside the contract) must stay a valid index
+        idx_out[o] = (int64_t)(li[s] == 0x7fffffff ? 0 : li[s]);
+        if (dist_out) dist_out[o] = ld[s];
       }
     }
   }
@@ -259,7 +238,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_merge_kernel(const float* __r
 //  * calls with few queries put kSplit warps on the same 32 queries, each sweeping a slice of the references: the
 //    slices' class minima are combined through shared memory after sweep 1 (one tau per query, as without slices) and
 //    warp 0 selects from the slices' candidate lists in slice order.
-// A query whose candidate list overflows (adversarial clustering) is flagged and redone by knn_kernel<1>.
+// A query whose candidate list overflows is redone inside the kernel by k exact minimum sweeps (see below).
 constexpr int kSelMaxK = 16;
 constexpr int kS2Tile = 128;                  // references per tile: 96 float4 = the rows' 384 floats verbatim
 constexpr int kS2Vec = kS2Tile * 3 / 4;       // float4 per tile
@@ -315,8 +294,7 @@ __device__ __forceinline__ void sorted_insert(float d, int r, float (&td)[kK], i
 template <int kStride, int kK, int kSplit>
 __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
     knn_select_kernel(const float* __restrict__ ref, const float* __restrict__ qry, int R, int Q, int k, int q_blocks,
-                      int aligned, int64_t* __restrict__ idx_out, float* __restrict__ dist_out,
-                      int* __restrict__ flags) {
+                      int aligned, int64_t* __restrict__ idx_out, float* __restrict__ dist_out) {
   __shared__ S2Smem smem[kSplit];
   __shared__ int counts[kSplit][32];
   const int lane = threadIdx.x & 31;
@@ -342,34 +320,36 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
 
   // Tile t -> three float4 per lane, fetched one tile ahead of its use.  The loads are unconditional (addresses
   // clamped into the slice); publish() swaps in the sentinels for floats past its end.
-  auto fetch = [&](int t, float4 (&v)[3]) {
+  auto fetch_range = [&](int t, int first, int end, float4 (&v)[3]) {
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
-      const int f0 = fl0 + (t * kS2Vec + e * 32 + lane) * 4;
+      const int f0 = first + (t * kS2Vec + e * 32 + lane) * 4;
       if (aligned) {
-        v[e] = __ldg(reinterpret_cast<const float4*>(Rb + min(f0, nfl - 4)));
+        v[e] = __ldg(reinterpret_cast<const float4*>(Rb + min(f0, end - 4)));
       } else {
-        v[e].x = __ldg(Rb + min(f0 + 0, nfl - 1));
-        v[e].y = __ldg(Rb + min(f0 + 1, nfl - 1));
-        v[e].z = __ldg(Rb + min(f0 + 2, nfl - 1));
-        v[e].w = __ldg(Rb + min(f0 + 3, nfl - 1));
+        v[e].x = __ldg(Rb + min(f0 + 0, end - 1));
+        v[e].y = __ldg(Rb + min(f0 + 1, end - 1));
+        v[e].z = __ldg(Rb + min(f0 + 2, end - 1));
+        v[e].w = __ldg(Rb + min(f0 + 3, end - 1));
       }
     }
   };
-  auto publish = [&](int t, const float4 (&v)[3]) {
+  auto publish_range = [&](int t, int first, int end, const float4 (&v)[3]) {
     __syncwarp();  // every lane is done with the previous tile
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
-      const int f0 = fl0 + (t * kS2Vec + e * 32 + lane) * 4;
+      const int f0 = first + (t * kS2Vec + e * 32 + lane) * 4;
       float4 wv = v[e];
-      if (f0 + 0 >= nfl) wv.x = kPadCoord();
-      if (f0 + 1 >= nfl) wv.y = kPadCoord();
-      if (f0 + 2 >= nfl) wv.z = kPadCoord();
-      if (f0 + 3 >= nfl) wv.w = kPadCoord();
+      if (f0 + 0 >= end) wv.x = kPadCoord();
+      if (f0 + 1 >= end) wv.y = kPadCoord();
+      if (f0 + 2 >= end) wv.z = kPadCoord();
+      if (f0 + 3 >= end) wv.w = kPadCoord();
       sm.tile[e * 32 + lane] = wv;
     }
     __syncwarp();
   };
+  auto fetch = [&](int t, float4 (&v)[3]) { fetch_range(t, fl0, nfl, v); };
+  auto publish = [&](int t, const float4 (&v)[3]) { publish_range(t, fl0, nfl, v); };
 
   // ---- sweep 1: 32 class minima over the sampled references ---------------------------------------------------
   float mn[32];
@@ -460,9 +440,44 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
 #pragma unroll
     for (int o = 1; o < kSplit; ++o) overflow |= counts[o][lane] > kS2Cap;
   }
-  if (!live) return;
-  flags[(size_t)b * Q + q] = overflow ? 1 : 0;
-  if (overflow) return;
+  const size_t o = ((size_t)b * Q + q) * k;
+
+  // ---- overflowed lists (a pure rank-statistics tail once ties are capped: practically never) -----------------------
+  // Exact but slow: the warp sweeps the WHOLE cloud k more times and each overflowed lane picks, per sweep, the
+  // smallest (distance, index) above its previous pick.  All lanes keep staging tiles; only those lanes compute.
+  if (__any_sync(0xffffffffu, overflow)) {
+    const int all_tiles = (R + kS2Tile - 1) / kS2Tile;
+    float pd = -1.f;  // previous pick; distances are >= 0
+    int pi = -1;
+    for (int j = 0; j < k; ++j) {
+      float bd = kInf;
+      int bi = 0x7fffffff;
+      fetch_range(0, 0, 3 * R, nx);
+      for (int t = 0; t < all_tiles; ++t) {
+        publish_range(t, 0, 3 * R, nx);
+        if (t + 1 < all_tiles) fetch_range(t + 1, 0, 3 * R, nx);
+        if (overflow) {
+          const int tn = min(kS2Tile, R - t * kS2Tile);
+          for (int i = 0; i < tn; ++i) {
+            const float d = sqdist(qx, qy, qz, tf[3 * i], tf[3 * i + 1], tf[3 * i + 2]);
+            const int r = t * kS2Tile + i;
+            const bool after = d > pd || (d == pd && r > pi);
+            if (after && d < bd) {  // strict: the first (lowest-index) reference at the minimal distance stays
+              bd = d;
+              bi = r;
+            }
+          }
+        }
+      }
+      if (overflow && live) {
+        idx_out[o + j] = (int64_t)(bi == 0x7fffffff ? 0 : bi);
+        if (dist_out) dist_out[o + j] = bd;
+      }
+      pd = bd;
+      pi = bi;
+    }
+  }
+  if (!live || overflow) return;
 
   // ---- select: stable insert into a register-resident sorted list ---------------------------------------------------
   float td[kK];
@@ -498,7 +513,6 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
       sorted_insert<kK>(d, r, td, ti);
     }
   }
-  const size_t o = ((size_t)b * Q + q) * k;
 #pragma unroll
   for (int j = 0; j < kK; ++j) {
     if (j < k) {
@@ -509,10 +523,9 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
   }
 }
 
-// Reference-range splits for the list kernel: only when the query count cannot fill the machine on its own.  In that
-// mode a warp owns ONE query (8 per CTA) instead of four in turn.
+// Reference-range splits for the list kernel: only when the query count cannot fill the machine on its own.
 static int knn_r_splits(int B, int R, int Q) {
-  const long long ctas4 = (long long)B * ((Q + kKnnQueriesPerCta - 1) / kKnnQueriesPerCta);
+  const long long ctas4 = (long long)B * ((Q + 31) / 32);
   if (ctas4 >= 296 || R < 2 * kKnnTile) return 1;
   const long long ctas = (long long)B * ((Q + kKnnWarps - 1) / kKnnWarps);
   static long long target = 0;
@@ -555,79 +568,68 @@ static KnnPlan knn_plan(int B, int R, int Q, int k) {
 
 size_t knn_workspace_bytes(int B, int R, int Q, int k) {
   const KnnPlan plan = knn_plan(B, R, Q, k);
-  if (plan.select) return sizeof(int) * (size_t)B * Q;  // overflow flags
-  return plan.splits > 1 ? (sizeof(float) + sizeof(int)) * (size_t)B * Q * plan.splits * k : 0;
+  if (plan.select || plan.splits <= 1) return 0;
+  return (sizeof(float) + sizeof(int)) * (size_t)B * Q * plan.splits * k;  // per-slice lists for knn_merge_kernel
 }
 
 template <int kSlots>
 static void knn_list_launch(const float* ref, const float* qry, int B, int R, int Q, int k, int64_t* idx, float* dist,
-                            const int* flags, void* split_ws, int rs, cudaStream_t stream) {
-  if (rs > 1 && flags == nullptr && split_ws != nullptr) {
-    const int q_blocks = (Q + kKnnWarps - 1) / kKnnWarps;
+                            void* split_ws, int rs, cudaStream_t stream) {
+  const int q_blocks = (Q + kKnnWarps - 1) / kKnnWarps;
+  if (rs > 1 && split_ws != nullptr) {
     dim3 grid((unsigned)((long long)B * q_blocks), rs);
     float* pd = static_cast<float*>(split_ws);
     int* pi = reinterpret_cast<int*>(pd + (size_t)B * Q * rs * k);
-    knn_kernel<kSlots, 1><<<grid, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, nullptr, rs, pd, pi);
+    knn_kernel<kSlots><<<grid, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, rs, pd, pi);
     const long long nq = (long long)B * Q;
     knn_merge_kernel<kSlots><<<(unsigned)((nq + kKnnWarps - 1) / kKnnWarps), kKnnThreads, 0, stream>>>(pd, pi, nq, k, rs,
                                                                                                      idx, dist);
     count_launch(2);
-  } else if (flags == nullptr) {
-    // one query per warp (measured 10-15 % faster than four queries per warp in turn on every encoder shape)
-    const int q_blocks = (Q + kKnnWarps - 1) / kKnnWarps;
-    dim3 grid((unsigned)((long long)B * q_blocks), 1);
-    knn_kernel<kSlots, 1><<<grid, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, nullptr, 1, nullptr,
-                                                            nullptr);
-    count_launch();
   } else {
-    const int q_blocks = (Q + kKnnQueriesPerCta - 1) / kKnnQueriesPerCta;
     dim3 grid((unsigned)((long long)B * q_blocks), 1);
-    knn_kernel<kSlots, 4><<<grid, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, flags, 1, nullptr,
-                                                            nullptr);
+    knn_kernel<kSlots><<<grid, kKnnThreads, 0, stream>>>(ref, qry, R, Q, k, q_blocks, idx, dist, 1, nullptr, nullptr);
     count_launch();
   }
 }
 
 template <int kStride, int kK, int kSplit>
 static void knn_select_launch(const float* ref, const float* qry, int B, int R, int Q, int k, int64_t* idx, float* dist,
-                              int* flags, cudaStream_t stream) {
+                              cudaStream_t stream) {
   const int qb = (Q + 31) / 32;
   const int aligned = (reinterpret_cast<uintptr_t>(ref) % 16 == 0 && R % 4 == 0) ? 1 : 0;
   knn_select_kernel<kStride, kK, kSplit><<<(unsigned)((long long)B * qb), 32 * kSplit, 0, stream>>>(
-      ref, qry, R, Q, k, qb, aligned, idx, dist, flags);
+      ref, qry, R, Q, k, qb, aligned, idx, dist);
+  count_launch();
 }
 
 template <int kK>
 static void knn_select_dispatch(const float* ref, const float* qry, int B, int R, int Q, int k, int splits, int64_t* idx,
-                                float* dist, int* flags, cudaStream_t stream) {
+                                float* dist, cudaStream_t stream) {
   if (splits == 4)
-    knn_select_launch<1, kK, 4>(ref, qry, B, R, Q, k, idx, dist, flags, stream);
+    knn_select_launch<1, kK, 4>(ref, qry, B, R, Q, k, idx, dist, stream);
   else if (splits == 2)
-    knn_select_launch<1, kK, 2>(ref, qry, B, R, Q, k, idx, dist, flags, stream);
+    knn_select_launch<1, kK, 2>(ref, qry, B, R, Q, k, idx, dist, stream);
   else if (R >= 1024)  // sampled sweep 1 only where the slice is long enough to pay for the extra candidates
-    knn_select_launch<2, kK, 1>(ref, qry, B, R, Q, k, idx, dist, flags, stream);
+    knn_select_launch<2, kK, 1>(ref, qry, B, R, Q, k, idx, dist, stream);
   else
-    knn_select_launch<1, kK, 1>(ref, qry, B, R, Q, k, idx, dist, flags, stream);
+    knn_select_launch<1, kK, 1>(ref, qry, B, R, Q, k, idx, dist, stream);
 }
 
 int knn_launch(const float* ref, const float* qry, int B, int R, int Q, int k, int64_t* idx, float* dist,
                void* workspace, cudaStream_t stream) {
   const KnnPlan plan = knn_plan(B, R, Q, k);
-  if (plan.select && workspace != nullptr) {
-    int* flags = static_cast<int*>(workspace);
+  if (plan.select) {
     if (k <= 8)
-      knn_select_dispatch<8>(ref, qry, B, R, Q, k, plan.splits, idx, dist, flags, stream);
+      knn_select_dispatch<8>(ref, qry, B, R, Q, k, plan.splits, idx, dist, stream);
     else
-      knn_select_dispatch<16>(ref, qry, B, R, Q, k, plan.splits, idx, dist, flags, stream);
-    count_launch();
-    knn_list_launch<1>(ref, qry, B, R, Q, k, idx, dist, flags, nullptr, 1, stream);  // flagged queries only
+      knn_select_dispatch<16>(ref, qry, B, R, Q, k, plan.splits, idx, dist, stream);
     return (int)cudaGetLastError();
   }
-  const int rs = (plan.select || workspace == nullptr) ? 1 : plan.splits;
+  const int rs = workspace == nullptr ? 1 : plan.splits;
   if (k <= 32)
-    knn_list_launch<1>(ref, qry, B, R, Q, k, idx, dist, nullptr, workspace, rs, stream);
+    knn_list_launch<1>(ref, qry, B, R, Q, k, idx, dist, workspace, rs, stream);
   else
-    knn_list_launch<2>(ref, qry, B, R, Q, k, idx, dist, nullptr, workspace, rs, stream);
+    knn_list_launch<2>(ref, qry, B, R, Q, k, idx, dist, workspace, rs, stream);
   return (int)cudaGetLastError();
 }
 

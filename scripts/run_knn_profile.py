@@ -13,7 +13,7 @@ xyz = synthetic.pcn_partial(gt, 2048, 304).to(dev)
 c512 = misc.fps(xyz, 512)
 c64 = xyz[:, :64].contiguous()
 for _ in range(2):
-    knn_point(16, xyz, xyz)      # knn_select_kernel (+ flagged list pass)
+    knn_point(16, xyz, xyz)      # knn_select_kernel
     knn_point(16, xyz, c512)     # knn_kernel<1,4>
     knn_point(32, g, c64)        # knn_kernel<1,1> split + knn_merge_kernel
 torch.cuda.synchronize()

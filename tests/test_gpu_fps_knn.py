@@ -127,6 +127,35 @@ def test_knn_select_path_slices_and_ties(dev, B, R, Q, k, kind):
     _knn_check(xyz, new_xyz, k, dev)
 
 
+@pytest.mark.parametrize("B,R,Q,near", [
+    (64, 2048, 1024, "odd_groups"),   # one warp per 32 queries, sampled sweep: dense cluster hidden in the unsampled groups
+    (16, 1000, 512, "few_classes"),   # full sweep: the cluster sits in 4 of the 32 classes, the other minima are far
+    (8, 2048, 1024, "few_classes8"),  # 4 slices: 8 classes per slice hold 128 near references each
+])
+def test_knn_select_overflow_falls_back_exactly(dev, B, R, Q, near):
+    """Adversarial index layouts that leave the class-minima bound loose, so queries near the cluster collect more
+    than the 112-entry candidate list holds and take the in-kernel exact fallback; the other queries of the same
+    warps stay on the fast path.  Bit-exact against the oracle either way."""
+    g = torch.Generator().manual_seed(77 + R)
+    xyz = torch.rand((B, R, 3), generator=g) - 0.5
+    r = torch.arange(R)
+    if near == "odd_groups":
+        sel = ((r // 4) % 2 == 1) & (r < 1600)          # 800 references of the groups sweep 1 skips
+        sel &= torch.rand(R, generator=g) < 0.3          # ~240 of them
+    elif near == "few_classes":
+        sel = (r % 32) < 4                               # 125 references in classes 0..3
+    else:
+        sel = (r % 32) < 8                               # 128 per 512-reference slice
+    n = int(sel.sum())
+    centre = torch.tensor([0.31, -0.27, 0.11])
+    xyz[:, sel] = centre + (torch.rand((B, n, 3), generator=g) - 0.5) * 2e-3
+    new_xyz = torch.rand((B, Q, 3), generator=g) - 0.5
+    hot = torch.rand(Q, generator=g) < 0.1               # a few queries per warp sit inside the cluster
+    new_xyz[:, hot] = centre + (torch.rand((B, int(hot.sum()), 3), generator=g) - 0.5) * 2e-3
+    _knn_check(xyz, new_xyz, 16, dev)
+    _knn_check(xyz, new_xyz, 7, dev)
+
+
 def test_knn_zero_padded_and_grid_ties(dev):
     gt = synthetic.pcn_gt(2, 4096, 303)
     xyz = synthetic.pcn_partial(gt, 2048, 305)
