@@ -9,6 +9,7 @@
 // (stable counting sort of idx built once and shared by all C channels) - no floating-point atomics, whereas the
 // reference's index backward accumulates with atomicAdd in run-dependent order.
 #include <cstdint>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -160,6 +161,107 @@ __global__ void __launch_bounds__(256) inv_fill_kernel(const long long* __restri
   }
 }
 
+// Clouds with at most kInvCtaBins bins take ONE launch instead of the three above: a CTA owns the cloud, its warps
+// own consecutive slices of the positions.  Pass 1 counts into warp-private shared-memory histograms (order free);
+// a block scan turns the bin totals into start[] and each histogram into that warp's write cursors (slices in
+// position order, so the sort stays stable); pass 2 re-reads the keys in order and places them - same-bin hits inside
+// a 32-key step take consecutive slots in lane order.  Every key hits, so the match/ballot work that the 64-bin
+// kernel above repeats in 32 warps per cloud is done once: 142 us -> 9 us at 48 clouds x 32768 positions x 2048 bins.
+constexpr int kInvCtaBins = 2048;
+constexpr int kInvCtaBits = 11;  // log2(kInvCtaBins)
+constexpr int kInvCtaWarps = 16;
+constexpr int kInvCtaThreads = 32 * kInvCtaWarps;
+
+__global__ void __launch_bounds__(kInvCtaThreads) inv_index_cta_kernel(const long long* __restrict__ idx, long long L,
+                                                                       int Nk, int* __restrict__ start,
+                                                                       int* __restrict__ perm) {
+  extern __shared__ int inv_hist[];  // [kInvCtaWarps][Nk]
+  __shared__ int warp_tot[kInvCtaWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  const long long* key = idx + (size_t)b * L;
+  int* out = perm + (size_t)b * L;
+  int* st = start + (size_t)b * (Nk + 1);
+  int* mine = inv_hist + warp * Nk;
+  for (int i = threadIdx.x; i < kInvCtaWarps * Nk; i += kInvCtaThreads) inv_hist[i] = 0;
+  __syncthreads();
+  const long long chunk = ((L + kInvCtaWarps - 1) / kInvCtaWarps + 31) / 32 * 32;
+  const long long p_lo = min(L, warp * chunk), p_hi = min(L, p_lo + chunk);
+  const unsigned lt = (1u << lane) - 1u;
+  constexpr int kAhead = 16;  // keys in flight per lane: both passes are bound by the L2 round trip of the key loads
+  for (long long p0 = p_lo; p0 < p_hi; p0 += 32 * kAhead) {
+    int kk[kAhead];
+#pragma unroll
+    for (int e = 0; e < kAhead; ++e) {
+      const long long p = p0 + e * 32 + lane;
+      kk[e] = p < p_hi ? (int)__ldg(key + p) : -1;
+    }
+#pragma unroll
+    for (int e = 0; e < kAhead; ++e)
+      if (kk[e] >= 0) atomicAdd(mine + kk[e], 1);  // (ballot-aggregated plain adds measured slower: 64 vs 44 us)
+  }
+  __syncthreads();
+
+  // block exclusive scan over the bins; thread t owns bins [t*per, (t+1)*per)
+  const int per = (Nk + kInvCtaThreads - 1) / kInvCtaThreads;
+  const int j0 = min(Nk, (int)threadIdx.x * per), j1 = min(Nk, j0 + per);
+  int local = 0;
+  for (int j = j0; j < j1; ++j)
+    for (int w = 0; w < kInvCtaWarps; ++w) local += inv_hist[w * Nk + j];
+  int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  int base = incl - local;
+  for (int w = 0; w < warp; ++w) base += warp_tot[w];
+  for (int j = j0; j < j1; ++j) {
+    st[j] = base;
+    for (int w = 0; w < kInvCtaWarps; ++w) {  // histogram -> this warp's first slot for the bin
+      const int t = inv_hist[w * Nk + j];
+      inv_hist[w * Nk + j] = base;
+      base += t;
+    }
+  }
+  if (threadIdx.x == 0) st[Nk] = (int)L;
+  __syncthreads();
+
+  for (long long p0 = p_lo; p0 < p_hi; p0 += 32 * kAhead) {
+    int kk[kAhead];
+#pragma unroll
+    for (int e = 0; e < kAhead; ++e) {
+      const long long p = p0 + e * 32 + lane;
+      kk[e] = p < p_hi ? (int)__ldg(key + p) : -1;
+    }
+#pragma unroll
+    for (int e = 0; e < kAhead; ++e) {
+      const bool valid = kk[e] >= 0;
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      if (vmask == 0u) break;  // warp-uniform: the slice ended
+      const int bin = valid ? kk[e] : 0;
+      const int first = valid ? mine[bin] : 0;
+      __syncwarp();  // every peer has read the cursor before one of them advances it
+      // lanes holding the same bin: AND of one ballot per key bit (independent VOTEs; MATCH.ANY measured ~100 cycles
+      // per warp instruction and serialised the whole pass)
+      unsigned peers = vmask;
+#pragma unroll
+      for (int bit = 0; bit < kInvCtaBits; ++bit) {
+        const unsigned set = __ballot_sync(0xffffffffu, (bin >> bit) & 1);
+        peers &= ((bin >> bit) & 1) ? set : ~set;
+      }
+      if (valid) {
+        const int rank = __popc(peers & lt);
+        out[first + rank] = (int)(p0 + e * 32 + lane);
+        if (rank == __popc(peers) - 1) mine[bin] = first + rank + 1;  // the last peer advances the cursor
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // ---- backward ------------------------------------------------------------------------------------------------
 // grad_x_q[b,c,q] = sum_j (go[b,C+c,q,j] - go[b,c,q,j])       (fixed order over j)
 __global__ void __launch_bounds__(256) graph_feature_grad_q_kernel(const float* __restrict__ go, int C, int Nq, int k,
@@ -204,6 +306,287 @@ __global__ void __launch_bounds__(256) graph_feature_grad_k_kernel(const float* 
       if (pp[e] >= 0) s = __fadd_rn(s, v[e]);
   }
   gk[((size_t)b * C + c) * Nk + n] = s;
+}
+
+// Both gradients of one (cloud, channel) plane from ONE pass over grad_out's lower half.  The plane go[b,c,:,:] is
+// staged in shared memory in chunks of whole query rows (coalesced 128-bit loads); grad_x_k's owner threads then gather
+// their inverse lists from shared memory instead of issuing a 32-byte sector read per 4-byte element (the kernel above:
+// 96 us for a 50 MB half), and grad_x_q subtracts the staged row from the upper half streamed from global memory.
+// Summation orders are those of the two kernels above, so the results are bit-identical to them.
+constexpr int kSlabThreads = 512;
+constexpr int kSlabBinsPerThread = 4;                                 // Nk <= 2048
+constexpr int kSlabFloats = 16384;                                    // 64 KB per chunk: 3 CTAs per SM
+
+__global__ void __launch_bounds__(kSlabThreads, 2) graph_feature_grad_slab_kernel(
+    const float* __restrict__ go, const int* __restrict__ start, const int* __restrict__ perm, int C, int Nq, int Nk,
+    int k, int rows_per_chunk, float* __restrict__ gq, float* __restrict__ gk) {
+  extern __shared__ __align__(16) float slab[];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const long long L = (long long)Nq * k;
+  const float* lo = go + ((size_t)b * 2 * C + c) * L;
+  const float* hi = go + ((size_t)b * 2 * C + C + c) * L;
+  const int* st = start + (size_t)b * (Nk + 1);
+  const int* pm = perm + (size_t)b * L;
+  const bool vec = (k % 4 == 0) && (reinterpret_cast<uintptr_t>(go) % 16 == 0);  // then every row start is 16-byte aligned
+
+  int cur[kSlabBinsPerThread], end[kSlabBinsPerThread];
+  float acc[kSlabBinsPerThread];
+#pragma unroll
+  for (int u = 0; u < kSlabBinsPerThread; ++u) {
+    const int n = u * kSlabThreads + threadIdx.x;
+    cur[u] = (gk != nullptr && n < Nk) ? __ldg(st + n) : 0;
+    end[u] = (gk != nullptr && n < Nk) ? __ldg(st + n + 1) : 0;
+    acc[u] = 0.f;
+  }
+
+  for (int q0 = 0; q0 < Nq; q0 += rows_per_chunk) {
+    const int rows = min(rows_per_chunk, Nq - q0);
+    const int p0 = q0 * k, pn = rows * k;  // positions [p0, p0 + pn)
+    __syncthreads();                        // the previous chunk has been consumed
+    if (vec) {
+      const float4* src = reinterpret_cast<const float4*>(lo + p0);
+      float4* dst = reinterpret_cast<float4*>(slab);
+      const int nv = pn / 4;
+      for (int i0 = 0; i0 < nv; i0 += 4 * kSlabThreads) {  // 4 independent 128-bit loads per thread before the stores
+        float4 v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = i0 + e * kSlabThreads + threadIdx.x;
+          if (i < nv) v[e] = __ldg(src + i);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = i0 + e * kSlabThreads + threadIdx.x;
+          if (i < nv) dst[i] = v[e];
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < pn; i += kSlabThreads) slab[i] = __ldg(lo + p0 + i);
+    }
+    // grad_x_q's upper-half rows are requested before the barrier so they travel while the slab settles
+    constexpr int kRowsAhead = 2;
+    float4 hrow[kRowsAhead][4];
+    const bool q_fast = gq != nullptr && vec && k == 16 && rows <= kRowsAhead * kSlabThreads;
+    if (q_fast) {
+#pragma unroll
+      for (int u = 0; u < kRowsAhead; ++u) {
+        const int r = u * kSlabThreads + threadIdx.x;
+        if (r < rows) {
+          const float4* h = reinterpret_cast<const float4*>(hi + (size_t)p0 + (size_t)r * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hrow[u][j] = __ldg(h + j);
+        }
+      }
+    }
+    __syncthreads();
+    if (gk != nullptr) {
+      // Inverse lists are ascending positions: each round asks for the next 4 entries of all this thread's bins
+      // (16 independent loads), then adds, in list order, those that fall inside the chunk.
+      bool more = true;
+      while (more) {
+        int pp[kSlabBinsPerThread][4];
+#pragma unroll
+        for (int u = 0; u < kSlabBinsPerThread; ++u)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pp[u][e] = (cur[u] + e < end[u]) ? __ldg(pm + cur[u] + e) - p0 : pn;
+        more = false;
+#pragma unroll
+        for (int u = 0; u < kSlabBinsPerThread; ++u) {
+          int took = 0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (pp[u][e] < pn && took == e) {
+              acc[u] = __fadd_rn(acc[u], slab[pp[u][e]]);
+              ++took;
+            }
+          }
+          cur[u] += took;
+          more |= took == 4;
+        }
+      }
+    }
+    if (q_fast) {
+#pragma unroll
+      for (int u = 0; u < kRowsAhead; ++u) {
+        const int r = u * kSlabThreads + threadIdx.x;
+        if (r < rows) {
+          const float4* l = reinterpret_cast<const float4*>(slab + (size_t)r * 16);
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 hv = hrow[u][j], lv = l[j];
+            s = __fadd_rn(s, __fsub_rn(hv.x, lv.x));
+            s = __fadd_rn(s, __fsub_rn(hv.y, lv.y));
+            s = __fadd_rn(s, __fsub_rn(hv.z, lv.z));
+            s = __fadd_rn(s, __fsub_rn(hv.w, lv.w));
+          }
+          gq[((size_t)b * C + c) * Nq + q0 + r] = s;
+        }
+      }
+    } else if (gq != nullptr) {
+      for (int r = threadIdx.x; r < rows; r += kSlabThreads) {
+        const float* h = hi + (size_t)(p0 + (size_t)r * k);
+        const float* l = slab + (size_t)r * k;
+        float s = 0.f;
+        if (vec) {
+          for (int j = 0; j < k; j += 4) {
+            const float4 hv = __ldg(reinterpret_cast<const float4*>(h + j));
+            const float4 lv = *reinterpret_cast<const float4*>(l + j);
+            s = __fadd_rn(s, __fsub_rn(hv.x, lv.x));
+            s = __fadd_rn(s, __fsub_rn(hv.y, lv.y));
+            s = __fadd_rn(s, __fsub_rn(hv.z, lv.z));
+            s = __fadd_rn(s, __fsub_rn(hv.w, lv.w));
+          }
+        } else {
+          for (int j = 0; j < k; ++j) s = __fadd_rn(s, __fsub_rn(__ldg(h + j), l[j]));
+        }
+        gq[((size_t)b * C + c) * Nq + q0 + r] = s;
+      }
+    }
+  }
+  if (gk != nullptr) {
+#pragma unroll
+    for (int u = 0; u < kSlabBinsPerThread; ++u) {
+      const int n = u * kSlabThreads + threadIdx.x;
+      if (n < Nk) gk[((size_t)b * C + c) * Nk + n] = acc[u];
+    }
+  }
+}
+
+// ---- whole-plane variant: one bulk (TMA) copy instead of register-staged loads ------------------------------------
+// When a (cloud, channel) plane of grad_out's lower half fits in shared memory (L <= 49152 floats: every DGCNN grouper
+// shape), thread 0 issues cp.async.bulk copies of the plane against an mbarrier and the CTA spends the flight time
+// fetching its inverse-list heads; after the wait, grad_x_k gathers from shared memory and grad_x_q streams the upper
+// half.  No chunk loop, no cursors, no register staging; same summation orders as above (bit-identical results).
+constexpr int kPlaneBins = 2;          // bins per thread: Nk <= 2 * threads, threads in {256, 512, 1024}
+constexpr int kPlaneHead = 12;         // inverse-list entries fetched during the copy (mean list length = k)
+constexpr int kPlaneMaxFloats = 49152; // 192 KB
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int kPlaneThreads>
+__global__ void __launch_bounds__(kPlaneThreads, 1024 / kPlaneThreads) graph_feature_grad_plane_kernel(
+    const float* __restrict__ go, const int* __restrict__ start, const int* __restrict__ perm, int C, int Nq, int Nk,
+    int k, float* __restrict__ gq, float* __restrict__ gk) {
+  extern __shared__ __align__(128) float plane[];
+  __shared__ __align__(8) unsigned long long bar;
+  const int c = blockIdx.x, b = blockIdx.y;
+  const int L = Nq * k;
+  const float* lo = go + ((size_t)b * 2 * C + c) * L;
+  const float* hi = go + ((size_t)b * 2 * C + C + c) * L;
+  const int* st = start + (size_t)b * (Nk + 1);
+  const int* pm = perm + (size_t)b * L;
+
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned bytes = (unsigned)L * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
+    for (unsigned off = 0; off < bytes; off += 32768u) {
+      const unsigned n = min(32768u, bytes - off);
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(reinterpret_cast<const char*>(plane) + off)),
+          "l"(reinterpret_cast<const char*>(lo) + off), "r"(n), "r"(smem_u32(&bar))
+          : "memory");
+    }
+  }
+
+  // while the plane travels: the heads of this thread's inverse lists
+  int s0[kPlaneBins], s1[kPlaneBins], head[kPlaneBins][kPlaneHead];
+#pragma unroll
+  for (int u = 0; u < kPlaneBins; ++u) {
+    const int n = u * kPlaneThreads + threadIdx.x;
+    const bool on = gk != nullptr && n < Nk;
+    s0[u] = on ? __ldg(st + n) : 0;
+    s1[u] = on ? __ldg(st + n + 1) : 0;
+  }
+#pragma unroll
+  for (int u = 0; u < kPlaneBins; ++u)
+#pragma unroll
+    for (int e = 0; e < kPlaneHead; ++e) head[u][e] = (s0[u] + e < s1[u]) ? __ldg(pm + s0[u] + e) : -1;
+
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(&bar))
+        : "memory");
+  }
+
+  if (gk != nullptr) {
+#pragma unroll
+    for (int u = 0; u < kPlaneBins; ++u) {
+      const int n = u * kPlaneThreads + threadIdx.x;
+      float acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < kPlaneHead; ++e)
+        if (head[u][e] >= 0) acc = __fadd_rn(acc, plane[head[u][e]]);
+      for (int i0 = s0[u] + kPlaneHead; i0 < s1[u]; i0 += 8) {  // the tail of a longer list, 8 entries per round
+        int pp[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pp[e] = (i0 + e < s1[u]) ? __ldg(pm + i0 + e) : -1;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (pp[e] >= 0) acc = __fadd_rn(acc, plane[pp[e]]);
+      }
+      if (n < Nk) gk[((size_t)b * C + c) * Nk + n] = acc;
+    }
+  }
+  if (gq != nullptr) {
+    for (int r0 = 0; r0 < Nq; r0 += 2 * kPlaneThreads) {
+      if (k == 16) {  // the grouper's k: both rows of this thread requested before either is consumed
+        float4 hv[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int r = r0 + u * kPlaneThreads + threadIdx.x;
+          if (r < Nq) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hv[u][j] = __ldg(reinterpret_cast<const float4*>(hi + (size_t)r * 16) + j);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int r = r0 + u * kPlaneThreads + threadIdx.x;
+          if (r < Nq) {
+            const float4* l = reinterpret_cast<const float4*>(plane + (size_t)r * 16);
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 lv = l[j];
+              s = __fadd_rn(s, __fsub_rn(hv[u][j].x, lv.x));
+              s = __fadd_rn(s, __fsub_rn(hv[u][j].y, lv.y));
+              s = __fadd_rn(s, __fsub_rn(hv[u][j].z, lv.z));
+              s = __fadd_rn(s, __fsub_rn(hv[u][j].w, lv.w));
+            }
+            gq[((size_t)b * C + c) * Nq + r] = s;
+          }
+        }
+      } else {
+        for (int u = 0; u < 2; ++u) {
+          const int r = r0 + u * kPlaneThreads + threadIdx.x;
+          if (r < Nq) {
+            const float* h = hi + (size_t)r * k;
+            const float* l = plane + (size_t)r * k;
+            float s = 0.f;
+            for (int j = 0; j < k; j += 4) {
+              const float4 hv = __ldg(reinterpret_cast<const float4*>(h + j));
+              const float4 lv = *reinterpret_cast<const float4*>(l + j);
+              s = __fadd_rn(s, __fsub_rn(hv.x, lv.x));
+              s = __fadd_rn(s, __fsub_rn(hv.y, lv.y));
+              s = __fadd_rn(s, __fsub_rn(hv.z, lv.z));
+              s = __fadd_rn(s, __fsub_rn(hv.w, lv.w));
+            }
+            gq[((size_t)b * C + c) * Nq + r] = s;
+          }
+        }
+      }
+    }
+  }
 }
 
 // ---- grouped gathers for the remaining pointnet2_ops entry points ---------------------
@@ -322,27 +705,91 @@ size_t graph_feature_grad_workspace_bytes(int B, int Nq, int Nk, int k) {
   return sizeof(int) * ((size_t)B * (Nk + 1) + (size_t)B * Nq * k);
 }
 
+// start[b, 0..Nk] and perm[b, 0..L): one launch when a CTA can hold the cloud's histograms, else count / scan / fill.
+static int inverse_index_launch(const long long* idx, int B, long long L, int Nk, int* start, int* perm,
+                                cudaStream_t stream) {
+  static const bool force3 = [] { const char* e = std::getenv("IAPT_INV_INDEX_3PASS"); return e && e[0] == '1'; }();
+  if (Nk <= kInvCtaBins && !force3) {
+    const size_t smem = sizeof(int) * (size_t)kInvCtaWarps * Nk;
+    static PerDeviceOnce once;
+    if (once.pending()) {
+      cudaFuncSetAttribute(inv_index_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(sizeof(int) * kInvCtaWarps * kInvCtaBins));
+      once.done();
+    }
+    inv_index_cta_kernel<<<B, kInvCtaThreads, smem, stream>>>(idx, L, Nk, start, perm);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
+  cudaError_t err;
+  if ((err = cudaMemsetAsync(start, 0, sizeof(int) * (size_t)B * (Nk + 1), stream)) != cudaSuccess) return (int)err;
+  dim3 gc((unsigned)grid1d(L, 256, 64), B);
+  inv_count_kernel<<<gc, 256, 0, stream>>>(idx, L, Nk, start);
+  inv_scan_kernel<<<B, 1024, 0, stream>>>(start, Nk);
+  dim3 gf((Nk + 8 * kInvBins - 1) / (8 * kInvBins), B);
+  inv_fill_kernel<<<gf, 256, 0, stream>>>(idx, L, Nk, start, perm);
+  count_launch(3);
+  return (int)cudaGetLastError();
+}
+
 int graph_feature_grad_launch(const float* go, const long long* idx, int B, int C, int Nq, int Nk, int k, float* gq,
                               float* gk, void* workspace, cudaStream_t stream) {
   const long long L = (long long)Nq * k;
   int* start = static_cast<int*>(workspace);
   int* perm = start + (size_t)B * (Nk + 1);
-  cudaError_t err;
+  static const bool no_slab = [] { const char* e = std::getenv("IAPT_GRAPH_GRAD_SLAB"); return e && e[0] == '0'; }();
+  if (gk) {
+    const int rc = inverse_index_launch(idx, B, L, Nk, start, perm, stream);
+    if (rc != 0) return rc;
+  }
+  static const bool no_plane = [] { const char* e = std::getenv("IAPT_GRAPH_GRAD_PLANE"); return e && e[0] == '0'; }();
+  if (!no_plane && !no_slab && Nk <= 1024 * kPlaneBins && L <= kPlaneMaxFloats && k % 4 == 0 &&
+      reinterpret_cast<uintptr_t>(go) % 16 == 0) {
+    static PerDeviceOnce once;
+    if (once.pending()) {
+      const int max_smem = (int)(sizeof(float) * kPlaneMaxFloats);
+      cudaFuncSetAttribute(graph_feature_grad_plane_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      cudaFuncSetAttribute(graph_feature_grad_plane_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      cudaFuncSetAttribute(graph_feature_grad_plane_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      once.done();
+    }
+    // smallest CTA that still gives every thread at most 2 bins and 2 query rows: small planes then run several
+    // CTAs per SM, which is what hides their copy and list latencies
+    const int need = max((Nk + kPlaneBins - 1) / kPlaneBins, (Nq + 1) / 2);
+    const dim3 grid(C, B);
+    const size_t smem = sizeof(float) * (size_t)L;
+    if (need <= 256)
+      graph_feature_grad_plane_kernel<256><<<grid, 256, smem, stream>>>(go, start, perm, C, Nq, Nk, k, gq, gk);
+    else if (need <= 512)
+      graph_feature_grad_plane_kernel<512><<<grid, 512, smem, stream>>>(go, start, perm, C, Nq, Nk, k, gq, gk);
+    else
+      graph_feature_grad_plane_kernel<1024><<<grid, 1024, smem, stream>>>(go, start, perm, C, Nq, Nk, k, gq, gk);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
+  if (!no_slab && Nk <= kSlabThreads * kSlabBinsPerThread && k <= kSlabFloats && L < (1LL << 31)) {
+    const int rows = min(Nq, kSlabFloats / k);
+    static PerDeviceOnce once;
+    if (once.pending()) {
+      cudaFuncSetAttribute(graph_feature_grad_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(sizeof(float) * kSlabFloats));
+      once.done();
+    }
+    dim3 grid(C, B);
+    graph_feature_grad_slab_kernel<<<grid, kSlabThreads, sizeof(float) * (size_t)rows * k, stream>>>(
+        go, start, perm, C, Nq, Nk, k, rows, gq, gk);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   if (gq) {
     const long long total = (long long)B * C * Nq;
     graph_feature_grad_q_kernel<<<grid1d(total, 256), 256, 0, stream>>>(go, C, Nq, k, gq, total);
     count_launch();
   }
   if (gk) {
-    if ((err = cudaMemsetAsync(start, 0, sizeof(int) * (size_t)B * (Nk + 1), stream)) != cudaSuccess) return (int)err;
-    dim3 gc((unsigned)grid1d(L, 256, 64), B);
-    inv_count_kernel<<<gc, 256, 0, stream>>>(idx, L, Nk, start);
-    inv_scan_kernel<<<B, 1024, 0, stream>>>(start, Nk);
-    dim3 gf((Nk + 8 * kInvBins - 1) / (8 * kInvBins), B);
-    inv_fill_kernel<<<gf, 256, 0, stream>>>(idx, L, Nk, start, perm);
     dim3 gg((Nk + 255) / 256, C, B);
     graph_feature_grad_k_kernel<<<gg, 256, 0, stream>>>(go, start, perm, C, L, Nk, gk);
-    count_launch(4);
+    count_launch();
   }
   return (int)cudaGetLastError();
 }
@@ -360,16 +807,11 @@ int group_gather_grad_launch(const float* go, const long long* idx, const float*
   const long long L = (long long)P * S;
   int* start = static_cast<int*>(workspace);
   int* perm = start + (size_t)B * (M + 1);
-  cudaError_t err;
-  if ((err = cudaMemsetAsync(start, 0, sizeof(int) * (size_t)B * (M + 1), stream)) != cudaSuccess) return (int)err;
-  dim3 gc((unsigned)grid1d(L, 256, 64), B);
-  inv_count_kernel<<<gc, 256, 0, stream>>>(idx, L, M, start);
-  inv_scan_kernel<<<B, 1024, 0, stream>>>(start, M);
-  dim3 gfill((M + 8 * kInvBins - 1) / (8 * kInvBins), B);
-  inv_fill_kernel<<<gfill, 256, 0, stream>>>(idx, L, M, start, perm);
+  const int rc = inverse_index_launch(idx, B, L, M, start, perm, stream);
+  if (rc != 0) return rc;
   dim3 gg((M + 255) / 256, C, B);
   group_gather_grad_kernel<<<gg, 256, 0, stream>>>(go, start, perm, w, C, L, S, reduce, M, gf);
-  count_launch(4);
+  count_launch();
   return (int)cudaGetLastError();
 }
 
