@@ -308,156 +308,14 @@ __global__ void __launch_bounds__(256) graph_feature_grad_k_kernel(const float* 
   gk[((size_t)b * C + c) * Nk + n] = s;
 }
 
-// Both gradients of one (cloud, channel) plane from ONE pass over grad_out's lower half.  The plane go[b,c,:,:] is
-// staged in shared memory in chunks of whole query rows (coalesced 128-bit loads); grad_x_k's owner threads then gather
-// their inverse lists from shared memory instead of issuing a 32-byte sector read per 4-byte element (the kernel above:
-// 96 us for a 50 MB half), and grad_x_q subtracts the staged row from the upper half streamed from global memory.
-// Summation orders are those of the two kernels above, so the results are bit-identical to them.
-constexpr int kSlabThreads = 512;
-constexpr int kSlabBinsPerThread = 4;                                 // Nk <= 2048
-constexpr int kSlabFloats = 16384;                                    // 64 KB per chunk: 3 CTAs per SM
-
-__global__ void __launch_bounds__(kSlabThreads, 2) graph_feature_grad_slab_kernel(
-    const float* __restrict__ go, const int* __restrict__ start, const int* __restrict__ perm, int C, int Nq, int Nk,
-    int k, int rows_per_chunk, float* __restrict__ gq, float* __restrict__ gk) {
-  extern __shared__ __align__(16) float slab[];
-  const int c = blockIdx.x, b = blockIdx.y;
-  const long long L = (long long)Nq * k;
-  const float* lo = go + ((size_t)b * 2 * C + c) * L;
-  const float* hi = go + ((size_t)b * 2 * C + C + c) * L;
-  const int* st = start + (size_t)b * (Nk + 1);
-  const int* pm = perm + (size_t)b * L;
-  const bool vec = (k % 4 == 0) && (reinterpret_cast<uintptr_t>(go) % 16 == 0);  // then every row start is 16-byte aligned
-
-  int cur[kSlabBinsPerThread], end[kSlabBinsPerThread];
-  float acc[kSlabBinsPerThread];
-#pragma unroll
-  for (int u = 0; u < kSlabBinsPerThread; ++u) {
-    const int n = u * kSlabThreads + threadIdx.x;
-    cur[u] = (gk != nullptr && n < Nk) ? __ldg(st + n) : 0;
-    end[u] = (gk != nullptr && n < Nk) ? __ldg(st + n + 1) : 0;
-    acc[u] = 0.f;
-  }
-
-  for (int q0 = 0; q0 < Nq; q0 += rows_per_chunk) {
-    const int rows = min(rows_per_chunk, Nq - q0);
-    const int p0 = q0 * k, pn = rows * k;  // positions [p0, p0 + pn)
-    __syncthreads();                        // the previous chunk has been consumed
-    if (vec) {
-      const float4* src = reinterpret_cast<const float4*>(lo + p0);
-      float4* dst = reinterpret_cast<float4*>(slab);
-      const int nv = pn / 4;
-      for (int i0 = 0; i0 < nv; i0 += 4 * kSlabThreads) {  // 4 independent 128-bit loads per thread before the stores
-        float4 v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = i0 + e * kSlabThreads + threadIdx.x;
-          if (i < nv) v[e] = __ldg(src + i);
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = i0 + e * kSlabThreads + threadIdx.x;
-          if (i < nv) dst[i] = v[e];
-        }
-      }
-    } else {
-      for (int i = threadIdx.x; i < pn; i += kSlabThreads) slab[i] = __ldg(lo + p0 + i);
-    }
-    // grad_x_q's upper-half rows are requested before the barrier so they travel while the slab settles
-    constexpr int kRowsAhead = 2;
-    float4 hrow[kRowsAhead][4];
-    const bool q_fast = gq != nullptr && vec && k == 16 && rows <= kRowsAhead * kSlabThreads;
-    if (q_fast) {
-#pragma unroll
-      for (int u = 0; u < kRowsAhead; ++u) {
-        const int r = u * kSlabThreads + threadIdx.x;
-        if (r < rows) {
-          const float4* h = reinterpret_cast<const float4*>(hi + (size_t)p0 + (size_t)r * 16);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) hrow[u][j] = __ldg(h + j);
-        }
-      }
-    }
-    __syncthreads();
-    if (gk != nullptr) {
-      // Inverse lists are ascending positions: each round asks for the next 4 entries of all this thread's bins
-      // (16 independent loads), then adds, in list order, those that fall inside the chunk.
-      bool more = true;
-      while (more) {
-        int pp[kSlabBinsPerThread][4];
-#pragma unroll
-        for (int u = 0; u < kSlabBinsPerThread; ++u)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) pp[u][e] = (cur[u] + e < end[u]) ? __ldg(pm + cur[u] + e) - p0 : pn;
-        more = false;
-#pragma unroll
-        for (int u = 0; u < kSlabBinsPerThread; ++u) {
-          int took = 0;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (pp[u][e] < pn && took == e) {
-              acc[u] = __fadd_rn(acc[u], slab[pp[u][e]]);
-              ++took;
-            }
-          }
-          cur[u] += took;
-          more |= took == 4;
-        }
-      }
-    }
-    if (q_fast) {
-#pragma unroll
-      for (int u = 0; u < kRowsAhead; ++u) {
-        const int r = u * kSlabThreads + threadIdx.x;
-        if (r < rows) {
-          const float4* l = reinterpret_cast<const float4*>(slab + (size_t)r * 16);
-          float s = 0.f;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 hv = hrow[u][j], lv = l[j];
-            s = __fadd_rn(s, __fsub_rn(hv.x, lv.x));
-            s = __fadd_rn(s, __fsub_rn(hv.y, lv.y));
-            s = __fadd_rn(s, __fsub_rn(hv.z, lv.z));
-            s = __fadd_rn(s, __fsub_rn(hv.w, lv.w));
-          }
-          gq[((size_t)b * C + c) * Nq + q0 + r] = s;
-        }
-      }
-    } else if (gq != nullptr) {
-      for (int r = threadIdx.x; r < rows; r += kSlabThreads) {
-        const float* h = hi + (size_t)(p0 + (size_t)r * k);
-        const float* l = slab + (size_t)r * k;
-        float s = 0.f;
-        if (vec) {
-          for (int j = 0; j < k; j += 4) {
-            const float4 hv = __ldg(reinterpret_cast<const float4*>(h + j));
-            const float4 lv = *reinterpret_cast<const float4*>(l + j);
-            s = __fadd_rn(s, __fsub_rn(hv.x, lv.x));
-            s = __fadd_rn(s, __fsub_rn(hv.y, lv.y));
-            s = __fadd_rn(s, __fsub_rn(hv.z, lv.z));
-            s = __fadd_rn(s, __fsub_rn(hv.w, lv.w));
-          }
-        } else {
-          for (int j = 0; j < k; ++j) s = __fadd_rn(s, __fsub_rn(__ldg(h + j), l[j]));
-        }
-        gq[((size_t)b * C + c) * Nq + q0 + r] = s;
-      }
-    }
-  }
-  if (gk != nullptr) {
-#pragma unroll
-    for (int u = 0; u < kSlabBinsPerThread; ++u) {
-      const int n = u * kSlabThreads + threadIdx.x;
-      if (n < Nk) gk[((size_t)b * C + c) * Nk + n] = acc[u];
-    }
-  }
-}
-
-// ---- whole-plane variant: one bulk (TMA) copy instead of register-staged loads ------------------------------------
-// When a (cloud, channel) plane of grad_out's lower half fits in shared memory (L <= 49152 floats: every DGCNN grouper
-// shape), thread 0 issues cp.async.bulk copies of the plane against an mbarrier and the CTA spends the flight time
-// fetching its inverse-list heads; after the wait, grad_x_k gathers from shared memory and grad_x_q streams the upper
-// half.  No chunk loop, no cursors, no register staging; same summation orders as above (bit-identical results).
+// ---- both gradients of one (cloud, channel) plane from ONE pass over grad_out's lower half ------------------------
+// When the plane go[b,c,:,:] fits in shared memory (L <= 49152 floats: every DGCNN grouper shape), thread 0 issues
+// cp.async.bulk (TMA) copies of it against an mbarrier and the CTA spends the flight time fetching the heads of its
+// inverse lists.  After the wait grad_x_k's owner threads gather from shared memory - instead of one 32-byte sector
+// read per 4-byte element, the kernel above - and grad_x_q subtracts the staged rows from the upper half streamed
+// from global memory.  Same summation orders as the two kernels above, so the results are bit-identical to them.
+// (A register-staged LDG -> STS version with a chunk loop measured 2x slower than this: every dependent round trip
+// to L2 costs ~1 us here.)
 constexpr int kPlaneBins = 2;          // bins per thread: Nk <= 2 * threads, threads in {256, 512, 1024}
 constexpr int kPlaneHead = 12;         // inverse-list entries fetched during the copy (mean list length = k)
 constexpr int kPlaneMaxFloats = 49152; // 192 KB
@@ -737,13 +595,12 @@ int graph_feature_grad_launch(const float* go, const long long* idx, int B, int 
   const long long L = (long long)Nq * k;
   int* start = static_cast<int*>(workspace);
   int* perm = start + (size_t)B * (Nk + 1);
-  static const bool no_slab = [] { const char* e = std::getenv("IAPT_GRAPH_GRAD_SLAB"); return e && e[0] == '0'; }();
   if (gk) {
     const int rc = inverse_index_launch(idx, B, L, Nk, start, perm, stream);
     if (rc != 0) return rc;
   }
   static const bool no_plane = [] { const char* e = std::getenv("IAPT_GRAPH_GRAD_PLANE"); return e && e[0] == '0'; }();
-  if (!no_plane && !no_slab && Nk <= 1024 * kPlaneBins && L <= kPlaneMaxFloats && k % 4 == 0 &&
+  if (!no_plane && Nk <= 1024 * kPlaneBins && L <= kPlaneMaxFloats && k % 4 == 0 &&
       reinterpret_cast<uintptr_t>(go) % 16 == 0) {
     static PerDeviceOnce once;
     if (once.pending()) {
@@ -764,20 +621,6 @@ int graph_feature_grad_launch(const float* go, const long long* idx, int B, int 
       graph_feature_grad_plane_kernel<512><<<grid, 512, smem, stream>>>(go, start, perm, C, Nq, Nk, k, gq, gk);
     else
       graph_feature_grad_plane_kernel<1024><<<grid, 1024, smem, stream>>>(go, start, perm, C, Nq, Nk, k, gq, gk);
-    count_launch();
-    return (int)cudaGetLastError();
-  }
-  if (!no_slab && Nk <= kSlabThreads * kSlabBinsPerThread && k <= kSlabFloats && L < (1LL << 31)) {
-    const int rows = min(Nq, kSlabFloats / k);
-    static PerDeviceOnce once;
-    if (once.pending()) {
-      cudaFuncSetAttribute(graph_feature_grad_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(sizeof(float) * kSlabFloats));
-      once.done();
-    }
-    dim3 grid(C, B);
-    graph_feature_grad_slab_kernel<<<grid, kSlabThreads, sizeof(float) * (size_t)rows * k, stream>>>(
-        go, start, perm, C, Nq, Nk, k, rows, gq, gk);
     count_launch();
     return (int)cudaGetLastError();
   }

@@ -68,6 +68,44 @@ def test_get_graph_feature_end_to_end_and_determinism(dev):
     assert float((grads[0][1] - b.grad).abs().max()) <= 1e-5 * float(b.grad.abs().max())
 
 
+@pytest.mark.parametrize("B,C,Nk,Nq,k", [
+    (3, 5, 300, 200, 16),     # whole-plane kernel, 256-thread CTAs
+    (3, 6, 1000, 700, 8),     # 512-thread CTAs
+    (2, 4, 2048, 2048, 16),   # 1024-thread CTAs, 128 KB plane
+    (2, 3, 2048, 3000, 16),   # plane of 48000 floats: the largest that still fits
+    (2, 3, 1500, 3200, 16),   # plane too large: separate grad_q / grad_k kernels, one-launch inverse index
+    (2, 3, 700, 300, 5),      # k not a multiple of 4: separate kernels
+    (2, 3, 3000, 500, 12),    # more than 2048 bins: count / scan / fill inverse index
+])
+def test_graph_feature_backward_every_kernel_path(dev, B, C, Nk, Nq, k):
+    """grad_x_q / grad_x_k against float64 autograd of the torch restatement, and bit-reproducible, on every dispatch
+    branch of iapt_graph_feature_grad (graph.cu: graph_feature_grad_launch / inverse_index_launch)."""
+    g = torch.Generator().manual_seed(100 + Nk + Nq)
+    x_k = torch.randn((B, C, Nk), generator=g).to(dev)
+    x_q = torch.randn((B, C, Nq), generator=g).to(dev)
+    idx = torch.randint(0, Nk, (B, Nq, k), generator=g).to(dev)
+    idx[:, : Nq // 4] = idx[:, :1]  # heavy fan-in: a quarter of the queries share one neighbour list
+    go = torch.randn((B, 2 * C, Nq, k), generator=g).to(dev)
+    runs = []
+    for _ in range(2):
+        a, b = x_q.clone().requires_grad_(True), x_k.clone().requires_grad_(True)
+        bb.graph_feature(a, b, idx).backward(go)
+        runs.append((a.grad.clone(), b.grad.clone()))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    a, b = x_q.double().requires_grad_(True), x_k.double().requires_grad_(True)
+    feat = torch.gather(b.unsqueeze(2).expand(B, C, Nq, Nk), 3, idx.unsqueeze(1).expand(B, C, Nq, k))
+    torch.cat((feat - a.unsqueeze(-1), a.unsqueeze(-1).expand(B, C, Nq, k)), 1).backward(go.double())
+    for got, want in ((runs[0][0], a.grad), (runs[0][1], b.grad)):
+        assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    # only one of the two gradients requested
+    a = x_q.clone().requires_grad_(True)
+    bb.graph_feature(a, x_k, idx).backward(go)
+    assert torch.equal(a.grad, runs[0][0])
+    b = x_k.clone().requires_grad_(True)
+    bb.graph_feature(x_q, b, idx).backward(go)
+    assert torch.equal(b.grad, runs[0][1])
+
+
 def test_fps_downsample_matches_reference_golden(dev):
     z = np.load(GOLD)
     nc, nx = bb.fps_downsample(_t(z, "fd_coor", dev), _t(z, "fd_x", dev), z["fd_new_coor"].shape[-1])
