@@ -71,4 +71,10 @@ def patch_reference_modules() -> list:
                     continue
                 setattr(mod, attr, new)
                 patched.append(f"{name}.{attr}")
+    ref_p3d = sys.modules.get("utils.from_pytorch3d")
+    if ref_p3d is not None:  # the vendored copy calls knn_points without defining it (utils/from_pytorch3d.py:76)
+        from .utils import from_pytorch3d as p3d
+
+        ref_p3d.knn_points = p3d.knn_points
+        patched.append("utils.from_pytorch3d.knn_points")
     return patched

@@ -237,3 +237,20 @@ def test_snowflake_query_knn(dev):
         D = oracle.torch_formulation.square_distance(q.double(), xyz.double())
         want = torch.argsort(D, dim=-1)[:, :, pad:16 + pad].int()
         assert got.dtype == torch.int32 and torch.equal(got, want)
+
+
+def test_pytorch3d_knn_points_shim(dev):
+    """K = 30 neighbourhoods as the reference's normal estimation asks for them (pctransformer.py:176)."""
+    from imgadapointr_b200.utils.from_pytorch3d import knn_points
+    xyz = synthetic.uniform(3, 700, 41)
+    x = xyz.to(dev)
+    out = knn_points(x, x, lengths1=torch.full((3,), 700), lengths2=torch.full((3,), 700), K=30, return_nn=True)
+    oi, od = oracle.knn(30, xyz.numpy(), xyz.numpy())
+    assert np.array_equal(out.idx.cpu().numpy(), oi) and np.array_equal(out.dists.cpu().numpy(), od)
+    want_nn = np.take_along_axis(xyz.numpy()[:, None], oi[..., None], axis=2)
+    assert out.knn.shape == (3, 700, 30, 3) and np.array_equal(out.knn.cpu().numpy(), want_nn)
+    D = torch.cdist(xyz.double(), xyz.double()) ** 2
+    assert torch.allclose(out.dists.cpu().double(), torch.sort(D, dim=-1).values[..., :30], atol=1e-6)
+    assert knn_points(x, x[:, :100].contiguous(), K=1).knn is None
+    with pytest.raises(NotImplementedError):
+        knn_points(x, x, lengths1=torch.tensor([700, 650, 700]), K=3)
