@@ -1,0 +1,83 @@
+"""Randomised parity sweep on the GPU against the CPU oracle (tests infrastructure, not product code):
+random batch / cloud sizes, duplicates, zero padding and exact-tie grids through chamfer forward / backward, FPS, kNN
+and graph-feature backward.  Usage: python scripts/fuzz_parity.py [seconds] [seed]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import oracle
+from imgadapointr_b200 import chamfer
+from imgadapointr_b200.models import base_blocks as bb
+from imgadapointr_b200.models.Transformer_utils import knn_point
+from imgadapointr_b200.pointnet2_ops import pointnet2_utils
+
+dev = torch.device("cuda:0")
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1234)
+pointnet2_utils.furthest_point_sample.reuse_prefix = False
+
+
+def cloud(B, N):
+    kind = rng.integers(0, 4)
+    if kind == 0:
+        x = rng.random((B, N, 3), dtype=np.float32) - 0.5
+    elif kind == 1:  # coarse grid: exact ties everywhere
+        x = (np.floor((rng.random((B, N, 3)) - 0.5) * 8) / 8).astype(np.float32)
+    elif kind == 2:  # zero-padded tail
+        x = rng.random((B, N, 3), dtype=np.float32) - 0.5
+        x[:, int(N * rng.uniform(0.3, 0.9)):] = 0.0
+    else:  # duplicates of a few points + wide dynamic range
+        x = (rng.standard_normal((B, N, 3)) * 10 ** rng.uniform(-3, 2)).astype(np.float32)
+        src = rng.integers(0, N, size=N // 3)
+        x[:, : N // 3] = x[:, src]
+    return np.ascontiguousarray(x)
+
+
+t_end, n_cases, fails = time.time() + budget, 0, []
+while time.time() < t_end:
+    B = int(rng.integers(1, 7))
+    N = int(rng.choice([1, 2, 31, 33, 64, 100, 255, 257, 700, 1024, 2048, 3000, 5000]))
+    M = int(rng.choice([1, 3, 32, 65, 128, 500, 1000, 2048, 4097]))
+    a, b = cloud(B, N), cloud(B, M)
+    ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    case = "B=%d N=%d M=%d" % (B, N, M)
+    try:
+        d1, d2, i1, i2 = chamfer.forward(ta, tb)
+        od1, od2, oi1, oi2 = oracle.chamfer_forward(a, b)
+        assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2), "chamfer dist"
+        assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2), "chamfer idx"
+        g1 = rng.standard_normal((B, N)).astype(np.float32)
+        g2 = rng.standard_normal((B, M)).astype(np.float32)
+        gx1, gx2 = chamfer.backward(ta, tb, i1, i2, torch.from_numpy(g1).to(dev), torch.from_numpy(g2).to(dev))
+        o1, o2 = oracle.chamfer_backward(a, b, oi1, oi2, g1, g2)
+        for got, want in ((gx1, o1), (gx2, o2)):
+            scale = max(float(np.abs(want).max()), 1e-30)
+            assert float(np.abs(got.cpu().numpy() - want).max()) <= 1e-5 * scale, "chamfer grad"
+        if N >= 2:
+            m = int(rng.integers(1, min(N, 600) + 1))
+            skip = bool(rng.integers(0, 2))
+            pointnet2_utils.furthest_point_sample.skip_near_origin = skip
+            fi = pointnet2_utils.furthest_point_sample(ta, m)
+            assert np.array_equal(fi.cpu().numpy(), oracle.fps(a, m, skip)), "fps m=%d skip=%d" % (m, skip)
+        k = int(rng.integers(1, min(N, 64) + 1))
+        ki, kd = knn_point(k, ta, tb, return_dist=True)
+        oi, od = oracle.knn(k, a, b)
+        assert np.array_equal(ki.cpu().numpy(), oi) and np.array_equal(kd.cpu().numpy(), od), "knn k=%d" % k
+        if N * k <= 60000:
+            C = int(rng.integers(1, 9))
+            xq = torch.randn((B, C, M), device=dev, requires_grad=True)
+            xk = torch.randn((B, C, N), device=dev, requires_grad=True)
+            go = torch.randn((B, 2 * C, M, k), device=dev)
+            bb.graph_feature(xq, xk, ki).backward(go)
+            aq, ak = xq.detach().double().requires_grad_(True), xk.detach().double().requires_grad_(True)
+            feat = torch.gather(ak.unsqueeze(2).expand(B, C, M, N), 3, ki.unsqueeze(1).expand(B, C, M, k))
+            torch.cat((feat - aq.unsqueeze(-1), aq.unsqueeze(-1).expand(B, C, M, k)), 1).backward(go.double())
+            for got, want in ((xq.grad, aq.grad), (xk.grad, ak.grad)):
+                assert float((got.double() - want).abs().max()) <= 1e-5 * max(float(want.abs().max()), 1e-30), "graph grad"
+    except AssertionError as e:
+        fails.append((case, str(e)))
+        print("FAIL", case, e, flush=True)
+    n_cases += 1
+pointnet2_utils.furthest_point_sample.skip_near_origin = True
+print("cases", n_cases, "failures", len(fails))
+sys.exit(1 if fails else 0)
