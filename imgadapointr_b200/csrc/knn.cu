@@ -2,11 +2,13 @@
 //
 // Replaces knn_point = square_distance + torch.topk(largest=False, sorted=False)
 // (reference models/Transformer_utils.py:19-51), which materialises the [B,Q,R] FP32 matrix (805 MB at
-// B=48, Q=R=2048) through a K=3 SGEMM and re-reads it in topk.  Here nothing is materialised: reference
-// points are staged once per CTA in shared memory (SoA) and every warp owns one query at a time, keeping the
-// current k best as a sorted list spread over its lanes (lane i = i-th smallest).  A 32-reference step costs one
-// direct-form distance per lane, a compare against the current k-th distance and one ballot; the (rare)
-// candidates are inserted with a ballot-computed position and one shuffle-up.
+// B=48, Q=R=2048) through a K=3 SGEMM and re-reads it in topk.  Here nothing is materialised.  Two kernels:
+//  * knn_kernel (any k <= 64, any batch): reference points are staged once per CTA in shared memory (float4) and every
+//    warp owns one query, keeping the current k best as a sorted list spread over its lanes (lane i = i-th smallest).
+//    A 32-reference step costs one direct-form distance per lane, a compare against the current k-th distance and one
+//    ballot; the (rare) candidates are inserted with a ballot-computed position and one shuffle-up;
+//  * knn_select_kernel (k <= 16 and at least 256 warps of queries - the encoder's calls): one THREAD per query, two
+//    sweeps and a threshold (see below); 2.9x faster than the list kernel at 48 x 2048 x 2048, k = 16.
 // Output is ascending by (distance, index); on exact distance ties the LOWEST index wins (references are scanned
 // in ascending index and only a strictly smaller distance displaces a list entry).
 #include <cstdlib>
@@ -17,7 +19,7 @@ namespace iapt {
 
 constexpr int kKnnThreads = 256;
 constexpr int kKnnWarps = kKnnThreads / 32;
-constexpr int kKnnTile = 2048;         // reference points per smem tile (24 KB SoA)
+constexpr int kKnnTile = 2048;         // reference points per smem tile (32 KB of float4)
 
 // Insert this step's candidates (one per lane: distance d, reference index my_idx; d = +inf for "none") into the
 // warp-distributed sorted list (entry s*32+lane).  Candidates are taken in lane order and only a strictly smaller
