@@ -87,7 +87,9 @@ def config1(dev):
     out = {"gpu_ms": {}, "cpu_ms": {}, "cpu_threads": torch.get_num_threads()}
     out["gpu_ms"]["chamfer_l1_fwd_bwd"] = gpu_time(lambda: fwd_bwd(l1))
     out["gpu_ms"]["chamfer_l2_fwd_bwd"] = gpu_time(lambda: fwd_bwd(l2))
+    pointnet2_utils.furthest_point_sample.reuse_prefix = False  # time real launches, not the prefix cache
     out["gpu_ms"]["fps_2048_512"] = gpu_time(lambda: pointnet2_utils.furthest_point_sample(p, 512))
+    pointnet2_utils.furthest_point_sample.reuse_prefix = True
     out["gpu_ms"]["knn_k16_2048x2048"] = gpu_time(lambda: knn_point(16, p, p))
 
     def cpu_l1():
@@ -157,6 +159,32 @@ def config3(dev, B=48):
             "reference_formulation_fwd": gpu_time(lambda: tf.get_graph_feature(16, cq, xq, ck, xk, idx=idx)),
             "ours_fwd_bwd": gpu_time(ours_fb), "reference_formulation_fwd_bwd": gpu_time(ref_fb),
             "out_MB": B * 2 * C * Q * 16 * 4 / 1e6}
+
+    # channels-last variant inside the geometry-aware transformer (DynamicGraphAttention, Transformer_utils.py:814-816):
+    # 512 tokens x 384 channels, k = 8
+    from imgadapointr_b200.models.Transformer_utils import graph_feature_cl
+
+    tq = torch.randn((B, 512, 384), device=dev, requires_grad=True)
+    tv = torch.randn((B, 512, 384), device=dev, requires_grad=True)
+    tidx = knn_point(8, c512, c512)
+    tgo = torch.randn((B, 512, 8, 768), device=dev)
+
+    def cl_ours():
+        tq.grad = tv.grad = None
+        graph_feature_cl(tq, tv, tidx).backward(tgo)
+
+    def cl_ref():
+        tq.grad = tv.grad = None
+        tf.dynamic_graph_feature(tq, tv, tidx).backward(tgo)
+
+    with torch.no_grad():
+        cl_f_ours = gpu_time(lambda: graph_feature_cl(tq, tv, tidx))
+        cl_f_ref = gpu_time(lambda: tf.dynamic_graph_feature(tq, tv, tidx))
+    out["graph_feature_channels_last_ms"] = {"shape": "B=%d N=M=512 C=384 k=8" % B, "out_MB": tgo.numel() * 4 / 1e6,
+                                             "ours_fwd": cl_f_ours, "reference_formulation_fwd": cl_f_ref,
+                                             "ours_fwd_bwd": gpu_time(cl_ours),
+                                             "reference_formulation_fwd_bwd": gpu_time(cl_ref)}
+    del tq, tv, tgo
 
     seq = gpu_time(sequence)
     pointnet2_utils.furthest_point_sample.reuse_prefix = True

@@ -51,6 +51,12 @@ SIGNATURES = {
     "iapt_graph_feature_grad": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p,
                                          _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "iapt_index_points": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, ctypes.c_longlong, _c_void_p, _c_void_p]),
+    "iapt_index_points_grad": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, ctypes.c_longlong, _c_void_p,
+                                        _c_void_p, _c_size_t, _c_void_p]),
+    "iapt_graph_feature_cl": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p,
+                                       _c_void_p]),
+    "iapt_graph_feature_cl_grad": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p,
+                                            _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "iapt_group_gather": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p,
                                    _c_void_p]),
     "iapt_group_gather_grad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,

@@ -37,6 +37,10 @@ int group_gather_grad_launch(const float*, const long long*, const float*, int, 
                              cudaStream_t);
 int ball_query_launch(const float*, const float*, int, int, int, float, int, int*, cudaStream_t);
 int graph_feature_grad_launch(const float*, const long long*, int, int, int, int, int, float*, float*, void*, cudaStream_t);
+int graph_feature_cl_launch(const float*, const float*, const long long*, int, int, int, int, int, float*, cudaStream_t);
+int graph_feature_cl_grad_launch(const float*, const long long*, int, int, int, int, int, float*, float*, void*,
+                                 cudaStream_t);
+int index_points_grad_launch(const float*, const long long*, int, int, int, long long, float*, void*, cudaStream_t);
 }  // namespace iapt
 
 using namespace iapt;
@@ -260,6 +264,39 @@ int iapt_index_points(const float* points, const int64_t* idx, int B, int N, int
   if (B == 0 || C == 0 || S == 0) return 0;
   IAPT_REQUIRE(points && idx && out);
   return index_points_launch(points, (const long long*)idx, B, N, C, S, out, (cudaStream_t)stream);
+}
+
+int iapt_index_points_grad(const float* grad_out, const int64_t* idx, int B, int N, int C, long long S,
+                           float* grad_points, void* workspace, size_t workspace_bytes, iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && N >= 1 && C >= 0 && S >= 0 && S < (1LL << 31));
+  if (B == 0 || C == 0) return 0;
+  IAPT_REQUIRE(grad_points);
+  if (S == 0) return (int)cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)B * N * C, (cudaStream_t)stream);
+  IAPT_REQUIRE(grad_out && idx);
+  if (workspace == nullptr || workspace_bytes < graph_feature_grad_workspace_bytes(B, (int)S, N, 1)) return IAPT_EWORKSPACE;
+  return index_points_grad_launch(grad_out, (const long long*)idx, B, N, C, S, grad_points, workspace,
+                                  (cudaStream_t)stream);
+}
+
+int iapt_graph_feature_cl(const float* q, const float* v, const int64_t* idx, int B, int N, int M, int C, int k,
+                          float* out, iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && N >= 0 && M >= 1 && C >= 0 && k >= 0);
+  if (B == 0 || N == 0 || C == 0 || k == 0) return 0;
+  IAPT_REQUIRE(q && v && idx && out);
+  return graph_feature_cl_launch(q, v, (const long long*)idx, B, N, M, C, k, out, (cudaStream_t)stream);
+}
+
+int iapt_graph_feature_cl_grad(const float* grad_out, const int64_t* idx, int B, int N, int M, int C, int k,
+                               float* grad_q, float* grad_v, void* workspace, size_t workspace_bytes,
+                               iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && N >= 0 && M >= 1 && C >= 0 && k >= 0 && (long long)N * k < (1LL << 31));
+  if (B == 0 || C == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0 || k == 0) return grad_v ? (int)cudaMemsetAsync(grad_v, 0, sizeof(float) * (size_t)B * M * C, st) : 0;
+  IAPT_REQUIRE(grad_out && idx);
+  if (grad_v && (workspace == nullptr || workspace_bytes < graph_feature_grad_workspace_bytes(B, N, M, k)))
+    return IAPT_EWORKSPACE;
+  return graph_feature_cl_grad_launch(grad_out, (const long long*)idx, B, N, M, C, k, grad_q, grad_v, workspace, st);
 }
 
 int iapt_group_gather(const float* features, const int64_t* idx, const float* weight, int B, int C, int M, int P, int S,

@@ -447,6 +447,155 @@ __global__ void __launch_bounds__(kPlaneThreads, 1024 / kPlaneThreads) graph_fea
   }
 }
 
+// ---- channels-last graph feature (DynamicGraphAttention, models/Transformer_utils.py:814-816,842-855) ------------
+// The geometry-aware transformer gathers token features [B,M,C] (C = 384) with the kNN indices and builds
+//   feature[b,n,j,:] = cat(v[b,idx[b,n,j],:] - q[b,n,:], q[b,n,:])            ([B,N,k,2C])
+// through index_points + expand + sub + cat: four passes over a 600 MB tensor at B=48, N=512, k=8.  Here one warp per
+// (b,n) writes its k rows directly (128-bit coalesced), and the backward is deterministic:
+//   grad_q[b,n,:] = sum_j (go[b,n,j,C:] - go[b,n,j,:C])           fixed order over j
+//   grad_v[b,m,:] = sum over the inverse list of m (ascending position) of go[b,p,:C]     - whole rows, coalesced
+// (the reference's index backward is an atomicAdd scatter in run-dependent order).
+constexpr int kClThreads = 256;
+
+__global__ void __launch_bounds__(kClThreads) graph_feature_cl_kernel(const float* __restrict__ q,
+                                                                      const float* __restrict__ v,
+                                                                      const long long* __restrict__ idx, int N, int M,
+                                                                      int C, int k, float* __restrict__ out,
+                                                                      long long rows, int vec) {
+  const int lane = threadIdx.x & 31;
+  const long long bn = ((long long)blockIdx.x * kClThreads + threadIdx.x) >> 5;  // warp = one (b, n)
+  if (bn >= rows) return;
+  const long long b = bn / N;
+  const float* qr = q + (size_t)bn * C;
+  const long long* ir = idx + (size_t)bn * k;
+  float* o = out + (size_t)bn * k * 2 * C;
+  if (vec) {
+    const int C4 = C >> 2;
+    for (int c0 = 0; c0 < C4; c0 += 32 * 4) {  // up to 4 float4 columns per lane stay in registers across the k rows
+      float4 qv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * 32 + lane;
+        qv[u] = c < C4 ? __ldg(reinterpret_cast<const float4*>(qr) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int j = 0; j < k; ++j) {
+        const float4* vr = reinterpret_cast<const float4*>(v + ((size_t)b * M + (size_t)__ldg(ir + j)) * C);
+        float4* lo = reinterpret_cast<float4*>(o + (size_t)j * 2 * C);
+        float4* hi = lo + C4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * 32 + lane;
+          if (c < C4) {
+            const float4 x = __ldg(vr + c);
+            lo[c] = make_float4(__fsub_rn(x.x, qv[u].x), __fsub_rn(x.y, qv[u].y), __fsub_rn(x.z, qv[u].z),
+                                __fsub_rn(x.w, qv[u].w));
+            hi[c] = qv[u];
+          }
+        }
+      }
+    }
+  } else {
+    for (int j = 0; j < k; ++j) {
+      const float* vr = v + ((size_t)b * M + (size_t)__ldg(ir + j)) * C;
+      float* lo = o + (size_t)j * 2 * C;
+      for (int c = lane; c < C; c += 32) {
+        const float x = __ldg(qr + c);
+        lo[c] = __fsub_rn(__ldg(vr + c), x);
+        lo[C + c] = x;
+      }
+    }
+  }
+}
+
+// grad_q: warp per (b, n)
+__global__ void __launch_bounds__(kClThreads) graph_feature_cl_grad_q_kernel(const float* __restrict__ go, int C, int k,
+                                                                             float* __restrict__ gq, long long rows,
+                                                                             int vec) {
+  const int lane = threadIdx.x & 31;
+  const long long bn = ((long long)blockIdx.x * kClThreads + threadIdx.x) >> 5;
+  if (bn >= rows) return;
+  const float* g = go + (size_t)bn * k * 2 * C;
+  float* o = gq + (size_t)bn * C;
+  if (vec) {
+    const int C4 = C >> 2;
+    for (int c = lane; c < C4; c += 32) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < k; ++j) {
+        const float4* row = reinterpret_cast<const float4*>(g + (size_t)j * 2 * C);
+        const float4 l = __ldg(row + c), h = __ldg(row + C4 + c);
+        s.x = __fadd_rn(s.x, __fsub_rn(h.x, l.x));
+        s.y = __fadd_rn(s.y, __fsub_rn(h.y, l.y));
+        s.z = __fadd_rn(s.z, __fsub_rn(h.z, l.z));
+        s.w = __fadd_rn(s.w, __fsub_rn(h.w, l.w));
+      }
+      reinterpret_cast<float4*>(o)[c] = s;
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) {
+      float s = 0.f;
+      for (int j = 0; j < k; ++j) s = __fadd_rn(s, __fsub_rn(__ldg(g + (size_t)j * 2 * C + C + c), __ldg(g + (size_t)j * 2 * C + c)));
+      o[c] = s;
+    }
+  }
+}
+
+// out[b,m,0:C] = sum over the inverse list of m (ascending position p) of src[b,p,0:C], rows of src are `ld` floats
+// apart (ld = 2C: lower half of the graph feature gradient; ld = C: index_points gradient).  Warp per (b, m).
+__global__ void __launch_bounds__(kClThreads) rows_gather_sum_kernel(const float* __restrict__ src,
+                                                                     const int* __restrict__ start,
+                                                                     const int* __restrict__ perm, int M, int C,
+                                                                     long long L, long long ld, float* __restrict__ out,
+                                                                     long long rows, int vec) {
+  const int lane = threadIdx.x & 31;
+  const long long bm = ((long long)blockIdx.x * kClThreads + threadIdx.x) >> 5;
+  if (bm >= rows) return;
+  const long long b = bm / M;
+  const int m = (int)(bm - b * M);
+  const int* st = start + (size_t)b * (M + 1);
+  const int s0 = __ldg(st + m), s1 = __ldg(st + m + 1);
+  const int* pm = perm + (size_t)b * L;
+  const float* base = src + (size_t)b * L * ld;
+  float* o = out + (size_t)bm * C;
+  if (vec) {
+    const int C4 = C >> 2;
+    for (int c0 = 0; c0 < C4; c0 += 32 * 4) {
+      float4 acc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i0 = s0; i0 < s1; i0 += 32) {
+        const int mine = (i0 + lane < s1) ? __ldg(pm + i0 + lane) : 0;  // 32 list entries per coalesced read
+        const int cnt = min(32, s1 - i0);
+        for (int e = 0; e < cnt; ++e) {
+          const int p = __shfl_sync(0xffffffffu, mine, e);
+          const float4* row = reinterpret_cast<const float4*>(base + (size_t)p * ld);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u * 32 + lane;
+            if (c < C4) {
+              const float4 x = __ldg(row + c);
+              acc[u].x = __fadd_rn(acc[u].x, x.x);
+              acc[u].y = __fadd_rn(acc[u].y, x.y);
+              acc[u].z = __fadd_rn(acc[u].z, x.z);
+              acc[u].w = __fadd_rn(acc[u].w, x.w);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * 32 + lane;
+        if (c < C4) reinterpret_cast<float4*>(o)[c] = acc[u];
+      }
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) {
+      float acc = 0.f;
+      for (int i = s0; i < s1; ++i) acc = __fadd_rn(acc, __ldg(base + (size_t)__ldg(pm + i) * ld + c));
+      o[c] = acc;
+    }
+  }
+}
+
 // ---- grouped gathers for the remaining pointnet2_ops entry points ---------------------
 // reduce == 0 (grouping_operation): out[b,c,p,s] = f[b,c,idx[b,p,s]]            (* w[b,p,s] when w != null)
 // reduce == 1 (three_interpolate):  out[b,c,p]   = sum_s w[b,p,s] * f[b,c,idx[b,p,s]]   (fixed order over s)
@@ -654,6 +803,56 @@ int group_gather_grad_launch(const float* go, const long long* idx, const float*
   if (rc != 0) return rc;
   dim3 gg((M + 255) / 256, C, B);
   group_gather_grad_kernel<<<gg, 256, 0, stream>>>(go, start, perm, w, C, L, S, reduce, M, gf);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+static inline bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
+
+int graph_feature_cl_launch(const float* q, const float* v, const long long* idx, int B, int N, int M, int C, int k,
+                            float* out, cudaStream_t stream) {
+  const long long rows = (long long)B * N;
+  const int vec = (C % 4 == 0 && aligned16(q) && aligned16(v) && aligned16(out)) ? 1 : 0;
+  const long long blocks = (rows * 32 + kClThreads - 1) / kClThreads;
+  graph_feature_cl_kernel<<<(unsigned)blocks, kClThreads, 0, stream>>>(q, v, idx, N, M, C, k, out, rows, vec);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int graph_feature_cl_grad_launch(const float* go, const long long* idx, int B, int N, int M, int C, int k, float* gq,
+                                 float* gv, void* workspace, cudaStream_t stream) {
+  const long long L = (long long)N * k;
+  if (gq) {
+    const long long rows = (long long)B * N;
+    const int vec = (C % 4 == 0 && aligned16(go) && aligned16(gq)) ? 1 : 0;
+    graph_feature_cl_grad_q_kernel<<<(unsigned)((rows * 32 + kClThreads - 1) / kClThreads), kClThreads, 0, stream>>>(
+        go, C, k, gq, rows, vec);
+    count_launch();
+  }
+  if (gv) {
+    int* start = static_cast<int*>(workspace);
+    int* perm = start + (size_t)B * (M + 1);
+    const int rc = inverse_index_launch(idx, B, L, M, start, perm, stream);
+    if (rc != 0) return rc;
+    const long long rows = (long long)B * M;
+    const int vec = (C % 4 == 0 && aligned16(go) && aligned16(gv)) ? 1 : 0;
+    rows_gather_sum_kernel<<<(unsigned)((rows * 32 + kClThreads - 1) / kClThreads), kClThreads, 0, stream>>>(
+        go, start, perm, M, C, L, 2LL * C, gv, rows, vec);
+    count_launch();
+  }
+  return (int)cudaGetLastError();
+}
+
+int index_points_grad_launch(const float* go, const long long* idx, int B, int N, int C, long long S, float* gp,
+                             void* workspace, cudaStream_t stream) {
+  int* start = static_cast<int*>(workspace);
+  int* perm = start + (size_t)B * (N + 1);
+  const int rc = inverse_index_launch(idx, B, S, N, start, perm, stream);
+  if (rc != 0) return rc;
+  const long long rows = (long long)B * N;
+  const int vec = (C % 4 == 0 && aligned16(go) && aligned16(gp)) ? 1 : 0;
+  rows_gather_sum_kernel<<<(unsigned)((rows * 32 + kClThreads - 1) / kClThreads), kClThreads, 0, stream>>>(
+      go, start, perm, N, C, S, (long long)C, gp, rows, vec);
   count_launch();
   return (int)cudaGetLastError();
 }

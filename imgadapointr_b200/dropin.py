@@ -71,6 +71,11 @@ def patch_reference_modules() -> list:
                     continue
                 setattr(mod, attr, new)
                 patched.append(f"{name}.{attr}")
+    ref_tu = sys.modules.get("models.Transformer_utils")
+    dga = getattr(ref_tu, "DynamicGraphAttention", None) if ref_tu is not None else None
+    if dga is not None:  # gather / sub / cat of the geometry-aware attention (Transformer_utils.py:796-860)
+        dga.forward = tu.dynamic_graph_attention_forward
+        patched.append("models.Transformer_utils.DynamicGraphAttention.forward")
     ref_p3d = sys.modules.get("utils.from_pytorch3d")
     if ref_p3d is not None:  # the vendored copy calls knn_points without defining it (utils/from_pytorch3d.py:76)
         from .utils import from_pytorch3d as p3d

@@ -56,25 +56,134 @@ def square_distance(src, dst):
     return dist
 
 
-def index_points(points, idx):
-    """points [B,N,C], idx [B,S] or [B,S,K] -> [B,S,C] / [B,S,K,C] (Transformer_utils.py:53-69).
+class _IndexPoints(torch.autograd.Function):
+    """points [B,N,C] float32 CUDA, flat idx [B,S] int64 -> [B,S,C]; deterministic row-sum backward."""
 
-    One gather kernel (iapt_index_points) instead of the reference's arange/repeat + advanced indexing; when
-    gradients w.r.t. ``points`` are needed the differentiable torch.gather formulation is used."""
-    B = points.shape[0]
-    C = points.shape[-1]
-    flat = idx.reshape(B, -1).to(torch.int64)
-    fast = (points.is_cuda and points.dtype == torch.float32 and points.dim() == 3 and flat.is_cuda
-            and not (torch.is_grad_enabled() and points.requires_grad))
-    if fast:
-        pts = points.contiguous()
-        flat = flat.contiguous()
+    @staticmethod
+    def forward(ctx, pts, flat):
+        B, N, C = pts.shape
         S = flat.size(1)
         dev = pts.device
         with _lib.on_device(dev):
             out = torch.empty((B, S, C), dtype=torch.float32, device=dev)
-            _lib.check(_lib.lib().iapt_index_points(_lib.ptr(pts), _lib.ptr(flat), B, pts.size(1), C, S, _lib.ptr(out),
+            _lib.check(_lib.lib().iapt_index_points(_lib.ptr(pts), _lib.ptr(flat), B, N, C, S, _lib.ptr(out),
                                                     _lib.stream_ptr(dev)), "iapt_index_points")
-        return out.reshape(*idx.shape, C)
+        ctx.save_for_backward(flat)
+        ctx.dims = (B, N, C, S)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (flat,) = ctx.saved_tensors
+        B, N, C, S = ctx.dims
+        grad_out = grad_out.to(torch.float32).contiguous()
+        dev = grad_out.device
+        L = _lib.lib()
+        with _lib.on_device(dev):
+            gp = torch.empty((B, N, C), dtype=torch.float32, device=dev)
+            ws_bytes = int(L.iapt_graph_feature_grad_workspace_bytes(B, S, N, 1))
+            ws = torch.empty((max(ws_bytes, 4),), dtype=torch.uint8, device=dev)
+            _lib.check(L.iapt_index_points_grad(_lib.ptr(grad_out), _lib.ptr(flat), B, N, C, S, _lib.ptr(gp), _lib.ptr(ws),
+                                                ws_bytes, _lib.stream_ptr(dev)), "iapt_index_points_grad")
+        return gp, None
+
+
+def index_points(points, idx):
+    """points [B,N,C], idx [B,S] or [B,S,K] -> [B,S,C] / [B,S,K,C] (Transformer_utils.py:53-69).
+
+    One gather kernel (iapt_index_points) instead of the reference's arange/repeat + advanced indexing, and when
+    ``points`` needs a gradient a deterministic backward (iapt_index_points_grad: every source row is the sum, in
+    ascending position, of the gradient rows that gathered it) instead of torch's atomicAdd scatter.  Anything that is
+    not a CUDA float32 [B,N,C] tensor takes the plain torch.gather formulation."""
+    B = points.shape[0]
+    C = points.shape[-1]
+    flat = idx.reshape(B, -1).to(torch.int64)
+    if points.is_cuda and points.dtype == torch.float32 and points.dim() == 3 and flat.is_cuda and C > 0 and flat.size(1) > 0:
+        return _IndexPoints.apply(points.contiguous(), flat.contiguous()).reshape(*idx.shape, C)
     out = torch.gather(points, 1, flat.unsqueeze(-1).expand(-1, -1, C))
     return out.reshape(*idx.shape, C)
+
+
+class _GraphFeatureCL(torch.autograd.Function):
+    """(q [B,N,C], v [B,M,C], idx [B,N,k] int64) -> [B,N,k,2C] = cat(v[idx] - q, q), channels last."""
+
+    @staticmethod
+    def forward(ctx, q, v, idx):
+        B, N, C = q.shape
+        M = v.size(1)
+        k = idx.size(2)
+        dev = q.device
+        with _lib.on_device(dev):
+            out = torch.empty((B, N, k, 2 * C), dtype=torch.float32, device=dev)
+            _lib.check(_lib.lib().iapt_graph_feature_cl(_lib.ptr(q), _lib.ptr(v), _lib.ptr(idx), B, N, M, C, k,
+                                                        _lib.ptr(out), _lib.stream_ptr(dev)), "iapt_graph_feature_cl")
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, N, M, C, k)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        B, N, M, C, k = ctx.dims
+        grad_out = grad_out.to(torch.float32).contiguous()
+        dev = grad_out.device
+        need_q, need_v = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        L = _lib.lib()
+        with _lib.on_device(dev):
+            gq = torch.empty((B, N, C), dtype=torch.float32, device=dev) if need_q else None
+            gv = torch.empty((B, M, C), dtype=torch.float32, device=dev) if need_v else None
+            ws_bytes = int(L.iapt_graph_feature_grad_workspace_bytes(B, N, M, k)) if need_v else 0
+            ws = torch.empty((max(ws_bytes, 4),), dtype=torch.uint8, device=dev)
+            _lib.check(L.iapt_graph_feature_cl_grad(_lib.ptr(grad_out), _lib.ptr(idx), B, N, M, C, k, _lib.ptr(gq),
+                                                    _lib.ptr(gv), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)),
+                       "iapt_graph_feature_cl_grad")
+        return gq, gv, None
+
+
+def graph_feature_cl(q, v, idx):
+    """``cat((index_points(v, idx) - q.unsqueeze(-2), q.unsqueeze(-2).expand(..)), -1)`` of DynamicGraphAttention
+    (Transformer_utils.py:814-816) in one kernel: q [B,N,C], v [B,M,C], idx [B,N,k] -> [B,N,k,2C]; bit-identical
+    values, deterministic gradients for q and v."""
+    _lib.require_cuda_f32(q, "q", 3)
+    _lib.require_cuda_f32(v, "v", 3)
+    if idx.dtype != torch.int64 or idx.dim() != 3 or not idx.is_cuda:
+        raise _lib.IaptError("idx must be a CUDA int64 [B, N, k] tensor (as knn_point returns)")
+    if v.size(0) != q.size(0) or v.size(2) != q.size(2) or idx.size(0) != q.size(0) or idx.size(1) != q.size(1):
+        raise _lib.IaptError("graph_feature_cl: shape mismatch")
+    return _GraphFeatureCL.apply(q.contiguous(), v.contiguous(), idx.contiguous())
+
+
+def dynamic_graph_attention_forward(self, q, q_pos, v=None, v_pos=None, idx=None, denoise_length=None):
+    """DynamicGraphAttention.forward (Transformer_utils.py:796-860) with its geometry on the B200 kernels: fused kNN and
+    one fused gather / subtract / concat kernel per neighbourhood query; ``self.knn_map`` (the learned Linear + LeakyReLU)
+    and the max over k are the module's own.  ``dropin.patch_reference_modules()`` installs it on the reference class."""
+    if denoise_length is None:
+        if v is None:
+            v = q
+        if v_pos is None:
+            v_pos = q_pos
+        assert len(v_pos.shape) == 3 and v_pos.size(-1) == 3, f'[ERROR] Got an unexpected shape for v_pos, expect it to be B N 3, but got {v_pos.shape}'
+        assert len(q_pos.shape) == 3 and q_pos.size(-1) == 3, f'[ERROR] Got an unexpected shape for q_pos, expect it to be B N 3, but got {q_pos.shape}'
+        assert q.size(-1) == v.size(-1) == self.dim
+        B, N, C = q.shape
+        if idx is None:
+            idx = knn_point(self.k, v_pos, q_pos)  # B N k
+        assert idx.size(-1) == self.k
+        feature = graph_feature_cl(q, v, idx)  # B N k 2C
+    else:
+        assert idx is None, f'we need online index calculation when denoise_length is set, denoise_length {denoise_length}'
+        assert v is None, f'mask for denoise_length is only consider in self-attention, but v is given'
+        assert v_pos is None, f'mask for denoise_length is only consider in self-attention, but v_pos is given'
+        v = q
+        v_pos = q_pos
+        assert len(v_pos.shape) == 3 and v_pos.size(-1) == 3, f'[ERROR] Got an unexpected shape for v_pos, expect it to be B N 3, but got {v_pos.shape}'
+        assert q.size(-1) == v.size(-1) == self.dim
+        B, N, C = q.shape
+        # reconstruction tokens look only among themselves, denoise tokens among all tokens (:838-849)
+        idx_r = knn_point(self.k, v_pos[:, :-denoise_length], q_pos[:, :-denoise_length])  # B N_r k
+        idx_n = knn_point(self.k, v_pos, q_pos[:, -denoise_length:])  # B N_n k
+        assert idx_n.size(1) == denoise_length
+        feature = graph_feature_cl(q, v, torch.cat([idx_r, idx_n], dim=1))  # indices of both parts address v directly
+    out = self.knn_map(feature).max(-2)[0]  # B N C
+    assert out.size(0) == B and out.size(1) == N and out.size(2) == C
+    return out

@@ -159,6 +159,20 @@ int iapt_graph_feature_grad(const float* grad_out, const int64_t* idx, int B, in
                             iapt_stream_t stream);
 int iapt_index_points(const float* points, const int64_t* idx, int B, int N, int C, long long S, float* out,
                       iapt_stream_t stream);
+/* Gradient of iapt_index_points w.r.t. points: grad_out [B,S,C] -> grad_points [B,N,C], each row the sum, in ascending
+ * position, of the grad_out rows that gathered it (deterministic; torch's index backward is an atomicAdd scatter).
+ * workspace: iapt_graph_feature_grad_workspace_bytes(B, S, N, 1). */
+int iapt_index_points_grad(const float* grad_out, const int64_t* idx, int B, int N, int C, long long S,
+                           float* grad_points, void* workspace, size_t workspace_bytes, iapt_stream_t stream);
+/* Channels-last graph feature of DynamicGraphAttention (models/Transformer_utils.py:814-816 and :842-855):
+ *   q [B,N,C], v [B,M,C], idx [B,N,k] int64  ->  out [B,N,k,2C] = cat(v[b,idx[b,n,j],:] - q[b,n,:], q[b,n,:])
+ * replacing index_points + unsqueeze/expand + sub + cat.  _grad: grad_out [B,N,k,2C] -> grad_q [B,N,C], grad_v [B,M,C]
+ * (either may be NULL); workspace (grad_v only): iapt_graph_feature_grad_workspace_bytes(B, N, M, k). */
+int iapt_graph_feature_cl(const float* q, const float* v, const int64_t* idx, int B, int N, int M, int C, int k,
+                          float* out, iapt_stream_t stream);
+int iapt_graph_feature_cl_grad(const float* grad_out, const int64_t* idx, int B, int N, int M, int C, int k,
+                               float* grad_q, float* grad_v, void* workspace, size_t workspace_bytes,
+                               iapt_stream_t stream);
 
 /* ---- the remaining pointnet2_ops entry points the reference imports (cold paths:
  * Deformable* blocks, models/Transformer_utils.py:228-232; SnowFlakeNet, models/external/SnowFlakeNet_utils.py:4,115-120) --

@@ -146,3 +146,28 @@ def ball_query(radius, nsample, xyz, new_xyz):
                 out[b, p, :] = int(hits[0])
                 out[b, p, :len(hits)] = hits.to(torch.int32)
     return out
+
+
+def dynamic_graph_feature(q, v, idx):
+    """The gather / expand / subtract / concat of DynamicGraphAttention.forward (models/Transformer_utils.py:814-816):
+    q [B,N,C], v [B,M,C], idx [B,N,k] -> [B,N,k,2C]."""
+    B, N, C = q.shape
+    k = idx.size(-1)
+    local_v = torch.gather(v, 1, idx.reshape(B, -1, 1).expand(-1, -1, C)).reshape(B, N, k, C)
+    qe = q.unsqueeze(-2).expand(-1, -1, k, -1)
+    return torch.cat((local_v - qe, qe), dim=-1)
+
+
+def dynamic_graph_attention(knn_map, k, q, q_pos, v=None, v_pos=None, denoise_length=None):
+    """DynamicGraphAttention.forward (models/Transformer_utils.py:796-860) restated with the reference formulation of
+    knn_point; ``knn_map`` is the module's learned map."""
+    if denoise_length is None:
+        v = q if v is None else v
+        v_pos = q_pos if v_pos is None else v_pos
+        feature = dynamic_graph_feature(q, v, knn_point(k, v_pos, q_pos))
+    else:
+        r = q.size(1) - denoise_length
+        f_r = dynamic_graph_feature(q[:, :r], q[:, :r], knn_point(k, q_pos[:, :r], q_pos[:, :r]))
+        f_n = dynamic_graph_feature(q[:, r:], q, knn_point(k, q_pos, q_pos[:, r:]))
+        feature = torch.cat([f_r, f_n], dim=1)
+    return knn_map(feature).max(-2)[0]

@@ -63,8 +63,22 @@ class DGCNN_Grouper:
     def get_graph_feature(self, coor_q, x_q, coor_k, x_k): raise RuntimeError("reference path")
 bb.knn_point = knn_point; bb.DGCNN_Grouper = DGCNN_Grouper
 sys.modules["models"] = models; sys.modules["models.base_blocks"] = bb
+tu = types.ModuleType("models.Transformer_utils")
+class DynamicGraphAttention(torch.nn.Module):   # attributes as in Transformer_utils.py:784-794, forward to be replaced
+    def __init__(self, dim, k=10):
+        super().__init__()
+        self.dim, self.k = dim, k
+        self.knn_map = torch.nn.Sequential(torch.nn.Linear(dim * 2, dim), torch.nn.LeakyReLU(negative_slope=0.2))
+    def forward(self, q, q_pos, v=None, v_pos=None, idx=None, denoise_length=None): raise RuntimeError("reference path")
+tu.DynamicGraphAttention = DynamicGraphAttention; tu.knn_point = knn_point
+sys.modules["models.Transformer_utils"] = tu
 patched = dropin.patch_reference_modules()
 assert "models.base_blocks.knn_point" in patched and "models.base_blocks.DGCNN_Grouper.get_graph_feature" in patched
+assert "models.Transformer_utils.DynamicGraphAttention.forward" in patched
+att = tu.DynamicGraphAttention(12, k=4).to(dev)
+tok = torch.randn(2, 700, 12, device=dev, requires_grad=True)
+o = att(tok, y); o.sum().backward()
+assert o.shape == (2, 700, 12) and tok.grad is not None and bool(torch.isfinite(tok.grad).all())
 idx = bb.knn_point(8, y, y[:, :50].contiguous())
 assert idx.dtype == torch.int64 and idx.shape == (2, 50, 8) and bool((idx[:, :, 0] == torch.arange(50, device=dev)).all())
 coor = y.transpose(1, 2).contiguous(); feat = torch.randn(2, 6, 700, device=dev)

@@ -170,3 +170,75 @@ def test_three_nn_interpolate_grouping_ball_query(dev):
     assert bq.dtype == torch.int32 and torch.equal(bq.cpu(), tf.ball_query(0.15, 8, known, unknown))
     far = pu.ball_query(1e-4, 4, known.to(dev), (unknown + 5.0).to(dev))
     assert int(far.abs().sum()) == 0
+
+
+@pytest.mark.parametrize("B,N,M,C,k", [(3, 100, 150, 384, 8), (2, 257, 64, 10, 5), (2, 64, 64, 516, 16), (1, 1, 3, 4, 2)])
+def test_channels_last_graph_feature_and_index_points_grad(dev, B, N, M, C, k):
+    """iapt_graph_feature_cl / _grad and iapt_index_points_grad against the torch restatement of DynamicGraphAttention's
+    gather / subtract / concat (Transformer_utils.py:814-816): forward bit-exact, gradients against float64 autograd
+    and bit-reproducible."""
+    from imgadapointr_b200.models.Transformer_utils import graph_feature_cl
+    g = torch.Generator().manual_seed(5 + N)
+    q = torch.randn((B, N, C), generator=g).to(dev)
+    v = torch.randn((B, M, C), generator=g).to(dev)
+    idx = torch.randint(0, M, (B, N, k), generator=g).to(dev)
+    idx[:, : max(1, N // 3)] = idx[:, :1]  # heavy fan-in
+    want = tf.dynamic_graph_feature(q, v, idx)
+    assert torch.equal(graph_feature_cl(q, v, idx), want)
+    assert torch.equal(index_points(v, idx), torch.gather(v, 1, idx.reshape(B, -1, 1).expand(-1, -1, C)).reshape(B, N, k, C))
+    go = torch.randn(want.shape, generator=g).to(dev)
+    runs = []
+    for _ in range(2):
+        a, b = q.clone().requires_grad_(True), v.clone().requires_grad_(True)
+        graph_feature_cl(a, b, idx).backward(go)
+        runs.append((a.grad.clone(), b.grad.clone()))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    a, b = q.double().requires_grad_(True), v.double().requires_grad_(True)
+    tf.dynamic_graph_feature(a, b, idx).backward(go.double())
+    for got, ref in ((runs[0][0], a.grad), (runs[0][1], b.grad)):
+        assert float((got.double() - ref).abs().max()) <= 1e-5 * max(float(ref.abs().max()), 1e-30)
+    b1 = v.clone().requires_grad_(True)   # only grad_v requested
+    graph_feature_cl(q, b1, idx).backward(go)
+    assert torch.equal(b1.grad, runs[0][1])
+    # index_points with a gradient: deterministic row sums instead of torch's atomicAdd scatter
+    gi = torch.randn((B, N, k, C), generator=g).to(dev)
+    outs = []
+    for _ in range(2):
+        b2 = v.clone().requires_grad_(True)
+        index_points(b2, idx).backward(gi)
+        outs.append(b2.grad.clone())
+    assert torch.equal(outs[0], outs[1])
+    b3 = v.double().requires_grad_(True)
+    torch.gather(b3, 1, idx.reshape(B, -1, 1).expand(-1, -1, C)).reshape(B, N, k, C).backward(gi.double())
+    assert float((outs[0].double() - b3.grad).abs().max()) <= 1e-5 * max(float(b3.grad.abs().max()), 1e-30)
+
+
+def test_dynamic_graph_attention_forward_mirror(dev):
+    """dynamic_graph_attention_forward (installed on the reference's DynamicGraphAttention by the drop-in) against the
+    restated reference forward, self- and cross-attention and the denoise-token branch, values and gradients."""
+    from imgadapointr_b200.models.Transformer_utils import dynamic_graph_attention_forward
+
+    class Stub(torch.nn.Module):  # the attributes the reference module has (Transformer_utils.py:784-794)
+        def __init__(self, dim, k):
+            super().__init__()
+            self.dim, self.k = dim, k
+            self.knn_map = torch.nn.Sequential(torch.nn.Linear(dim * 2, dim), torch.nn.LeakyReLU(negative_slope=0.2))
+
+    torch.manual_seed(11)
+    m = Stub(48, 8).to(dev)
+    g = torch.Generator().manual_seed(12)
+    q = torch.randn((3, 200, 48), generator=g).to(dev)
+    qp = (torch.rand((3, 200, 3), generator=g) - 0.5).to(dev)
+    v = torch.randn((3, 300, 48), generator=g).to(dev)
+    vp = (torch.rand((3, 300, 3), generator=g) - 0.5).to(dev)
+    for kwargs, ref_kwargs in (({}, {}), ({"v": v, "v_pos": vp}, {"v": v, "v_pos": vp}), ({"denoise_length": 40}, {"denoise_length": 40})):
+        a = q.clone().requires_grad_(True)
+        out = dynamic_graph_attention_forward(m, a, qp, **kwargs)
+        b = q.clone().requires_grad_(True)
+        ref = tf.dynamic_graph_attention(m.knn_map, m.k, b, qp, **ref_kwargs)
+        assert out.shape == ref.shape == (3, 200, 48)
+        assert float((out - ref).detach().abs().max()) <= 1e-5 * float(ref.detach().abs().max())
+        w = torch.randn(out.shape, generator=g).to(dev)
+        (out * w).sum().backward()
+        (ref * w).sum().backward()
+        assert float((a.grad - b.grad).abs().max()) <= 1e-4 * float(b.grad.abs().max())
