@@ -118,5 +118,21 @@ def test_fps_gather_knn_graph_stay_in_bounds(dev, B, N, m, k):
     _lib.check(L.iapt_graph_feature_grad(gf.ptr, kidx.ptr, B, C, Q, N, kk, gq.ptr, gk.ptr, w2.ptr, wn, st), "gfg")
     ip = Guarded(4 * B * Q * kk * 3, dev)
     _lib.check(L.iapt_index_points(xyz.data_ptr(), kidx.ptr, B, N, 3, Q * kk, ip.ptr, st), "ip")
+    # channels-last consumers: index_points gradient, DynamicGraphAttention feature + gradients (C = 5 scalar path,
+    # C = 8 vector path)
+    ipg = Guarded(4 * B * N * 3, dev)
+    wi = L.iapt_graph_feature_grad_workspace_bytes(B, Q * kk, N, 1)
+    w3 = Guarded(wi, dev)
+    _lib.check(L.iapt_index_points_grad(ip.ptr, kidx.ptr, B, N, 3, Q * kk, ipg.ptr, w3.ptr, wi, st), "ipg")
+    guards = [gf, gq, gk, w2, ip, kidx, ipg, w3]
+    for Cc in (5, 8):
+        tq = torch.randn((B, Q, Cc), device=dev)
+        tv = torch.randn((B, N, Cc), device=dev)
+        fcl = Guarded(4 * B * Q * kk * 2 * Cc, dev)
+        _lib.check(L.iapt_graph_feature_cl(tq.data_ptr(), tv.data_ptr(), kidx.ptr, B, Q, N, Cc, kk, fcl.ptr, st), "gfcl")
+        cq, cv = Guarded(4 * B * Q * Cc, dev), Guarded(4 * B * N * Cc, dev)
+        w4 = Guarded(wn, dev)
+        _lib.check(L.iapt_graph_feature_cl_grad(fcl.ptr, kidx.ptr, B, Q, N, Cc, kk, cq.ptr, cv.ptr, w4.ptr, wn, st), "gfclg")
+        guards += [fcl, cq, cv, w4]
     torch.cuda.synchronize()
-    assert all(g.intact() for g in (gf, gq, gk, w2, ip, kidx))
+    assert all(g.intact() for g in guards)
