@@ -62,6 +62,10 @@ SIGNATURES = {
     "iapt_group_gather_grad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                         _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "iapt_ball_query": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_int, _c_void_p, _c_void_p]),
+    "iapt_emd_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
+    "iapt_emd_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p,
+                                  _c_size_t, _c_void_p]),
+    "iapt_emd_backward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
     "iapt_knn_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
     "iapt_knn": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t,
                           _c_void_p]),

@@ -41,6 +41,9 @@ int graph_feature_cl_launch(const float*, const float*, const long long*, int, i
 int graph_feature_cl_grad_launch(const float*, const long long*, int, int, int, int, int, float*, float*, void*,
                                  cudaStream_t);
 int index_points_grad_launch(const float*, const long long*, int, int, int, long long, float*, void*, cudaStream_t);
+size_t emd_workspace_bytes(int B, int n);
+int emd_forward_launch(const float*, const float*, int, int, float, int, float*, int*, void*, cudaStream_t);
+int emd_backward_launch(const float*, const float*, const float*, const int*, int, int, float*, cudaStream_t);
 }  // namespace iapt
 
 using namespace iapt;
@@ -327,6 +330,28 @@ int iapt_ball_query(const float* xyz, const float* new_xyz, int B, int N, int P,
   if (B == 0 || P == 0) return 0;
   IAPT_REQUIRE(xyz && new_xyz && idx);
   return ball_query_launch(xyz, new_xyz, B, N, P, radius, nsample, idx, (cudaStream_t)stream);
+}
+
+size_t iapt_emd_workspace_bytes(int B, int n) {
+  if (B <= 0 || n <= 0) return 0;
+  return emd_workspace_bytes(B, n);
+}
+
+int iapt_emd_forward(const float* xyz1, const float* xyz2, int B, int n, float eps, int iters, float* dist,
+                     int32_t* assignment, void* workspace, size_t workspace_bytes, iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && n >= 0 && iters >= 1 && B <= 65535 && eps >= 0.f);
+  if (B == 0 || n == 0) return 0;
+  IAPT_REQUIRE(xyz1 && xyz2 && dist && assignment);
+  if (workspace == nullptr || workspace_bytes < emd_workspace_bytes(B, n)) return IAPT_EWORKSPACE;
+  return emd_forward_launch(xyz1, xyz2, B, n, eps, iters, dist, assignment, workspace, (cudaStream_t)stream);
+}
+
+int iapt_emd_backward(const float* xyz1, const float* xyz2, const float* grad_dist, const int32_t* assignment, int B,
+                      int n, float* grad_xyz1, iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && n >= 0);
+  if (B == 0 || n == 0) return 0;
+  IAPT_REQUIRE(xyz1 && xyz2 && grad_dist && assignment && grad_xyz1);
+  return emd_backward_launch(xyz1, xyz2, grad_dist, assignment, B, n, grad_xyz1, (cudaStream_t)stream);
 }
 
 }  // extern "C"

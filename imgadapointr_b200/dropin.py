@@ -4,6 +4,7 @@ After ``imgadapointr_b200.dropin.install()``:
     import chamfer                                  -> imgadapointr_b200.chamfer
     from pointnet2_ops import pointnet2_utils       -> imgadapointr_b200.pointnet2_ops.pointnet2_utils
     from extensions.chamfer_dist import ...         -> imgadapointr_b200.extensions.chamfer_dist   (optional)
+    from extensions.emd import emd_module           -> imgadapointr_b200.extensions.emd.emd_module (optional)
 and ``patch_reference_modules()`` swaps ``knn_point`` / ``fps`` / ``Metrics`` inside already-imported reference modules
 (models.Transformer_utils, models.base_blocks, utils.misc, utils.metrics, ...), which is needed because the reference
 star-imports ``knn_point`` into every model module (models/base_blocks.py:9, models/external/AdaPoinTr.py:14).
@@ -15,7 +16,7 @@ import sys
 
 def install(override_extensions: bool = True) -> None:
     from . import chamfer, pointnet2_ops
-    from .extensions import chamfer_dist
+    from .extensions import chamfer_dist, emd
     from .pointnet2_ops import pointnet2_utils
 
     sys.modules["chamfer"] = chamfer
@@ -27,6 +28,8 @@ def install(override_extensions: bool = True) -> None:
         from . import extensions as our_extensions
 
         sys.modules["extensions.chamfer_dist"] = chamfer_dist
+        sys.modules["extensions.emd"] = emd  # utils/metrics.py:13 imports it at module load; install.sh never builds it
+        sys.modules["extensions.emd.emd_module"] = emd.emd_module
         ext = sys.modules.get("extensions")
         if ext is None:
             try:
@@ -37,6 +40,7 @@ def install(override_extensions: bool = True) -> None:
                 sys.modules["extensions"] = ext = our_extensions
         if ext is not None:
             setattr(ext, "chamfer_dist", chamfer_dist)
+            setattr(ext, "emd", emd)
 
 
 def patch_reference_modules() -> list:

@@ -192,6 +192,21 @@ int iapt_group_gather_grad(const float* grad_out, const int64_t* idx, const floa
 int iapt_ball_query(const float* xyz, const float* new_xyz, int B, int N, int P, float radius, int nsample, int32_t* idx,
                     iapt_stream_t stream);
 
+/* ---- EMD approximation by auction ---------------------------------------------------
+ * Replaces extensions/emd: emd.forward / emd.backward (emd.cpp:14-30, emd_cuda.cu:230-308) behind emdFunction
+ * (emd_module.py:31-72), the test-time EMDistance metric (utils/metrics.py:111-116, eps = 0.005, 100 iterations).
+ *   xyz1 [B,n,3] predictions, xyz2 [B,n,3] targets (same size, coordinates in [0,1] as upstream assumes)
+ *   -> dist [B,n] squared distance of every prediction to its assigned target, assignment [B,n] int32.
+ * The result is an approximation and the assignment need not be a bijection (as upstream).  Where the reference leaves
+ * a choice to thread scheduling it is fixed: equal best values keep the lowest target index, of several bidders within
+ * 1e-6 of a target's best increment the highest prediction index wins - so the output is deterministic.
+ * No restriction of n to multiples of 1024 or of B to 512.  backward: grad_xyz1 [B,n,3] (xyz2 receives none upstream). */
+size_t iapt_emd_workspace_bytes(int B, int n);
+int iapt_emd_forward(const float* xyz1, const float* xyz2, int B, int n, float eps, int iters, float* dist,
+                     int32_t* assignment, void* workspace, size_t workspace_bytes, iapt_stream_t stream);
+int iapt_emd_backward(const float* xyz1, const float* xyz2, const float* grad_dist, const int32_t* assignment, int B,
+                      int n, float* grad_xyz1, iapt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

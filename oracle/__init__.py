@@ -145,3 +145,14 @@ def fscore(pred, gt, th: float = 0.01):
 
 
 from . import torch_formulation  # noqa: E402,F401
+
+
+def emd_forward(xyz1, xyz2, eps: float, iters: int):
+    """Auction EMD of extensions/emd (emd_cuda.cu:95-281) with explicit tie rules -> (dist [B,n] f32, assignment [B,n] i32)."""
+    a, b = _f32(xyz1), _f32(xyz2)
+    B, n, _ = a.shape
+    assert b.shape == a.shape, "the reference requires clouds of the same size (emd_cuda.cu:238-241)"
+    dist = np.empty((B, n), dtype=np.float32)
+    asg = np.empty((B, n), dtype=np.int32)
+    lib().oracle_emd_forward(_p(a), _p(b), B, n, ctypes.c_float(eps), int(iters), _p(dist), _p(asg))
+    return dist, asg

@@ -17,6 +17,10 @@
  *   kNN              : models/Transformer_utils.py:19-51 (selection restated with an explicit
  *                      (distance, index) order because torch.topk(sorted=False) defines none)
  *   F-Score          : utils/metrics.py:67-90
+ *   EMD (auction)    : extensions/emd/emd_cuda.cu:95-228 (Bid / GetMax / Assign / CalcDist), driven as
+ *                      emd_cuda_forward :230-281 and emd_module.py:31-64; sequential semantics (the reference kernels
+ *                      race on exact ties and on Assign's read of `assignment`, so its output is one of several
+ *                      valid executions: see oracle_emd_forward)
  *
  * Rounding: the reference kernel's `x2*x2 + y2*y2 + z2*z2` is contracted by nvcc 12.9 for sm_100a to
  * fma(dz,dz, fma(dx,dx, dy*dy)) (checked with cuobjdump -sass); sqdist_f32() below
@@ -379,4 +383,100 @@ void oracle_fscore_counts(const float *pred, const float *gt, int B, int N, int 
   parallel_for(2 * B, fs_item, &c);
   for (int b = 0; b < B; ++b) boundary[b] = b2[2 * b] + b2[2 * b + 1];
   free(b2);
+}
+
+
+/* ---- EMD approximation by auction (extensions/emd/emd_cuda.cu) ---------------------------------------------------
+ * State per cloud: assignment[j] (pred j -> gt k, -1 = unassigned), assignment_inv[k], price[k] = 0,
+ * max_inc[k] = 0 (the module allocates it with torch.zeros, emd_module.py:52).  One iteration (emd_cuda.cu:256-268):
+ *   Bid   (:95-179) every unassigned j scans all k with value v = (float)(3.0 - (double)sqrtf(d2) - (double)price[k])
+ *                   (`3.0` is a double literal, so the two subtractions run in double), keeps the best and second best
+ *                   value, bids best_i with increment best - better + eps, and max_inc[best_i] = max(.., increment);
+ *   GetMax(:181-194) a bidder whose increment is within 1e-6 (double compare) of max_inc[bid] becomes max_idx[bid];
+ *   Assign(:196-215) the winner takes the target (its previous owner becomes unassigned), price += increment,
+ *                   max_inc = -1e9; in the LAST iteration every unassigned j simply takes its bid.
+ * Tie rules made explicit here and in the CUDA kernels (the reference leaves them to thread scheduling): equal best
+ * values keep the LOWEST k; of several bidders within 1e-6 of the maximum the HIGHEST j wins.
+ * d2 uses the same nvcc contraction as everywhere else (cuobjdump of the reference's Bid: FMUL y, FFMA x, FFMA z). */
+typedef struct {
+  const float *x1, *x2;
+  const float *price;
+  const int32_t *unass;
+  int n;
+  float eps;
+  int32_t *bid;
+  float *inc;
+} emd_bid_ctx;
+
+static void emd_bid_item(int u, void *vctx) {
+  emd_bid_ctx *c = (emd_bid_ctx *)vctx;
+  const int j = c->unass[u];
+  const float *a = c->x1 + 3 * (size_t)j;
+  float best = -1e9, better = -1e9;
+  int best_i = -1;
+  for (int k = 0; k < c->n; ++k) {
+    const float d2 = sqdist_f32(a, c->x2 + 3 * (size_t)k);
+    const float v = (float)(3.0 - (double)sqrtf(d2) - (double)c->price[k]);
+    if (v > best) {
+      better = best;
+      best = v;
+      best_i = k;
+    } else if (v > better) {
+      better = v;
+    }
+  }
+  c->bid[j] = best_i;
+  c->inc[j] = best - better + c->eps;
+}
+
+void oracle_emd_forward(const float *xyz1, const float *xyz2, int B, int n, float eps, int iters, float *dist,
+                        int32_t *assignment) {
+  int32_t *inv = (int32_t *)malloc(sizeof(int32_t) * n), *bid = (int32_t *)malloc(sizeof(int32_t) * n);
+  int32_t *unass = (int32_t *)malloc(sizeof(int32_t) * n), *winner = (int32_t *)malloc(sizeof(int32_t) * n);
+  float *price = (float *)malloc(sizeof(float) * n), *inc = (float *)malloc(sizeof(float) * n);
+  float *max_inc = (float *)malloc(sizeof(float) * n);
+  for (int b = 0; b < B; ++b) {
+    const float *x1 = xyz1 + (size_t)b * n * 3, *x2 = xyz2 + (size_t)b * n * 3;
+    int32_t *asg = assignment + (size_t)b * n;
+    for (int i = 0; i < n; ++i) {
+      asg[i] = -1;
+      inv[i] = -1;
+      price[i] = 0.f;
+      max_inc[i] = 0.f;
+      bid[i] = 0;
+      inc[i] = 0.f;
+    }
+    for (int it = 0; it < iters; ++it) {
+      const int last = it == iters - 1;
+      int cnt = 0;
+      for (int j = 0; j < n; ++j)
+        if (asg[j] == -1) unass[cnt++] = j;
+      if (cnt == 0) break; /* nothing left to do in any later iteration either */
+      emd_bid_ctx c = {x1, x2, price, unass, n, eps, bid, inc};
+      parallel_for(cnt, emd_bid_item, &c);
+      for (int u = 0; u < cnt; ++u) {
+        const int j = unass[u];
+        if (inc[j] > max_inc[bid[j]]) max_inc[bid[j]] = inc[j];
+      }
+      for (int k = 0; k < n; ++k) winner[k] = -1;
+      for (int u = 0; u < cnt; ++u) { /* ascending j: the last qualifying writer = the highest j */
+        const int j = unass[u];
+        const double bi = (double)inc[j], mi = (double)max_inc[bid[j]];
+        if (bi - 1e-6 <= mi && mi <= bi + 1e-6) winner[bid[j]] = j;
+      }
+      for (int u = 0; u < cnt; ++u) {
+        const int j = unass[u], k = bid[j];
+        if (last || winner[k] == j) {
+          const int prev = inv[k];
+          if (!last && prev != -1) asg[prev] = -1;
+          inv[k] = j;
+          asg[j] = k;
+          price[k] += inc[j];
+          max_inc[k] = -1e9;
+        }
+      }
+    }
+    for (int j = 0; j < n; ++j) dist[(size_t)b * n + j] = sqdist_f32(x1 + 3 * (size_t)j, x2 + 3 * (size_t)asg[j]);
+  }
+  free(inv); free(bid); free(unass); free(winner); free(price); free(inc); free(max_inc);
 }
