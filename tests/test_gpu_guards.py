@@ -136,3 +136,27 @@ def test_fps_gather_knn_graph_stay_in_bounds(dev, B, N, m, k):
         guards += [fcl, cq, cv, w4]
     torch.cuda.synchronize()
     assert all(g.intact() for g in guards)
+
+
+@pytest.mark.parametrize("B,n,iters", [(1, 1, 3), (2, 33, 5), (3, 1025, 20), (1, 5000, 10)])
+def test_emd_entry_points_stay_in_bounds(dev, B, n, iters):
+    L = _lib.lib()
+    st = _lib.stream_ptr(dev)
+    g = torch.Generator().manual_seed(n)
+    x1 = torch.rand((B, n, 3), generator=g).to(dev)
+    x2 = torch.rand((B, n, 3), generator=g).to(dev)
+    dist, asg = Guarded(4 * B * n, dev), Guarded(4 * B * n, dev)
+    wn = L.iapt_emd_workspace_bytes(B, n)
+    ws = Guarded(wn, dev)
+    _lib.check(L.iapt_emd_forward(x1.data_ptr(), x2.data_ptr(), B, n, ctypes.c_float(0.005), iters, dist.ptr, asg.ptr,
+                                  ws.ptr, wn, st), "emd")
+    grad = Guarded(12 * B * n, dev)
+    _lib.check(L.iapt_emd_backward(x1.data_ptr(), x2.data_ptr(), dist.ptr, asg.ptr, B, n, grad.ptr, st), "emdb")
+    torch.cuda.synchronize()
+    assert all(gd.intact() for gd in (dist, asg, ws, grad))
+    a = asg.view(torch.int32, (B, n))
+    assert int(a.min()) >= 0 and int(a.max()) < n
+    assert L.iapt_emd_forward(x1.data_ptr(), x2.data_ptr(), B, n, ctypes.c_float(0.005), 0, dist.ptr, asg.ptr, ws.ptr, wn,
+                              st) == -1  # at least one iteration
+    assert L.iapt_emd_forward(x1.data_ptr(), x2.data_ptr(), B, n, ctypes.c_float(0.005), 5, dist.ptr, asg.ptr, None, 0,
+                              st) == -2  # workspace required
