@@ -1,12 +1,13 @@
 """Randomised parity sweep on the GPU against the CPU oracle (tests infrastructure, not product code):
-random batch / cloud sizes, duplicates, zero padding and exact-tie grids through chamfer forward / backward, FPS, kNN
-and graph-feature backward.  Usage: python scripts/fuzz_parity.py [seconds] [seed]"""
+random batch / cloud sizes, duplicates, zero padding and exact-tie grids through chamfer forward / backward, FPS, kNN,
+graph-feature backward and the auction EMD.  Usage: python scripts/fuzz_parity.py [seconds] [seed]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import oracle
 from imgadapointr_b200 import chamfer
+from imgadapointr_b200.extensions.emd import emd_module as emd
 from imgadapointr_b200.models import base_blocks as bb
 from imgadapointr_b200.models.Transformer_utils import knn_point
 from imgadapointr_b200.pointnet2_ops import pointnet2_utils
@@ -50,9 +51,19 @@ while time.time() < t_end:
         g2 = rng.standard_normal((B, M)).astype(np.float32)
         gx1, gx2 = chamfer.backward(ta, tb, i1, i2, torch.from_numpy(g1).to(dev), torch.from_numpy(g2).to(dev))
         o1, o2 = oracle.chamfer_backward(a, b, oi1, oi2, g1, g2)
-        for got, want in ((gx1, o1), (gx2, o2)):
+        # 1e-5 of the gradient scale, plus the float32 accumulation bound of an ordered sum for points with a large
+        # fan-in (hundreds of terms that may cancel; the reference's float atomicAdd has the same bound)
+        ai1, ai2 = oi1.astype(np.int64), oi2.astype(np.int64)
+        v1 = np.abs(2 * g1[..., None] * (a - np.take_along_axis(b, ai1[..., None], 1))).astype(np.float64)
+        v2 = np.abs(2 * g2[..., None] * (b - np.take_along_axis(a, ai2[..., None], 1))).astype(np.float64)
+        mag1, mag2 = v1.copy(), v2.copy()
+        for bb_ in range(B):
+            np.add.at(mag2[bb_], ai1[bb_], v1[bb_])
+            np.add.at(mag1[bb_], ai2[bb_], v2[bb_])
+        for got, want, mag in ((gx1, o1, mag1), (gx2, o2, mag2)):
             scale = max(float(np.abs(want).max()), 1e-30)
-            assert float(np.abs(got.cpu().numpy() - want).max()) <= 1e-5 * scale, "chamfer grad"
+            err = np.abs(got.cpu().numpy() - want)
+            assert bool((err <= 1e-5 * scale + 1e-6 * mag).all()), "chamfer grad"
         if N >= 2:
             m = int(rng.integers(1, min(N, 600) + 1))
             skip = bool(rng.integers(0, 2))
@@ -72,8 +83,19 @@ while time.time() < t_end:
             aq, ak = xq.detach().double().requires_grad_(True), xk.detach().double().requires_grad_(True)
             feat = torch.gather(ak.unsqueeze(2).expand(B, C, M, N), 3, ki.unsqueeze(1).expand(B, C, M, k))
             torch.cat((feat - aq.unsqueeze(-1), aq.unsqueeze(-1).expand(B, C, M, k)), 1).backward(go.double())
+            mag = float(go.abs().max()) * k * max(1, M // max(N, 1))  # size of the sums behind one gradient entry
             for got, want in ((xq.grad, aq.grad), (xk.grad, ak.grad)):
-                assert float((got.double() - want).abs().max()) <= 1e-5 * max(float(want.abs().max()), 1e-30), "graph grad"
+                assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-6 * mag, "graph grad"
+        if n_cases % 5 == 0:  # auction EMD needs clouds of one size: reuse a, resample b
+            n_e = int(rng.choice([1, 7, 64, 300, 700]))
+            ea = np.ascontiguousarray(rng.random((B, n_e, 3), dtype=np.float32))
+            eb = np.ascontiguousarray(rng.random((B, n_e, 3), dtype=np.float32))
+            if rng.integers(0, 2):
+                eb[:, n_e // 2:] = eb[:, : n_e - n_e // 2]  # duplicated targets: exact ties
+            it_e = int(rng.integers(1, 40))
+            ed, eas = emd.emdModule()(torch.from_numpy(ea).to(dev), torch.from_numpy(eb).to(dev), 0.005, it_e)
+            od_, oa_ = oracle.emd_forward(ea, eb, 0.005, it_e)
+            assert np.array_equal(eas.cpu().numpy(), oa_) and np.array_equal(ed.cpu().numpy(), od_), "emd n=%d it=%d" % (n_e, it_e)
     except AssertionError as e:
         fails.append((case, str(e)))
         print("FAIL", case, e, flush=True)
