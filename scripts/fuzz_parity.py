@@ -37,8 +37,8 @@ def cloud(B, N):
 t_end, n_cases, fails = time.time() + budget, 0, []
 while time.time() < t_end:
     B = int(rng.integers(1, 7))
-    N = int(rng.choice([1, 2, 31, 33, 64, 100, 255, 257, 700, 1024, 2048, 3000, 5000]))
-    M = int(rng.choice([1, 3, 32, 65, 128, 500, 1000, 2048, 4097]))
+    N = int(rng.choice([1, 2, 31, 33, 64, 100, 255, 257, 700, 1024, 2048, 3000, 5000, 8193, 16384]))
+    M = int(rng.choice([1, 3, 32, 65, 128, 500, 1000, 2048, 4097, 9000]))
     a, b = cloud(B, N), cloud(B, M)
     ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
     case = "B=%d N=%d M=%d" % (B, N, M)
