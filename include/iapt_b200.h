@@ -1,6 +1,7 @@
 /*
  * iapt_b200.h - C ABI of libiapt_b200.so: hand-written sm_100a kernels for ImgAdaPoinTr's point-cloud
- * geometry hot path (Chamfer nearest-neighbour search fwd/bwd, furthest-point sampling, gather, kNN).
+ * geometry hot path (Chamfer nearest-neighbour search fwd/bwd and fused losses, furthest-point sampling, gather,
+ * kNN, the kNN consumers of the grouper and the geometry-aware transformer, pointnet2-style grouping, auction EMD).
  *
  * This header is the drop-in boundary.  Each entry point names the reference interface it replaces
  * (paths relative to the reference repo root); INTEGRATION.md shows the reference-side bindings.
@@ -14,7 +15,7 @@
  *     argument errors (the reference printf()s CUDA errors and continues, chamfer.cu:166-169 - we return them);
  *     iapt_error_string() describes any of them;
  *   - workspaces are caller-allocated (so a framework's caching allocator owns all memory); the *_workspace_bytes
- *     functions are pure host arithmetic and never touch the GPU.
+ *     functions are host arithmetic and launch nothing (iapt_emd_workspace_bytes reads the current device's SM count).
  */
 #ifndef IAPT_B200_H_
 #define IAPT_B200_H_
