@@ -367,8 +367,7 @@ static void emd_plan(int B, int n, int* sms_out, int* slices, int* cap) {
 
 size_t emd_workspace_bytes(int B, int n) {
   const size_t bn = (size_t)B * n;
-  int sms, slices, cap;
-  emd_plan(B, n, &sms, &slices, &cap);
+  const int cap = n < 2048 ? n : 2048;  // as emd_plan: independent of the device
   return sizeof(int) * (7 * bn + (size_t)B) + sizeof(float) * 3 * bn + 12 * (size_t)B * cap + 128;
 }
 

@@ -15,7 +15,7 @@
  *     argument errors (the reference printf()s CUDA errors and continues, chamfer.cu:166-169 - we return them);
  *     iapt_error_string() describes any of them;
  *   - workspaces are caller-allocated (so a framework's caching allocator owns all memory); the *_workspace_bytes
- *     functions are host arithmetic and launch nothing (iapt_emd_workspace_bytes reads the current device's SM count).
+ *     functions are pure host arithmetic and never touch the GPU.
  */
 #ifndef IAPT_B200_H_
 #define IAPT_B200_H_
