@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libiapt_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 
@@ -38,6 +38,12 @@ SIGNATURES = {
     "iapt_chamfer_backward_fused": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
                                              _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
                                              _c_size_t, _c_void_p]),
+    "iapt_chamfer_step_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "iapt_chamfer_step": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,
+                                   _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                   _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "iapt_chamfer_step_stats": (_c_int, [_c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]),
+    "iapt_scale": (_c_int, [_c_void_p, _c_void_p, ctypes.c_longlong, _c_void_p, _c_void_p]),
     "iapt_chamfer_reduce": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
     "iapt_fscore_counts": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p]),
     "iapt_fps_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),

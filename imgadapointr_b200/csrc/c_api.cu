@@ -3,25 +3,15 @@
 #include <cstdio>
 
 #include "../../include/iapt_b200.h"
+#include "chamfer_step.h"
 #include "common.cuh"
 
 namespace iapt {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
-size_t chamfer_forward_workspace_bytes(int B, int N, int M);
-int chamfer_forward_launch(const float*, const float*, int, int, int, float*, float*, int32_t*, int32_t*, void*,
-                           cudaStream_t);
-size_t chamfer_backward_workspace_bytes(int B, int N, int M);
-int chamfer_backward_launch(const float*, const float*, const int32_t*, const int32_t*, const float*, const float*, int,
-                            int, int, float*, float*, void*, cudaStream_t);
 int chamfer_metrics_launch(const float*, const float*, int, int, int, float, float*, int32_t*, cudaStream_t);
 int chamfer_loss_launch(const float*, const float*, int, int, int, int, float*, float*, cudaStream_t);
-int chamfer_backward_fused_launch(const float*, const float*, const int32_t*, const int32_t*, const float*, const float*,
-                                  int, float, float, const float*, int, int, int, int, float*, float*, void*,
-                                  cudaStream_t);
-void profile_enable(bool on);
-int profile_collect(double* total_ms, int* launches);
 size_t fps_workspace_bytes(int B, int N, int npoint);
 int fps_launch(const float*, int, int, int, int, int32_t*, void*, cudaStream_t);
 int gather_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
@@ -103,12 +93,121 @@ int iapt_chamfer_forward(const float* xyz1, const float* xyz2, int B, int N, int
   IAPT_REQUIRE(xyz1 && xyz2 && workspace);
   IAPT_REQUIRE((long long)B * N < (1LL << 31) && (long long)B * M < (1LL << 31));
   if (workspace_bytes < chamfer_forward_workspace_bytes(B, N, M)) return IAPT_EWORKSPACE;
-  return chamfer_forward_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, workspace, st);
+  StepArgs a;
+  a.xyz1 = xyz1;
+  a.xyz2 = xyz2;
+  a.B = B;
+  a.N = N;
+  a.M = M;
+  a.dist1 = dist1;
+  a.dist2 = dist2;
+  a.idx1 = idx1;
+  a.idx2 = idx2;
+  a.workspace = workspace;
+  return chamfer_step_launch(a, st);
+}
+
+// (mode, scale1, scale2, stride of the upstream scalars) of the analytic loss gradient, extensions/chamfer_dist/
+// __init__.py:43-44,61-62,82-84,101-103: d mean(x) = 1/count, d sqrt(d) = 0.5/sqrt(d).
+static void loss_gradient_weights(int kind, int B, int N, int M, int* mode, float* s1, float* s2, int* stride) {
+  const float n1 = (float)B * (float)N, n2 = (float)B * (float)M;
+  *stride = 0;
+  switch (kind) {
+    case IAPT_LOSS_L1: *mode = 1; *s1 = 0.25f / n1; *s2 = 0.25f / n2; break;  // (q1+q2)/2
+    case IAPT_LOSS_L2: *mode = 2; *s1 = 1.f / n1; *s2 = 1.f / n2; break;
+    case IAPT_LOSS_L2_SPLIT: *mode = 2; *s1 = 1.f / n1; *s2 = 1.f / n2; *stride = 1; break;
+    default: *mode = 1; *s1 = 0.5f / n1; *s2 = 0.f; break;                    // L1_PM: mean sqrt(dist1) only
+  }
+}
+
+size_t iapt_chamfer_step_workspace_bytes(int B, int N, int M) {
+  if (B <= 0 || N <= 0 || M <= 0) return 0;
+  return chamfer_step_workspace_bytes(B, N, M);
+}
+
+int iapt_chamfer_step(const float* xyz1, const float* xyz2, int B, int N, int M, int kind, int flags, float fscore_th,
+                      float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* sums, int32_t* counts,
+                      int32_t* valid, float* loss, const float* grad_loss, float* grad_xyz1, float* grad_xyz2,
+                      void* workspace, size_t workspace_bytes, iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && N >= 1 && M >= 1 && kind >= 0 && kind <= IAPT_LOSS_L1_PM);
+  if (B == 0) return 0;
+  IAPT_REQUIRE(xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2 && workspace);
+  IAPT_REQUIRE((long long)B * N < (1LL << 31) && (long long)B * M < (1LL << 31));
+  IAPT_REQUIRE(loss == nullptr || kind != 0);
+  IAPT_REQUIRE(!(flags & IAPT_STEP_GATE_ON_VALID) || valid != nullptr);
+  const bool grads = grad_xyz1 != nullptr || grad_xyz2 != nullptr;
+  if (grads) {
+    IAPT_REQUIRE(kind != 0);
+    // the two outputs of L2_split carry independent upstream gradients: they must be given
+    if (kind == IAPT_LOSS_L2_SPLIT && grad_loss == nullptr) return IAPT_EUNSUPPORTED;
+    // the mean over the unmasked points is only known on the device
+    if (flags & IAPT_STEP_IGNORE_ZERO_SUM) return IAPT_EUNSUPPORTED;
+  }
+  if (workspace_bytes < chamfer_step_workspace_bytes(B, N, M)) return IAPT_EWORKSPACE;
+  StepArgs a;
+  a.xyz1 = xyz1;
+  a.xyz2 = xyz2;
+  a.B = B;
+  a.N = N;
+  a.M = M;
+  a.mask_zero_sum = (flags & IAPT_STEP_IGNORE_ZERO_SUM) != 0;
+  a.stats = (flags & IAPT_STEP_STATS) != 0;
+  a.dist1 = dist1;
+  a.dist2 = dist2;
+  a.idx1 = idx1;
+  a.idx2 = idx2;
+  a.th = fscore_th;
+  a.kind = kind;
+  a.sums = sums;
+  a.counts = counts;
+  a.valid = valid;
+  a.valid_is_input = (flags & IAPT_STEP_GATE_ON_VALID) != 0;
+  a.loss = loss;
+  if (grads) {
+    loss_gradient_weights(kind, B, N, M, &a.mode, &a.scale1, &a.scale2, &a.grad_out_stride);
+    a.grad_out = grad_loss;
+    a.gw1 = a.scale1 != 0.f ? dist1 : nullptr;
+    a.gw2 = a.scale2 != 0.f ? dist2 : nullptr;
+    a.grad_xyz1 = grad_xyz1;
+    a.grad_xyz2 = grad_xyz2;
+  }
+  a.workspace = workspace;
+  return chamfer_step_launch(a, (cudaStream_t)stream);
+}
+
+int iapt_chamfer_step_stats(const void* workspace, unsigned long long* stats_host) {
+  IAPT_REQUIRE(workspace && stats_host);
+  return (int)cudaMemcpy(stats_host, workspace, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+}
+
+int iapt_scale(const float* src, const float* factor, long long n, float* dst, iapt_stream_t stream) {
+  IAPT_REQUIRE(n >= 0);
+  if (n == 0) return 0;
+  IAPT_REQUIRE(src && factor && dst);
+  return scale_launch(src, factor, n, dst, (cudaStream_t)stream);
 }
 
 size_t iapt_chamfer_backward_workspace_bytes(int B, int N, int M) {
   if (B <= 0 || N <= 0 || M <= 0) return 0;
   return chamfer_backward_workspace_bytes(B, N, M);
+}
+
+static int backward_common(StepArgs& a, const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
+                           int B, int N, int M, float* grad_xyz1, float* grad_xyz2, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st) {
+  if (workspace == nullptr || workspace_bytes < chamfer_backward_workspace_bytes(B, N, M)) return IAPT_EWORKSPACE;
+  a.xyz1 = xyz1;
+  a.xyz2 = xyz2;
+  a.B = B;
+  a.N = N;
+  a.M = M;
+  a.search = false;
+  a.idx1 = const_cast<int32_t*>(idx1);  // inputs in a backward-only launch
+  a.idx2 = const_cast<int32_t*>(idx2);
+  a.grad_xyz1 = grad_xyz1;
+  a.grad_xyz2 = grad_xyz2;
+  a.workspace = workspace;
+  return chamfer_step_launch(a, st);
 }
 
 int iapt_chamfer_backward(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
@@ -123,10 +222,13 @@ int iapt_chamfer_backward(const float* xyz1, const float* xyz2, const int32_t* i
     if (e == cudaSuccess && M > 0 && grad_xyz2) e = cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * 3 * (size_t)B * M, st);
     return (int)e;
   }
-  IAPT_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && grad_xyz1 && grad_xyz2);
-  if (workspace != nullptr && workspace_bytes < chamfer_backward_workspace_bytes(B, N, M)) return IAPT_EWORKSPACE;
-  return chamfer_backward_launch(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2, B, N, M, grad_xyz1, grad_xyz2,
-                                 workspace, st);
+  IAPT_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && (grad_xyz1 || grad_xyz2));
+  IAPT_REQUIRE((long long)B * N < (1LL << 31) && (long long)B * M < (1LL << 31));
+  StepArgs a;
+  a.mode = 0;
+  a.gw1 = grad_dist1;
+  a.gw2 = grad_dist2;
+  return backward_common(a, xyz1, xyz2, idx1, idx2, B, N, M, grad_xyz1, grad_xyz2, workspace, workspace_bytes, st);
 }
 
 int iapt_chamfer_loss(const float* dist1, const float* dist2, int B, int N, int M, int kind, float* sums, float* loss,
@@ -141,19 +243,15 @@ int iapt_chamfer_backward_fused(const float* xyz1, const float* xyz2, const int3
                                 int M, float* grad_xyz1, float* grad_xyz2, void* workspace, size_t workspace_bytes,
                                 iapt_stream_t stream) {
   IAPT_REQUIRE(B >= 1 && N >= 1 && M >= 1 && kind >= IAPT_LOSS_L1 && kind <= IAPT_LOSS_L1_PM);
-  IAPT_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && dist1 && dist2 && grad_xyz1 && grad_xyz2);
-  if (workspace != nullptr && workspace_bytes < chamfer_backward_workspace_bytes(B, N, M)) return IAPT_EWORKSPACE;
-  const float n1 = (float)B * (float)N, n2 = (float)B * (float)M;
-  int mode = 1, stride = 0;
-  float s1 = 0.f, s2 = 0.f;
-  switch (kind) {
-    case IAPT_LOSS_L1: mode = 1; s1 = 0.25f / n1; s2 = 0.25f / n2; break;       // ((q1+q2)/2, d sqrt = 0.5/sqrt)
-    case IAPT_LOSS_L2: mode = 2; s1 = 1.f / n1; s2 = 1.f / n2; break;
-    case IAPT_LOSS_L2_SPLIT: mode = 2; s1 = 1.f / n1; s2 = 1.f / n2; stride = 1; break;
-    default: mode = 1; s1 = 0.5f / n1; s2 = 0.f; break;                           // L1_PM: mean sqrt(dist1) only
-  }
-  return chamfer_backward_fused_launch(xyz1, xyz2, idx1, idx2, dist1, dist2, mode, s1, s2, grad_loss, stride, B, N, M,
-                                       grad_xyz1, grad_xyz2, workspace, (cudaStream_t)stream);
+  IAPT_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && dist1 && dist2 && (grad_xyz1 || grad_xyz2));
+  IAPT_REQUIRE((long long)B * N < (1LL << 31) && (long long)B * M < (1LL << 31));
+  StepArgs a;
+  loss_gradient_weights(kind, B, N, M, &a.mode, &a.scale1, &a.scale2, &a.grad_out_stride);
+  a.grad_out = grad_loss;
+  a.gw1 = a.scale1 != 0.f ? dist1 : nullptr;
+  a.gw2 = a.scale2 != 0.f ? dist2 : nullptr;
+  return backward_common(a, xyz1, xyz2, idx1, idx2, B, N, M, grad_xyz1, grad_xyz2, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
 }
 
 int iapt_chamfer_reduce(const float* dist1, const float* dist2, int B, int N, int M, float* sums,

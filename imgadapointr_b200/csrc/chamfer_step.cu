@@ -1,0 +1,1305 @@
+// chamfer_step.cu - the whole Chamfer step (search, index resolution, loss reduction, gradient) as ONE persistent,
+// dependency-driven kernel for sm_100a.
+//
+// Replaces chamfer_dist_kernel x2 + chamfer_dist_grad_kernel x2 (reference extensions/chamfer_dist/chamfer.cu:15-145
+// launched :159-164, and :173-201 launched :215-222) and the torch.sqrt / torch.mean epilogues of the loss modules
+// (extensions/chamfer_dist/__init__.py:43-44,61-62,82-84,101-103).
+//
+// Work is cut into ITEMS handed out by one atomic ticket to a persistent grid (2 CTAs per SM).  Items are ordered by
+// phase and, inside a phase, by cloud; an item only ever waits for items with SMALLER tickets (per-cloud completion
+// counters), so whatever the residency of the grid the scheme cannot deadlock:
+//
+//   PAIR     (cloud, A tile of 256*QT points, range of 32-point S chunks)   the O(N*M) search, DESIGN.md section 3.1
+//   RESOLVE  (cloud, side, rc points)   waits PAIR(cloud): exact index recovery, dist/idx write-out, per-32-point
+//                                       partial sums (sum d, sum sqrt d, #sqrt d < th), fan-in COUNT of the neighbour
+//   PREFIX   (cloud, side)              waits RESOLVE(cloud): exclusive scan of the fan-in counts -> CSR offsets
+//   FILL     (cloud, side, rc points)   waits PREFIX(cloud): every point drops its index into its neighbour's segment
+//   GATHER   (cloud, side, rc points)   waits FILL(cloud): own term + fan-in segment summed in ASCENDING source index
+//
+// The CTA that completes the last RESOLVE item of a cloud folds that cloud's partials in a fixed order (per-cloud sums,
+// F-Score counts); the one that completes the last cloud forms the loss scalars.  So a fused loss step is one memset
+// (0xFF over keys, counters and counts - every counter is read as value+1) and one kernel, instead of the reference's
+// 4 memsets + 4 kernels + the autograd chain of sqrt/mean, and no phase leaves the machine idle while another drains.
+//
+// PAIR (unchanged arithmetic): every unordered (a, s) pair is evaluated once and feeds both
+// directions; A points live in registers (QT per thread, packed f32x2: FADD2/FMUL2/FFMA2), S points stream through
+// double-buffered shared memory read with broadcast LDS.128; only minima are tracked (FMNMX3) and the index is
+// recovered exactly afterwards from (first 32-point chunk in which the row minimum strictly decreased | lowest lane
+// group holding the column minimum), folded across items by a 64-bit atomicMin on (distance bits << 32 | coarse id)
+// = the reference's lowest-index tie rule (chamfer.cu:47-50,137-140).
+//
+// GATHER is deterministic without floating-point atomics: the CSR segment of a point is ordered (sorting network in
+// registers for <= 8 entries, warp bitonic sort in shared memory up to 1024, a windowed bitmap of the source indices
+// beyond that) and summed sequentially in ascending source index - the same order for every size, so results do not
+// depend on the launch geometry and a collapsed prediction (thousands of points sharing one neighbour) costs a short
+// serial chain instead of the reference's atomicAdd contention (chamfer.cu:193-198).
+#include <cstdlib>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "chamfer_step.h"
+
+namespace iapt {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kSStage = 512;                    // streamed points per smem stage
+constexpr int kChunk = 32;                      // streamed points per row-index chunk
+constexpr int kStageChunks = kSStage / kChunk;  // 16
+constexpr int kWarpSort = 1024;                 // fan-in entries a single warp sorts in shared memory
+constexpr int kBitWin = 32768;                  // source indices per bitmap window (segments > kWarpSort)
+constexpr int kMaxRc = 2048;                    // points per RESOLVE / FILL / GATHER item (upper bound)
+
+struct StepParams {
+  // ---- geometry: side 0 = xyz1, side 1 = xyz2; the register ("A") side of the pair phase is xyz[reg] -------------
+  const float* xyz[2];
+  int n[2];
+  int B;
+  int reg;
+  int mask_zero_sum;  // points with x+y+z == 0 neither query nor answer (ignore_zeros, chamfer_dist/__init__.py:37-41)
+  // ---- search state ------------------------------------------------------------------------------------------
+  u64* key[2];       // [B, n[s]] packed (distance bits, coarse id); all-ones = never lowered
+  float* dist[2];    // [B, n[s]]   (a direction may be skipped in search-only launches: both null)
+  int32_t* idx[2];
+  // ---- counters: every one starts at 0xFFFFFFFF and is read as value + 1 -----------------------------------------
+  unsigned* ticket;
+  unsigned* done_pair;   // [B]
+  unsigned* done_res;    // [B]
+  unsigned* done_pre;    // [B]
+  unsigned* done_fill;   // [B]
+  unsigned* done_final;  // clouds whose partials were folded
+  // ---- item layout -----------------------------------------------------------------------------------------------
+  int a_tiles, s_splits, chunks_per_item;
+  int rc;               // points per RESOLVE / FILL / GATHER item (multiple of 256)
+  int rc_items[2];      // ceil(n[s] / rc)
+  int pair_per_cloud, rc_per_cloud;
+  int first_res, first_pre, first_fill, first_gat, total_items;
+  // ---- loss / metric epilogue ----------------------------------------------------------------------------------------
+  float4* part[2];      // [B, ceil(n[s]/32)] {sum d, sum sqrt d, count(sqrt d < th) as int bits, #unmasked as int bits}
+  float th;
+  float* sums;          // [B,4] {sum d1, sum d2, sum sqrt d1, sum sqrt d2} or null
+  int32_t* counts;      // [B,2] or null
+  int32_t* valid;       // [B,2] points with a non-zero coordinate sum per cloud and side, or null
+  int valid_is_input;   // gate: `valid` comes from an earlier launch; if it equals (n[0], n[1]) everywhere, do nothing
+  float* loss;          // [2] or null
+  int kind;             // IAPT_LOSS_* (0 = none)
+  // ---- gradient ------------------------------------------------------------------------------------------------------
+  int mode;             // 0: weights from gw = grad_dist;  1: scale/sqrt(gw = dist);  2: scale
+  float scale[2];
+  const float* grad_out;  // device upstream scalar(s) or null (= 1)
+  int grad_out_stride;
+  const float* gw[2];   // per-point weight source of side s (null: side s contributes nothing)
+  float* grad[2];       // [B, n[s], 3] or null
+  int need_list[2];     // fan-in list of side s is built (grad[s] wanted and side 1-s contributes)
+  int* cnt[2];          // [B, n[s]]      fan-in count - 1 (starts at -1), consumed again by FILL
+  int* off[2];          // [B, n[s] + 1]  CSR offsets
+  int* csr[2];          // [B, n[1-s]]    source indices grouped by neighbour
+  u64* stats;           // optional (globaltimer ns): [0] min start of PAIR items, [1] of the kernel, [2] max end of PAIR items, [3] of the kernel
+};
+
+template <int QT>
+struct __align__(16) PairSmem {
+  ulonglong2 sxy[2][kSStage];       // (x,x),(y,y)
+  ulonglong2 szz[2][kSStage / 2];   // (z,z) of two consecutive points
+  uint4 col[kWarps][kSStage / 2];   // per warp, per streamed point pair: (min bits, ballot) x2
+  float4 prev[QT / 4][kThreads];    // running minima at the last chunk boundary
+  unsigned bestc[QT][kThreads];     // first chunk in which the running minimum strictly decreased
+};
+template <>
+struct __align__(16) PairSmem<0> {
+  int unused;
+};
+
+struct __align__(16) TailSmem {
+  int sortbuf[kWarps][kWarpSort];    // warp-sorted fan-in segments
+  unsigned bitmap[kBitWin / 32];     // presence bitmap of one window of source indices
+  float stage[3][kThreads];          // ordered terms of one 256-index block
+  unsigned short deferred[kMaxRc];   // points of this item whose segment needs a cooperative pass
+  float redf[32];
+  int redi[32];
+  int wcnt[kWarps];
+  int n_deferred;
+};
+
+struct CtlSmem {
+  unsigned next_item;
+  int flag;
+};
+
+template <int QT>
+struct StepSmem {
+  static constexpr size_t kCtlOff = sizeof(PairSmem<QT>) > sizeof(TailSmem) ? sizeof(PairSmem<QT>) : sizeof(TailSmem);
+  static constexpr size_t kBytes = kCtlOff + sizeof(CtlSmem);
+};
+
+// ---- small device helpers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ u64 globaltimer_ns() {
+  u64 t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Thread 0 spins until `count` increments of *ctr (which started at 0xFFFFFFFF) are visible, then the CTA proceeds.
+__device__ __forceinline__ void wait_done(const unsigned* ctr, int count) {
+  if (threadIdx.x == 0 && count > 0) {
+    unsigned ns = 20;
+    u64 t0 = 0;
+    while (ld_acquire_u32(ctr) != (unsigned)(count - 1)) {
+      __nanosleep(ns);
+      if (ns < 640) {
+        ns <<= 1;
+      } else {  // a producer always holds a smaller ticket and is running: waiting this long means a broken launch -
+        const u64 t = globaltimer_ns();  // fail loudly (launch error) rather than hang the GPU
+        if (t0 == 0) t0 = t;
+        if (t - t0 > 4000000000ull) __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+// All of the CTA's global writes of this item -> one increment.  Returns (to every thread) whether this increment was
+// the `count`-th, i.e. the item completed its group.
+__device__ __forceinline__ bool signal_done(unsigned* ctr, int count, CtlSmem& ctl) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned old = atomicAdd(ctr, 1u);
+    ctl.flag = (old + 2u == (unsigned)count) ? 1 : 0;
+    if (ctl.flag) __threadfence();  // acquire side of the last-arriver pattern
+  }
+  __syncthreads();
+  return ctl.flag != 0;
+}
+
+__device__ __forceinline__ bool zero_sum(float x, float y, float z) { return __fadd_rn(__fadd_rn(x, y), z) == 0.f; }
+
+__device__ __forceinline__ float block_sum_f(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float t = (threadIdx.x < kWarps) ? sh[threadIdx.x] : 0.f;
+  if (warp == 0) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, o));
+  }
+  return t;  // valid in thread 0
+}
+__device__ __forceinline__ int block_sum_i(int v, int* sh) {
+  v = __reduce_add_sync(0xffffffffu, v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  int t = (threadIdx.x < kWarps) ? sh[threadIdx.x] : 0;
+  if (warp == 0) t = __reduce_add_sync(0xffffffffu, t);
+  return t;
+}
+
+// =====================================================================================================================
+// PAIR
+// =====================================================================================================================
+__device__ __forceinline__ void stage_fill_load(const float* __restrict__ Sb, int NS, int base, int end, int tid,
+                                                bool mask, float (&v)[2][3]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int s = base + 2 * tid + h;
+    if (s < end) {
+      v[h][0] = __ldg(Sb + 3 * (size_t)s + 0);
+      v[h][1] = __ldg(Sb + 3 * (size_t)s + 1);
+      v[h][2] = __ldg(Sb + 3 * (size_t)s + 2);
+      if (mask && zero_sum(v[h][0], v[h][1], v[h][2])) v[h][0] = v[h][1] = v[h][2] = kPadCoord();
+    } else {
+      v[h][0] = v[h][1] = v[h][2] = kPadCoord();
+    }
+  }
+}
+
+template <int QT>
+__device__ __forceinline__ void stage_fill_store(PairSmem<QT>& sm, int buf, int tid, const float (&v)[2][3]) {
+  ulonglong2 zz;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    ulonglong2 xy;
+    xy.x = pack2(v[h][0], v[h][0]);
+    xy.y = pack2(v[h][1], v[h][1]);
+    sm.sxy[buf][2 * tid + h] = xy;
+  }
+  zz.x = pack2(v[0][2], v[0][2]);
+  zz.y = pack2(v[1][2], v[1][2]);
+  sm.szz[buf][tid] = zz;
+}
+
+template <int QT>
+__device__ __forceinline__ void pair_item(const StepParams& p, unsigned char* smem_raw, int b, int at, int ss) {
+  PairSmem<QT>& sm = *reinterpret_cast<PairSmem<QT>*>(smem_raw);
+  constexpr int kATile = kThreads * QT;
+  constexpr int kPairs = QT / 2;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const float kInf = __int_as_float(0x7f800000);
+  const int NA = p.n[p.reg], NS = p.n[p.reg ^ 1];
+  const float* __restrict__ Ab = p.xyz[p.reg] + (size_t)b * NA * 3;
+  const float* __restrict__ Sb = p.xyz[p.reg ^ 1] + (size_t)b * NS * 3;
+  u64* PA = p.key[p.reg] + (size_t)b * NA;
+  u64* PS = p.key[p.reg ^ 1] + (size_t)b * NS;
+  const bool mask = p.mask_zero_sum != 0;
+
+  // this item's streamed range, in points: [s_begin, s_end)
+  const int s_begin = ss * p.chunks_per_item * kChunk;
+  const int s_end = min(NS, s_begin + p.chunks_per_item * kChunk);
+  const int n_stages = (s_end - s_begin + kSStage - 1) / kSStage;
+
+  // ---- this thread's QT consecutive A points -> QT/2 f32x2 pairs per coordinate ---------------------------------
+  const int a0 = at * kATile + tid * QT;
+  u64 qx[kPairs], qy[kPairs], qz[kPairs];
+  {
+    float f[3 * QT];
+    const float* Ap = Ab + 3 * (size_t)a0;
+    if (a0 + QT <= NA && (reinterpret_cast<uintptr_t>(Ap) & 15) == 0) {  // 128-bit loads: QT*12 contiguous bytes
+#pragma unroll
+      for (int i = 0; i < 3 * QT / 4; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(Ap) + i);
+        f[4 * i + 0] = v.x;
+        f[4 * i + 1] = v.y;
+        f[4 * i + 2] = v.z;
+        f[4 * i + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < QT; ++h) {
+        const bool in = a0 + h < NA;
+        f[3 * h + 0] = in ? __ldg(Ap + 3 * h + 0) : -kPadCoord();
+        f[3 * h + 1] = in ? __ldg(Ap + 3 * h + 1) : -kPadCoord();
+        f[3 * h + 2] = in ? __ldg(Ap + 3 * h + 2) : -kPadCoord();
+      }
+    }
+    if (mask) {
+#pragma unroll
+      for (int h = 0; h < QT; ++h)
+        if (zero_sum(f[3 * h], f[3 * h + 1], f[3 * h + 2])) f[3 * h] = f[3 * h + 1] = f[3 * h + 2] = -kPadCoord();
+    }
+#pragma unroll
+    for (int i = 0; i < kPairs; ++i) {
+      qx[i] = pack2(f[6 * i + 0], f[6 * i + 3]);
+      qy[i] = pack2(f[6 * i + 1], f[6 * i + 4]);
+      qz[i] = pack2(f[6 * i + 2], f[6 * i + 5]);
+    }
+  }
+  float m[QT];
+#pragma unroll
+  for (int i = 0; i < QT; ++i) {
+    m[i] = kInf;
+    sm.bestc[i][tid] = 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < QT / 4; ++i) sm.prev[i][tid] = make_float4(kInf, kInf, kInf, kInf);
+
+  {  // prologue: first stage -> buffer 0
+    float v[2][3];
+    stage_fill_load(Sb, NS, s_begin, s_end, tid, mask, v);
+    stage_fill_store<QT>(sm, 0, tid, v);
+  }
+  __syncthreads();
+
+  for (int st = 0; st < n_stages; ++st) {
+    const int buf = st & 1;
+    const int s_base = s_begin + st * kSStage;
+    float nxt[2][3];
+    const bool has_next = (st + 1 < n_stages);
+    if (has_next) stage_fill_load(Sb, NS, s_base + kSStage, s_end, tid, mask, nxt);
+
+    // number of 32-point chunks that hold at least one real point of this item
+    const int n_valid = min(kSStage, s_end - s_base);
+    const int n_chunks = (n_valid + kChunk - 1) / kChunk;
+    const ulonglong2* __restrict__ sxy = sm.sxy[buf];
+    const ulonglong2* __restrict__ szz = sm.szz[buf];
+
+    for (int c = 0; c < n_chunks; ++c) {
+#pragma unroll 4
+      for (int rr = 0; rr < kChunk; rr += 2) {
+        const int r = c * kChunk + rr;
+        const ulonglong2 cxy0 = sxy[r];
+        const ulonglong2 cxy1 = sxy[r + 1];
+        const ulonglong2 czz = szz[r >> 1];
+        float c0 = kInf, c1 = kInf;
+#pragma unroll
+        for (int i = 0; i < kPairs; ++i) {
+          const u64 d = sqdist2(qx[i], qy[i], qz[i], cxy0.x, cxy0.y, czz.x);
+          const u64 e = sqdist2(qx[i], qy[i], qz[i], cxy1.x, cxy1.y, czz.y);
+          float dl, dh, el, eh;
+          unpack2(d, dl, dh);
+          unpack2(e, el, eh);
+          m[2 * i] = fmin3(m[2 * i], dl, el);
+          m[2 * i + 1] = fmin3(m[2 * i + 1], dh, eh);
+          c0 = fmin3(c0, dl, dh);
+          c1 = fmin3(c1, el, eh);
+        }
+        const unsigned u0 = __float_as_uint(c0), u1 = __float_as_uint(c1);
+        const unsigned w0 = redux_min_u32(u0);
+        const unsigned w1 = redux_min_u32(u1);
+        const unsigned b0 = __ballot_sync(0xffffffffu, u0 == w0);
+        const unsigned b1 = __ballot_sync(0xffffffffu, u1 == w1);
+        if (lane == 0) sm.col[warp][r >> 1] = make_uint4(w0, b0, w1, b1);
+      }
+      // chunk boundary: which running minima strictly decreased inside this chunk?
+      const unsigned gchunk = (unsigned)((s_base >> 5) + c);
+#pragma unroll
+      for (int i = 0; i < QT / 4; ++i) {
+        const float4 pv = sm.prev[i][tid];
+        if (m[4 * i + 0] < pv.x) sm.bestc[4 * i + 0][tid] = gchunk;
+        if (m[4 * i + 1] < pv.y) sm.bestc[4 * i + 1][tid] = gchunk;
+        if (m[4 * i + 2] < pv.z) sm.bestc[4 * i + 2][tid] = gchunk;
+        if (m[4 * i + 3] < pv.w) sm.bestc[4 * i + 3][tid] = gchunk;
+        sm.prev[i][tid] = make_float4(m[4 * i + 0], m[4 * i + 1], m[4 * i + 2], m[4 * i + 3]);
+      }
+    }
+
+    if (has_next) stage_fill_store<QT>(sm, buf ^ 1, tid, nxt);
+    __syncthreads();  // col[][] of this stage complete; next stage's points visible
+
+    {
+      // fold the 8 warps' column minima (lowest warp wins ties -> lowest A index) and publish
+      const uint2* colp = reinterpret_cast<const uint2*>(&sm.col[0][0]);
+#pragma unroll
+      for (int h = 0; h < kSStage / kThreads; ++h) {
+        const int r = tid + h * kThreads;
+        if (r < n_chunks * kChunk) {
+          uint2 best = colp[r];
+          int bw = 0;
+#pragma unroll
+          for (int w = 1; w < kWarps; ++w) {
+            uint2 v = colp[w * kSStage + r];
+            if (v.x < best.x) {
+              best = v;
+              bw = w;
+            }
+          }
+          const int s = s_base + r;
+          if (s < s_end) {
+            const unsigned gid = (unsigned)(at * kThreads + bw * 32 + (__ffs(best.y) - 1));
+            atomicMin(PS + s, ((u64)best.x << 32) | gid);
+          }
+        }
+      }
+      __syncthreads();  // col[][] may be overwritten by the next stage
+    }
+  }
+
+  // ---- publish row minima: transposed through shared memory so that a warp's 32 atomics hit 32 consecutive keys -----
+  {
+    u64* keys = reinterpret_cast<u64*>(smem_raw);  // the stage buffers are free now: (kATile + kThreads) * 8 bytes
+#pragma unroll
+    for (int i = 0; i < QT; ++i) keys[tid * (QT + 1) + i] = pack_key(m[i], sm.bestc[i][tid]);
+    // bestc[][] lies behind the staging area (sxy + szz + col >= 34.8 KB); all reads above precede this barrier
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < QT; ++r) {
+      const int pt = r * kThreads + tid;
+      const int a = at * kATile + pt;
+      if (a < NA) atomicMin(PA + a, keys[pt + pt / QT]);
+    }
+  }
+}
+
+// =====================================================================================================================
+// RESOLVE: exact index recovery + write-out + partial sums + fan-in count
+// =====================================================================================================================
+// Warp-cooperative: the lanes of a warp evaluate the candidates of one point in parallel (coalesced candidate reads), a
+// ballot of the exact matches gives the first (lowest-index) one.
+//   register side: candidates are the 32 streamed points of chunk `id` (one point per warp step);
+//   streamed side: the `group` register-side points of group `id` (32/group points per warp step).
+// The candidate distance is evaluated with the identical instruction sequence as the search, so exactly-equal compares
+// are well defined.  kRU warp steps are issued together so kRU gathers are in flight per lane.
+template <bool kRow>
+__device__ __forceinline__ void resolve_item(const StepParams& p, int b, int side, int p0, int p1, int group) {
+  constexpr int kRU = 8;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int other = side ^ 1;
+  const int nX = p.n[side], nY = p.n[other];
+  const float* __restrict__ Xb = p.xyz[side] + (size_t)b * nX * 3;
+  const float* __restrict__ Yb = p.xyz[other] + (size_t)b * nY * 3;
+  const u64* keys = p.key[side] + (size_t)b * nX;
+  float* dist = p.dist[side] ? p.dist[side] + (size_t)b * nX : nullptr;
+  int32_t* idx = p.idx[side] ? p.idx[side] + (size_t)b * nX : nullptr;
+  float4* part = p.part[side] ? p.part[side] + (size_t)b * ((nX + 31) / 32) : nullptr;
+  int* cnt_other = p.need_list[other] ? p.cnt[other] + (size_t)b * nY : nullptr;
+  const bool mask = p.mask_zero_sum != 0;
+
+  for (int t0 = p0 + warp * 32; t0 < p1; t0 += kWarps * 32) {
+    const int t = t0 + lane;
+    const bool valid = t < p1;
+    u64 key = 0ull;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    if (valid) {
+      key = __ldcg(keys + t);
+      sx = __ldg(Xb + 3 * (size_t)t);
+      sy = __ldg(Xb + 3 * (size_t)t + 1);
+      sz = __ldg(Xb + 3 * (size_t)t + 2);
+    }
+    const bool zs = zero_sum(sx, sy, sz);
+    const bool masked = mask && zs;
+    int myidx = 0;
+    if (kRow) {
+#pragma unroll 1
+      for (int j0 = 0; j0 < 32; j0 += kRU) {
+        if (t0 + j0 >= p1) break;  // warp-uniform
+        float cx[kRU], cy[kRU], cz[kRU];
+        bool ok[kRU];
+        unsigned kd[kRU];
+        int base[kRU];
+#pragma unroll
+        for (int u = 0; u < kRU; ++u) {
+          const int j = j0 + u;
+          const u64 kj = __shfl_sync(0xffffffffu, key, j);
+          kd[u] = (unsigned)(kj >> 32);
+          // a key that was never lowered (all-ones: every distance of this point was NaN - outside the contract)
+          // must not be turned into an address
+          const bool valid_key = kj != ~0ull;
+          base[u] = valid_key ? (int)(unsigned)kj * kChunk : 0;
+          const int cand = base[u] + lane;
+          ok[u] = valid_key && (t0 + j < p1) && (cand < nY);
+          cx[u] = cy[u] = cz[u] = 0.f;
+          if (ok[u]) {
+            const float* c = Yb + (size_t)cand * 3;
+            cx[u] = __ldg(c);
+            cy[u] = __ldg(c + 1);
+            cz[u] = __ldg(c + 2);
+            if (mask && zero_sum(cx[u], cy[u], cz[u])) cx[u] = cy[u] = cz[u] = kPadCoord();
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kRU; ++u) {
+          const int j = j0 + u;
+          float x = __shfl_sync(0xffffffffu, sx, j);
+          float y = __shfl_sync(0xffffffffu, sy, j);
+          float z = __shfl_sync(0xffffffffu, sz, j);
+          if (mask && zero_sum(x, y, z)) x = y = z = -kPadCoord();
+          const bool eq = ok[u] && (sqdist(x, y, z, cx[u], cy[u], cz[u]) == __uint_as_float(kd[u]));
+          const unsigned hits = __ballot_sync(0xffffffffu, eq);
+          if (lane == j) myidx = base[u] + (hits ? (__ffs(hits) - 1) : 0);
+        }
+      }
+    } else {
+      const int per_step = 32 / group;  // group is 8 or 16
+      const int sub = lane / group, offl = lane % group;
+      const unsigned gmask = (1u << group) - 1u;
+#pragma unroll 1
+      for (int j0 = 0; j0 < 32; j0 += kRU * per_step) {
+        if (t0 + j0 >= p1) break;  // warp-uniform
+        float cx[kRU], cy[kRU], cz[kRU];
+        bool ok[kRU];
+        unsigned kd[kRU];
+#pragma unroll
+        for (int q = 0; q < kRU; ++q) {
+          const int j = j0 + q * per_step + sub;  // the point this lane helps with
+          const u64 kj = __shfl_sync(0xffffffffu, key, j & 31);
+          kd[q] = (unsigned)(kj >> 32);
+          const bool valid_key = kj != ~0ull;
+          const int cand = valid_key ? (int)(unsigned)kj * group + offl : 0;
+          ok[q] = valid_key && (j < 32) && (t0 + j < p1) && (cand < nY);
+          cx[q] = cy[q] = cz[q] = 0.f;
+          if (ok[q]) {
+            const float* c = Yb + (size_t)cand * 3;
+            cx[q] = __ldg(c);
+            cy[q] = __ldg(c + 1);
+            cz[q] = __ldg(c + 2);
+            if (mask && zero_sum(cx[q], cy[q], cz[q])) cx[q] = cy[q] = cz[q] = -kPadCoord();
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kRU; ++q) {
+          const int jb = j0 + q * per_step;  // first point of this step
+          const int j = jb + sub;
+          float x = __shfl_sync(0xffffffffu, sx, j & 31);
+          float y = __shfl_sync(0xffffffffu, sy, j & 31);
+          float z = __shfl_sync(0xffffffffu, sz, j & 31);
+          if (mask && zero_sum(x, y, z)) x = y = z = kPadCoord();
+          const bool eq = ok[q] && (sqdist(cx[q], cy[q], cz[q], x, y, z) == __uint_as_float(kd[q]));
+          const unsigned hits = __ballot_sync(0xffffffffu, eq);
+          const int owner_sub = lane - jb;  // lane jb + s owns sub-group s of this step
+          if (owner_sub >= 0 && owner_sub < per_step) {
+            const unsigned mine = (hits >> (owner_sub * group)) & gmask;
+            myidx = (key != ~0ull) ? (int)(unsigned)key * group + (mine ? (__ffs(mine) - 1) : 0) : 0;
+          }
+        }
+      }
+    }
+    const float d = __uint_as_float((unsigned)(key >> 32));
+    if (valid) {
+      if (dist) dist[t] = d;
+      if (idx) idx[t] = myidx;
+      if (cnt_other && !masked) atomicAdd(cnt_other + myidx, 1);
+    }
+    if (part) {  // fixed butterfly over the 32 points of this step: independent of the launch geometry
+      const bool in = valid && !masked;
+      const float r = sqrtf(d);  // IEEE sqrt.rn (no fast-math), same as torch.sqrt
+      float s1 = in ? d : 0.f, s2 = in ? r : 0.f;
+      int c1 = (in && r < p.th) ? 1 : 0, c2 = (valid && !zs) ? 1 : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 = __fadd_rn(s1, __shfl_xor_sync(0xffffffffu, s1, o));
+        s2 = __fadd_rn(s2, __shfl_xor_sync(0xffffffffu, s2, o));
+      }
+      c1 = __reduce_add_sync(0xffffffffu, c1);
+      c2 = __reduce_add_sync(0xffffffffu, c2);
+      if (lane == 0) part[t0 >> 5] = make_float4(s1, s2, __int_as_float(c1), __int_as_float(c2));
+    }
+  }
+}
+
+// backward-only launches: the indices are given, RESOLVE items only count the fan-in
+__device__ __forceinline__ void count_item(const StepParams& p, int b, int side, int p0, int p1) {
+  const int other = side ^ 1;
+  if (!p.need_list[other]) return;
+  const int32_t* __restrict__ idx = p.idx[side] + (size_t)b * p.n[side];
+  int* cnt_other = p.cnt[other] + (size_t)b * p.n[other];
+  for (int t = p0 + threadIdx.x; t < p1; t += kThreads) {
+    const unsigned j = (unsigned)__ldg(idx + t);
+    if (j < (unsigned)p.n[other]) atomicAdd(cnt_other + j, 1);  // out-of-range indices (caller garbage) are dropped
+  }
+}
+
+// Fixed-order fold of one cloud's partials -> sums[b], counts[b], valid[b].
+__device__ __forceinline__ void finalize_cloud(const StepParams& p, TailSmem& ts, int b) {
+  for (int side = 0; side < 2; ++side) {
+    if (!p.part[side]) continue;
+    const int P = (p.n[side] + 31) / 32;
+    const float4* part = p.part[side] + (size_t)b * P;
+    float s1 = 0.f, s2 = 0.f;
+    int c1 = 0, c2 = 0;
+    for (int i = threadIdx.x; i < P; i += kThreads) {
+      const float4 v = __ldcg(part + i);
+      s1 = __fadd_rn(s1, v.x);
+      s2 = __fadd_rn(s2, v.y);
+      c1 += __float_as_int(v.z);
+      c2 += __float_as_int(v.w);
+    }
+    const float t1 = block_sum_f(s1, ts.redf);
+    const float t2 = block_sum_f(s2, ts.redf);
+    const int k1 = block_sum_i(c1, ts.redi);
+    const int k2 = block_sum_i(c2, ts.redi);
+    if (threadIdx.x == 0) {
+      if (p.sums) {
+        p.sums[b * 4 + side] = t1;
+        p.sums[b * 4 + 2 + side] = t2;
+      }
+      if (p.counts) p.counts[b * 2 + side] = k1;
+      if (p.valid && !p.valid_is_input) p.valid[b * 2 + side] = k2;
+    }
+  }
+}
+
+// Fixed-order fold of the per-cloud sums into the loss scalars of the four reference modules
+// (extensions/chamfer_dist/__init__.py:43-44,61-62,82-84,101-103).  Means are over the UNMASKED points.
+__device__ __forceinline__ void finalize_loss(const StepParams& p, TailSmem& ts) {
+  if (!p.loss || !p.sums) return;
+  float t[4];
+  for (int c = 0; c < 4; ++c) {
+    float v = 0.f;
+    for (int b = threadIdx.x; b < p.B; b += kThreads) v = __fadd_rn(v, __ldcg(p.sums + b * 4 + c));
+    t[c] = block_sum_f(v, ts.redf);
+  }
+  int nv[2] = {0, 0};
+  if (p.mask_zero_sum && p.valid) {
+    for (int s = 0; s < 2; ++s) {
+      int v = 0;
+      for (int b = threadIdx.x; b < p.B; b += kThreads) v += __ldcg(p.valid + b * 2 + s);
+      nv[s] = block_sum_i(v, ts.redi);
+    }
+  }
+  if (threadIdx.x == 0) {
+    const float n1 = p.mask_zero_sum ? (float)nv[0] : (float)p.B * (float)p.n[0];
+    const float n2 = p.mask_zero_sum ? (float)nv[1] : (float)p.B * (float)p.n[1];
+    const float m1 = t[0] / n1, m2 = t[1] / n2, q1 = t[2] / n1, q2 = t[3] / n2;
+    float l0, l1 = 0.f;
+    if (p.kind == 1) {
+      l0 = (q1 + q2) / 2;
+    } else if (p.kind == 2) {
+      l0 = m1 + m2;
+    } else if (p.kind == 3) {
+      l0 = m1;
+      l1 = m2;
+    } else {
+      l0 = q1;
+    }
+    p.loss[0] = l0;
+    p.loss[1] = l1;
+  }
+}
+
+// =====================================================================================================================
+// PREFIX / FILL
+// =====================================================================================================================
+__device__ __forceinline__ void prefix_item(const StepParams& p, TailSmem& ts, int b, int side) {
+  if (!p.need_list[side]) return;
+  const int n = p.n[side];
+  const int* cnt = p.cnt[side] + (size_t)b * n;
+  int* off = p.off[side] + (size_t)b * (n + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int carry = 0;
+  for (int base = 0; base < n; base += kThreads * 4) {
+    int v[4];
+    const int i0 = base + tid * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = (i0 + e < n) ? __ldcg(cnt + i0 + e) + 1 : 0;
+    const int mine = v[0] + v[1] + v[2] + v[3];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    __syncthreads();  // wcnt free
+    if (lane == 31) ts.wcnt[warp] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const int c = ts.wcnt[w];
+      if (w < warp) wbase += c;
+      total += c;
+    }
+    int run = carry + wbase + incl - mine;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (i0 + e < n) off[i0 + e] = run;
+      run += v[e];
+    }
+    carry += total;
+  }
+  if (tid == 0) off[n] = carry;
+}
+
+__device__ __forceinline__ void fill_item(const StepParams& p, int b, int side, int p0, int p1) {
+  const int other = side ^ 1;
+  if (!p.need_list[other]) return;
+  const int nX = p.n[side], nY = p.n[other];
+  const float* __restrict__ Xb = p.xyz[side] + (size_t)b * nX * 3;
+  const int32_t* idx = p.idx[side] + (size_t)b * nX;
+  int* cnt = p.cnt[other] + (size_t)b * nY;
+  const int* off = p.off[other] + (size_t)b * (nY + 1);
+  int* csr = p.csr[other] + (size_t)b * nX;
+  for (int t = p0 + threadIdx.x; t < p1; t += kThreads) {
+    if (p.mask_zero_sum && zero_sum(__ldg(Xb + 3 * (size_t)t), __ldg(Xb + 3 * (size_t)t + 1), __ldg(Xb + 3 * (size_t)t + 2)))
+      continue;
+    const unsigned j = (unsigned)__ldcg(idx + t);
+    if (j >= (unsigned)nY) continue;
+    const int slot = atomicAdd(cnt + j, -1);  // remaining - 1: slots count down to 0
+    csr[__ldcg(off + j) + slot] = t;
+  }
+}
+
+// =====================================================================================================================
+// GATHER
+// =====================================================================================================================
+__device__ __forceinline__ float point_weight(int mode, float scaled_upstream, const float* g, int i) {
+  // returns 2 * dLoss/d dist[i]
+  if (mode == 0) return __fmul_rn(__ldcg(g + i), 2.f);
+  float w = scaled_upstream;
+  if (mode == 1) w = __fdiv_rn(w, sqrtf(__ldcg(g + i)));  // d/dd sqrt(d) = 0.5/sqrt(d); the 0.5 is in scale
+  return __fmul_rn(w, 2.f);
+}
+
+__device__ __forceinline__ void cswap(int& a, int& b) {
+  const int lo = min(a, b), hi = max(a, b);
+  a = lo;
+  b = hi;
+}
+
+__device__ __forceinline__ void gather_item(const StepParams& p, TailSmem& ts, int b, int side, int p0, int p1) {
+  if (!p.grad[side]) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int other = side ^ 1;
+  const int nX = p.n[side], nY = p.n[other];
+  const float* __restrict__ Xb = p.xyz[side] + (size_t)b * nX * 3;
+  const float* __restrict__ Yb = p.xyz[other] + (size_t)b * nY * 3;
+  const float* gX = p.gw[side] ? p.gw[side] + (size_t)b * nX : nullptr;
+  const float* gY = p.gw[other] ? p.gw[other] + (size_t)b * nY : nullptr;
+  const bool fan = p.need_list[side] != 0;
+  const int32_t* idxX = p.idx[side] + (size_t)b * nX;
+  const int* off = fan ? p.off[side] + (size_t)b * (nX + 1) : nullptr;
+  const int* csr = fan ? p.csr[side] + (size_t)b * nY : nullptr;
+  float* out = p.grad[side] + (size_t)b * nX * 3;
+  float up0 = 1.f, up1 = 1.f;
+  if (p.mode != 0 && p.grad_out != nullptr) {
+    up0 = __ldg(p.grad_out);
+    up1 = __ldg(p.grad_out + p.grad_out_stride);
+  }
+  const int mode = p.mode;
+  const float wX = __fmul_rn(side ? up1 : up0, p.scale[side]);
+  const float wY = __fmul_rn(side ? up0 : up1, p.scale[other]);
+  const bool mask = p.mask_zero_sum != 0;
+
+  auto own_term = [&](int j, float x0, float x1, float x2, float& ox, float& oy, float& oz) {
+    ox = oy = oz = 0.f;
+    if (gX != nullptr && !(mask && zero_sum(x0, x1, x2))) {
+      const unsigned j2 = (unsigned)__ldcg(idxX + j);
+      if (j2 < (unsigned)nY) {
+        const float g = point_weight(mode, wX, gX, j);
+        ox = __fmul_rn(g, __fsub_rn(x0, __ldg(Yb + 3 * (size_t)j2 + 0)));
+        oy = __fmul_rn(g, __fsub_rn(x1, __ldg(Yb + 3 * (size_t)j2 + 1)));
+        oz = __fmul_rn(g, __fsub_rn(x2, __ldg(Yb + 3 * (size_t)j2 + 2)));
+      }
+    }
+  };
+
+  if (tid == 0) ts.n_deferred = 0;
+  __syncthreads();
+  // ---- pass 1: one thread per point; segments of <= 8 entries (mean fan-in ~1) are ordered in registers --------------
+  for (int j = p0 + tid; j < p1; j += kThreads) {
+    int o0 = 0, c = 0;
+    if (fan) {
+      o0 = __ldcg(off + j);
+      c = __ldcg(off + j + 1) - o0;
+    }
+    if (c > 8) {
+      ts.deferred[atomicAdd(&ts.n_deferred, 1)] = (unsigned short)(j - p0);
+      continue;
+    }
+    int e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = (i < c) ? __ldcg(csr + o0 + i) : 0x7fffffff;
+    const float x0 = __ldg(Xb + 3 * (size_t)j), x1 = __ldg(Xb + 3 * (size_t)j + 1), x2 = __ldg(Xb + 3 * (size_t)j + 2);
+    float ox, oy, oz;
+    own_term(j, x0, x1, x2, ox, oy, oz);
+    if (c > 1) {  // 8-input sorting network (19 compare-exchanges)
+      cswap(e[0], e[1]); cswap(e[2], e[3]); cswap(e[4], e[5]); cswap(e[6], e[7]);
+      cswap(e[0], e[2]); cswap(e[1], e[3]); cswap(e[4], e[6]); cswap(e[5], e[7]);
+      cswap(e[1], e[2]); cswap(e[5], e[6]); cswap(e[0], e[4]); cswap(e[3], e[7]);
+      cswap(e[1], e[5]); cswap(e[2], e[6]);
+      cswap(e[1], e[4]); cswap(e[3], e[6]);
+      cswap(e[2], e[4]); cswap(e[3], e[5]);
+      cswap(e[3], e[4]);
+    }
+    // all gathers first (independent), then the ordered sum
+    float gw[8], yx[8], yy[8], yz[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < c) {
+        const int k = e[i];
+        gw[i] = point_weight(mode, wY, gY, k);
+        yx[i] = __ldg(Yb + 3 * (size_t)k + 0);
+        yy[i] = __ldg(Yb + 3 * (size_t)k + 1);
+        yz[i] = __ldg(Yb + 3 * (size_t)k + 2);
+      }
+    }
+    float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < c) {
+        ax = __fadd_rn(ax, __fmul_rn(gw[i], __fsub_rn(yx[i], x0)));
+        ay = __fadd_rn(ay, __fmul_rn(gw[i], __fsub_rn(yy[i], x1)));
+        az = __fadd_rn(az, __fmul_rn(gw[i], __fsub_rn(yz[i], x2)));
+      }
+    }
+    out[3 * (size_t)j + 0] = __fsub_rn(ox, ax);
+    out[3 * (size_t)j + 1] = __fsub_rn(oy, ay);
+    out[3 * (size_t)j + 2] = __fsub_rn(oz, az);
+  }
+  __syncthreads();
+  const int n_def = ts.n_deferred;
+  if (n_def == 0) return;  // CTA-uniform
+
+  // ---- pass 2: one warp per deferred point of <= kWarpSort entries: bitonic sort in shared memory, then the lanes ----
+  // gather 32 terms in parallel and add them one after the other in ascending source index
+  bool any_huge = false;
+  for (int d = warp; d < n_def; d += kWarps) {
+    const int j = p0 + ts.deferred[d];
+    const int o0 = __ldcg(off + j);
+    const int c = __ldcg(off + j + 1) - o0;
+    if (c > kWarpSort) {
+      any_huge = true;
+      continue;
+    }
+    int* buf = ts.sortbuf[warp];
+    int P = 32;
+    while (P < c) P <<= 1;
+    for (int i = lane; i < P; i += 32) buf[i] = (i < c) ? __ldcg(csr + o0 + i) : 0x7fffffff;
+    __syncwarp();
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int jj = k >> 1; jj > 0; jj >>= 1) {
+        for (int i = lane; i < P; i += 32) {
+          const int ixj = i ^ jj;
+          if (ixj > i) {
+            const int a = buf[i], bb = buf[ixj];
+            const bool up = (i & k) == 0;
+            if ((a > bb) == up) {
+              buf[i] = bb;
+              buf[ixj] = a;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    const float x0 = __ldg(Xb + 3 * (size_t)j), x1 = __ldg(Xb + 3 * (size_t)j + 1), x2 = __ldg(Xb + 3 * (size_t)j + 2);
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int i0 = 0; i0 < c; i0 += 32) {
+      const int i = i0 + lane;
+      float tx = 0.f, ty = 0.f, tz = 0.f;
+      if (i < c) {
+        const int k = buf[i];
+        const float g = point_weight(mode, wY, gY, k);
+        tx = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 0), x0));
+        ty = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 1), x1));
+        tz = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 2), x2));
+      }
+      const int mrem = min(32, c - i0);
+      for (int l = 0; l < mrem; ++l) {
+        ax = __fadd_rn(ax, __shfl_sync(0xffffffffu, tx, l));
+        ay = __fadd_rn(ay, __shfl_sync(0xffffffffu, ty, l));
+        az = __fadd_rn(az, __shfl_sync(0xffffffffu, tz, l));
+      }
+    }
+    __syncwarp();  // buf is reused by this warp's next point
+    if (lane == 0) {
+      float ox, oy, oz;
+      own_term(j, x0, x1, x2, ox, oy, oz);
+      out[3 * (size_t)j + 0] = __fsub_rn(ox, ax);
+      out[3 * (size_t)j + 1] = __fsub_rn(oy, ay);
+      out[3 * (size_t)j + 2] = __fsub_rn(oz, az);
+    }
+  }
+  if (!__syncthreads_or(any_huge ? 1 : 0)) return;
+
+  // ---- pass 3: the whole CTA per point with a huge segment (a collapsed prediction).  Source indices are unique, so a
+  // bitmap of one window of them, walked in order, IS the ascending order: no sort.  Threads 0..2 keep the running sums.
+  float acc = 0.f;
+  for (int d = 0; d < n_def; ++d) {
+    const int j = p0 + ts.deferred[d];
+    const int o0 = __ldcg(off + j);
+    const int c = __ldcg(off + j + 1) - o0;
+    if (c <= kWarpSort) continue;  // CTA-uniform
+    const float x0 = __ldg(Xb + 3 * (size_t)j), x1 = __ldg(Xb + 3 * (size_t)j + 1), x2 = __ldg(Xb + 3 * (size_t)j + 2);
+    acc = 0.f;
+    for (int lo = 0; lo < nY; lo += kBitWin) {
+      for (int i = tid; i < kBitWin / 32; i += kThreads) ts.bitmap[i] = 0u;
+      __syncthreads();
+      for (int i = tid; i < c; i += kThreads) {
+        const unsigned k = (unsigned)(__ldcg(csr + o0 + i) - lo);
+        if (k < (unsigned)kBitWin) atomicOr(&ts.bitmap[k >> 5], 1u << (k & 31));
+      }
+      __syncthreads();
+      const int hi = min(nY - lo, kBitWin);
+      for (int blk = 0; blk < hi; blk += kThreads) {
+        const unsigned w = ts.bitmap[(blk >> 5) + warp];  // words beyond `hi` are zero
+        if (lane == 0) ts.wcnt[warp] = __popc(w);
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int q = 0; q < kWarps; ++q) {
+          const int cq = ts.wcnt[q];
+          if (q < warp) wbase += cq;
+          total += cq;
+        }
+        if (total != 0) {  // CTA-uniform
+          if ((w >> lane) & 1u) {
+            const int k = lo + blk + warp * 32 + lane;
+            const int pos = wbase + __popc(w & ((1u << lane) - 1u));
+            const float g = point_weight(mode, wY, gY, k);
+            ts.stage[0][pos] = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 0), x0));
+            ts.stage[1][pos] = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 1), x1));
+            ts.stage[2][pos] = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 2), x2));
+          }
+          __syncthreads();
+          if (tid < 3) {
+            const float* s = ts.stage[tid];
+#pragma unroll 8
+            for (int i = 0; i < total; ++i) acc = __fadd_rn(acc, s[i]);
+          }
+        }
+        __syncthreads();  // stage[] / wcnt[] free
+      }
+    }
+    float ox, oy, oz;
+    own_term(j, x0, x1, x2, ox, oy, oz);
+    if (tid < 3) out[3 * (size_t)j + tid] = __fsub_rn(tid == 0 ? ox : (tid == 1 ? oy : oz), acc);
+  }
+}
+
+// =====================================================================================================================
+// the persistent kernel
+// =====================================================================================================================
+// QT: A-side points per thread of the PAIR phase (8 or 16); QT = 0: no PAIR / RESOLVE code (backward-only launches).
+template <int QT>
+__global__ void __launch_bounds__(kThreads, QT == 0 ? 3 : 2) chamfer_step_kernel(const StepParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CtlSmem& ctl = *reinterpret_cast<CtlSmem*>(smem_raw + StepSmem<QT>::kCtlOff);
+  TailSmem& ts = *reinterpret_cast<TailSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  if (p.valid_is_input) {  // gated launch (ignore_zeros second pass): nothing to do when no cloud holds a masked point
+    int differs = 0;
+    for (int i = tid; i < 2 * p.B; i += kThreads) differs |= (__ldcg(p.valid + i) != p.n[i & 1]) ? 1 : 0;
+    if (!__syncthreads_or(differs)) return;
+  }
+  if (p.stats && tid == 0) atomicMin(p.stats + 1, globaltimer_ns());
+
+  for (;;) {
+    __syncthreads();  // everyone is done with smem (incl. next_item) of the previous item
+    if (tid == 0) ctl.next_item = atomicAdd(p.ticket, 1u) + 1u;
+    __syncthreads();
+    const int item = (int)ctl.next_item;
+    if (item >= p.total_items) break;
+
+    if (item < p.first_res) {
+      if constexpr (QT != 0) {
+        const int b = item / p.pair_per_cloud;
+        const int rem = item - b * p.pair_per_cloud;
+        const int at = rem / p.s_splits;
+        const int ss = rem - at * p.s_splits;
+        if (p.stats && tid == 0) atomicMin(p.stats + 0, globaltimer_ns());
+        pair_item<QT>(p, smem_raw, b, at, ss);
+        signal_done(p.done_pair + b, p.pair_per_cloud, ctl);
+        if (p.stats && tid == 0) atomicMax(p.stats + 2, globaltimer_ns());
+      }
+    } else if (item < p.first_pre) {
+      const int r = item - p.first_res;
+      const int b = r / p.rc_per_cloud;
+      const int q = r - b * p.rc_per_cloud;
+      const int side = q < p.rc_items[0] ? 0 : 1;
+      const int p0 = (side ? q - p.rc_items[0] : q) * p.rc;
+      const int p1 = min(p.n[side], p0 + p.rc);
+      if constexpr (QT != 0) {
+        wait_done(p.done_pair + b, p.pair_per_cloud);
+        if (side == p.reg)
+          resolve_item<true>(p, b, side, p0, p1, QT);
+        else
+          resolve_item<false>(p, b, side, p0, p1, QT);
+      } else {
+        count_item(p, b, side, p0, p1);
+      }
+      const bool last_of_cloud = signal_done(p.done_res + b, p.rc_per_cloud, ctl);
+      if (last_of_cloud && (p.part[0] || p.part[1])) {
+        finalize_cloud(p, ts, b);
+        if (signal_done(p.done_final, p.B, ctl)) finalize_loss(p, ts);
+      }
+    } else if (item < p.first_fill) {
+      const int r = item - p.first_pre;
+      const int b = r >> 1, side = r & 1;
+      wait_done(p.done_res + b, p.rc_per_cloud);
+      prefix_item(p, ts, b, side);
+      signal_done(p.done_pre + b, 2, ctl);
+    } else if (item < p.first_gat) {
+      const int r = item - p.first_fill;
+      const int b = r / p.rc_per_cloud;
+      const int q = r - b * p.rc_per_cloud;
+      const int side = q < p.rc_items[0] ? 0 : 1;
+      const int p0 = (side ? q - p.rc_items[0] : q) * p.rc;
+      const int p1 = min(p.n[side], p0 + p.rc);
+      wait_done(p.done_pre + b, 2);
+      fill_item(p, b, side, p0, p1);
+      signal_done(p.done_fill + b, p.rc_per_cloud, ctl);
+    } else {
+      const int r = item - p.first_gat;
+      const int b = r / p.rc_per_cloud;
+      const int q = r - b * p.rc_per_cloud;
+      const int side = q < p.rc_items[0] ? 0 : 1;
+      const int p0 = (side ? q - p.rc_items[0] : q) * p.rc;
+      const int p1 = min(p.n[side], p0 + p.rc);
+      wait_done(p.done_fill + b, p.rc_per_cloud);
+      gather_item(p, ts, b, side, p0, p1);
+    }
+  }
+  if (p.stats && tid == 0) atomicMax(p.stats + 3, globaltimer_ns());
+}
+
+// =====================================================================================================================
+// host side
+// =====================================================================================================================
+// ---- optional per-launch timing of the step kernel (bench.py's roofline.achieved) --------------------------------
+// CUDA events are recorded on the launch stream immediately around the kernel; nothing is synchronised until collect.
+static bool g_profile = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
+
+void profile_enable(bool on) {
+  for (auto& e : g_events) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  g_events.clear();
+  g_profile = on;
+}
+
+int profile_collect(double* total_ms, int* launches) {
+  double tot = 0.0;
+  int n = 0;
+  for (auto& e : g_events) {
+    cudaError_t err = cudaEventSynchronize(e.second);
+    if (err != cudaSuccess) return (int)err;
+    float ms = 0.f;
+    if ((err = cudaEventElapsedTime(&ms, e.first, e.second)) != cudaSuccess) return (int)err;
+    tot += ms;
+    ++n;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = n;
+  return 0;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct StepLayout {
+  size_t stats, memset_begin, key[2], cnt[2], counters, memset_end, off[2], csr[2], part[2], sums, valid, total;
+};
+
+// Workspace layout.  `search`: keys present; `lists`: cnt/off/csr present; `parts`: partial sums present.
+static StepLayout step_layout(int B, int N, int M, bool search, bool lists, bool parts) {
+  StepLayout L;
+  const size_t n[2] = {(size_t)N, (size_t)M};
+  L.stats = 0;  // fixed place: iapt_chamfer_step_stats reads it without knowing the launch's flags
+  size_t o = 256;
+  L.memset_begin = o;
+  for (int s = 0; s < 2; ++s) {
+    L.key[s] = o;
+    if (search) o += align256(sizeof(u64) * B * n[s]);
+  }
+  for (int s = 0; s < 2; ++s) {
+    L.cnt[s] = o;
+    if (lists) o += align256(sizeof(int) * B * n[s]);
+  }
+  L.counters = o;
+  o += align256(64 + sizeof(unsigned) * 4 * (size_t)B);
+  L.memset_end = o;
+  for (int s = 0; s < 2; ++s) {
+    L.off[s] = o;
+    if (lists) o += align256(sizeof(int) * B * (n[s] + 1));
+  }
+  for (int s = 0; s < 2; ++s) {
+    L.csr[s] = o;
+    if (lists) o += align256(sizeof(int) * B * n[1 - s]);
+  }
+  for (int s = 0; s < 2; ++s) {
+    L.part[s] = o;
+    if (parts) o += align256(sizeof(float4) * B * ((n[s] + 31) / 32));
+  }
+  L.sums = o;
+  if (parts) o += align256(sizeof(float) * 4 * (size_t)B);
+  L.valid = o;
+  if (parts) o += align256(sizeof(int32_t) * 2 * (size_t)B);
+  L.total = o;
+  return L;
+}
+
+size_t chamfer_step_workspace_bytes(int B, int N, int M) { return step_layout(B, N, M, true, true, true).total; }
+size_t chamfer_forward_workspace_bytes(int B, int N, int M) { return step_layout(B, N, M, true, false, false).total; }
+size_t chamfer_backward_workspace_bytes(int B, int N, int M) { return step_layout(B, N, M, false, true, false).total; }
+
+static int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e && *e ? std::atoi(e) : dflt;
+}
+
+static int device_sms() {
+  static int sms_of_device[256] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int num_sms = sms_of_device[dev & 255];
+  if (num_sms == 0) {
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+    sms_of_device[dev & 255] = num_sms;
+  }
+  return num_sms;
+}
+
+// A-side points per thread.  QT=16 halves the per-pair LDS/REDUX overhead but makes 4096-point tiles: it is used when
+// 4096-point tiles with at least one full stage each still give every resident CTA 4 items; otherwise QT=8
+// (2048-point tiles).  IAPT_FWD_VARIANT=8|16 forces one (read per call: the parity tests run both over every suite).
+static int pick_qt(int B, int NA, int NS, int slots) {
+  const int forced = env_int("IAPT_FWD_VARIANT", 0);
+  if (forced == 8 || forced == 16) return forced;
+  const long long tiles16 = (NA + kThreads * 16 - 1) / (kThreads * 16);
+  const long long stages = (NS + kSStage - 1) / kSStage;
+  return (NA >= 4096 && (long long)B * tiles16 * stages >= 4LL * slots) ? 16 : 8;
+}
+
+template <int QT>
+static cudaError_t launch_step(const StepParams& p, int grid, cudaStream_t stream) {
+  static PerDeviceOnce once;
+  if (once.pending()) {
+    cudaFuncSetAttribute(chamfer_step_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)StepSmem<QT>::kBytes);
+    once.done();
+  }
+  chamfer_step_kernel<QT><<<grid, kThreads, StepSmem<QT>::kBytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+int chamfer_step_launch(const StepArgs& a, cudaStream_t stream) {
+  const int B = a.B, N = a.N, M = a.M;
+  const bool search = a.search;
+  const bool want_grad[2] = {a.grad_xyz1 != nullptr, a.grad_xyz2 != nullptr};
+  const bool parts = search && (a.sums || a.counts || a.valid || a.loss);
+
+  StepParams p{};
+  p.xyz[0] = a.xyz1;
+  p.xyz[1] = a.xyz2;
+  p.n[0] = N;
+  p.n[1] = M;
+  p.B = B;
+  p.reg = N < M ? 1 : 0;  // register side = the larger cloud (its tile is 256*QT points; the streamed side pads to 32)
+  p.mask_zero_sum = a.mask_zero_sum ? 1 : 0;
+  p.dist[0] = a.dist1;
+  p.dist[1] = a.dist2;
+  p.idx[0] = a.idx1;
+  p.idx[1] = a.idx2;
+  p.th = a.th;
+  p.kind = a.kind;
+  p.mode = a.mode;
+  p.scale[0] = a.scale1;
+  p.scale[1] = a.scale2;
+  p.grad_out = a.grad_out;
+  p.grad_out_stride = a.grad_out_stride;
+  p.gw[0] = a.gw1;
+  p.gw[1] = a.gw2;
+  p.grad[0] = a.grad_xyz1;
+  p.grad[1] = a.grad_xyz2;
+  bool lists = false;
+  for (int s = 0; s < 2; ++s) {
+    p.need_list[s] = (want_grad[s] && p.gw[1 - s] != nullptr) ? 1 : 0;
+    lists = lists || p.need_list[s];
+  }
+  const bool grads = want_grad[0] || want_grad[1];
+
+  const StepLayout L = step_layout(B, N, M, search, lists, parts);
+  unsigned char* ws = static_cast<unsigned char*>(a.workspace);
+  for (int s = 0; s < 2; ++s) {
+    p.key[s] = search ? reinterpret_cast<u64*>(ws + L.key[s]) : nullptr;
+    p.cnt[s] = lists ? reinterpret_cast<int*>(ws + L.cnt[s]) : nullptr;
+    p.off[s] = lists ? reinterpret_cast<int*>(ws + L.off[s]) : nullptr;
+    p.csr[s] = lists ? reinterpret_cast<int*>(ws + L.csr[s]) : nullptr;
+    p.part[s] = parts ? reinterpret_cast<float4*>(ws + L.part[s]) : nullptr;
+  }
+  unsigned* ctr = reinterpret_cast<unsigned*>(ws + L.counters);
+  p.ticket = ctr;
+  p.done_final = ctr + 1;
+  p.done_pair = ctr + 16;
+  p.done_res = p.done_pair + B;
+  p.done_pre = p.done_res + B;
+  p.done_fill = p.done_pre + B;
+  p.sums = parts ? (a.sums ? a.sums : reinterpret_cast<float*>(ws + L.sums)) : nullptr;
+  p.counts = parts ? a.counts : nullptr;
+  p.valid = parts ? (a.valid ? a.valid : reinterpret_cast<int32_t*>(ws + L.valid)) : nullptr;
+  p.valid_is_input = (parts && a.valid && a.valid_is_input) ? 1 : 0;
+  p.loss = parts ? a.loss : nullptr;
+  p.stats = a.stats ? reinterpret_cast<u64*>(ws + L.stats) : nullptr;
+
+  cudaError_t err;
+  // one memset: keys = all-ones, every counter and fan-in count = 0xFFFFFFFF (read as value + 1)
+  if ((err = cudaMemsetAsync(ws + L.memset_begin, 0xFF, L.memset_end - L.memset_begin, stream)) != cudaSuccess)
+    return (int)err;
+  if (p.stats) {  // measurement only: two more memsets (min slots all-ones, max slots zero)
+    if ((err = cudaMemsetAsync(ws + L.stats, 0xFF, 16, stream)) != cudaSuccess) return (int)err;
+    if ((err = cudaMemsetAsync(ws + L.stats + 16, 0, 16, stream)) != cudaSuccess) return (int)err;
+  }
+
+  const int num_sms = device_sms();
+  int qt = 0, slots = num_sms * 3;
+  if (search) {
+    slots = num_sms * 2;
+    const int NA = p.n[p.reg], NS = p.n[p.reg ^ 1];
+    qt = pick_qt(B, NA, NS, slots);
+    const int a_tile = kThreads * qt;
+    p.a_tiles = (NA + a_tile - 1) / a_tile;
+    const int total_chunks = (NS + kChunk - 1) / kChunk;
+    const long long base_items = (long long)B * p.a_tiles;
+    // Split the streamed side (in 32-point chunks) until there are ~16 items per resident CTA slot: measured at B=48 x
+    // 16384^2: 8 -> 3.20 ms, 16 -> 3.09 ms, 32/64 -> 3.23 ms.  Items of a stage or more are whole stages (a partial
+    // stage costs the same barriers as a full one); an item is never smaller than kMinChunks chunks.
+    const long long items_per_slot = env_int("IAPT_ITEMS_PER_SLOT", 16);
+    const int min_chunks = env_int("IAPT_MIN_CHUNKS", 4);
+    long long splits = (items_per_slot * slots + base_items - 1) / base_items;
+    if (splits < 1) splits = 1;
+    long long cpi = (total_chunks + splits - 1) / splits;
+    if (cpi < min_chunks) cpi = min_chunks;
+    if (cpi > kStageChunks) cpi = (cpi + kStageChunks - 1) / kStageChunks * kStageChunks;
+    if (cpi > total_chunks) cpi = total_chunks;
+    p.chunks_per_item = (int)cpi;
+    p.s_splits = (int)((total_chunks + cpi - 1) / cpi);
+    p.pair_per_cloud = p.a_tiles * p.s_splits;
+  } else {
+    p.a_tiles = p.s_splits = p.chunks_per_item = 0;
+    p.pair_per_cloud = 0;
+  }
+  // RESOLVE / FILL / GATHER items: rc points, small enough that every phase has >= 2 items per resident slot
+  int rc = kMaxRc;
+  while (rc > 256 && (long long)B * ((N + rc - 1) / rc + (M + rc - 1) / rc) < 2LL * slots) rc >>= 1;
+  p.rc = rc;
+  p.rc_items[0] = (N + rc - 1) / rc;
+  p.rc_items[1] = (M + rc - 1) / rc;
+  p.rc_per_cloud = p.rc_items[0] + p.rc_items[1];
+  const long long n_pair = (long long)B * p.pair_per_cloud;
+  const long long n_rc = (long long)B * p.rc_per_cloud;
+  const long long first_res = n_pair;
+  const long long first_pre = first_res + n_rc;
+  const long long first_fill = first_pre + (lists ? 2LL * B : 0);
+  const long long first_gat = first_fill + (lists ? n_rc : 0);
+  const long long total = first_gat + (grads ? n_rc : 0);
+  if (total >= (1LL << 31) - 2) return -3;  // IAPT_EUNSUPPORTED
+  p.first_res = (int)first_res;
+  p.first_pre = (int)first_pre;
+  p.first_fill = (int)first_fill;
+  p.first_gat = (int)first_gat;
+  p.total_items = (int)total;
+
+  const int grid = (int)(total < (long long)slots ? total : (long long)slots);
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (g_profile && search) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, stream);
+  }
+  err = qt == 16 ? launch_step<16>(p, grid, stream) : (qt == 8 ? launch_step<8>(p, grid, stream) : launch_step<0>(p, grid, stream));
+  count_launch();
+  if (g_profile && search) {
+    cudaEventRecord(ev1, stream);
+    g_events.emplace_back(ev0, ev1);
+  }
+  return (int)err;
+}
+
+// dst[i] = src[i] * factor[0]  (the upstream gradient of a loss whose unit gradient was formed in the forward launch)
+__global__ void __launch_bounds__(256) scale_kernel(const float* __restrict__ src, const float* __restrict__ factor,
+                                                    long long n, float* __restrict__ dst) {
+  const float f = __ldg(factor);
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    for (; i < n4; i += stride) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+      v.x = __fmul_rn(v.x, f);
+      v.y = __fmul_rn(v.y, f);
+      v.z = __fmul_rn(v.z, f);
+      v.w = __fmul_rn(v.w, f);
+      reinterpret_cast<float4*>(dst)[i] = v;
+    }
+    for (long long t = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+      dst[t] = __fmul_rn(__ldg(src + t), f);
+  } else {
+    for (; i < n; i += stride) dst[i] = __fmul_rn(__ldg(src + i), f);
+  }
+}
+
+int scale_launch(const float* src, const float* factor, long long n, float* dst, cudaStream_t stream) {
+  long long blocks = ((n >> 2) + 255) / 256;
+  const long long cap = (long long)device_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  scale_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, factor, n, dst);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace iapt

@@ -20,27 +20,42 @@ class ChamferFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_dist1, grad_dist2):
         xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
-        grad_xyz1, grad_xyz2 = chamfer.backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2)
+        grad_xyz1, grad_xyz2 = chamfer.backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2,
+                                                ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return grad_xyz1, grad_xyz2
 
 
 class FusedChamferLoss(torch.autograd.Function):
-    """Search + loss reduction + analytic gradient as 5 kernels, no sqrt/mean autograd chain (SURVEY.md section 8f
-    rank 1).  Same values as composing ChamferFunction with torch.sqrt / torch.mean (tests compare both paths);
-    returns a 0-dim tensor (a pair for L2_split)."""
+    """Search + loss reduction + analytic gradient as ONE kernel launch (``iapt_chamfer_step``), no sqrt/mean autograd
+    chain.  When an input needs a gradient the launch also forms d loss / d xyz for upstream
+    1 and ``backward`` only applies the upstream scalar (``iapt_scale``); gradients nobody asked for (the ground truth
+    in training) are never computed.  ``L2_split`` has two independent upstream scalars, so its gradient is a second
+    launch from the saved indices (``iapt_chamfer_backward_fused``).  Same values as composing ChamferFunction with
+    torch.sqrt / torch.mean (tests compare both paths); returns a 0-dim tensor (a pair for L2_split)."""
 
     @staticmethod
     def forward(ctx, xyz1, xyz2, kind):
-        dist1, dist2, idx1, idx2 = chamfer.forward(xyz1, xyz2)
-        loss, _ = chamfer.loss_forward(dist1, dist2, kind)
-        ctx.save_for_backward(xyz1, xyz2, idx1, idx2, dist1, dist2)
-        ctx.kind = kind
+        need1, need2 = bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1])
+        one_launch = (need1 or need2) and kind != chamfer.LOSS_L2_SPLIT
+        r = chamfer.step(xyz1, xyz2, kind, grad1=one_launch and need1, grad2=one_launch and need2)
+        ctx.kind, ctx.one_launch, ctx.need = kind, one_launch, (need1, need2)
+        if one_launch:
+            ctx.save_for_backward(*[g for g in (r.grad1, r.grad2) if g is not None])
+        elif need1 or need2:
+            ctx.save_for_backward(xyz1, xyz2, r.idx1, r.idx2, r.dist1, r.dist2)
         if kind == chamfer.LOSS_L2_SPLIT:
-            return loss[0], loss[1]
-        return loss[0]
+            return r.loss[0], r.loss[1]
+        return r.loss[0]
 
     @staticmethod
     def backward(ctx, *grads):
+        need1, need2 = ctx.need
+        if ctx.one_launch:
+            saved = list(ctx.saved_tensors)
+            g = grads[0].reshape(1)
+            gx1 = chamfer.scale(saved.pop(0), g) if need1 else None
+            gx2 = chamfer.scale(saved.pop(0), g) if need2 else None
+            return gx1, gx2, None
         xyz1, xyz2, idx1, idx2, dist1, dist2 = ctx.saved_tensors
         if ctx.kind == chamfer.LOSS_L2_SPLIT:
             g = torch.stack([grads[0] if grads[0] is not None else torch.zeros_like(dist1[0, 0]),
@@ -48,7 +63,7 @@ class FusedChamferLoss(torch.autograd.Function):
         else:
             g = grads[0].reshape(1)
         gx1, gx2 = chamfer.loss_backward(xyz1.detach().contiguous(), xyz2.detach().contiguous(), idx1, idx2, dist1,
-                                         dist2, ctx.kind, g)
+                                         dist2, ctx.kind, g, need1, need2)
         return gx1, gx2, None
 
 
@@ -77,7 +92,7 @@ class _ChamferBase(torch.nn.Module):
 
     def _fused(self, xyz1, xyz2, kind):
         xyz1, xyz2 = _filter_zeros(xyz1, xyz2, self.ignore_zeros)
-        if xyz1.size(1) == 0 or xyz2.size(1) == 0:
+        if xyz1.size(0) == 0 or xyz1.size(1) == 0 or xyz2.size(1) == 0:
             return None  # degenerate: let the composed path reproduce the reference's NaN-from-empty-mean behaviour
         return FusedChamferLoss.apply(xyz1, xyz2, kind)
 

@@ -1,7 +1,7 @@
 """CUDA-graph replay of the fused Chamfer loss step for small / launch-bound problems.
 
-The fused loss path is 1 memset + 5 kernels; below ~1e8 point-pairs their combined run time is shorter than the host
-cost of issuing them from Python (~170 us).  ``GraphedChamferLoss`` captures search + loss reduction + analytic
+The fused loss path is 1 memset + 1 kernel (+ 1 to apply the upstream gradient); for tiny problems even that is
+shorter than the host cost of issuing it from Python.  ``GraphedChamferLoss`` captures search + loss reduction + analytic
 gradient once per (kind, B, N, M, device) into a ``torch.cuda.CUDAGraph`` (every launch of libiapt_b200.so goes to
 torch's current stream, so stream capture sees them) and replays it with one ``cudaGraphLaunch``.  Values and gradients
 are bit-identical to ``ChamferDistanceL1/L2/L2_split/L1_PM`` (same kernels); it is an optimisation of HOW the kernels
@@ -39,14 +39,16 @@ class _Captured:
             self._run()
 
     def _run(self):
-        d1, d2, i1, i2 = chamfer.forward(self.x1, self.x2)
-        self.loss, _ = chamfer.loss_forward(d1, d2, self.kind)
         if self.kind == chamfer.LOSS_L2_SPLIT:
             # the two outputs have independent upstream gradients: keep the per-output gradients separately
-            self.g1a, self.g2a = chamfer.loss_backward(self.x1, self.x2, i1, i2, d1, d2, self.kind, self.e0)
-            self.g1b, self.g2b = chamfer.loss_backward(self.x1, self.x2, i1, i2, d1, d2, self.kind, self.e1)
+            r = chamfer.step(self.x1, self.x2, self.kind, grad1=True, grad2=True, grad_loss=self.e0)
+            self.g1a, self.g2a = r.grad1, r.grad2
+            self.g1b, self.g2b = chamfer.loss_backward(self.x1, self.x2, r.idx1, r.idx2, r.dist1, r.dist2, self.kind,
+                                                       self.e1)
         else:
-            self.g1, self.g2 = chamfer.loss_backward(self.x1, self.x2, i1, i2, d1, d2, self.kind, self.unit)
+            r = chamfer.step(self.x1, self.x2, self.kind, grad1=True, grad2=True)
+            self.g1, self.g2 = r.grad1, r.grad2
+        self.loss = r.loss
 
 
 class _GraphedFn(torch.autograd.Function):

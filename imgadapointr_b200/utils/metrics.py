@@ -23,18 +23,18 @@ from ..extensions.chamfer_dist import ChamferDistanceL1, ChamferDistanceL2
 from . import dist_utils
 
 
-def _search(pred, gt):
+def _search(pred, gt, th=0.01, valid=False):
+    """One launch: nearest-neighbour distances + per-cloud sums [B,4] + F-Score counts [B,2] (+ valid [B,2])."""
     with torch.no_grad():
-        dist1, dist2, _, _ = chamfer.forward(pred, gt)
-    return dist1, dist2
+        return chamfer.step(pred, gt, sums=True, counts=True, valid=valid, th=th)
 
 
-def _cd_from_sums(sums, N, M):
-    """sums [B,4] -> (CDL1, CDL2) 0-dim tensors with the reference's reductions over ALL B*N / B*M elements."""
-    B = sums.size(0)
+def _cd_from_sums(sums, n1, n2):
+    """sums [B,4] -> (CDL1, CDL2) 0-dim tensors with the reference's reductions over ALL elements; n1 / n2 = number of
+    elements of each side (python numbers or 0-dim device tensors)."""
     tot = sums.sum(dim=0)
-    cdl2 = tot[0] / (B * N) + tot[1] / (B * M)
-    cdl1 = (tot[2] / (B * N) + tot[3] / (B * M)) / 2
+    cdl2 = tot[0] / n1 + tot[1] / n2
+    cdl1 = (tot[2] / n1 + tot[3] / n2) / 2
     return cdl1, cdl2
 
 
@@ -89,19 +89,22 @@ class Metrics(object):
         assert pred.size(0) == gt.size(0)
         B, N, _ = pred.shape
         M = gt.size(1)
-        dist1, dist2 = _search(pred, gt)
-        f = _f_from_counts(chamfer.fscore_counts(dist1, dist2, th), N, M)
-        filtered = False
-        if B == 1:  # ignore_zeros=True only acts for batch size 1 (chamfer_dist/__init__.py:36-41)
-            nz1 = torch.sum(pred, dim=2).ne(0)
-            nz2 = torch.sum(gt, dim=2).ne(0)
-            filtered = not bool(torch.logical_and(nz1.all(), nz2.all()))
-        if filtered:
-            p2, g2 = pred[nz1].unsqueeze(0), gt[nz2].unsqueeze(0)
-            d1, d2 = _search(p2, g2)
-            cdl1, cdl2 = _cd_from_sums(chamfer.reduce_sums(d1, d2), p2.size(1), g2.size(1))
+        r = _search(pred, gt, th, valid=(B == 1))
+        f = _f_from_counts(r.counts, N, M)
+        if B == 1:
+            # ignore_zeros=True only acts for batch size 1 (chamfer_dist/__init__.py:36-41): CD is then measured between
+            # the points whose coordinate sum is not zero.  Whether there are any such points is only known on the
+            # device, so the filtered search is ISSUED unconditionally, gated on the first launch's `valid` counts (it
+            # exits at once when nothing is filtered), and the result is selected on the device: no D2H sync
+            # (the reference's boolean-mask indexing syncs on every call).
+            with torch.no_grad():
+                r2 = chamfer.step(pred, gt, sums=True, ignore_zero_sum=True, gate_valid=r.valid)
+            nv = r.valid[0].to(torch.float32)
+            filtered = (r.valid[0, 0] != N) | (r.valid[0, 1] != M)
+            sums = torch.where(filtered, r2.sums, r.sums)
+            cdl1, cdl2 = _cd_from_sums(sums, nv[0], nv[1])
         else:
-            cdl1, cdl2 = _cd_from_sums(chamfer.reduce_sums(dist1, dist2), N, M)
+            cdl1, cdl2 = _cd_from_sums(r.sums, B * N, B * M)
         out = {'F-Score': f.to(gt.device), 'CDL1': cdl1 * 1000, 'CDL2': cdl2 * 1000}
         out['EMDistance'] = cls._get_emd_distance(pred, gt) if require_emd else torch.tensor(0.).to(gt.device)
         return out
@@ -116,9 +119,8 @@ class Metrics(object):
 
     @classmethod
     def _get_f_score(cls, pred, gt, th=0.01):
-        B, N, _ = pred.shape
-        dist1, dist2 = _search(pred, gt)
-        return _f_from_counts(chamfer.fscore_counts(dist1, dist2, th), N, gt.size(1)).to(pred.device)
+        N = pred.size(1)
+        return _f_from_counts(_search(pred, gt, th).counts, N, gt.size(1)).to(pred.device)
 
     @classmethod
     def _get_chamfer_distancel1(cls, pred, gt):
@@ -214,9 +216,8 @@ def per_cloud_metrics(pred, gt, th=0.01):
     Equals ``Metrics.get`` called cloud by cloud when no point has a zero coordinate sum."""
     B, N, _ = pred.shape
     M = gt.size(1)
-    dist1, dist2 = _search(pred, gt)
-    sums = chamfer.reduce_sums(dist1, dist2)
-    counts = chamfer.fscore_counts(dist1, dist2, th)
+    r = _search(pred, gt, th)
+    sums, counts = r.sums, r.counts
     precision = counts[:, 0].to(torch.float64) / float(N)
     recall = counts[:, 1].to(torch.float64) / float(M)
     s = precision + recall

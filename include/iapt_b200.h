@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IAPT_ABI_VERSION 1
+#define IAPT_ABI_VERSION 2
 
 #define IAPT_EINVAL (-1)     /* bad size / null pointer */
 #define IAPT_EWORKSPACE (-2) /* workspace too small */
@@ -40,10 +40,10 @@ const char* iapt_error_string(int code);
 /* Number of kernels launched through this library by the calling process so far (bench.py's gpu_launches). */
 unsigned long long iapt_launch_count(void);
 
-/* Measurement hook (bench.py roofline): when enabled, every iapt_chamfer_forward records a CUDA-event pair on its
- * launch stream tightly around the dominant kernel (chamfer_pair_kernel).  iapt_profile_collect() synchronises those
- * events and returns the summed device time in ms and the number of launches; enabling (or disabling) clears the
- * records.  Not thread-safe; for benchmarking only. */
+/* Measurement hook (bench.py roofline): when enabled, every launch that runs the nearest-neighbour search records a
+ * CUDA-event pair on its launch stream tightly around the dominant kernel (chamfer_step_kernel).
+ * iapt_profile_collect() synchronises those events and returns the summed device time in ms and the number of
+ * launches; enabling (or disabling) clears the records.  Not thread-safe; for benchmarking only. */
 int iapt_profile_enable(int on);
 int iapt_profile_collect(double* total_ms, int* launches);
 
@@ -64,12 +64,11 @@ int iapt_chamfer_forward(const float* xyz1, const float* xyz2, int B, int N, int
 
 /* Replaces chamfer.backward -> chamfer_cuda_backward (chamfer_cuda.cpp:27-34, chamfer.cu:203-229; kernel :173-201).
  *   grad_xyz1[b,j] = 2 g1[b,j] (x1_j - x2_idx1[j]) - sum_{k: idx2[k]==j} 2 g2[b,k] (x2_k - x1_j), and symmetrically
- *   for grad_xyz2.  Deterministic and free of floating-point atomics: every output point is owned by one warp
- *   that adds its fan-in in ascending source index.  Outputs are fully written (no pre-zeroing needed). */
-/* The workspace is optional.  With it, per-point fan-in lists are built (integer atomics) and gathered by one thread
- * per point - equal in speed to scanning at the benchmark size, clearly faster for small batches; bins whose list
- * overflows, and everything when workspace == NULL (or IAPT_BWD_LISTS=0), go through the scanning kernel.  Both paths
- * add every output's contributions in ascending source index: bit-identical to each other. */
+ *   for grad_xyz2.  Deterministic and free of floating-point atomics: the points that chose j as nearest neighbour are
+ *   grouped per j (counting sort with integer atomics), ordered, and added in ascending source index by j's owner.
+ *   Outputs are fully written (no pre-zeroing needed); either gradient may be NULL (not wanted), a NULL grad_dist
+ *   means zeros.  The workspace is REQUIRED (iapt_chamfer_backward_workspace_bytes: 12 bytes per point + O(B)).
+ *   Indices outside [0, other side's size) are ignored (the reference would read out of bounds). */
 size_t iapt_chamfer_backward_workspace_bytes(int B, int N, int M);
 int iapt_chamfer_backward(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
                           const float* grad_dist1, const float* grad_dist2, int B, int N, int M, float* grad_xyz1,
@@ -91,7 +90,7 @@ int iapt_chamfer_reduce(const float* dist1, const float* dist2, int B, int N, in
  *   IAPT_LOSS_L1_PM    loss[0] =  mean sqrt d1                              (ChamferDistanceL1_PM,    :86-103)
  * iapt_chamfer_backward_fused: the gradient of that loss w.r.t. xyz1/xyz2 in ONE kernel - iapt_chamfer_backward with
  * grad_dist formed on the fly (upstream * 0.5/sqrt(d)/count resp. upstream/count), replacing the sqrt/mean autograd
- * chain.  grad_loss points to the upstream gradient scalar(s) on the device (2 floats for L2_SPLIT, 1 otherwise;
+ * chain; same workspace as iapt_chamfer_backward (required), either gradient may be NULL.  grad_loss points to the upstream gradient scalar(s) on the device (2 floats for L2_SPLIT, 1 otherwise;
  * NULL = 1).  A zero distance under L1 yields inf*0 = NaN exactly like the reference's sqrt backward. */
 #define IAPT_LOSS_L1 1
 #define IAPT_LOSS_L2 2
@@ -103,6 +102,42 @@ int iapt_chamfer_backward_fused(const float* xyz1, const float* xyz2, const int3
                                 const float* dist1, const float* dist2, int kind, const float* grad_loss, int B, int N,
                                 int M, float* grad_xyz1, float* grad_xyz2, void* workspace, size_t workspace_bytes,
                                 iapt_stream_t stream);
+
+/* ---- the whole Chamfer step in ONE launch ------------------------------------------------------------------------
+ * iapt_chamfer_step = iapt_chamfer_forward + iapt_chamfer_loss + iapt_fscore_counts + iapt_chamfer_backward_fused as a
+ * single persistent kernel (plus one memset): what ChamferDistanceL1(pred, gt) followed by loss.backward() does in
+ * the reference with 2+2 kernels, 6 memsets and the sqrt/mean autograd chain (extensions/chamfer_dist/__init__.py:
+ * 13-25,64-84; chamfer.cu:147-229), and what Metrics.get does with two searches and two KD-tree passes
+ * (utils/metrics.py:45-109).
+ *   dist1/dist2/idx1/idx2  required outputs (as iapt_chamfer_forward);
+ *   kind                   0 or IAPT_LOSS_*: which reduction `loss` [2] receives (loss may be NULL);
+ *   sums [B,4], counts [B,2] (threshold fscore_th), valid [B,2]   optional per-cloud outputs (valid = number of
+ *                          points whose coordinate sum is not zero, i.e. that survive `ignore_zeros`);
+ *   grad_xyz1 / grad_xyz2  optional: gradient of the loss `kind` w.r.t. the clouds.  grad_loss = device pointer to the
+ *                          upstream scalar(s) (2 floats for L2_SPLIT), NULL = 1: a caller that learns the upstream
+ *                          gradient later (autograd) takes the unit gradient here and applies iapt_scale then.
+ *   flags                  IAPT_STEP_IGNORE_ZERO_SUM: points with x+y+z == 0 neither query nor answer and are left out
+ *                          of every sum and count - the `ignore_zeros` filter of chamfer_dist/__init__.py:37-41 without
+ *                          compacting the clouds (dist/idx of such points are meaningless; not combinable with
+ *                          gradients);  IAPT_STEP_GATE_ON_VALID: `valid` is an INPUT written by an earlier launch on the
+ *                          same clouds - if it equals (N, M) for every cloud (nothing to ignore) the launch does
+ *                          nothing and leaves its outputs untouched, so a caller can issue the `ignore_zeros` pass
+ *                          unconditionally, without reading anything back;
+ *                          IAPT_STEP_STATS: record device timestamps for iapt_chamfer_step_stats.
+ * Per-cloud sums are folded in a fixed order that does not depend on B or the GPU: bit-reproducible.
+ * iapt_chamfer_step_stats (synchronous, measurement only): stats_host[4] = globaltimer ns {first start of a search
+ * item, kernel start, last end of a search item, kernel end} of the last IAPT_STEP_STATS launch on that workspace.
+ * iapt_scale: dst[i] = src[i] * factor[0] (factor on the device) - applies the upstream gradient to a unit gradient. */
+#define IAPT_STEP_IGNORE_ZERO_SUM 1
+#define IAPT_STEP_STATS 2
+#define IAPT_STEP_GATE_ON_VALID 4
+size_t iapt_chamfer_step_workspace_bytes(int B, int N, int M);
+int iapt_chamfer_step(const float* xyz1, const float* xyz2, int B, int N, int M, int kind, int flags, float fscore_th,
+                      float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* sums, int32_t* counts,
+                      int32_t* valid, float* loss, const float* grad_loss, float* grad_xyz1, float* grad_xyz2,
+                      void* workspace, size_t workspace_bytes, iapt_stream_t stream);
+int iapt_chamfer_step_stats(const void* workspace, unsigned long long* stats_host);
+int iapt_scale(const float* src, const float* factor, long long n, float* dst, iapt_stream_t stream);
 
 /* F-Score pieces (utils/metrics.py:67-90) from the same search: counts[b] = { #{j: sqrt(dist1[b,j]) < th},
  * #{k: sqrt(dist2[b,k]) < th} } as int32 [B,2]. */

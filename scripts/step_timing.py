@@ -1,0 +1,49 @@
+"""Dev: time the one-launch Chamfer step (iapt_chamfer_step) at the BASELINE shapes, with the device-side split between
+the search items and the rest, and check it against the separate entry points.
+    python scripts/step_timing.py [B N M] ...   (default: the config 2 / 4 / 5 / 1 shapes)"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from imgadapointr_b200 import _lib, chamfer  # noqa: E402
+from imgadapointr_b200.utils import synthetic  # noqa: E402
+
+dev = torch.device("cuda:0")
+PEAK = 148 * 128 * 2 * 1.965e9
+
+
+def ev(fn, warm=3, it=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(it):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / it
+
+
+shapes = [(48, 16384, 16384), (32, 16384, 16384), (24, 16384, 16384), (12, 16384, 16384), (6, 16384, 16384),
+          (2, 65536, 65536), (1, 16384, 16384), (1, 2048, 16384), (48, 512, 16384), (48, 2048, 2048)]
+if len(sys.argv) > 3:
+    a = list(map(int, sys.argv[1:]))
+    shapes = [tuple(a[i:i + 3]) for i in range(0, len(a), 3)]
+for (B, N, M) in shapes:
+    p, g = synthetic.pcn_pair(B, max(N, M), 5)
+    p, g = p[:, :N].contiguous().to(dev), g[:, :M].contiguous().to(dev)
+    t_fwd = ev(lambda: chamfer.forward(p, g))
+    t_step = ev(lambda: chamfer.step(p, g, chamfer.LOSS_L1, grad1=True))
+    t_step2 = ev(lambda: chamfer.step(p, g, chamfer.LOSS_L1, grad1=True, grad2=True))
+    r = chamfer.step(p, g, chamfer.LOSS_L1, grad1=True, stats=True)
+    search_ms, kern_ms = chamfer.step_stats(r.workspace)
+    d1, d2, i1, i2 = chamfer.forward(p, g)
+    t_bwd = ev(lambda: chamfer.loss_backward(p, g, i1, i2, d1, d2, chamfer.LOSS_L1, None))
+    ok = torch.equal(r.dist1, d1) and torch.equal(r.idx2, i2)
+    fl = 16.0 * B * N * M
+    print(f"B={B:3d} {N:5d}x{M:5d}  fwd {t_fwd:7.4f}  step(g1) {t_step:7.4f} ({fl / t_step / 1e-3 / PEAK:.3f} of fp32 peak)  "
+          f"step(g1,g2) {t_step2:7.4f}  bwd-only {t_bwd:7.4f}  [device: search {search_ms:7.4f} kernel {kern_ms:7.4f}]  "
+          f"same={ok}", flush=True)

@@ -49,7 +49,10 @@ int main(void) {
   const float ones[4] = {1, 1, 1, 1};
   CK(cudaMemcpyAsync(g1, ones, 4 * N, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(g2, ones, 4 * M, cudaMemcpyHostToDevice, st));
-  CK(iapt_chamfer_backward(x1, x2, i1, i2, g1, g2, B, N, M, gx1, gx2, NULL, 0, st));
+  void* bws;
+  size_t bwsb = iapt_chamfer_backward_workspace_bytes(B, N, M);
+  CK(cudaMalloc(&bws, bwsb));
+  CK(iapt_chamfer_backward(x1, x2, i1, i2, g1, g2, B, N, M, gx1, gx2, bws, bwsb, st));
   CK(iapt_fps(x1, B, N, 3, 0, fi, NULL, 0, st));
   size_t kwb = iapt_knn_workspace_bytes(B, N, N, 2);
   void* kws = NULL;

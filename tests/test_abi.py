@@ -53,14 +53,28 @@ def test_no_torch_types_cross_the_boundary():
 
 def test_version_errors_and_workspace_arithmetic():
     L = _lib.lib()
-    assert L.iapt_abi_version() == 1
+    assert L.iapt_abi_version() == 2 == _lib.ABI_VERSION
     assert b"invalid" in L.iapt_error_string(-1)
     assert b"workspace" in L.iapt_error_string(-2)
     assert L.iapt_error_string(0) == b"success"
-    assert L.iapt_chamfer_forward_workspace_bytes(48, 16384, 16384) == 8 * 48 * 2 * 16384 + 256
     assert L.iapt_chamfer_forward_workspace_bytes(0, 5, 5) == 0
-    for (B, N, M) in [(1, 1, 1), (3, 700, 16384), (256, 16384, 16384)]:  # chamfer.py computes this inline
-        assert L.iapt_chamfer_forward_workspace_bytes(B, N, M) == 8 * B * (N + M) + 256
+    for (B, N, M) in [(1, 1, 1), (3, 700, 16384), (48, 16384, 16384), (256, 16384, 16384)]:
+        fw = L.iapt_chamfer_forward_workspace_bytes(B, N, M)   # keys (8 B / point) + counters
+        bw = L.iapt_chamfer_backward_workspace_bytes(B, N, M)  # counts + offsets + CSR (12 B / point) + counters
+        sw = L.iapt_chamfer_step_workspace_bytes(B, N, M)      # everything + per-32-point partial sums
+        pts = B * (N + M)
+        assert 8 * pts <= fw <= 8 * pts + 16 * B + 4096
+        assert 12 * pts <= bw <= 12 * pts + 24 * B + 4096
+        assert fw + bw - 4096 <= sw <= 21 * pts + 64 * B + 8192
+    # the one-launch step validates before any CUDA call
+    assert L.iapt_chamfer_step(None, None, 1, 4, 4, 1, 0, 0.0, None, None, None, None, None, None, None, None, None, None,
+                               None, None, 0, None) == -1
+    assert L.iapt_chamfer_step(None, None, 0, 4, 4, 1, 0, 0.0, None, None, None, None, None, None, None, None, None, None,
+                               None, None, 0, None) == 0  # empty batch
+    assert L.iapt_chamfer_step(None, None, 1, 4, 4, 5, 0, 0.0, None, None, None, None, None, None, None, None, None, None,
+                               None, None, 0, None) == -1  # unknown loss kind
+    assert L.iapt_chamfer_backward(None, None, None, None, None, None, 1, 0, 4, None, None, None, 0, None) == 0
+    assert L.iapt_scale(None, None, 0, None, None) == 0 and L.iapt_scale(None, None, 5, None, None) == -1
     assert L.iapt_fps_workspace_bytes(4, 2048, 512) == 0
     assert L.iapt_fps_workspace_bytes(2, 65536, 512) == 2 * 65536 * 4
     # argument validation happens before any CUDA call

@@ -30,24 +30,6 @@ class Guarded:
         return bool((self.buf[:GUARD] == PATTERN).all()) and bool((self.buf[GUARD + self.n:] == PATTERN).all())
 
 
-def _run_list_path_in_subprocess():
-    """The backward path is fixed when the library first launches a backward (IAPT_BWD_LISTS): run this file's chamfer
-    test in a child process with the scan-only setting too (in-process the default list path is compared with the
-    scan path bit for bit; the child covers the scan-only configuration end to end)."""
-    import os, subprocess, sys
-    env = dict(os.environ, IAPT_BWD_LISTS="0", IAPT_GUARD_CHILD="1")
-    out = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", "stay_in_bounds"],
-                         env=env, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-
-
-def test_scan_only_backward_configuration(dev):
-    import os
-    if os.environ.get("IAPT_GUARD_CHILD") == "1":
-        pytest.skip("child process")
-    _run_list_path_in_subprocess()
-
-
 @pytest.mark.parametrize("B,N,M", [(1, 1, 1), (2, 33, 7), (3, 513, 2049), (2, 4097, 300), (1, 9000, 8191)])
 def test_chamfer_entry_points_stay_in_bounds(dev, B, N, M):
     L = _lib.lib()
@@ -67,20 +49,42 @@ def test_chamfer_entry_points_stay_in_bounds(dev, B, N, M):
     bws = Guarded(bwn, dev)
     _lib.check(L.iapt_chamfer_backward(x1.data_ptr(), x2.data_ptr(), i1.ptr, i2.ptr, d1.ptr, d2.ptr, B, N, M, gx1.ptr,
                                        gx2.ptr, bws.ptr, bwn, st), "bwd")
-    gz1, gz2 = Guarded(12 * B * N, dev), Guarded(12 * B * M, dev)  # scan-only path (no workspace): bit-identical
+    assert L.iapt_chamfer_backward(x1.data_ptr(), x2.data_ptr(), i1.ptr, i2.ptr, d1.ptr, d2.ptr, B, N, M, gx1.ptr,
+                                   gx2.ptr, None, 0, st) == -2  # workspace required
+    gz1 = Guarded(12 * B * N, dev)  # one side only: identical bits for the side that is computed
     _lib.check(L.iapt_chamfer_backward(x1.data_ptr(), x2.data_ptr(), i1.ptr, i2.ptr, d1.ptr, d2.ptr, B, N, M, gz1.ptr,
-                                       gz2.ptr, None, 0, st), "bwd-scan")
+                                       None, bws.ptr, bwn, st), "bwd-one-side")
     sums, loss, cnt = Guarded(16 * B, dev), Guarded(8, dev), Guarded(8 * B, dev)
     _lib.check(L.iapt_chamfer_loss(d1.ptr, d2.ptr, B, N, M, 1, sums.ptr, loss.ptr, st), "loss")
     _lib.check(L.iapt_fscore_counts(d1.ptr, d2.ptr, B, N, M, ctypes.c_float(0.1), cnt.ptr, st), "fs")
     gy1, gy2 = Guarded(12 * B * N, dev), Guarded(12 * B * M, dev)
     _lib.check(L.iapt_chamfer_backward_fused(x1.data_ptr(), x2.data_ptr(), i1.ptr, i2.ptr, d1.ptr, d2.ptr, 1, None, B, N,
                                              M, gy1.ptr, gy2.ptr, bws.ptr, bwn, st), "bwdf")
+    # the whole step in one launch: every output and the workspace guarded, all optional outputs requested
+    e1, e2 = Guarded(4 * B * N, dev), Guarded(4 * B * M, dev)
+    j1, j2 = Guarded(4 * B * N, dev), Guarded(4 * B * M, dev)
+    s2, c2, v2, l2 = Guarded(16 * B, dev), Guarded(8 * B, dev), Guarded(8 * B, dev), Guarded(8, dev)
+    h1, h2 = Guarded(12 * B * N, dev), Guarded(12 * B * M, dev)
+    swn = L.iapt_chamfer_step_workspace_bytes(B, N, M)
+    sws = Guarded(swn, dev)
+    _lib.check(L.iapt_chamfer_step(x1.data_ptr(), x2.data_ptr(), B, N, M, 1, 2, ctypes.c_float(0.1), e1.ptr, e2.ptr,
+                                   j1.ptr, j2.ptr, s2.ptr, c2.ptr, v2.ptr, l2.ptr, None, h1.ptr, h2.ptr, sws.ptr, swn,
+                                   st), "step")
+    k1 = Guarded(12 * B * N, dev)
+    one = torch.full((1,), 0.5, device=dev)
+    _lib.check(L.iapt_scale(h1.ptr, one.data_ptr(), 3 * B * N, k1.ptr, st), "scale")
     torch.cuda.synchronize()
-    assert all(g.intact() for g in (gx1, gx2, gz1, gz2, bws, sums, loss, cnt, gy1, gy2, d1, d2, i1, i2))
-    assert torch.equal(gx1.view(torch.float32, (B, N, 3)), gz1.view(torch.float32, (B, N, 3)))
-    assert torch.equal(gx2.view(torch.float32, (B, M, 3)), gz2.view(torch.float32, (B, M, 3)))
-    assert torch.isfinite(gx1.view(torch.float32, (B, N, 3))).all()
+    assert all(g.intact() for g in (gx1, gx2, gz1, bws, sums, loss, cnt, gy1, gy2, d1, d2, i1, i2))
+    assert all(g.intact() for g in (e1, e2, j1, j2, s2, c2, v2, l2, h1, h2, sws, k1))
+    f3 = lambda g, n: g.view(torch.float32, (B, n, 3))
+    assert torch.equal(f3(gx1, N), f3(gz1, N))
+    assert torch.isfinite(f3(gx1, N)).all()
+    # the one-launch step reproduces the separate entry points bit for bit (same search, same gradient order)
+    assert torch.equal(e1.view(torch.float32, (B, N)), d1.view(torch.float32, (B, N)))
+    assert torch.equal(j2.view(torch.int32, (B, M)), i2.view(torch.int32, (B, M)))
+    assert torch.equal(f3(h1, N), f3(gy1, N)) and torch.equal(f3(h2, M), f3(gy2, M))
+    assert torch.equal(f3(k1, N), f3(h1, N) * 0.5)
+    assert int(v2.view(torch.int32, (B, 2))[:, 0].min()) == N
 
 
 @pytest.mark.parametrize("B,N,m,k", [(2, 7, 7, 3), (3, 129, 64, 16), (2, 3000, 100, 33), (1, 20000, 50, 8)])

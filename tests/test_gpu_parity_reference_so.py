@@ -72,3 +72,55 @@ def test_backward_matches_reference_kernel(dev, ref, kind, B, N, M):
     o1, o2 = chamfer.backward(a, b, i1, i2, g1, g2)
     for got, want in ((o1, r1), (o2, r2)):
         assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+# ---- the configurations BASELINE.json quotes the metric on, through the kernel variant bench.py actually times ------
+FULL_CASES = [("pcn", 48, 16384, 16384), ("uniform", 2, 65536, 65536), ("pcn", 6, 16384, 16384)]
+
+
+@pytest.mark.parametrize("kind,B,N,M", FULL_CASES)
+def test_full_size_forward_and_backward_vs_reference_kernel(dev, ref, kind, B, N, M):
+    """B=48 x 16384 x 16384 (config 2, the QT=16 tiles), 2 x 65536^2 (config 5 per GPU) and the strong-scaling shard
+    6 x 16384^2: EVERY cloud's dist and idx bit-identical to the reference kernel
+    (extensions/chamfer_dist/chamfer.cu:15-145), gradients within 1e-5 (chamfer.cu:173-201)."""
+    x1, x2 = _inputs(kind, B, N, M)
+    a, b = x1.to(dev), x2.to(dev)
+    rd1, rd2, ri1, ri2 = ref.forward(a, b)
+    torch.cuda.synchronize()
+    d1, d2, i1, i2 = chamfer.forward(a, b)
+    assert torch.equal(d1, rd1) and torch.equal(d2, rd2)
+    assert torch.equal(i1, ri1) and torch.equal(i2, ri2)
+    g1 = torch.randn(d1.shape, generator=torch.Generator().manual_seed(1)).to(dev)
+    g2 = torch.randn(d2.shape, generator=torch.Generator().manual_seed(2)).to(dev)
+    r1, r2 = ref.backward(a, b, ri1, ri2, g1, g2)
+    torch.cuda.synchronize()
+    o1, o2 = chamfer.backward(a, b, i1, i2, g1, g2)
+    for got, want in ((o1, r1), (o2, r2)):
+        assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    # the one-launch loss step (what bench.py times) finds the same neighbours and the same loss gradient
+    r = chamfer.step(a, b, chamfer.LOSS_L1, grad1=True, grad2=True)
+    assert torch.equal(r.dist1, rd1) and torch.equal(r.idx1, ri1) and torch.equal(r.dist2, rd2) and torch.equal(r.idx2, ri2)
+    w1 = 0.25 / torch.sqrt(rd1) / rd1.numel()
+    w2 = 0.25 / torch.sqrt(rd2) / rd2.numel()
+    q1, q2 = ref.backward(a, b, ri1, ri2, w1, w2)
+    torch.cuda.synchronize()
+    for got, want in ((r.grad1, q1), (r.grad2, q2)):
+        ok = torch.isfinite(want)
+        assert float((got[ok] - want[ok]).abs().max()) <= 1e-5 * float(want[ok].abs().max())
+    want_loss = (torch.sqrt(rd1.double()).mean() + torch.sqrt(rd2.double()).mean()) / 2
+    assert abs(float(r.loss[0]) - float(want_loss)) <= 1e-5 * float(want_loss)
+
+
+@pytest.mark.parametrize("variant", ["8", "16"])
+@pytest.mark.parametrize("kind,B,N,M", CASES)
+def test_both_tile_variants_bit_identical_to_reference_kernel(dev, ref, monkeypatch, variant, kind, B, N, M):
+    """IAPT_FWD_VARIANT forces the 2048-point (QT=8) or 4096-point (QT=16) register tile, whatever the heuristic would
+    pick for the shape: both must reproduce the reference kernel bit for bit."""
+    monkeypatch.setenv("IAPT_FWD_VARIANT", variant)
+    x1, x2 = _inputs(kind, B, N, M)
+    a, b = x1.to(dev), x2.to(dev)
+    rd1, rd2, ri1, ri2 = ref.forward(a, b)
+    torch.cuda.synchronize()
+    d1, d2, i1, i2 = chamfer.forward(a, b)
+    assert torch.equal(d1, rd1) and torch.equal(d2, rd2)
+    assert torch.equal(i1, ri1) and torch.equal(i2, ri2)
