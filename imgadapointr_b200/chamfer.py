@@ -142,9 +142,19 @@ def step_stats(workspace: torch.Tensor):
     """(search_ms, kernel_ms) of the last ``stats=True`` step on this workspace, from device timestamps (synchronises)."""
     import ctypes
 
-    out = (ctypes.c_ulonglong * 4)()
+    out = (ctypes.c_ulonglong * 9)()
     _lib.check(_lib.lib().iapt_chamfer_step_stats(_lib.ptr(workspace), out), "iapt_chamfer_step_stats")
     return (out[2] - out[0]) * 1e-6, (out[3] - out[1]) * 1e-6
+
+
+def step_phase_ends(workspace: torch.Tensor):
+    """ms after kernel start at which the last item of each phase (search, resolve, prefix, fill, gather) ended; None
+    for a phase that did not run."""
+    import ctypes
+
+    out = (ctypes.c_ulonglong * 9)()
+    _lib.check(_lib.lib().iapt_chamfer_step_stats(_lib.ptr(workspace), out), "iapt_chamfer_step_stats")
+    return [((out[4 + h] - out[1]) * 1e-6 if out[4 + h] else None) for h in range(5)]
 
 
 def scale(src: torch.Tensor, factor: torch.Tensor) -> torch.Tensor:

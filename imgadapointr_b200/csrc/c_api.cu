@@ -177,7 +177,7 @@ int iapt_chamfer_step(const float* xyz1, const float* xyz2, int B, int N, int M,
 
 int iapt_chamfer_step_stats(const void* workspace, unsigned long long* stats_host) {
   IAPT_REQUIRE(workspace && stats_host);
-  return (int)cudaMemcpy(stats_host, workspace, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return (int)cudaMemcpy(stats_host, workspace, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
 }
 
 int iapt_scale(const float* src, const float* factor, long long n, float* dst, iapt_stream_t stream) {

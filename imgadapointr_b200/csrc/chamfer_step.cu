@@ -28,11 +28,11 @@
 // group holding the column minimum), folded across items by a 64-bit atomicMin on (distance bits << 32 | coarse id)
 // = the reference's lowest-index tie rule (chamfer.cu:47-50,137-140).
 //
-// GATHER is deterministic without floating-point atomics: the CSR segment of a point is ordered (sorting network in
-// registers for <= 8 entries, warp bitonic sort in shared memory up to 1024, a windowed bitmap of the source indices
-// beyond that) and summed sequentially in ascending source index - the same order for every size, so results do not
-// depend on the launch geometry and a collapsed prediction (thousands of points sharing one neighbour) costs a short
-// serial chain instead of the reference's atomicAdd contention (chamfer.cu:193-198).
+// GATHER is deterministic without floating-point atomics: a CSR segment of <= 8 entries (mean fan-in is ~1) is ordered
+// by a sorting network in registers and summed in ascending source index; a longer one is summed EXACTLY in 64-bit
+// fixed point (scale = a power of two from the segment's largest term), which needs no order at all - so results do
+// not depend on scheduling or launch geometry, and a collapsed prediction (thousands of points sharing one neighbour)
+// is a parallel reduction instead of the reference's atomicAdd contention (chamfer.cu:193-198).
 #include <cstdlib>
 #include <utility>
 #include <vector>
@@ -47,8 +47,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kSStage = 512;                    // streamed points per smem stage
 constexpr int kChunk = 32;                      // streamed points per row-index chunk
 constexpr int kStageChunks = kSStage / kChunk;  // 16
-constexpr int kWarpSort = 1024;                 // fan-in entries a single warp sorts in shared memory
-constexpr int kBitWin = 32768;                  // source indices per bitmap window (segments > kWarpSort)
+constexpr int kWarpSeg = 1024;                  // fan-in entries a single warp sums; longer segments take the CTA
 constexpr int kMaxRc = 2048;                    // points per RESOLVE / FILL / GATHER item (upper bound)
 
 struct StepParams {
@@ -74,7 +73,12 @@ struct StepParams {
   int rc;               // points per RESOLVE / FILL / GATHER item (multiple of 256)
   int rc_items[2];      // ceil(n[s] / rc)
   int pair_per_cloud, rc_per_cloud;
-  int first_res, first_pre, first_fill, first_gat, total_items;
+  // Ticket order: STEPS t = 0, 1, ...; step t holds, in phase order, the items of phase ph for cloud t - lag[ph]
+  // (when that is a cloud).  lag[] is non-decreasing, so an item only waits for smaller tickets.
+  int per_cloud[5];     // items per cloud of PAIR, RESOLVE, PREFIX, FILL, GATHER (0: phase absent)
+  int lag[5];
+  int n_steps;          // B + lag[4]
+  int total_items;
   // ---- loss / metric epilogue ----------------------------------------------------------------------------------------
   float4* part[2];      // [B, ceil(n[s]/32)] {sum d, sum sqrt d, count(sqrt d < th) as int bits, #unmasked as int bits}
   float th;
@@ -95,7 +99,8 @@ struct StepParams {
   int* cnt[2];          // [B, n[s]]      fan-in count - 1 (starts at -1), consumed again by FILL
   int* off[2];          // [B, n[s] + 1]  CSR offsets
   int* csr[2];          // [B, n[1-s]]    source indices grouped by neighbour
-  u64* stats;           // optional (globaltimer ns): [0] min start of PAIR items, [1] of the kernel, [2] max end of PAIR items, [3] of the kernel
+  u64* stats;           // optional (globaltimer ns): [0] min start of PAIR items, [1] of the kernel, [2] max end of PAIR
+                        // items, [3] of the kernel, [4 + ph] max end of the items of phase ph
 };
 
 template <int QT>
@@ -112,9 +117,7 @@ struct __align__(16) PairSmem<0> {
 };
 
 struct __align__(16) TailSmem {
-  int sortbuf[kWarps][kWarpSort];    // warp-sorted fan-in segments
-  unsigned bitmap[kBitWin / 32];     // presence bitmap of one window of source indices
-  float stage[3][kThreads];          // ordered terms of one 256-index block
+  long long redl[3 * kWarps];
   unsigned short deferred[kMaxRc];   // points of this item whose segment needs a cooperative pass
   float redf[32];
   int redi[32];
@@ -123,7 +126,7 @@ struct __align__(16) TailSmem {
 };
 
 struct CtlSmem {
-  unsigned next_item;
+  int ph, b, q;  // next item: phase (-1: none left), cloud, index inside (phase, cloud)
   int flag;
 };
 
@@ -292,6 +295,17 @@ __device__ __forceinline__ void pair_item(const StepParams& p, unsigned char* sm
       qx[i] = pack2(f[6 * i + 0], f[6 * i + 3]);
       qy[i] = pack2(f[6 * i + 1], f[6 * i + 4]);
       qz[i] = pack2(f[6 * i + 2], f[6 * i + 5]);
+    }
+    // Pass every pair through one packed add of +0 (x + 0 == x for the subtractions that follow; a multiply by 1 is
+    // folded away by ptxas): the RESULT of an f32x2 instruction is an aligned register pair.  Without it ptxas leaves
+    // the halves in the registers of the 128-bit loads and re-packs them with two moves in front of every FADD2 of the
+    // hot loop (+75 % instructions, 3.09 -> 4.46 ms at config 2).
+    const u64 zero2 = pack2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kPairs; ++i) {
+      asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(qx[i]) : "l"(zero2));
+      asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(qy[i]) : "l"(zero2));
+      asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(qz[i]) : "l"(zero2));
     }
   }
   float m[QT];
@@ -474,8 +488,12 @@ __device__ __forceinline__ void resolve_item(const StepParams& p, int b, int sid
             cx[u] = __ldg(c);
             cy[u] = __ldg(c + 1);
             cz[u] = __ldg(c + 2);
-            if (mask && zero_sum(cx[u], cy[u], cz[u])) cx[u] = cy[u] = cz[u] = kPadCoord();
           }
+        }
+        if (mask) {  // after ALL loads of the batch were issued (a use inside the batch would serialise them)
+#pragma unroll
+          for (int u = 0; u < kRU; ++u)
+            if (zero_sum(cx[u], cy[u], cz[u])) cx[u] = cy[u] = cz[u] = kPadCoord();
         }
 #pragma unroll
         for (int u = 0; u < kRU; ++u) {
@@ -513,8 +531,12 @@ __device__ __forceinline__ void resolve_item(const StepParams& p, int b, int sid
             cx[q] = __ldg(c);
             cy[q] = __ldg(c + 1);
             cz[q] = __ldg(c + 2);
-            if (mask && zero_sum(cx[q], cy[q], cz[q])) cx[q] = cy[q] = cz[q] = -kPadCoord();
           }
+        }
+        if (mask) {
+#pragma unroll
+          for (int q = 0; q < kRU; ++q)
+            if (zero_sum(cx[q], cy[q], cz[q])) cx[q] = cy[q] = cz[q] = -kPadCoord();
         }
 #pragma unroll
         for (int q = 0; q < kRU; ++q) {
@@ -810,120 +832,157 @@ __device__ __forceinline__ void gather_item(const StepParams& p, TailSmem& ts, i
   const int n_def = ts.n_deferred;
   if (n_def == 0) return;  // CTA-uniform
 
-  // ---- pass 2: one warp per deferred point of <= kWarpSort entries: bitonic sort in shared memory, then the lanes ----
-  // gather 32 terms in parallel and add them one after the other in ascending source index
+  // ---- pass 2 / 3: segments of more than 8 entries are summed EXACTLY, so no order has to be established: every term is
+  // scaled by a power of two S chosen from the segment's largest |term| (|term * S| < 2^38), rounded once to a 64-bit
+  // integer (absolute error <= 2^-39 of the largest term - far below the n * 2^-24 of any float32 summation order) and
+  // the integers are added - associative, hence independent of the order of the CSR segment (which the FILL atomics
+  // leave to scheduling), of the warp / CTA shape and of the launch geometry.  Non-finite terms (0 distance under L1:
+  // inf * 0, like the reference's sqrt backward) bypass the integers: sums over {0, +-Inf, NaN} are order-free too.
+  // A warp takes a segment of <= kWarpSeg entries, the whole CTA a longer one (a collapsed prediction: thousands of
+  // points sharing one neighbour) - a parallel reduction instead of the reference's serialised atomicAdds
+  // (chamfer.cu:193-198).
+  auto term = [&](int k, float x0, float x1, float x2, float& tx, float& ty, float& tz) {
+    const float g = point_weight(mode, wY, gY, k);
+    tx = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 0), x0));
+    ty = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 1), x1));
+    tz = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 2), x2));
+  };
+  auto finite_abs = [](float t) { return (__float_as_uint(t) & 0x7f800000u) != 0x7f800000u ? fabsf(t) : 0.f; };
+  auto nonfinite = [](float t) { return (__float_as_uint(t) & 0x7f800000u) != 0x7f800000u ? 0.f : t; };
+  // S = 2^(37 - e) for the largest finite |term| = 1.m * 2^e (so |term * S| < 2^38), clamped to float range
+  auto scale_for = [](float mx, float& S, float& invS) {
+    int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;  // denormal maximum: e = -127 (terms * S stay tiny)
+    int se = 37 - e;
+    se = max(-100, min(100, se));
+    S = __uint_as_float((unsigned)(se + 127) << 23);
+    invS = __uint_as_float((unsigned)(127 - se) << 23);
+  };
+  auto to_fixed = [](float t, float S) -> long long {
+    return (__float_as_uint(t) & 0x7f800000u) != 0x7f800000u ? __float2ll_rn(__fmul_rn(t, S)) : 0ll;
+  };
+
   bool any_huge = false;
   for (int d = warp; d < n_def; d += kWarps) {
     const int j = p0 + ts.deferred[d];
     const int o0 = __ldcg(off + j);
     const int c = __ldcg(off + j + 1) - o0;
-    if (c > kWarpSort) {
+    if (c > kWarpSeg) {
       any_huge = true;
       continue;
     }
-    int* buf = ts.sortbuf[warp];
-    int P = 32;
-    while (P < c) P <<= 1;
-    for (int i = lane; i < P; i += 32) buf[i] = (i < c) ? __ldcg(csr + o0 + i) : 0x7fffffff;
-    __syncwarp();
-    for (int k = 2; k <= P; k <<= 1) {
-      for (int jj = k >> 1; jj > 0; jj >>= 1) {
-        for (int i = lane; i < P; i += 32) {
-          const int ixj = i ^ jj;
-          if (ixj > i) {
-            const int a = buf[i], bb = buf[ixj];
-            const bool up = (i & k) == 0;
-            if ((a > bb) == up) {
-              buf[i] = bb;
-              buf[ixj] = a;
-            }
-          }
-        }
-        __syncwarp();
-      }
-    }
     const float x0 = __ldg(Xb + 3 * (size_t)j), x1 = __ldg(Xb + 3 * (size_t)j + 1), x2 = __ldg(Xb + 3 * (size_t)j + 2);
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    for (int i0 = 0; i0 < c; i0 += 32) {
-      const int i = i0 + lane;
-      float tx = 0.f, ty = 0.f, tz = 0.f;
-      if (i < c) {
-        const int k = buf[i];
-        const float g = point_weight(mode, wY, gY, k);
-        tx = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 0), x0));
-        ty = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 1), x1));
-        tz = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 2), x2));
-      }
-      const int mrem = min(32, c - i0);
-      for (int l = 0; l < mrem; ++l) {
-        ax = __fadd_rn(ax, __shfl_sync(0xffffffffu, tx, l));
-        ay = __fadd_rn(ay, __shfl_sync(0xffffffffu, ty, l));
-        az = __fadd_rn(az, __shfl_sync(0xffffffffu, tz, l));
-      }
+    float mx = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+    for (int i = lane; i < c; i += 32) {
+      float tx, ty, tz;
+      term(__ldcg(csr + o0 + i), x0, x1, x2, tx, ty, tz);
+      mx = fmaxf(mx, fmaxf(finite_abs(tx), fmaxf(finite_abs(ty), finite_abs(tz))));
+      nx = __fadd_rn(nx, nonfinite(tx));
+      ny = __fadd_rn(ny, nonfinite(ty));
+      nz = __fadd_rn(nz, nonfinite(tz));
     }
-    __syncwarp();  // buf is reused by this warp's next point
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      nx = __fadd_rn(nx, __shfl_xor_sync(0xffffffffu, nx, o));
+      ny = __fadd_rn(ny, __shfl_xor_sync(0xffffffffu, ny, o));
+      nz = __fadd_rn(nz, __shfl_xor_sync(0xffffffffu, nz, o));
+    }
+    float S, invS;
+    scale_for(mx, S, invS);
+    long long sx = 0, sy = 0, sz = 0;
+    for (int i = lane; i < c; i += 32) {
+      float tx, ty, tz;
+      term(__ldcg(csr + o0 + i), x0, x1, x2, tx, ty, tz);
+      sx += to_fixed(tx, S);
+      sy += to_fixed(ty, S);
+      sz += to_fixed(tz, S);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
     if (lane == 0) {
       float ox, oy, oz;
       own_term(j, x0, x1, x2, ox, oy, oz);
-      out[3 * (size_t)j + 0] = __fsub_rn(ox, ax);
-      out[3 * (size_t)j + 1] = __fsub_rn(oy, ay);
-      out[3 * (size_t)j + 2] = __fsub_rn(oz, az);
+      out[3 * (size_t)j + 0] = __fsub_rn(ox, __fadd_rn(__fmul_rn(__ll2float_rn(sx), invS), nx));
+      out[3 * (size_t)j + 1] = __fsub_rn(oy, __fadd_rn(__fmul_rn(__ll2float_rn(sy), invS), ny));
+      out[3 * (size_t)j + 2] = __fsub_rn(oz, __fadd_rn(__fmul_rn(__ll2float_rn(sz), invS), nz));
     }
   }
   if (!__syncthreads_or(any_huge ? 1 : 0)) return;
 
-  // ---- pass 3: the whole CTA per point with a huge segment (a collapsed prediction).  Source indices are unique, so a
-  // bitmap of one window of them, walked in order, IS the ascending order: no sort.  Threads 0..2 keep the running sums.
-  float acc = 0.f;
   for (int d = 0; d < n_def; ++d) {
     const int j = p0 + ts.deferred[d];
     const int o0 = __ldcg(off + j);
     const int c = __ldcg(off + j + 1) - o0;
-    if (c <= kWarpSort) continue;  // CTA-uniform
+    if (c <= kWarpSeg) continue;  // CTA-uniform
     const float x0 = __ldg(Xb + 3 * (size_t)j), x1 = __ldg(Xb + 3 * (size_t)j + 1), x2 = __ldg(Xb + 3 * (size_t)j + 2);
-    acc = 0.f;
-    for (int lo = 0; lo < nY; lo += kBitWin) {
-      for (int i = tid; i < kBitWin / 32; i += kThreads) ts.bitmap[i] = 0u;
-      __syncthreads();
-      for (int i = tid; i < c; i += kThreads) {
-        const unsigned k = (unsigned)(__ldcg(csr + o0 + i) - lo);
-        if (k < (unsigned)kBitWin) atomicOr(&ts.bitmap[k >> 5], 1u << (k & 31));
-      }
-      __syncthreads();
-      const int hi = min(nY - lo, kBitWin);
-      for (int blk = 0; blk < hi; blk += kThreads) {
-        const unsigned w = ts.bitmap[(blk >> 5) + warp];  // words beyond `hi` are zero
-        if (lane == 0) ts.wcnt[warp] = __popc(w);
-        __syncthreads();
-        int wbase = 0, total = 0;
-#pragma unroll
-        for (int q = 0; q < kWarps; ++q) {
-          const int cq = ts.wcnt[q];
-          if (q < warp) wbase += cq;
-          total += cq;
-        }
-        if (total != 0) {  // CTA-uniform
-          if ((w >> lane) & 1u) {
-            const int k = lo + blk + warp * 32 + lane;
-            const int pos = wbase + __popc(w & ((1u << lane) - 1u));
-            const float g = point_weight(mode, wY, gY, k);
-            ts.stage[0][pos] = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 0), x0));
-            ts.stage[1][pos] = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 1), x1));
-            ts.stage[2][pos] = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 2), x2));
-          }
-          __syncthreads();
-          if (tid < 3) {
-            const float* s = ts.stage[tid];
-#pragma unroll 8
-            for (int i = 0; i < total; ++i) acc = __fadd_rn(acc, s[i]);
-          }
-        }
-        __syncthreads();  // stage[] / wcnt[] free
-      }
+    float mx = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+    for (int i = tid; i < c; i += kThreads) {
+      float tx, ty, tz;
+      term(__ldcg(csr + o0 + i), x0, x1, x2, tx, ty, tz);
+      mx = fmaxf(mx, fmaxf(finite_abs(tx), fmaxf(finite_abs(ty), finite_abs(tz))));
+      nx = __fadd_rn(nx, nonfinite(tx));
+      ny = __fadd_rn(ny, nonfinite(ty));
+      nz = __fadd_rn(nz, nonfinite(tz));
     }
-    float ox, oy, oz;
-    own_term(j, x0, x1, x2, ox, oy, oz);
-    if (tid < 3) out[3 * (size_t)j + tid] = __fsub_rn(tid == 0 ? ox : (tid == 1 ? oy : oz), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      nx = __fadd_rn(nx, __shfl_xor_sync(0xffffffffu, nx, o));
+      ny = __fadd_rn(ny, __shfl_xor_sync(0xffffffffu, ny, o));
+      nz = __fadd_rn(nz, __shfl_xor_sync(0xffffffffu, nz, o));
+    }
+    __syncthreads();  // red arrays free
+    if (lane == 0) {
+      ts.redf[warp] = mx;
+      ts.redf[8 + warp] = nx;
+      ts.redf[16 + warp] = ny;
+      ts.redf[24 + warp] = nz;
+    }
+    __syncthreads();
+    mx = nx = ny = nz = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      mx = fmaxf(mx, ts.redf[w]);
+      nx = __fadd_rn(nx, ts.redf[8 + w]);
+      ny = __fadd_rn(ny, ts.redf[16 + w]);
+      nz = __fadd_rn(nz, ts.redf[24 + w]);
+    }
+    float S, invS;
+    scale_for(mx, S, invS);
+    long long sx = 0, sy = 0, sz = 0;
+    for (int i = tid; i < c; i += kThreads) {
+      float tx, ty, tz;
+      term(__ldcg(csr + o0 + i), x0, x1, x2, tx, ty, tz);
+      sx += to_fixed(tx, S);
+      sy += to_fixed(ty, S);
+      sz += to_fixed(tz, S);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    if (lane == 0) {
+      ts.redl[warp] = sx;
+      ts.redl[8 + warp] = sy;
+      ts.redl[16 + warp] = sz;
+    }
+    __syncthreads();
+    if (tid < 3) {
+      long long t = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) t += ts.redl[8 * tid + w];
+      float ox, oy, oz;
+      own_term(j, x0, x1, x2, ox, oy, oz);
+      const float own = tid == 0 ? ox : (tid == 1 ? oy : oz);
+      const float nf = tid == 0 ? nx : (tid == 1 ? ny : nz);
+      out[3 * (size_t)j + tid] = __fsub_rn(own, __fadd_rn(__fmul_rn(__ll2float_rn(t), invS), nf));
+    }
   }
 }
 
@@ -945,30 +1004,72 @@ __global__ void __launch_bounds__(kThreads, QT == 0 ? 3 : 2) chamfer_step_kernel
   if (p.stats && tid == 0) atomicMin(p.stats + 1, globaltimer_ns());
 
   for (;;) {
-    __syncthreads();  // everyone is done with smem (incl. next_item) of the previous item
-    if (tid == 0) ctl.next_item = atomicAdd(p.ticket, 1u) + 1u;
+    __syncthreads();  // everyone is done with smem (incl. ctl) of the previous item
+    if (tid == 0) {
+      const long long item = (long long)(unsigned)(atomicAdd(p.ticket, 1u) + 1u);  // counters start at 0xFFFFFFFF
+      int ph = -1, b = 0, q = 0;
+      if (item < (long long)p.total_items) {
+        // items before step t: C(t) = sum_ph per_cloud[ph] * clamp(t - lag[ph], 0, B); find the step that holds `item`
+        auto before = [&](int t) {
+          long long c = 0;
+#pragma unroll
+          for (int h = 0; h < 5; ++h) c += (long long)p.per_cloud[h] * min(max(t - p.lag[h], 0), p.B);
+          return c;
+        };
+        int lo = 0, hi = p.n_steps;  // C(lo) <= item < C(hi)
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (before(mid) <= item) lo = mid; else hi = mid;
+        }
+        int rem = (int)(item - before(lo));
+#pragma unroll
+        for (int h = 0; h < 5; ++h) {
+          const int c = lo - p.lag[h];
+          if (ph < 0 && c >= 0 && c < p.B) {
+            if (rem < p.per_cloud[h]) {
+              ph = h;
+              b = c;
+              q = rem;
+            } else {
+              rem -= p.per_cloud[h];
+            }
+          }
+        }
+      }
+      ctl.ph = ph;
+      ctl.b = b;
+      ctl.q = q;
+    }
     __syncthreads();
-    const int item = (int)ctl.next_item;
-    if (item >= p.total_items) break;
+    const int ph = ctl.ph, b = ctl.b, q = ctl.q;
+    if (ph < 0) break;
 
-    if (item < p.first_res) {
+    if (ph == 0) {
       if constexpr (QT != 0) {
-        const int b = item / p.pair_per_cloud;
-        const int rem = item - b * p.pair_per_cloud;
-        const int at = rem / p.s_splits;
-        const int ss = rem - at * p.s_splits;
+        const int at = q / p.s_splits;
+        const int ss = q - at * p.s_splits;
         if (p.stats && tid == 0) atomicMin(p.stats + 0, globaltimer_ns());
         pair_item<QT>(p, smem_raw, b, at, ss);
         signal_done(p.done_pair + b, p.pair_per_cloud, ctl);
-        if (p.stats && tid == 0) atomicMax(p.stats + 2, globaltimer_ns());
+        if (p.stats && tid == 0) {
+          atomicMax(p.stats + 2, globaltimer_ns());
+          atomicMax(p.stats + 4, globaltimer_ns());
+        }
       }
-    } else if (item < p.first_pre) {
-      const int r = item - p.first_res;
-      const int b = r / p.rc_per_cloud;
-      const int q = r - b * p.rc_per_cloud;
-      const int side = q < p.rc_items[0] ? 0 : 1;
-      const int p0 = (side ? q - p.rc_items[0] : q) * p.rc;
-      const int p1 = min(p.n[side], p0 + p.rc);
+      continue;
+    }
+    if (ph == 2) {
+      wait_done(p.done_res + b, p.rc_per_cloud);
+      prefix_item(p, ts, b, q);
+      signal_done(p.done_pre + b, 2, ctl);
+      if (p.stats && tid == 0) atomicMax(p.stats + 6, globaltimer_ns());
+      continue;
+    }
+    // RESOLVE / FILL / GATHER items address `rc` points of one side
+    const int side = q < p.rc_items[0] ? 0 : 1;
+    const int p0 = (side ? q - p.rc_items[0] : q) * p.rc;
+    const int p1 = min(p.n[side], p0 + p.rc);
+    if (ph == 1) {
       if constexpr (QT != 0) {
         wait_done(p.done_pair + b, p.pair_per_cloud);
         if (side == p.reg)
@@ -983,31 +1084,18 @@ __global__ void __launch_bounds__(kThreads, QT == 0 ? 3 : 2) chamfer_step_kernel
         finalize_cloud(p, ts, b);
         if (signal_done(p.done_final, p.B, ctl)) finalize_loss(p, ts);
       }
-    } else if (item < p.first_fill) {
-      const int r = item - p.first_pre;
-      const int b = r >> 1, side = r & 1;
-      wait_done(p.done_res + b, p.rc_per_cloud);
-      prefix_item(p, ts, b, side);
-      signal_done(p.done_pre + b, 2, ctl);
-    } else if (item < p.first_gat) {
-      const int r = item - p.first_fill;
-      const int b = r / p.rc_per_cloud;
-      const int q = r - b * p.rc_per_cloud;
-      const int side = q < p.rc_items[0] ? 0 : 1;
-      const int p0 = (side ? q - p.rc_items[0] : q) * p.rc;
-      const int p1 = min(p.n[side], p0 + p.rc);
+    } else if (ph == 3) {
       wait_done(p.done_pre + b, 2);
       fill_item(p, b, side, p0, p1);
       signal_done(p.done_fill + b, p.rc_per_cloud, ctl);
     } else {
-      const int r = item - p.first_gat;
-      const int b = r / p.rc_per_cloud;
-      const int q = r - b * p.rc_per_cloud;
-      const int side = q < p.rc_items[0] ? 0 : 1;
-      const int p0 = (side ? q - p.rc_items[0] : q) * p.rc;
-      const int p1 = min(p.n[side], p0 + p.rc);
-      wait_done(p.done_fill + b, p.rc_per_cloud);
+      // without fan-in lists (e.g. L1_PM with only xyz1 wanted) there are no PREFIX / FILL items: dist / idx suffice
+      wait_done(p.per_cloud[3] ? p.done_fill + b : p.done_res + b, p.rc_per_cloud);
       gather_item(p, ts, b, side, p0, p1);
+    }
+    if (p.stats) {
+      __syncthreads();
+      if (tid == 0) atomicMax(p.stats + 4 + ph, globaltimer_ns());
     }
   }
   if (p.stats && tid == 0) atomicMax(p.stats + 3, globaltimer_ns());
@@ -1200,7 +1288,7 @@ int chamfer_step_launch(const StepArgs& a, cudaStream_t stream) {
     return (int)err;
   if (p.stats) {  // measurement only: two more memsets (min slots all-ones, max slots zero)
     if ((err = cudaMemsetAsync(ws + L.stats, 0xFF, 16, stream)) != cudaSuccess) return (int)err;
-    if ((err = cudaMemsetAsync(ws + L.stats + 16, 0, 16, stream)) != cudaSuccess) return (int)err;
+    if ((err = cudaMemsetAsync(ws + L.stats + 16, 0, 56, stream)) != cudaSuccess) return (int)err;
   }
 
   const int num_sms = device_sms();
@@ -1232,25 +1320,35 @@ int chamfer_step_launch(const StepArgs& a, cudaStream_t stream) {
     p.pair_per_cloud = 0;
   }
   // RESOLVE / FILL / GATHER items: rc points, small enough that every phase has >= 2 items per resident slot
-  int rc = kMaxRc;
+  int rc = kMaxRc / 2;
   while (rc > 256 && (long long)B * ((N + rc - 1) / rc + (M + rc - 1) / rc) < 2LL * slots) rc >>= 1;
+  if (const int forced_rc = env_int("IAPT_RC", 0)) rc = forced_rc;  // development knob: 256, 512, 1024 or 2048
   p.rc = rc;
   p.rc_items[0] = (N + rc - 1) / rc;
   p.rc_items[1] = (M + rc - 1) / rc;
   p.rc_per_cloud = p.rc_items[0] + p.rc_items[1];
-  const long long n_pair = (long long)B * p.pair_per_cloud;
-  const long long n_rc = (long long)B * p.rc_per_cloud;
-  const long long first_res = n_pair;
-  const long long first_pre = first_res + n_rc;
-  const long long first_fill = first_pre + (lists ? 2LL * B : 0);
-  const long long first_gat = first_fill + (lists ? n_rc : 0);
-  const long long total = first_gat + (grads ? n_rc : 0);
+  p.per_cloud[0] = p.pair_per_cloud;
+  p.per_cloud[1] = p.rc_per_cloud;
+  p.per_cloud[2] = lists ? 2 : 0;
+  p.per_cloud[3] = lists ? p.rc_per_cloud : 0;
+  p.per_cloud[4] = grads ? p.rc_per_cloud : 0;
+  long long total = 0;
+  for (int h = 0; h < 5; ++h) total += (long long)B * p.per_cloud[h];
   if (total >= (1LL << 31) - 2) return -3;  // IAPT_EUNSUPPORTED
-  p.first_res = (int)first_res;
-  p.first_pre = (int)first_pre;
-  p.first_fill = (int)first_fill;
-  p.first_gat = (int)first_gat;
   p.total_items = (int)total;
+  // Ticket order: phase-major (all PAIR items, then all RESOLVE items, ...), clouds in order inside a phase.  The
+  // general form - phase ph of cloud b at step b + lag[ph] - exists to MEASURE the alternative of running the tail
+  // phases of finished clouds beside the search of later ones (IAPT_LAG = L: RESOLVE lags the search by L clouds,
+  // PREFIX / FILL / GATHER one more step each).  It loses at every lag (config 2: L = 2 / 4 / 8 -> 4.4 / 3.85 / 3.36 ms
+  // against 3.26 phase-major): the search needs both resident CTAs of an SM to fill the FP32 issue port, so a CTA slot
+  // spent on a latency-bound tail item costs more search time than the tail it hides.
+  {
+    int L = B;
+    if (const int forced = env_int("IAPT_LAG", -1); forced >= 0) L = forced;
+    const bool phase_major = L >= B;
+    for (int h = 0; h < 5; ++h) p.lag[h] = phase_major ? h * B : (h == 0 ? 0 : L + h - 1);
+    p.n_steps = B + p.lag[4];
+  }
 
   const int grid = (int)(total < (long long)slots ? total : (long long)slots);
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

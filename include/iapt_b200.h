@@ -125,8 +125,9 @@ int iapt_chamfer_backward_fused(const float* xyz1, const float* xyz2, const int3
  *                          unconditionally, without reading anything back;
  *                          IAPT_STEP_STATS: record device timestamps for iapt_chamfer_step_stats.
  * Per-cloud sums are folded in a fixed order that does not depend on B or the GPU: bit-reproducible.
- * iapt_chamfer_step_stats (synchronous, measurement only): stats_host[4] = globaltimer ns {first start of a search
- * item, kernel start, last end of a search item, kernel end} of the last IAPT_STEP_STATS launch on that workspace.
+ * iapt_chamfer_step_stats (synchronous, measurement only): stats_host[9] = globaltimer ns {first start of a search
+ * item, kernel start, last end of a search item, kernel end, last end of the search / index-resolution / prefix / fill /
+ * gather items} of the last IAPT_STEP_STATS launch on that workspace.
  * iapt_scale: dst[i] = src[i] * factor[0] (factor on the device) - applies the upstream gradient to a unit gradient. */
 #define IAPT_STEP_IGNORE_ZERO_SUM 1
 #define IAPT_STEP_STATS 2

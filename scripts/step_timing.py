@@ -40,10 +40,50 @@ for (B, N, M) in shapes:
     t_step2 = ev(lambda: chamfer.step(p, g, chamfer.LOSS_L1, grad1=True, grad2=True))
     r = chamfer.step(p, g, chamfer.LOSS_L1, grad1=True, stats=True)
     search_ms, kern_ms = chamfer.step_stats(r.workspace)
+    ends = " ".join("-" if e is None else f"{e:.3f}" for e in chamfer.step_phase_ends(r.workspace))
     d1, d2, i1, i2 = chamfer.forward(p, g)
     t_bwd = ev(lambda: chamfer.loss_backward(p, g, i1, i2, d1, d2, chamfer.LOSS_L1, None))
     ok = torch.equal(r.dist1, d1) and torch.equal(r.idx2, i2)
     fl = 16.0 * B * N * M
     print(f"B={B:3d} {N:5d}x{M:5d}  fwd {t_fwd:7.4f}  step(g1) {t_step:7.4f} ({fl / t_step / 1e-3 / PEAK:.3f} of fp32 peak)  "
           f"step(g1,g2) {t_step2:7.4f}  bwd-only {t_bwd:7.4f}  [device: search {search_ms:7.4f} kernel {kern_ms:7.4f}]  "
-          f"same={ok}", flush=True)
+          f"same={ok}  phase ends [{ends}]", flush=True)
+
+# ---- collapsed predictions (what an untrained network emits): every gt point picks one of 4 prediction points --------
+gt = synthetic.pcn_gt(48, 16384, 303).to(dev)
+for n in (512, 16384):
+    p = torch.rand(48, 4, 3, device=dev).repeat(1, n // 4, 1).contiguous()
+    t_step = ev(lambda: chamfer.step(p, gt, chamfer.LOSS_L1, grad1=True))
+    r = chamfer.step(p, gt, chamfer.LOSS_L1, grad1=True, stats=True)
+    ends = " ".join("-" if e is None else f"{e:.3f}" for e in chamfer.step_phase_ends(r.workspace))
+    d1, d2, i1, i2 = chamfer.forward(p, gt)
+    t_bwd = ev(lambda: chamfer.loss_backward(p, gt, i1, i2, d1, d2, chamfer.LOSS_L1, None))
+    print(f"collapsed B=48 {n}x16384 (4 distinct): step(g1) {t_step:.4f}  bwd-only {t_bwd:.4f}  phase ends [{ends}]", flush=True)
+
+# ---- knob sweep at config 2 (env is read per launch) -------------------------------------------------------------------
+if os.environ.get("SWEEP", "1") == "1":
+    B, N, M = 48, 16384, 16384
+    p, g = synthetic.pcn_pair(B, N, 5)
+    p, g = p.to(dev), g.to(dev)
+    for lag in (8, 100):
+        for rc in (256, 512, 1024, 2048):
+            os.environ["IAPT_RC"] = str(rc)
+            os.environ["IAPT_LAG"] = str(lag)
+            t = ev(lambda: chamfer.step(p, g, chamfer.LOSS_L1, grad1=True))
+            r = chamfer.step(p, g, chamfer.LOSS_L1, grad1=True, stats=True)
+            search_ms, kern_ms = chamfer.step_stats(r.workspace)
+            print(f"config2 lag={lag} rc={rc}: step(g1) {t:.4f} ms  [device: search {search_ms:.4f} kernel {kern_ms:.4f}]", flush=True)
+    os.environ.pop("IAPT_RC")
+    os.environ.pop("IAPT_LAG")
+    # the module path (python + autograd overhead included), config 2 and config 1
+    from imgadapointr_b200.extensions.chamfer_dist import ChamferDistanceL1
+    mod = ChamferDistanceL1()
+    for (B, N, M) in [(48, 16384, 16384), (1, 2048, 16384), (1, 16384, 16384)]:
+        p, g = synthetic.pcn_pair(B, max(N, M), 5)
+        p, g = p[:, :N].contiguous().to(dev), g[:, :M].contiguous().to(dev)
+
+        def fb():
+            x = p.detach().requires_grad_(True)
+            mod(x, g).backward()
+
+        print(f"module fwd+bwd B={B} {N}x{M}: {ev(fb, 5, 20):.4f} ms", flush=True)

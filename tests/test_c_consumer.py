@@ -33,7 +33,7 @@ def test_c_consumer_runs_on_gpu(dev):
     out = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     lines = dict(l.split(" ", 1) for l in out.stdout.strip().splitlines())
-    assert lines["abi"] == "1"
+    assert lines["abi"] == "2"
     assert lines["idx1"] == "0 0 1 1"          # 0->0.1, 1->0.1 (0.81 < 1.44), 2->2.2, 3->2.2
     assert lines["idx2"] == "0 2 3"            # 0.1->0, 2.2->2, 10->3
     d1 = [float(x) for x in lines["dist1"].split()]
