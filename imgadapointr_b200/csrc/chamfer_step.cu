@@ -69,9 +69,9 @@ struct StepParams {
   unsigned* done_fill;   // [B]
   unsigned* done_final;  // clouds whose partials were folded
   // ---- item layout -----------------------------------------------------------------------------------------------
-  int a_tiles, s_splits, chunks_per_item;
-  int rc;               // points per RESOLVE / FILL / GATHER item (multiple of 256)
-  int rc_items[2];      // ceil(n[s] / rc)
+  int a_tiles, s_splits, total_chunks;  // PAIR item ss of a tile streams chunks [ss*total/s_splits, (ss+1)*total/s_splits)
+  int rc[2];            // points of side s per RESOLVE / FILL / GATHER item (multiple of 32)
+  int rc_items[2];      // ceil(n[s] / rc[s])
   int pair_per_cloud, rc_per_cloud;
   // Ticket order: STEPS t = 0, 1, ...; step t holds, in phase order, the items of phase ph for cloud t - lag[ph]
   // (when that is a cloud).  lag[] is non-decreasing, so an item only waits for smaller tickets.
@@ -118,11 +118,12 @@ struct __align__(16) PairSmem<0> {
 
 struct __align__(16) TailSmem {
   long long redl[3 * kWarps];
-  unsigned short deferred[kMaxRc];   // points of this item whose segment needs a cooperative pass
+  unsigned short deferred[kMaxRc];   // points of this item whose segment (> 8 entries) needs a cooperative pass
+  unsigned short medium[kMaxRc];     // points of this item with 3..8 entries
   float redf[32];
   int redi[32];
   int wcnt[kWarps];
-  int n_deferred;
+  int n_deferred, n_medium;
 };
 
 struct CtlSmem {
@@ -257,8 +258,8 @@ __device__ __forceinline__ void pair_item(const StepParams& p, unsigned char* sm
   const bool mask = p.mask_zero_sum != 0;
 
   // this item's streamed range, in points: [s_begin, s_end)
-  const int s_begin = ss * p.chunks_per_item * kChunk;
-  const int s_end = min(NS, s_begin + p.chunks_per_item * kChunk);
+  const int s_begin = (int)((long long)ss * p.total_chunks / p.s_splits) * kChunk;
+  const int s_end = min(NS, (int)((long long)(ss + 1) * p.total_chunks / p.s_splits) * kChunk);
   const int n_stages = (s_end - s_begin + kSStage - 1) / kSStage;
 
   // ---- this thread's QT consecutive A points -> QT/2 f32x2 pairs per coordinate ---------------------------------
@@ -434,8 +435,14 @@ __device__ __forceinline__ void pair_item(const StepParams& p, unsigned char* sm
 // The candidate distance is evaluated with the identical instruction sequence as the search, so exactly-equal compares
 // are well defined.  kRU warp steps are issued together so kRU gathers are in flight per lane.
 template <bool kRow>
-__device__ __forceinline__ void resolve_item(const StepParams& p, int b, int side, int p0, int p1, int group) {
-  constexpr int kRU = 8;
+__device__ __noinline__ void resolve_item(const StepParams& p, int b, int side, int p0, int p1, int group) {
+#ifndef IAPT_RU
+#define IAPT_RU 16
+#endif
+#ifndef IAPT_PREFETCH
+#define IAPT_PREFETCH 1
+#endif
+  constexpr int kRU = IAPT_RU;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int other = side ^ 1;
@@ -449,17 +456,33 @@ __device__ __forceinline__ void resolve_item(const StepParams& p, int b, int sid
   int* cnt_other = p.need_list[other] ? p.cnt[other] + (size_t)b * nY : nullptr;
   const bool mask = p.mask_zero_sum != 0;
 
+  // this lane's point of a warp step: key + coordinates (fetched one warp step ahead)
+  u64 nkey = 0ull;
+  float nsx = 0.f, nsy = 0.f, nsz = 0.f;
+  auto fetch = [&](int t) {
+    nkey = 0ull;
+    nsx = nsy = nsz = 0.f;
+    if (t < p1) {
+      nkey = __ldcg(keys + t);
+      nsx = __ldg(Xb + 3 * (size_t)t);
+      nsy = __ldg(Xb + 3 * (size_t)t + 1);
+      nsz = __ldg(Xb + 3 * (size_t)t + 2);
+    }
+  };
+#if IAPT_PREFETCH
+  fetch(p0 + warp * 32 + lane);
+#endif
   for (int t0 = p0 + warp * 32; t0 < p1; t0 += kWarps * 32) {
     const int t = t0 + lane;
     const bool valid = t < p1;
-    u64 key = 0ull;
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    if (valid) {
-      key = __ldcg(keys + t);
-      sx = __ldg(Xb + 3 * (size_t)t);
-      sy = __ldg(Xb + 3 * (size_t)t + 1);
-      sz = __ldg(Xb + 3 * (size_t)t + 2);
-    }
+#if !IAPT_PREFETCH
+    fetch(t);
+#endif
+    const u64 key = nkey;
+    const float sx = nsx, sy = nsy, sz = nsz;
+#if IAPT_PREFETCH
+    fetch(t + kWarps * 32);
+#endif
     const bool zs = zero_sum(sx, sy, sz);
     const bool masked = mask && zs;
     int myidx = 0;
@@ -468,22 +491,19 @@ __device__ __forceinline__ void resolve_item(const StepParams& p, int b, int sid
       for (int j0 = 0; j0 < 32; j0 += kRU) {
         if (t0 + j0 >= p1) break;  // warp-uniform
         float cx[kRU], cy[kRU], cz[kRU];
-        bool ok[kRU];
-        unsigned kd[kRU];
-        int base[kRU];
+        unsigned okm = 0u;
 #pragma unroll
         for (int u = 0; u < kRU; ++u) {
           const int j = j0 + u;
           const u64 kj = __shfl_sync(0xffffffffu, key, j);
-          kd[u] = (unsigned)(kj >> 32);
           // a key that was never lowered (all-ones: every distance of this point was NaN - outside the contract)
           // must not be turned into an address
           const bool valid_key = kj != ~0ull;
-          base[u] = valid_key ? (int)(unsigned)kj * kChunk : 0;
-          const int cand = base[u] + lane;
-          ok[u] = valid_key && (t0 + j < p1) && (cand < nY);
+          const int cand = (valid_key ? (int)(unsigned)kj * kChunk : 0) + lane;
+          const bool ok = valid_key && (t0 + j < p1) && (cand < nY);
           cx[u] = cy[u] = cz[u] = 0.f;
-          if (ok[u]) {
+          if (ok) {
+            okm |= 1u << u;
             const float* c = Yb + (size_t)cand * 3;
             cx[u] = __ldg(c);
             cy[u] = __ldg(c + 1);
@@ -502,9 +522,10 @@ __device__ __forceinline__ void resolve_item(const StepParams& p, int b, int sid
           float y = __shfl_sync(0xffffffffu, sy, j);
           float z = __shfl_sync(0xffffffffu, sz, j);
           if (mask && zero_sum(x, y, z)) x = y = z = -kPadCoord();
-          const bool eq = ok[u] && (sqdist(x, y, z, cx[u], cy[u], cz[u]) == __uint_as_float(kd[u]));
+          const u64 kj = __shfl_sync(0xffffffffu, key, j);  // (again: cheaper than 2 x kRU live registers)
+          const bool eq = ((okm >> u) & 1u) && (sqdist(x, y, z, cx[u], cy[u], cz[u]) == __uint_as_float((unsigned)(kj >> 32)));
           const unsigned hits = __ballot_sync(0xffffffffu, eq);
-          if (lane == j) myidx = base[u] + (hits ? (__ffs(hits) - 1) : 0);
+          if (lane == j) myidx = (kj != ~0ull ? (int)(unsigned)kj * kChunk : 0) + (hits ? (__ffs(hits) - 1) : 0);
         }
       }
     } else {
@@ -515,18 +536,17 @@ __device__ __forceinline__ void resolve_item(const StepParams& p, int b, int sid
       for (int j0 = 0; j0 < 32; j0 += kRU * per_step) {
         if (t0 + j0 >= p1) break;  // warp-uniform
         float cx[kRU], cy[kRU], cz[kRU];
-        bool ok[kRU];
-        unsigned kd[kRU];
+        unsigned okm = 0u;
 #pragma unroll
         for (int q = 0; q < kRU; ++q) {
           const int j = j0 + q * per_step + sub;  // the point this lane helps with
           const u64 kj = __shfl_sync(0xffffffffu, key, j & 31);
-          kd[q] = (unsigned)(kj >> 32);
           const bool valid_key = kj != ~0ull;
           const int cand = valid_key ? (int)(unsigned)kj * group + offl : 0;
-          ok[q] = valid_key && (j < 32) && (t0 + j < p1) && (cand < nY);
+          const bool ok = valid_key && (j < 32) && (t0 + j < p1) && (cand < nY);
           cx[q] = cy[q] = cz[q] = 0.f;
-          if (ok[q]) {
+          if (ok) {
+            okm |= 1u << q;
             const float* c = Yb + (size_t)cand * 3;
             cx[q] = __ldg(c);
             cy[q] = __ldg(c + 1);
@@ -546,7 +566,8 @@ __device__ __forceinline__ void resolve_item(const StepParams& p, int b, int sid
           float y = __shfl_sync(0xffffffffu, sy, j & 31);
           float z = __shfl_sync(0xffffffffu, sz, j & 31);
           if (mask && zero_sum(x, y, z)) x = y = z = kPadCoord();
-          const bool eq = ok[q] && (sqdist(cx[q], cy[q], cz[q], x, y, z) == __uint_as_float(kd[q]));
+          const unsigned kd = (unsigned)(__shfl_sync(0xffffffffu, key, j & 31) >> 32);
+          const bool eq = ((okm >> q) & 1u) && (sqdist(cx[q], cy[q], cz[q], x, y, z) == __uint_as_float(kd));
           const unsigned hits = __ballot_sync(0xffffffffu, eq);
           const int owner_sub = lane - jb;  // lane jb + s owns sub-group s of this step
           if (owner_sub >= 0 && owner_sub < per_step) {
@@ -580,7 +601,7 @@ __device__ __forceinline__ void resolve_item(const StepParams& p, int b, int sid
 }
 
 // backward-only launches: the indices are given, RESOLVE items only count the fan-in
-__device__ __forceinline__ void count_item(const StepParams& p, int b, int side, int p0, int p1) {
+__device__ __noinline__ void count_item(const StepParams& p, int b, int side, int p0, int p1) {
   const int other = side ^ 1;
   if (!p.need_list[other]) return;
   const int32_t* __restrict__ idx = p.idx[side] + (size_t)b * p.n[side];
@@ -592,7 +613,7 @@ __device__ __forceinline__ void count_item(const StepParams& p, int b, int side,
 }
 
 // Fixed-order fold of one cloud's partials -> sums[b], counts[b], valid[b].
-__device__ __forceinline__ void finalize_cloud(const StepParams& p, TailSmem& ts, int b) {
+__device__ __noinline__ void finalize_cloud(const StepParams& p, TailSmem& ts, int b) {
   for (int side = 0; side < 2; ++side) {
     if (!p.part[side]) continue;
     const int P = (p.n[side] + 31) / 32;
@@ -623,7 +644,7 @@ __device__ __forceinline__ void finalize_cloud(const StepParams& p, TailSmem& ts
 
 // Fixed-order fold of the per-cloud sums into the loss scalars of the four reference modules
 // (extensions/chamfer_dist/__init__.py:43-44,61-62,82-84,101-103).  Means are over the UNMASKED points.
-__device__ __forceinline__ void finalize_loss(const StepParams& p, TailSmem& ts) {
+__device__ __noinline__ void finalize_loss(const StepParams& p, TailSmem& ts) {
   if (!p.loss || !p.sums) return;
   float t[4];
   for (int c = 0; c < 4; ++c) {
@@ -662,7 +683,7 @@ __device__ __forceinline__ void finalize_loss(const StepParams& p, TailSmem& ts)
 // =====================================================================================================================
 // PREFIX / FILL
 // =====================================================================================================================
-__device__ __forceinline__ void prefix_item(const StepParams& p, TailSmem& ts, int b, int side) {
+__device__ __noinline__ void prefix_item(const StepParams& p, TailSmem& ts, int b, int side) {
   if (!p.need_list[side]) return;
   const int n = p.n[side];
   const int* cnt = p.cnt[side] + (size_t)b * n;
@@ -702,7 +723,7 @@ __device__ __forceinline__ void prefix_item(const StepParams& p, TailSmem& ts, i
   if (tid == 0) off[n] = carry;
 }
 
-__device__ __forceinline__ void fill_item(const StepParams& p, int b, int side, int p0, int p1) {
+__device__ __noinline__ void fill_item(const StepParams& p, int b, int side, int p0, int p1) {
   const int other = side ^ 1;
   if (!p.need_list[other]) return;
   const int nX = p.n[side], nY = p.n[other];
@@ -732,13 +753,21 @@ __device__ __forceinline__ float point_weight(int mode, float scaled_upstream, c
   return __fmul_rn(w, 2.f);
 }
 
+// the same weight from an already loaded source value (gw[i]; unused for mode 2)
+__device__ __forceinline__ float weight_from(int mode, float scaled_upstream, float src) {
+  if (mode == 0) return __fmul_rn(src, 2.f);
+  float w = scaled_upstream;
+  if (mode == 1) w = __fdiv_rn(w, sqrtf(src));
+  return __fmul_rn(w, 2.f);
+}
+
 __device__ __forceinline__ void cswap(int& a, int& b) {
   const int lo = min(a, b), hi = max(a, b);
   a = lo;
   b = hi;
 }
 
-__device__ __forceinline__ void gather_item(const StepParams& p, TailSmem& ts, int b, int side, int p0, int p1) {
+__device__ __noinline__ void gather_item(const StepParams& p, TailSmem& ts, int b, int side, int p0, int p1) {
   if (!p.grad[side]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int other = side ^ 1;
@@ -775,34 +804,108 @@ __device__ __forceinline__ void gather_item(const StepParams& p, TailSmem& ts, i
     }
   };
 
-  if (tid == 0) ts.n_deferred = 0;
+  if (tid == 0) ts.n_deferred = ts.n_medium = 0;
   __syncthreads();
-  // ---- pass 1: one thread per point; segments of <= 8 entries (mean fan-in ~1) are ordered in registers --------------
-  for (int j = p0 + tid; j < p1; j += kThreads) {
-    int o0 = 0, c = 0;
-    if (fan) {
-      o0 = __ldcg(off + j);
-      c = __ldcg(off + j + 1) - o0;
+  // ---- pass 1: one thread per point, kG points of a thread in flight together (the chain offsets -> entries ->
+  // coordinates is three dependent L2 round trips; at 16 warps per SM only instruction-level parallelism hides them).
+  // Segments of <= 2 entries (92 % at a mean fan-in of 1) finish here; 3..8 go to pass 1b, longer ones to pass 2 / 3.
+  constexpr int kG = 4;
+  for (int jb = p0 + tid; jb < p1; jb += kG * kThreads) {
+    int o0[kG], c[kG];
+    unsigned nb[kG];
+    float x[kG][3], wsrc[kG];
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      const int j = jb + g * kThreads;
+      const bool in = j < p1;
+      o0[g] = (fan && in) ? __ldcg(off + j) : 0;
+      c[g] = (fan && in) ? __ldcg(off + j + 1) : 0;
+      nb[g] = (gX != nullptr && in) ? (unsigned)__ldcg(idxX + j) : 0xffffffffu;
+      wsrc[g] = (gX != nullptr && in && mode != 2) ? __ldcg(gX + j) : 1.f;
+#pragma unroll
+      for (int e = 0; e < 3; ++e) x[g][e] = in ? __ldg(Xb + 3 * (size_t)j + e) : 0.f;
     }
-    if (c > 8) {
-      ts.deferred[atomicAdd(&ts.n_deferred, 1)] = (unsigned short)(j - p0);
-      continue;
+    int e0[kG], e1[kG];
+    float y[kG][3];
+    bool fast[kG];
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      const int j = jb + g * kThreads;
+      c[g] -= o0[g];
+      fast[g] = j < p1 && c[g] <= 2;
+      if (j < p1 && c[g] > 2) {
+        if (c[g] > 8)
+          ts.deferred[atomicAdd(&ts.n_deferred, 1)] = (unsigned short)(j - p0);
+        else
+          ts.medium[atomicAdd(&ts.n_medium, 1)] = (unsigned short)(j - p0);
+      }
+      e0[g] = (fast[g] && c[g] >= 1) ? __ldcg(csr + o0[g]) : -1;
+      e1[g] = (fast[g] && c[g] >= 2) ? __ldcg(csr + o0[g] + 1) : -1;
+      if (nb[g] >= (unsigned)nY || (mask && zero_sum(x[g][0], x[g][1], x[g][2]))) nb[g] = 0xffffffffu;
+#pragma unroll
+      for (int e = 0; e < 3; ++e) y[g][e] = nb[g] != 0xffffffffu ? __ldg(Yb + 3 * (size_t)nb[g] + e) : 0.f;
     }
+    float z0[kG][3], z1[kG][3], w0[kG], w1[kG];
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      if (e1[g] >= 0 && e1[g] < e0[g]) {  // ascending source index
+        const int t = e0[g];
+        e0[g] = e1[g];
+        e1[g] = t;
+      }
+      w0[g] = (e0[g] >= 0 && mode != 2) ? __ldcg(gY + e0[g]) : 1.f;
+      w1[g] = (e1[g] >= 0 && mode != 2) ? __ldcg(gY + e1[g]) : 1.f;
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        z0[g][e] = e0[g] >= 0 ? __ldg(Yb + 3 * (size_t)e0[g] + e) : 0.f;
+        z1[g][e] = e1[g] >= 0 ? __ldg(Yb + 3 * (size_t)e1[g] + e) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      if (!fast[g]) continue;
+      const int j = jb + g * kThreads;
+      float o[3] = {0.f, 0.f, 0.f}, a[3] = {0.f, 0.f, 0.f};
+      if (nb[g] != 0xffffffffu) {
+        const float gw = weight_from(mode, wX, wsrc[g]);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) o[e] = __fmul_rn(gw, __fsub_rn(x[g][e], y[g][e]));
+      }
+      if (e0[g] >= 0) {
+        const float gw = weight_from(mode, wY, w0[g]);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) a[e] = __fadd_rn(a[e], __fmul_rn(gw, __fsub_rn(z0[g][e], x[g][e])));
+      }
+      if (e1[g] >= 0) {
+        const float gw = weight_from(mode, wY, w1[g]);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) a[e] = __fadd_rn(a[e], __fmul_rn(gw, __fsub_rn(z1[g][e], x[g][e])));
+      }
+#pragma unroll
+      for (int e = 0; e < 3; ++e) out[3 * (size_t)j + e] = __fsub_rn(o[e], a[e]);
+    }
+  }
+  __syncthreads();
+  // ---- pass 1b: segments of 3..8 entries, one thread each: ordered by a sorting network in registers ------------------
+  const int n_med = ts.n_medium;
+  for (int d = tid; d < n_med; d += kThreads) {
+    const int j = p0 + ts.medium[d];
+    const int o0 = __ldcg(off + j);
+    const int c = __ldcg(off + j + 1) - o0;
     int e[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) e[i] = (i < c) ? __ldcg(csr + o0 + i) : 0x7fffffff;
     const float x0 = __ldg(Xb + 3 * (size_t)j), x1 = __ldg(Xb + 3 * (size_t)j + 1), x2 = __ldg(Xb + 3 * (size_t)j + 2);
     float ox, oy, oz;
     own_term(j, x0, x1, x2, ox, oy, oz);
-    if (c > 1) {  // 8-input sorting network (19 compare-exchanges)
-      cswap(e[0], e[1]); cswap(e[2], e[3]); cswap(e[4], e[5]); cswap(e[6], e[7]);
-      cswap(e[0], e[2]); cswap(e[1], e[3]); cswap(e[4], e[6]); cswap(e[5], e[7]);
-      cswap(e[1], e[2]); cswap(e[5], e[6]); cswap(e[0], e[4]); cswap(e[3], e[7]);
-      cswap(e[1], e[5]); cswap(e[2], e[6]);
-      cswap(e[1], e[4]); cswap(e[3], e[6]);
-      cswap(e[2], e[4]); cswap(e[3], e[5]);
-      cswap(e[3], e[4]);
-    }
+    // 8-input sorting network (19 compare-exchanges)
+    cswap(e[0], e[1]); cswap(e[2], e[3]); cswap(e[4], e[5]); cswap(e[6], e[7]);
+    cswap(e[0], e[2]); cswap(e[1], e[3]); cswap(e[4], e[6]); cswap(e[5], e[7]);
+    cswap(e[1], e[2]); cswap(e[5], e[6]); cswap(e[0], e[4]); cswap(e[3], e[7]);
+    cswap(e[1], e[5]); cswap(e[2], e[6]);
+    cswap(e[1], e[4]); cswap(e[3], e[6]);
+    cswap(e[2], e[4]); cswap(e[3], e[5]);
+    cswap(e[3], e[4]);
     // all gathers first (independent), then the ordered sum
     float gw[8], yx[8], yy[8], yz[8];
 #pragma unroll
@@ -828,7 +931,6 @@ __device__ __forceinline__ void gather_item(const StepParams& p, TailSmem& ts, i
     out[3 * (size_t)j + 1] = __fsub_rn(oy, ay);
     out[3 * (size_t)j + 2] = __fsub_rn(oz, az);
   }
-  __syncthreads();
   const int n_def = ts.n_deferred;
   if (n_def == 0) return;  // CTA-uniform
 
@@ -841,11 +943,30 @@ __device__ __forceinline__ void gather_item(const StepParams& p, TailSmem& ts, i
   // A warp takes a segment of <= kWarpSeg entries, the whole CTA a longer one (a collapsed prediction: thousands of
   // points sharing one neighbour) - a parallel reduction instead of the reference's serialised atomicAdds
   // (chamfer.cu:193-198).
-  auto term = [&](int k, float x0, float x1, float x2, float& tx, float& ty, float& tz) {
-    const float g = point_weight(mode, wY, gY, k);
-    tx = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 0), x0));
-    ty = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 1), x1));
-    tz = __fmul_rn(g, __fsub_rn(__ldg(Yb + 3 * (size_t)k + 2), x2));
+  // terms of the entries seg[i0 + u * stride], u < kSU (zero beyond c): all index loads, then all gathers, then the math -
+  // two dependent L2 round trips per kSU entries instead of per entry
+  constexpr int kSU = 4;
+  auto terms = [&](const int* seg, int i0, int stride, int c, float x0, float x1, float x2, float (&tx)[kSU],
+                   float (&ty)[kSU], float (&tz)[kSU]) {
+    int k[kSU];
+#pragma unroll
+    for (int u = 0; u < kSU; ++u) k[u] = (i0 + u * stride < c) ? __ldcg(seg + i0 + u * stride) : -1;
+    float w[kSU], yx[kSU], yy[kSU], yz[kSU];
+#pragma unroll
+    for (int u = 0; u < kSU; ++u) {
+      const bool in = k[u] >= 0;
+      w[u] = (in && mode != 2) ? __ldcg(gY + k[u]) : 1.f;
+      yx[u] = in ? __ldg(Yb + 3 * (size_t)k[u] + 0) : 0.f;
+      yy[u] = in ? __ldg(Yb + 3 * (size_t)k[u] + 1) : 0.f;
+      yz[u] = in ? __ldg(Yb + 3 * (size_t)k[u] + 2) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kSU; ++u) {
+      const float g = k[u] >= 0 ? weight_from(mode, wY, w[u]) : 0.f;
+      tx[u] = k[u] >= 0 ? __fmul_rn(g, __fsub_rn(yx[u], x0)) : 0.f;
+      ty[u] = k[u] >= 0 ? __fmul_rn(g, __fsub_rn(yy[u], x1)) : 0.f;
+      tz[u] = k[u] >= 0 ? __fmul_rn(g, __fsub_rn(yz[u], x2)) : 0.f;
+    }
   };
   auto finite_abs = [](float t) { return (__float_as_uint(t) & 0x7f800000u) != 0x7f800000u ? fabsf(t) : 0.f; };
   auto nonfinite = [](float t) { return (__float_as_uint(t) & 0x7f800000u) != 0x7f800000u ? 0.f : t; };
@@ -872,13 +993,16 @@ __device__ __forceinline__ void gather_item(const StepParams& p, TailSmem& ts, i
     }
     const float x0 = __ldg(Xb + 3 * (size_t)j), x1 = __ldg(Xb + 3 * (size_t)j + 1), x2 = __ldg(Xb + 3 * (size_t)j + 2);
     float mx = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
-    for (int i = lane; i < c; i += 32) {
-      float tx, ty, tz;
-      term(__ldcg(csr + o0 + i), x0, x1, x2, tx, ty, tz);
-      mx = fmaxf(mx, fmaxf(finite_abs(tx), fmaxf(finite_abs(ty), finite_abs(tz))));
-      nx = __fadd_rn(nx, nonfinite(tx));
-      ny = __fadd_rn(ny, nonfinite(ty));
-      nz = __fadd_rn(nz, nonfinite(tz));
+    for (int i0 = lane; i0 < c; i0 += 32 * kSU) {
+      float tx[kSU], ty[kSU], tz[kSU];
+      terms(csr + o0, i0, 32, c, x0, x1, x2, tx, ty, tz);
+#pragma unroll
+      for (int u = 0; u < kSU; ++u) {
+        mx = fmaxf(mx, fmaxf(finite_abs(tx[u]), fmaxf(finite_abs(ty[u]), finite_abs(tz[u]))));
+        nx = __fadd_rn(nx, nonfinite(tx[u]));
+        ny = __fadd_rn(ny, nonfinite(ty[u]));
+        nz = __fadd_rn(nz, nonfinite(tz[u]));
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -890,12 +1014,15 @@ __device__ __forceinline__ void gather_item(const StepParams& p, TailSmem& ts, i
     float S, invS;
     scale_for(mx, S, invS);
     long long sx = 0, sy = 0, sz = 0;
-    for (int i = lane; i < c; i += 32) {
-      float tx, ty, tz;
-      term(__ldcg(csr + o0 + i), x0, x1, x2, tx, ty, tz);
-      sx += to_fixed(tx, S);
-      sy += to_fixed(ty, S);
-      sz += to_fixed(tz, S);
+    for (int i0 = lane; i0 < c; i0 += 32 * kSU) {
+      float tx[kSU], ty[kSU], tz[kSU];
+      terms(csr + o0, i0, 32, c, x0, x1, x2, tx, ty, tz);
+#pragma unroll
+      for (int u = 0; u < kSU; ++u) {
+        sx += to_fixed(tx[u], S);
+        sy += to_fixed(ty[u], S);
+        sz += to_fixed(tz[u], S);
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -920,13 +1047,16 @@ __device__ __forceinline__ void gather_item(const StepParams& p, TailSmem& ts, i
     if (c <= kWarpSeg) continue;  // CTA-uniform
     const float x0 = __ldg(Xb + 3 * (size_t)j), x1 = __ldg(Xb + 3 * (size_t)j + 1), x2 = __ldg(Xb + 3 * (size_t)j + 2);
     float mx = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
-    for (int i = tid; i < c; i += kThreads) {
-      float tx, ty, tz;
-      term(__ldcg(csr + o0 + i), x0, x1, x2, tx, ty, tz);
-      mx = fmaxf(mx, fmaxf(finite_abs(tx), fmaxf(finite_abs(ty), finite_abs(tz))));
-      nx = __fadd_rn(nx, nonfinite(tx));
-      ny = __fadd_rn(ny, nonfinite(ty));
-      nz = __fadd_rn(nz, nonfinite(tz));
+    for (int i0 = tid; i0 < c; i0 += kThreads * kSU) {
+      float tx[kSU], ty[kSU], tz[kSU];
+      terms(csr + o0, i0, kThreads, c, x0, x1, x2, tx, ty, tz);
+#pragma unroll
+      for (int u = 0; u < kSU; ++u) {
+        mx = fmaxf(mx, fmaxf(finite_abs(tx[u]), fmaxf(finite_abs(ty[u]), finite_abs(tz[u]))));
+        nx = __fadd_rn(nx, nonfinite(tx[u]));
+        ny = __fadd_rn(ny, nonfinite(ty[u]));
+        nz = __fadd_rn(nz, nonfinite(tz[u]));
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -954,12 +1084,15 @@ __device__ __forceinline__ void gather_item(const StepParams& p, TailSmem& ts, i
     float S, invS;
     scale_for(mx, S, invS);
     long long sx = 0, sy = 0, sz = 0;
-    for (int i = tid; i < c; i += kThreads) {
-      float tx, ty, tz;
-      term(__ldcg(csr + o0 + i), x0, x1, x2, tx, ty, tz);
-      sx += to_fixed(tx, S);
-      sy += to_fixed(ty, S);
-      sz += to_fixed(tz, S);
+    for (int i0 = tid; i0 < c; i0 += kThreads * kSU) {
+      float tx[kSU], ty[kSU], tz[kSU];
+      terms(csr + o0, i0, kThreads, c, x0, x1, x2, tx, ty, tz);
+#pragma unroll
+      for (int u = 0; u < kSU; ++u) {
+        sx += to_fixed(tx[u], S);
+        sy += to_fixed(ty[u], S);
+        sz += to_fixed(tz[u], S);
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -991,7 +1124,7 @@ __device__ __forceinline__ void gather_item(const StepParams& p, TailSmem& ts, i
 // =====================================================================================================================
 // QT: A-side points per thread of the PAIR phase (8 or 16); QT = 0: no PAIR / RESOLVE code (backward-only launches).
 template <int QT>
-__global__ void __launch_bounds__(kThreads, QT == 0 ? 3 : 2) chamfer_step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kThreads, 2) chamfer_step_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtlSmem& ctl = *reinterpret_cast<CtlSmem*>(smem_raw + StepSmem<QT>::kCtlOff);
   TailSmem& ts = *reinterpret_cast<TailSmem*>(smem_raw);
@@ -1067,8 +1200,8 @@ __global__ void __launch_bounds__(kThreads, QT == 0 ? 3 : 2) chamfer_step_kernel
     }
     // RESOLVE / FILL / GATHER items address `rc` points of one side
     const int side = q < p.rc_items[0] ? 0 : 1;
-    const int p0 = (side ? q - p.rc_items[0] : q) * p.rc;
-    const int p1 = min(p.n[side], p0 + p.rc);
+    const int p0 = (side ? q - p.rc_items[0] : q) * p.rc[side];
+    const int p1 = min(p.n[side], p0 + p.rc[side]);
     if (ph == 1) {
       if constexpr (QT != 0) {
         wait_done(p.done_pair + b, p.pair_per_cloud);
@@ -1200,15 +1333,59 @@ static int device_sms() {
   return num_sms;
 }
 
-// A-side points per thread.  QT=16 halves the per-pair LDS/REDUX overhead but makes 4096-point tiles: it is used when
-// 4096-point tiles with at least one full stage each still give every resident CTA 4 items; otherwise QT=8
-// (2048-point tiles).  IAPT_FWD_VARIANT=8|16 forces one (read per call: the parity tests run both over every suite).
-static int pick_qt(int B, int NA, int NS, int slots) {
-  const int forced = env_int("IAPT_FWD_VARIANT", 0);
-  if (forced == 8 || forced == 16) return forced;
-  const long long tiles16 = (NA + kThreads * 16 - 1) / (kThreads * 16);
-  const long long stages = (NS + kSStage - 1) / kSStage;
-  return (NA >= 4096 && (long long)B * tiles16 * stages >= 4LL * slots) ? 16 : 8;
+// PAIR item shape: A-side points per thread (QT = 16 or 8: tiles of 4096 / 2048 points) and the number of ranges the
+// streamed side is split into.  Measured (profiles/r02g_split_sweep.txt, B = 6..48 x 16384^2): the search time follows
+//     ceil(items / SMs) / (items / SMs)  x  (1 + o * s_splits / chunks),     o ~ 0.35 chunks of per-item cost
+// i.e. the SM (its two resident CTAs share the work fluidly) is the unit that quantises, and an item costs about a third
+// of a 32-point chunk in tile loads and key publishing; QT = 16 needs ~4 % fewer issue slots per pair than QT = 8.
+// The model is evaluated for every split count (a few hundred integer operations; the choice is cached per shape).
+// IAPT_FWD_VARIANT = 8|16 and IAPT_S_SPLITS force either (read per call: the parity tests run both over every suite).
+struct PairShape {
+  int qt, s_splits;
+};
+static PairShape pick_pair_shape(int B, int NA, int NS, int num_sms) {
+  struct Key {
+    int B, NA, NS, sms, fq, fs;
+    bool operator==(const Key& o) const { return B == o.B && NA == o.NA && NS == o.NS && sms == o.sms && fq == o.fq && fs == o.fs; }
+  };
+  thread_local Key last_key{-1, 0, 0, 0, 0, 0};
+  thread_local PairShape last{8, 1};
+  const int forced_qt = env_int("IAPT_FWD_VARIANT", 0), forced_s = env_int("IAPT_S_SPLITS", 0);
+  const Key key{B, NA, NS, num_sms, forced_qt, forced_s};
+  if (key == last_key) return last;
+  const int chunks = (NS + kChunk - 1) / kChunk;
+  const int min_chunks = 4;
+  PairShape best{8, 1};
+  double best_cost = 1e300;
+  for (int qt = 8; qt <= 16; qt += 8) {
+    if (forced_qt == 8 || forced_qt == 16) {
+      if (qt != forced_qt) continue;
+    } else if (qt == 16 && NA < 4096) {
+      continue;
+    }
+    const int tile = kThreads * qt;
+    const long long base = (long long)B * ((NA + tile - 1) / tile);
+    const double per_chunk = (double)tile * (qt == 16 ? 1.0 : 1.04);  // issue time of one chunk against one tile
+    const double overhead = qt == 16 ? 0.35 : 0.5;                    // per item, in chunks
+    const int s_max = chunks / min_chunks > 1 ? chunks / min_chunks : 1;
+    for (int s = 1; s <= s_max; ++s) {
+      if (forced_s && s != (forced_s < s_max ? forced_s : s_max)) continue;
+      const long long items = base * s;
+      const long long rounds = (items + num_sms - 1) / num_sms;
+      const double csize = (double)chunks / s;
+      // every SM runs `rounds` items of chunks / s chunks (+ overhead); fewer than 4 rounds leave nothing for the
+      // dynamic ticket to even out, which is charged as half an item
+      double cost = (double)rounds * (csize + overhead) * per_chunk;
+      if (rounds < 4) cost += 0.5 * (csize + overhead) * per_chunk;
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = PairShape{qt, s};
+      }
+    }
+  }
+  last_key = key;
+  last = best;
+  return best;
 }
 
 template <int QT>
@@ -1292,40 +1469,36 @@ int chamfer_step_launch(const StepArgs& a, cudaStream_t stream) {
   }
 
   const int num_sms = device_sms();
-  int qt = 0, slots = num_sms * 3;
+  int qt = 0;
+  const int slots = num_sms * 2;
   if (search) {
-    slots = num_sms * 2;
     const int NA = p.n[p.reg], NS = p.n[p.reg ^ 1];
-    qt = pick_qt(B, NA, NS, slots);
+    const PairShape shape = pick_pair_shape(B, NA, NS, num_sms);
+    qt = shape.qt;
     const int a_tile = kThreads * qt;
     p.a_tiles = (NA + a_tile - 1) / a_tile;
     const int total_chunks = (NS + kChunk - 1) / kChunk;
-    const long long base_items = (long long)B * p.a_tiles;
-    // Split the streamed side (in 32-point chunks) until there are ~16 items per resident CTA slot: measured at B=48 x
-    // 16384^2: 8 -> 3.20 ms, 16 -> 3.09 ms, 32/64 -> 3.23 ms.  Items of a stage or more are whole stages (a partial
-    // stage costs the same barriers as a full one); an item is never smaller than kMinChunks chunks.
-    const long long items_per_slot = env_int("IAPT_ITEMS_PER_SLOT", 16);
-    const int min_chunks = env_int("IAPT_MIN_CHUNKS", 4);
-    long long splits = (items_per_slot * slots + base_items - 1) / base_items;
-    if (splits < 1) splits = 1;
-    long long cpi = (total_chunks + splits - 1) / splits;
-    if (cpi < min_chunks) cpi = min_chunks;
-    if (cpi > kStageChunks) cpi = (cpi + kStageChunks - 1) / kStageChunks * kStageChunks;
-    if (cpi > total_chunks) cpi = total_chunks;
-    p.chunks_per_item = (int)cpi;
-    p.s_splits = (int)((total_chunks + cpi - 1) / cpi);
+    p.s_splits = shape.s_splits;
+    p.total_chunks = total_chunks;
     p.pair_per_cloud = p.a_tiles * p.s_splits;
   } else {
-    p.a_tiles = p.s_splits = p.chunks_per_item = 0;
+    p.a_tiles = p.s_splits = p.total_chunks = 0;
     p.pair_per_cloud = 0;
   }
-  // RESOLVE / FILL / GATHER items: rc points, small enough that every phase has >= 2 items per resident slot
-  int rc = kMaxRc / 2;
-  while (rc > 256 && (long long)B * ((N + rc - 1) / rc + (M + rc - 1) / rc) < 2LL * slots) rc >>= 1;
-  if (const int forced_rc = env_int("IAPT_RC", 0)) rc = forced_rc;  // development knob: 256, 512, 1024 or 2048
-  p.rc = rc;
-  p.rc_items[0] = (N + rc - 1) / rc;
-  p.rc_items[1] = (M + rc - 1) / rc;
+  // RESOLVE / FILL / GATHER items: rc[s] points of side s (a power of two), small enough that the side alone gives
+  // every resident slot 2 items.  A side whose points collect many sources each (n[s] << n[1-s]: the coarse 512-point
+  // prediction against 16384 ground-truth points) gets items down to 32 points - its GATHER work per point is a whole
+  // warp's; otherwise an item is at least 256 points (one per thread).
+  for (int sd = 0; sd < 2; ++sd) {
+    const long long fan = p.n[sd] > 0 ? (long long)p.n[1 - sd] / p.n[sd] : 1;
+    int lo = 256;
+    while (fan > 2 && lo > 32 && (long long)(256 / lo) < fan) lo >>= 1;
+    int rc = kMaxRc / 2;
+    while (rc > lo && (long long)B * ((p.n[sd] + rc - 1) / rc) < 2LL * slots) rc >>= 1;
+    if (const int forced_rc = env_int("IAPT_RC", 0)) rc = forced_rc;  // development knob: 32 .. 2048, power of two
+    p.rc[sd] = rc;
+    p.rc_items[sd] = (p.n[sd] + rc - 1) / rc;
+  }
   p.rc_per_cloud = p.rc_items[0] + p.rc_items[1];
   p.per_cloud[0] = p.pair_per_cloud;
   p.per_cloud[1] = p.rc_per_cloud;

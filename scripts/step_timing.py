@@ -65,14 +65,28 @@ if os.environ.get("SWEEP", "1") == "1":
     B, N, M = 48, 16384, 16384
     p, g = synthetic.pcn_pair(B, N, 5)
     p, g = p.to(dev), g.to(dev)
-    for lag in (8, 100):
-        for rc in (256, 512, 1024, 2048):
-            os.environ["IAPT_RC"] = str(rc)
-            os.environ["IAPT_LAG"] = str(lag)
-            t = ev(lambda: chamfer.step(p, g, chamfer.LOSS_L1, grad1=True))
-            r = chamfer.step(p, g, chamfer.LOSS_L1, grad1=True, stats=True)
-            search_ms, kern_ms = chamfer.step_stats(r.workspace)
-            print(f"config2 lag={lag} rc={rc}: step(g1) {t:.4f} ms  [device: search {search_ms:.4f} kernel {kern_ms:.4f}]", flush=True)
+    for (B, N, M, qts, splits) in [(48, 16384, 16384, (16, 8), (3, 6, 9, 12, 13, 14, 15, 16, 17, 18, 20, 23, 26, 29, 32, 40, 43)),
+                                   (6, 16384, 16384, (16, 8), (12, 24, 37, 49, 61, 74, 86, 98)),
+                                   (12, 16384, 16384, (16, 8), (6, 12, 18, 24, 30, 37, 43, 49)),
+                                   (32, 16384, 16384, (16,), (9, 16, 18, 23, 25, 27, 30, 32))]:
+        p, g = synthetic.pcn_pair(B, N, 5)
+        p, g = p.to(dev), g.to(dev)
+        for qt in qts:
+            for sp in splits:
+                if qt == 8 and sp % 2 == 0:
+                    sp //= 2
+                elif qt == 8:
+                    continue
+                os.environ["IAPT_FWD_VARIANT"] = str(qt)
+                os.environ["IAPT_S_SPLITS"] = str(sp)
+                t = ev(lambda: chamfer.step(p, g, chamfer.LOSS_L1, grad1=True))
+                r = chamfer.step(p, g, chamfer.LOSS_L1, grad1=True, stats=True)
+                search_ms, kern_ms = chamfer.step_stats(r.workspace)
+                items = B * (N // (256 * qt)) * sp
+                print(f"B={B} qt={qt} s_splits={sp} items/slot={items / 296:.2f}: step(g1) {t:.4f} ms  [device: search {search_ms:.4f} kernel {kern_ms:.4f}]", flush=True)
+    os.environ.pop("IAPT_FWD_VARIANT")
+    os.environ.pop("IAPT_S_SPLITS")
+    os.environ["IAPT_RC"] = os.environ["IAPT_LAG"] = "0"
     os.environ.pop("IAPT_RC")
     os.environ.pop("IAPT_LAG")
     # the module path (python + autograd overhead included), config 2 and config 1
