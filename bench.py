@@ -17,9 +17,10 @@ unordered pair once, i.e. 8*B*N*M real FLOPs, and is still scored with the algor
 
 One JSON line on stdout (rank 0).  ``value`` = device-resident throughput; ``e2e`` = the same through the public
 API from pinned HOST buffers (H2D of pred+gt and D2H of the loss inside the timed region); ``roofline`` = the dominant
-kernel (chamfer_pair_kernel) timed with CUDA events on its launch stream inside the timed region;
+kernel (chamfer_step_kernel: the whole step is one launch) timed with CUDA events on its launch stream inside the timed
+region; ``strong`` = fixed-total-work runs of BASELINE configs[1], [3] and [4] sharded over the same ranks;
 ``cpu_baseline`` = the reference's PyTorch CPU formulation (oracle.torch_formulation) on a bounded sample.
-``--impl reference`` times that CPU formulation alone with all host threads (the reference has no CPU Chamfer of its
+``--impl reference`` times that CPU formulation alone with all host threads, 4 clouds per step (the reference has no CPU Chamfer of its
 own: its only implementation is the CUDA extension, which is timed on the GPU as ``ref_cuda_kernel`` in our arm).
 """
 from __future__ import annotations
@@ -42,6 +43,7 @@ B_PER_GPU = 48
 N_PTS = 16384
 METRIC = "chamfer_l1_fwd_bwd_point_pairs_per_s"
 UNIT = "point-pairs/s"
+PACKED_FFMA_PER_CYCLE_PER_SMSP = 0.467  # measured: profiles/r01_pipe_mix_microbench.txt, mode 0
 N_INPUT_SETS = 8  # 8 x 18.9 MB of inputs = 151 MB > 126 MB L2: rotating them defeats L2 reuse between steps
 
 
@@ -169,8 +171,22 @@ def cpu_chamfer_l1_fwd_bwd_rate(n_clouds, threads):
     return n_clouds * N_PTS * N_PTS / dt, dt
 
 
-def run_reference(args, rank):
-    """--impl reference: the CPU formulation with all host threads; each step = one 16384x16384 cloud fwd+bwd."""
+REF_CLOUDS_PER_STEP = 4
+
+
+def workload_config(world, distributed):
+    """`config` of the JSON line: identical for both arms (the driver compares them)."""
+    B, N, M = B_PER_GPU, N_PTS, N_PTS
+    return {"workload": f"Chamfer-L1 fwd+bwd, B={B}/GPU x {N} pred x {M} gt (BASELINE configs[1], PCN training-loss shape)",
+            "global_batch": world * B, "points": [N, M], "parallelism": f"batch-sharded x{world}",
+            "l2_policy": f"rotating {N_INPUT_SETS} input sets = {N_INPUT_SETS * 2 * B * N * 12 / 1e6:.0f} MB > 126 MB L2",
+            "collective": "one all_reduce(SUM)/world of the scalar loss per step (utils/dist_utils.py:41-48)"
+                          if distributed else "none (1 GPU)"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU formulation with all host threads on the same workload; each step is a bounded sample
+    of the batch - REF_CLOUDS_PER_STEP of its 16384 x 16384 clouds, forward + backward - and the rate is per pair."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
@@ -178,21 +194,27 @@ def run_reference(args, rank):
     from oracle import torch_formulation as tf
 
     torch.set_num_threads(threads)
-    pred, gt = synthetic.pcn_pair(1, N_PTS, seed=202)
+    n = REF_CLOUDS_PER_STEP
+    pred, gt = synthetic.pcn_pair(n, N_PTS, seed=202)
+
+    def one_step():
+        for i in range(n):
+            tf.chamfer_l1_fwd_bwd(pred[i:i + 1], gt[i:i + 1])
+
     for _ in range(args.warmup):
-        tf.chamfer_l1_fwd_bwd(pred, gt)
+        one_step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        tf.chamfer_l1_fwd_bwd(pred, gt)
+        one_step()
     dt = time.perf_counter() - t0
-    value = args.steps * N_PTS * N_PTS / dt
-    sample = f"1 cloud of {N_PTS}x{N_PTS} per step (of the {B_PER_GPU}-cloud batch), torch.cdist+min+autograd, float32"
+    value = args.steps * n * N_PTS * N_PTS / dt
+    sample = (f"{n} clouds of {N_PTS}x{N_PTS} per step (of the {B_PER_GPU}-cloud batch), torch.cdist+min+autograd "
+              f"fwd+bwd, float32, {threads} threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Chamfer-L1 fwd+bwd, B={B_PER_GPU}/GPU x {N_PTS} pred x {N_PTS} gt (BASELINE configs[1])",
-                   "reference_arm": "PyTorch CPU formulation on host cores; bounded sample"},
+        "config": workload_config(world, world > 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -264,6 +286,91 @@ def secondary_cpu(threads, n_clouds=4):
             "knn_k16_2048x2048": n_clouds / t_knn}
 
 
+def strong_block(dev, rank, world, fp32_peak_tflops):
+    """Strong scaling: a FIXED total workload batch-sharded over the ranks (the headline keeps 48 clouds per rank).
+    BASELINE configs[1] (48 clouds in total), configs[4] (Chamfer-L2 fwd+bwd, B=256 x 16384^2 and B=16 x 65536^2) and
+    configs[3] (the 1200-cloud metric sweep).  Every rank runs this; times are CUDA events, L2 flushed before each
+    timed iteration, median of 5, max over ranks."""
+    import torch.distributed as dist
+
+    import bench_extra
+    from imgadapointr_b200.extensions.chamfer_dist import ChamferDistanceL1, ChamferDistanceL2
+    from imgadapointr_b200.utils import dist_utils, synthetic
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def timed(fn, warm=2, iters=5):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return bench_extra.max_over_ranks(ts[len(ts) // 2], dev)
+
+    out = {"scaling": "strong", "n_gpus": world, "timing": "CUDA events, L2 flushed before each iteration, median of 5, "
+                                                          "max over ranks; one scalar all-reduce per step when N > 1"}
+    cases = [("config2_B48_16384_L1", ChamferDistanceL1(), 48, 16384, "pcn", 202),
+             ("config5_B256_16384_L2", ChamferDistanceL2(), 256, 16384, "uniform", 505),
+             ("config5_B16_65536_L2", ChamferDistanceL2(), 16, 65536, "uniform", 605)]
+    for name, mod, B, N, kind, seed in cases:
+        b, e = dist_utils.shard_range(B, rank, world)
+        nb = e - b
+        if kind == "pcn":
+            x, y = synthetic.pcn_pair(B, N, seed=seed)
+            x, y = x[b:e].contiguous().to(dev), y[b:e].contiguous().to(dev)
+        else:
+            g = torch.Generator().manual_seed(seed + rank)
+            x = (torch.rand((nb, N, 3), generator=g) - 0.5).to(dev)
+            y = (torch.rand((nb, N, 3), generator=g) - 0.5).to(dev)
+
+        def step():
+            p = x.detach().requires_grad_(True)
+            loss = mod(p, y)
+            loss.backward()
+            if dist.is_initialized():
+                dist_utils.finish_reduce(*dist_utils.reduce_tensor_async(loss.detach()))
+
+        ms = timed(step)
+        pairs = B * N * N
+        out[name] = {"global_batch": B, "clouds_per_rank": nb, "ms_per_step": ms, "point_pairs_per_s": pairs / (ms * 1e-3),
+                     "frac_fp32_peak_per_gpu": 16.0 * pairs / world / (ms * 1e-3) / 1e12 / fp32_peak_tflops}
+        del x, y
+        torch.cuda.empty_cache()
+    c4 = bench_extra.config4(dev, rank, world, emd=False)
+    out["config4_sweep_1200_clouds"] = {k: c4[k] for k in ("clouds", "clouds_per_rank", "sweep_ms", "clouds_per_s",
+                                                           "point_pairs_per_s", "overall_F_CDL1_CDL2")}
+    out["config4_sweep_1200_clouds"]["frac_fp32_peak_per_gpu"] = c4["frac_fp32_peak_aggregate"]
+    return out
+
+
+def multidevice_selftest():
+    """Several GPUs driven from ONE process (the reference's default nn.DataParallel path, tools/runner.py:96): the
+    same clouds on cuda:0 and cuda:1 must give bit-identical results.  Returns 'ok', a failure text, or None with
+    fewer than two visible GPUs."""
+    if torch.cuda.device_count() < 2:
+        return None
+    from imgadapointr_b200 import chamfer
+    from imgadapointr_b200.utils import synthetic
+
+    p, g = synthetic.pcn_pair(3, 4096, seed=77)
+    res = []
+    for d in (0, 1):
+        dv = torch.device("cuda", d)
+        r = chamfer.step(p.to(dv), g.to(dv), chamfer.LOSS_L1, grad1=True)
+        torch.cuda.synchronize(dv)
+        res.append((r.dist1.cpu(), r.idx1.cpu(), r.idx2.cpu(), r.loss.cpu(), r.grad1.cpu()))
+    same = all(torch.equal(a, b) for a, b in zip(*res))
+    return "ok" if same else "MISMATCH between cuda:0 and cuda:1"
+
+
 def time_ref_cuda_kernel(pred, gt, iters=3):
     """The reference's own CUDA extension (oracle/_ref, built unmodified for sm_100a) on the same inputs: the
     'kernel to beat'.  Returns ms per fwd+bwd or None if the .so is absent."""
@@ -304,6 +411,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == "ours" else 0)
 
@@ -312,7 +420,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
 
     import torch.distributed as dist
@@ -361,6 +469,15 @@ def main():
             loss = dist_utils.reduce_tensor(loss.detach())
         return loss, p.grad
 
+    def step_async(pred, gt):
+        """The same step with the all-reduce taken off the launch stream: it runs on NCCL's stream behind this step's
+        kernel while the next step's kernel starts; the result is consumed (work.wait + / world) one step later."""
+        p = pred.detach().requires_grad_(True)
+        loss = loss_mod(p, gt)
+        loss.backward()
+        rt, work = dist_utils.reduce_tensor_async(loss.detach())
+        return rt, work, p.grad
+
     def barrier():
         if distributed:
             dist.barrier()
@@ -379,8 +496,13 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    pending = None
     for k in range(args.steps):
-        loss, grad = step(*dev_sets[k % N_INPUT_SETS])
+        rt, work, grad = step_async(*dev_sets[k % N_INPUT_SETS])
+        if pending is not None:
+            dist_utils.finish_reduce(*pending)  # the previous step's loss: its all-reduce ran under this step's kernel
+        pending = (rt, work)
+    loss = dist_utils.finish_reduce(*pending)  # every step's collective completes inside the timed region
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -451,16 +573,19 @@ def main():
                "wall_ms_per_step": wall_ms / args.steps,
                "note": "pinned host pred+gt -> device each step (copy stream, double buffered), loss read back each step"}
 
+    # ---- strong scaling (every rank takes part) ------------------------------------------------------------------------
+    peaks, peak_src = measured_peaks()
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    fp32_peak = n_sm * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s: SMs x FP32 lanes x 2 (FMA) x max SM clock
+    strong = None if args.no_strong else strong_block(dev, rank, world, fp32_peak)
+
     if rank != 0:
         if distributed:
             dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------------
-    peaks, peak_src = measured_peaks()
-    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-    fp32_peak = n_sm * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s: SMs x FP32 lanes x 2 (FMA) x max SM clock
     alg_flops = 16.0 * B * N * M  # per launch (one rank): 8 FLOP per ordered pair, both directions
     kern_avg_ms = kern_ms / max(kern_n, 1)
     achieved = alg_flops / (kern_avg_ms * 1e-3) / 1e12
@@ -468,12 +593,19 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("chamfer_pair_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("chamfer_step_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {
-        "bound": "fp32_fma", "kernel": "chamfer_pair_kernel", "achieved": achieved, "peak": fp32_peak,
+        "bound": "fp32_fma", "kernel": "chamfer_step_kernel<16> (search + index resolution + loss sums + CSR fan-in + "
+                                       "gradient: the whole step is this one launch)",
+        "achieved": achieved, "peak": fp32_peak,
         "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": traffic,
+        "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per "
+                          "launch of the same command; a profiler pass cannot run inside the timed region)",
+        "peak_measured": PACKED_FFMA_PER_CYCLE_PER_SMSP * 4 * n_sm * 64 * 2 * sm_max * 1e6 / 1e12,
+        "peak_measured_source": "scripts/microbench/pipe_mix.cu on this GPU type (profiles/r01_pipe_mix_microbench.txt): "
+                                "0.467 FFMA2 (64 lane-FMAs) per cycle per SMSP sustained = 0.934 of the derived peak",
         "peak_source": f"{n_sm} SMs x 128 FP32 lanes x 2 x sm_max_mhz={sm_max:.0f} ({peak_src} MEASURED_PEAKS.json; it "
                        "holds no FP32 figure, so the FMA peak is derived from its max SM clock)",
         "algorithmic_flops_per_launch": alg_flops, "real_flops_per_launch": alg_flops / 2,
@@ -490,17 +622,16 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"Chamfer-L1 fwd+bwd, B={B}/GPU x {N} pred x {M} gt (BASELINE configs[1], PCN training-loss shape)",
-                   "global_batch": world * B, "points": [N, M], "parallelism": f"batch-sharded x{world}",
-                   "l2_policy": f"rotating {N_INPUT_SETS} input sets = {N_INPUT_SETS * 2 * B * N * 12 / 1e6:.0f} MB > 126 MB L2",
-                   "collective": "one all_reduce(SUM)/world of the scalar loss per step (utils/dist_utils.py:41-48)" if distributed else "none (1 GPU)"},
+        "config": workload_config(world, distributed),
         "frac_fp32_peak": 16.0 * pairs_per_step / world / (ms_per_step * 1e-3) / 1e12 / fp32_peak,
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "loss": float(loss.detach()),
+        "allreduce": "async (NCCL stream, consumed one step later, all inside the timed region)" if distributed else None,
     }
 
     # ---- secondary metrics of BASELINE.json ("FPS/kNN clouds/s"): config 3 shapes, B = 48, rank 0's GPU --------------
     out["secondary"] = secondary_gpu(dev)
+    out["strong"] = strong
 
     ref_ms = time_ref_cuda_kernel(dev_sets[0][0], dev_sets[0][1])
     if ref_ms is not None:
@@ -509,6 +640,11 @@ def main():
                                           "(oracle/_ref), forward+backward on the same inputs, 1 GPU"}
     if distributed:
         dist.destroy_process_group()
+    if world >= 2:  # the box has several GPUs: also drive two of them from this one process
+        try:
+            out["multidevice_single_process"] = multidevice_selftest()
+        except Exception as ex:  # reported, never fatal for the bench line
+            out["multidevice_single_process"] = f"error: {ex}"
 
     if not args.no_cpu_baseline and world >= 1:
         threads = os.cpu_count() or 1

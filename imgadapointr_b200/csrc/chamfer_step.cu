@@ -33,6 +33,7 @@
 // fixed point (scale = a power of two from the segment's largest term), which needs no order at all - so results do
 // not depend on scheduling or launch geometry, and a collapsed prediction (thousands of points sharing one neighbour)
 // is a parallel reduction instead of the reference's atomicAdd contention (chamfer.cu:193-198).
+#include <cmath>
 #include <cstdlib>
 #include <utility>
 #include <vector>
@@ -1371,7 +1372,9 @@ static PairShape pick_pair_shape(int B, int NA, int NS, int num_sms) {
     for (int s = 1; s <= s_max; ++s) {
       if (forced_s && s != (forced_s < s_max ? forced_s : s_max)) continue;
       const long long items = base * s;
-      const long long rounds = (items + num_sms - 1) / num_sms;
+      // an exact multiple of the SM count behaves like one item too many (any jitter makes some CTA start an extra
+      // item alone): at least 3 % of an item of slack is required
+      const long long rounds = (long long)std::ceil((double)items / num_sms + 0.03);
       const double csize = (double)chunks / s;
       // every SM runs `rounds` items of chunks / s chunks (+ overhead); fewer than 4 rounds leave nothing for the
       // dynamic ticket to even out, which is charged as half an item

@@ -38,6 +38,32 @@ def reduce_tensor(tensor, args=None):
     return rt
 
 
+class _Done:
+    """Stand-in for a finished collective (single process)."""
+
+    def wait(self):
+        return True
+
+
+def reduce_tensor_async(tensor, args=None):
+    """``reduce_tensor`` off the critical path: returns ``(rt, work)``; the all-reduce runs on the collective's own
+    stream behind the kernels already queued, and the launch stream only waits for it when the consumer calls
+    ``work.wait()`` (a stream-side wait, not a host block) - i.e. at read-back.  ``rt`` holds the SUM until then and the
+    mean (SUM / world_size, utils/dist_utils.py:41-48) after ``finish_reduce(rt, work)``."""
+    rt = tensor.clone()
+    if dist.is_available() and dist.is_initialized():
+        return rt, dist.all_reduce(rt, op=dist.ReduceOp.SUM, async_op=True)
+    return rt, _Done()
+
+
+def finish_reduce(rt, work, args=None):
+    """Consume a ``reduce_tensor_async`` result: wait on the launch stream, then divide by the world size."""
+    work.wait()
+    if dist.is_available() and dist.is_initialized():
+        rt /= getattr(args, "world_size", None) or dist.get_world_size()
+    return rt
+
+
 def gather_tensor(tensor, args=None):
     """utils/dist_utils.py:50-54."""
     if not (dist.is_available() and dist.is_initialized()):
