@@ -260,7 +260,7 @@ def secondary_gpu(dev, B=B_PER_GPU):
         t_knn = _event_ms(lambda: knn_point(16, xyz, xyz))
         t_seq = _event_ms(sequence)
     finally:
-        fps.reuse_prefix = True
+        fps.reuse_prefix = False
     return {"unit": "clouds/s", "batch": B,
             "fps_2048_to_512": B / (t_fps * 1e-3), "knn_k16_2048x2048": B / (t_knn * 1e-3),
             "encoder_geometry_sequence": B / (t_seq * 1e-3),

@@ -73,6 +73,7 @@ SIGNATURES = {
                                   _c_size_t, _c_void_p]),
     "iapt_emd_backward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
     "iapt_knn_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
+    "iapt_square_distance": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
     "iapt_knn": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t,
                           _c_void_p]),
 }
@@ -99,6 +100,44 @@ def lib() -> ctypes.CDLL:
             raise IaptError(f"ABI mismatch: library {handle.iapt_abi_version()} != binding {ABI_VERSION}")
         _lib = handle
     return _lib
+
+
+_ext = False  # not looked up yet
+
+
+def torch_ext():
+    """The compiled PyTorch binding over the same C ABI (csrc/torch_binding.cpp -> iapt_torch_ext*.so), or None when it
+    is not built or ``IAPT_BINDING=ctypes`` / ``set_binding("ctypes")`` selects the torch-free ctypes table below.
+    Both bindings call the same entry points of libiapt_b200.so; the compiled one validates, allocates and launches
+    from C++ (TORCH_CHECK, at::empty, CUDAGuard, getCurrentCUDAStream) and costs a fraction of the host time."""
+    global _ext
+    if _ext is False:
+        _ext = None
+        if os.environ.get("IAPT_BINDING", "torch") != "ctypes":
+            lib()  # the CUDA library must be present either way: no fallback
+            try:
+                from . import iapt_torch_ext as mod
+            except ImportError:
+                mod = None
+            if mod is not None:
+                if mod.abi_version() != ABI_VERSION:
+                    raise IaptError(f"ABI mismatch: iapt_torch_ext {mod.abi_version()} != binding {ABI_VERSION}")
+                _ext = mod
+    return _ext
+
+
+def set_binding(kind: str) -> None:
+    """``"torch"`` (compiled extension; raises if it is not built) or ``"ctypes"`` - for tests and timing."""
+    global _ext
+    if kind == "ctypes":
+        _ext = None
+    elif kind == "torch":
+        _ext = False
+        os.environ.pop("IAPT_BINDING", None)
+        if torch_ext() is None:
+            raise IaptError("iapt_torch_ext is not built (python imgadapointr_b200/csrc/build_torch_ext.py)")
+    else:
+        raise ValueError(kind)
 
 
 def check(code: int, what: str) -> None:

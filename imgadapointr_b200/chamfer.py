@@ -35,6 +35,9 @@ def _workspace(nbytes, dev):
 
 def forward(xyz1: torch.Tensor, xyz2: torch.Tensor):
     xyz1, xyz2 = _prep(xyz1.detach(), xyz2.detach())
+    ext = _lib.torch_ext()
+    if ext is not None:
+        return ext.forward(xyz1, xyz2)
     B, N, _ = xyz1.shape
     M = xyz2.size(1)
     dev = xyz1.device
@@ -68,6 +71,9 @@ def backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2, need1: bool = True,
         raise _lib.IaptError("backward: shape mismatch between xyz, idx and grad_dist")
     if not (need1 or need2):
         return [None, None]
+    ext = _lib.torch_ext()
+    if ext is not None:
+        return ext.backward(xyz1, xyz2, idx1, idx2, g1, g2, bool(need1), bool(need2))
     L = _lib.lib()
     with _lib.on_device(dev):
         gx1 = torch.empty_like(xyz1) if need1 else None
@@ -115,6 +121,12 @@ def step(xyz1, xyz2, kind: int = LOSS_NONE, *, sums: bool = False, counts: bool 
         grad_loss = grad_loss.to(torch.float32).contiguous()
         if grad_loss.numel() != (2 if kind == LOSS_L2_SPLIT else 1):
             raise _lib.IaptError("step: grad_loss has the wrong number of elements")
+    ext = _lib.torch_ext()
+    if ext is not None:
+        (r.dist1, r.dist2, r.idx1, r.idx2, r.sums, r.counts, r.valid, r.loss, r.grad1, r.grad2,
+         r.workspace) = ext.step(xyz1, xyz2, int(kind), flags & ~STEP_GATE_ON_VALID, float(th), bool(sums), bool(counts),
+                                 bool(valid), gate_valid, bool(grad1), bool(grad2), grad_loss)
+        return r
     with _lib.on_device(dev):
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
@@ -161,6 +173,9 @@ def scale(src: torch.Tensor, factor: torch.Tensor) -> torch.Tensor:
     """src * factor[0] with the factor read on the device (no host sync): applies an upstream gradient (iapt_scale)."""
     src = src.contiguous()
     factor = factor.to(torch.float32).reshape(-1).contiguous()
+    ext = _lib.torch_ext()
+    if ext is not None:
+        return ext.scale(src, factor)
     dev = src.device
     with _lib.on_device(dev):
         dst = torch.empty_like(src)
@@ -219,6 +234,10 @@ def loss_backward(xyz1, xyz2, idx1, idx2, dist1, dist2, kind: int, grad_loss, ne
             raise _lib.IaptError("loss_backward: grad_loss has the wrong number of elements")
     if not (need1 or need2):
         return None, None
+    ext = _lib.torch_ext()
+    if ext is not None:
+        gx1, gx2 = ext.loss_backward(xyz1, xyz2, idx1, idx2, dist1, dist2, int(kind), grad_loss, bool(need1), bool(need2))
+        return gx1, gx2
     L = _lib.lib()
     with _lib.on_device(dev):
         gx1 = torch.empty_like(xyz1) if need1 else None

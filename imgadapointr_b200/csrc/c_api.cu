@@ -19,6 +19,7 @@ int gather_xyz_launch(const float*, const int32_t*, int, int, int, float*, cudaS
 int gather_grad_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
 size_t knn_workspace_bytes(int B, int R, int Q, int k);
 int knn_launch(const float*, const float*, int, int, int, int, int64_t*, float*, void*, cudaStream_t);
+int square_distance_launch(const float*, const float*, int, int, int, int, float*, cudaStream_t);
 int graph_feature_launch(const float*, const float*, const long long*, int, int, int, int, int, float*, cudaStream_t);
 int index_points_launch(const float*, const long long*, int, int, int, long long, float*, cudaStream_t);
 size_t graph_feature_grad_workspace_bytes(int B, int Nq, int Nk, int k);
@@ -329,6 +330,14 @@ int iapt_knn(const float* ref, const float* query, int B, int R, int Q, int k, i
   return knn_launch(ref, query, B, R, Q, k, idx, dist, need ? workspace : nullptr, (cudaStream_t)stream);
 }
 
+int iapt_square_distance(const float* src, const float* dst, int B, int N, int M, int C, float* out,
+                         iapt_stream_t stream) {
+  IAPT_REQUIRE(B >= 0 && N >= 0 && M >= 0 && C >= 1 && B <= 65535 && (N + 7) / 8 <= 65535);
+  if (B == 0 || N == 0 || M == 0) return 0;
+  IAPT_REQUIRE(src && dst && out);
+  return square_distance_launch(src, dst, B, N, M, C, out, (cudaStream_t)stream);
+}
+
 int iapt_graph_feature(const float* x_q, const float* x_k, const int64_t* idx, int B, int C, int Nq, int Nk, int k,
                        float* out, iapt_stream_t stream) {
   IAPT_REQUIRE(B >= 0 && C >= 0 && Nq >= 0 && Nk >= 1 && k >= 0 && B <= 65535);
@@ -345,7 +354,8 @@ size_t iapt_graph_feature_grad_workspace_bytes(int B, int Nq, int Nk, int k) {
 int iapt_graph_feature_grad(const float* grad_out, const int64_t* idx, int B, int C, int Nq, int Nk, int k,
                             float* grad_x_q, float* grad_x_k, void* workspace, size_t workspace_bytes,
                             iapt_stream_t stream) {
-  IAPT_REQUIRE(B >= 0 && C >= 0 && Nq >= 0 && Nk >= 1 && k >= 0 && B <= 65535 && C <= 65535);
+  IAPT_REQUIRE(B >= 0 && C >= 0 && Nq >= 0 && Nk >= 1 && k >= 0 && B <= 65535 && C <= 65535 &&
+               (long long)Nq * k < (1LL << 31));  // positions are ints inside the inverse index
   if (B == 0 || C == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (Nq == 0 || k == 0) {
@@ -411,7 +421,8 @@ int iapt_group_gather(const float* features, const int64_t* idx, const float* we
 int iapt_group_gather_grad(const float* grad_out, const int64_t* idx, const float* weight, int B, int C, int M, int P,
                            int S, int reduce, float* grad_features, void* workspace, size_t workspace_bytes,
                            iapt_stream_t stream) {
-  IAPT_REQUIRE(B >= 0 && C >= 0 && M >= 1 && P >= 0 && S >= 1 && (reduce == 0 || reduce == 1) && B <= 65535 && C <= 65535);
+  IAPT_REQUIRE(B >= 0 && C >= 0 && M >= 1 && P >= 0 && S >= 1 && (reduce == 0 || reduce == 1) && B <= 65535 && C <= 65535 &&
+               (long long)P * S < (1LL << 31));
   if (B == 0 || C == 0) return 0;
   IAPT_REQUIRE(grad_features);
   if (P == 0)

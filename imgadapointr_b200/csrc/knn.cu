@@ -635,4 +635,68 @@ int knn_launch(const float* ref, const float* qry, int B, int R, int Q, int k, i
   return (int)cudaGetLastError();
 }
 
+// ---- square_distance (models/Transformer_utils.py:32-51) ---------------------------------------------------------------
+// The reference's API: the full [B,N,M] matrix in the EXPANSION form it uses, in its op order
+//     dist = -2 * (src @ dst^T);  dist += sum(src^2, -1)[:, :, None];  dist += sum(dst^2, -1)[:, None, :]
+// (knn_point above never materialises it; this serves callers that want the matrix itself).  HBM-write bound:
+// a CTA covers 8 rows x 1024 columns, a thread 4 consecutive columns of every row -> 128-bit coalesced stores.
+constexpr int kSqRows = 8, kSqThreads = 256, kSqMaxC = 16;
+
+__global__ void __launch_bounds__(kSqThreads) square_distance_kernel(const float* __restrict__ src,
+                                                                     const float* __restrict__ dst, int N, int M, int C,
+                                                                     float* __restrict__ out) {
+  __shared__ float s_src[kSqRows][kSqMaxC + 1];
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.y * kSqRows;
+  const int m0 = (blockIdx.x * kSqThreads + threadIdx.x) * 4;
+  for (int i = threadIdx.x; i < kSqRows * C; i += kSqThreads) {
+    const int r = i / C, c = i - r * C;
+    s_src[r][c] = (n0 + r < N) ? __ldg(src + ((size_t)b * N + n0 + r) * C + c) : 0.f;
+  }
+  __syncthreads();
+  if (m0 >= M) return;
+  float d[4][kSqMaxC];
+  float dsum[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    dsum[j] = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = (m0 + j < M) ? __ldg(dst + ((size_t)b * M + m0 + j) * C + c) : 0.f;
+      d[j][c] = v;
+      dsum[j] = c == 0 ? __fmul_rn(v, v) : __fadd_rn(dsum[j], __fmul_rn(v, v));
+    }
+  }
+  const bool vec = (M & 3) == 0;
+  for (int r = 0; r < kSqRows; ++r) {
+    const int n = n0 + r;
+    if (n >= N) break;
+    float ssum = 0.f;
+    for (int c = 0; c < C; ++c) ssum = c == 0 ? __fmul_rn(s_src[r][c], s_src[r][c]) : __fadd_rn(ssum, __fmul_rn(s_src[r][c], s_src[r][c]));
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = 0.f;
+      for (int c = 0; c < C; ++c) t = c == 0 ? __fmul_rn(s_src[r][c], d[j][c]) : __fmaf_rn(s_src[r][c], d[j][c], t);
+      o[j] = __fadd_rn(__fadd_rn(__fmul_rn(-2.f, t), ssum), dsum[j]);
+    }
+    float* row = out + ((size_t)b * N + n) * M + m0;
+    if (vec) {
+      *reinterpret_cast<float4*>(row) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (m0 + j < M) row[j] = o[j];
+    }
+  }
+}
+
+int square_distance_launch(const float* src, const float* dst, int B, int N, int M, int C, float* out,
+                           cudaStream_t stream) {
+  if (C > kSqMaxC) return -3;  // IAPT_EUNSUPPORTED
+  const dim3 grid((M + kSqThreads * 4 - 1) / (kSqThreads * 4), (N + kSqRows - 1) / kSqRows, B);
+  square_distance_kernel<<<grid, kSqThreads, 0, stream>>>(src, dst, N, M, C, out);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 }  // namespace iapt

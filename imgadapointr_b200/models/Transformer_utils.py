@@ -34,6 +34,10 @@ def knn_point(nsample, xyz, new_xyz, return_dist=False):
     k = int(nsample)
     if k > R:
         raise RuntimeError(f"knn_point: nsample={k} exceeds the number of points {R} (torch.topk raises here too)")
+    ext = _lib.torch_ext()
+    if ext is not None:
+        idx, dist = ext.knn(xyz, new_xyz, k, bool(return_dist))
+        return (idx, dist) if return_dist else idx
     dev = xyz.device
     with _lib.on_device(dev):
         idx = torch.empty((B, Q, k), dtype=torch.int64, device=dev)
@@ -46,14 +50,27 @@ def knn_point(nsample, xyz, new_xyz, return_dist=False):
 
 
 def square_distance(src, dst):
-    """[B,N,C],[B,M,C] -> [B,N,M] squared distances (Transformer_utils.py:32-51).  Kept for API parity: nothing on the
-    accelerated path materialises this matrix any more (knn_point is fused); plain torch ops, same op order."""
-    B, N, _ = src.shape
-    _, M, _ = dst.shape
-    dist = -2 * torch.matmul(src, dst.permute(0, 2, 1))
-    dist += torch.sum(src ** 2, -1).view(B, N, 1)
-    dist += torch.sum(dst ** 2, -1).view(B, 1, M)
-    return dist
+    """[B,N,C],[B,M,C] -> [B,N,M] squared distances in the reference's expansion form and op order
+    (Transformer_utils.py:32-51: ``-2 src.dst^T``, ``+= sum(src^2)``, ``+= sum(dst^2)``), one kernel writing the matrix
+    once (iapt_square_distance).  Kept for API parity: ``knn_point`` is fused and never materialises it.  CUDA float32
+    only, like every entry point here; not differentiable (the reference only uses it under ``knn_point``)."""
+    src, dst = src.detach(), dst.detach()
+    _lib.require_cuda_f32(src, "src", 3)
+    _lib.require_cuda_f32(dst, "dst", 3)
+    if src.size(0) != dst.size(0) or src.size(2) != dst.size(2):
+        raise _lib.IaptError("square_distance: src [B,N,C] and dst [B,M,C] must share B and C")
+    src, dst = src.contiguous(), dst.contiguous()
+    ext = _lib.torch_ext()
+    if ext is not None:
+        return ext.square_distance(src, dst)
+    B, N, C = src.shape
+    M = dst.size(1)
+    dev = src.device
+    with _lib.on_device(dev):
+        out = torch.empty((B, N, M), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().iapt_square_distance(_lib.ptr(src), _lib.ptr(dst), B, N, M, C, _lib.ptr(out),
+                                                   _lib.stream_ptr(dev)), "iapt_square_distance")
+    return out
 
 
 class _IndexPoints(torch.autograd.Function):
@@ -93,15 +110,19 @@ def index_points(points, idx):
 
     One gather kernel (iapt_index_points) instead of the reference's arange/repeat + advanced indexing, and when
     ``points`` needs a gradient a deterministic backward (iapt_index_points_grad: every source row is the sum, in
-    ascending position, of the gradient rows that gathered it) instead of torch's atomicAdd scatter.  Anything that is
-    not a CUDA float32 [B,N,C] tensor takes the plain torch.gather formulation."""
+    ascending position, of the gradient rows that gathered it) instead of torch's atomicAdd scatter.  CUDA float32
+    ``points`` and CUDA integer ``idx`` only - like every other entry point there is no eager / CPU path."""
+    _lib.require_cuda_f32(points, "points", 3)
+    if not (isinstance(idx, torch.Tensor) and idx.is_cuda and not idx.is_floating_point() and idx.dim() >= 2):
+        raise _lib.IaptError("index_points: idx must be a CUDA integer tensor [B, S] or [B, S, K]")
     B = points.shape[0]
     C = points.shape[-1]
+    if idx.size(0) != B:
+        raise _lib.IaptError("index_points: points and idx must share the batch size")
     flat = idx.reshape(B, -1).to(torch.int64)
-    if points.is_cuda and points.dtype == torch.float32 and points.dim() == 3 and flat.is_cuda and C > 0 and flat.size(1) > 0:
-        return _IndexPoints.apply(points.contiguous(), flat.contiguous()).reshape(*idx.shape, C)
-    out = torch.gather(points, 1, flat.unsqueeze(-1).expand(-1, -1, C))
-    return out.reshape(*idx.shape, C)
+    if C == 0 or flat.size(1) == 0 or B == 0:  # nothing to gather
+        return points.new_empty((*idx.shape, C))
+    return _IndexPoints.apply(points.contiguous(), flat.contiguous()).reshape(*idx.shape, C)
 
 
 class _GraphFeatureCL(torch.autograd.Function):

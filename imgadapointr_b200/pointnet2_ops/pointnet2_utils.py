@@ -31,6 +31,9 @@ def _fps(xyz: torch.Tensor, npoint: int, skip_near_origin: bool) -> torch.Tensor
         raise _lib.IaptError("xyz must be contiguous (upstream CHECK_CONTIGUOUS)")
     B, N, _ = xyz.shape
     npoint = int(npoint)
+    ext = _lib.torch_ext()
+    if ext is not None:
+        return ext.furthest_point_sampling(xyz, npoint, 1 if skip_near_origin else 0)
     dev = xyz.device
     L = _lib.lib()
     with _lib.on_device(dev):
@@ -59,10 +62,18 @@ class FurthestPointSampling(torch.autograd.Function):
 # ---- prefix reuse --------------------------------------------------------------------
 # Greedy FPS always starts at index 0, so the m-point sample of a cloud is a PREFIX of any longer sample of the same
 # cloud.  The reference samples the same tensor several times per forward (AdaPoinTr.py:113 -> 256 points, :126 -> 64
-# points of the same `xyz`); the second call is served from the first one's result.  A cached result is reused only
-# for the very same live tensor object (weak reference) at the same autograd version, i.e. provably unmodified.
+# points of the same `xyz`); inside a ``prefix_reuse()`` scope - one model forward - the second call is served from
+# the first one's result.  Reuse is OPT-IN and scoped because nothing visible from Python proves a tensor unmodified:
+# the autograd version counter misses `.data` writes, CUDA-graph replays into a static tensor and DLPack writers, and
+# inference tensors have no counter at all.  A cached result is reused only for the very same live tensor object
+# (weak reference) at the same version; inference tensors are never cached; the cache keeps a private copy of the
+# indices and is dropped when the scope ends.
 _prefix_cache = []  # [(weakref(xyz), version, skip, idx)], most recent first
 _PREFIX_CACHE_SIZE = 4
+
+
+def _cacheable(xyz):
+    return (isinstance(xyz, torch.Tensor) and not torch.is_inference_mode_enabled() and not xyz.is_inference())
 
 
 def _prefix_lookup(xyz, npoint, skip):
@@ -75,25 +86,42 @@ def _prefix_lookup(xyz, npoint, skip):
 def furthest_point_sample(xyz, npoint):
     skip = SKIP_NEAR_ORIGIN_DEFAULT if furthest_point_sample.skip_near_origin is None \
         else furthest_point_sample.skip_near_origin
-    if furthest_point_sample.reuse_prefix and isinstance(xyz, torch.Tensor):
+    reuse = furthest_point_sample.reuse_prefix and _cacheable(xyz)
+    if reuse:
         hit = _prefix_lookup(xyz, int(npoint), skip)
         if hit is not None:
             furthest_point_sample.prefix_hits += 1
-            return hit[:, :int(npoint)].contiguous()
+            return hit[:, :int(npoint)].contiguous()  # a fresh tensor: callers may modify it
     out = FurthestPointSampling.apply(xyz, npoint)
-    if furthest_point_sample.reuse_prefix:
+    if reuse:
         import weakref
 
         try:
-            _prefix_cache.insert(0, (weakref.ref(xyz), xyz._version, skip, out))
+            _prefix_cache.insert(0, (weakref.ref(xyz), xyz._version, skip, out.clone()))
             del _prefix_cache[_PREFIX_CACHE_SIZE:]
-        except TypeError:
+        except (TypeError, RuntimeError):  # not weak-referenceable / no version counter: simply not cached
             pass
     return out
 
 
+class prefix_reuse:
+    """``with prefix_reuse(): model(partial)`` - FPS calls on the same (unmodified) tensor inside the scope share one
+    launch.  The tensor must not be written between the calls by means autograd cannot see."""
+
+    def __enter__(self):
+        self._prev = furthest_point_sample.reuse_prefix
+        furthest_point_sample.reuse_prefix = True
+        return self
+
+    def __exit__(self, *exc):
+        furthest_point_sample.reuse_prefix = self._prev
+        if not self._prev:
+            _prefix_cache.clear()
+        return False
+
+
 furthest_point_sample.skip_near_origin = None  # None -> SKIP_NEAR_ORIGIN_DEFAULT
-furthest_point_sample.reuse_prefix = True
+furthest_point_sample.reuse_prefix = False     # opt-in: see prefix_reuse
 furthest_point_sample.prefix_hits = 0
 
 
@@ -113,10 +141,14 @@ class GatherOperation(torch.autograd.Function):
         idx = _check_idx(idx, B)
         m = idx.size(1)
         dev = features.device
-        with _lib.on_device(dev):
-            out = torch.empty((B, C, m), dtype=torch.float32, device=dev)
-            _lib.check(_lib.lib().iapt_gather(_lib.ptr(features), _lib.ptr(idx), B, C, N, m, _lib.ptr(out),
-                                              _lib.stream_ptr(dev)), "iapt_gather")
+        ext = _lib.torch_ext()
+        if ext is not None:
+            out = ext.gather_points(features, idx)
+        else:
+            with _lib.on_device(dev):
+                out = torch.empty((B, C, m), dtype=torch.float32, device=dev)
+                _lib.check(_lib.lib().iapt_gather(_lib.ptr(features), _lib.ptr(idx), B, C, N, m, _lib.ptr(out),
+                                                  _lib.stream_ptr(dev)), "iapt_gather")
         ctx.save_for_backward(idx)
         ctx.N = N
         return out
@@ -127,6 +159,9 @@ class GatherOperation(torch.autograd.Function):
         grad_out = grad_out.to(torch.float32).contiguous()
         B, C, m = grad_out.shape
         dev = grad_out.device
+        ext = _lib.torch_ext()
+        if ext is not None:
+            return ext.gather_points_grad(grad_out, idx, ctx.N), None
         with _lib.on_device(dev):
             gfeat = torch.empty((B, C, ctx.N), dtype=torch.float32, device=dev)
             _lib.check(_lib.lib().iapt_gather_grad(_lib.ptr(grad_out), _lib.ptr(idx), B, C, ctx.N, m, _lib.ptr(gfeat),
@@ -144,6 +179,9 @@ def gather_xyz(xyz: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     B, N, _ = xyz.shape
     idx = _check_idx(idx, B)
     m = idx.size(1)
+    ext = _lib.torch_ext()
+    if ext is not None:
+        return ext.gather_xyz(xyz, idx)
     dev = xyz.device
     with _lib.on_device(dev):
         out = torch.empty((B, m, 3), dtype=torch.float32, device=dev)

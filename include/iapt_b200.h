@@ -180,6 +180,13 @@ size_t iapt_knn_workspace_bytes(int B, int R, int Q, int k); /* per-slice lists 
 int iapt_knn(const float* ref, const float* query, int B, int R, int Q, int k, int64_t* idx, float* dist,
              void* workspace, size_t workspace_bytes, iapt_stream_t stream);
 
+/* Replaces models/Transformer_utils.py:32-51 square_distance(src, dst) for callers that want the matrix itself:
+ *   src [B,N,C], dst [B,M,C] -> out [B,N,M] = -2 src.dst^T + |src|^2 + |dst|^2, the reference's expansion form in its
+ * op order (so values agree with the reference's to FP32 rounding, NOT with the direct-form distances of iapt_knn /
+ * iapt_chamfer_forward).  1 <= C <= 16. */
+int iapt_square_distance(const float* src, const float* dst, int B, int N, int M, int C, float* out,
+                         iapt_stream_t stream);
+
 /* ---- kNN consumers -----------------------------------------------------------------
  * iapt_graph_feature replaces the gather / expand / cat after knn_point in DGCNN_Grouper.get_graph_feature
  * (models/base_blocks.py:582-588):   x_q [B,C,Nq], x_k [B,C,Nk], idx [B,Nq,k] int64 (as knn_point returns)  ->
@@ -187,7 +194,10 @@ int iapt_knn(const float* ref, const float* query, int B, int R, int Q, int k, i
  * iapt_graph_feature_grad: grad_out [B,2C,Nq,k] -> grad_x_q [B,C,Nq] and grad_x_k [B,C,Nk] (either may be NULL),
  * deterministic (inverse index by a stable counting sort of idx, shared by all channels; no float atomics).
  * iapt_index_points replaces index_points (models/Transformer_utils.py:53-69): points [B,N,C], idx [B,S] int64 (S may be
- * the flattened Q*k) -> out [B,S,C]. */
+ * the flattened Q*k) -> out [B,S,C].
+ * Preconditions of every idx-consuming entry point: 0 <= idx < the indexed extent (the reference's advanced indexing
+ * raises a device assert otherwise; here an out-of-range index is undefined behaviour), and the number of positions per
+ * cloud (Nq*k, P*S, S) fits in an int (checked: IAPT_EINVAL). */
 int iapt_graph_feature(const float* x_q, const float* x_k, const int64_t* idx, int B, int C, int Nq, int Nk, int k,
                        float* out, iapt_stream_t stream);
 size_t iapt_graph_feature_grad_workspace_bytes(int B, int Nq, int Nk, int k);

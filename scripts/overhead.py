@@ -13,6 +13,20 @@ def t(fn, n=300):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(n): fn()
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e6
+from imgadapointr_b200 import _lib
+for kind in ("torch", "ctypes"):  # compiled PyTorch binding vs the ctypes table, same C ABI underneath
+    _lib.set_binding(kind)
+    d1, d2, i1, i2 = chamfer.forward(x, y)
+    print(f"[{kind:6s} binding] host us/call:  chamfer.forward {t(lambda: chamfer.forward(x, y)):6.1f}   "
+          f"chamfer.backward {t(lambda: chamfer.backward(x, y, i1, i2, d1, d2)):6.1f}   "
+          f"chamfer.step(L1, grad1) {t(lambda: chamfer.step(x, y, chamfer.LOSS_L1, grad1=True)):6.1f}   "
+          f"knn_point {t(lambda: knn_point(8, x, y)):6.1f}   fps {t(lambda: pointnet2_utils.furthest_point_sample(x, 16)):6.1f}",
+          flush=True)
+    l1m = ChamferDistanceL1()
+    def fbm():
+        p = x.detach().requires_grad_(True); l1m(p, y).backward()
+    print(f"[{kind:6s} binding] ChamferDistanceL1 module fwd+bwd us/call {t(fbm):6.1f}", flush=True)
+_lib.set_binding("torch")
 print("chamfer.forward us/call", t(lambda: chamfer.forward(x, y)))
 d1, d2, i1, i2 = chamfer.forward(x, y)
 print("chamfer.backward us/call", t(lambda: chamfer.backward(x, y, i1, i2, d1, d2)))

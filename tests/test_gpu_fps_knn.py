@@ -201,28 +201,44 @@ def test_demo_sample_fixtures(dev):
 
 
 def test_fps_prefix_reuse_is_exact_and_safe(dev):
-    """SURVEY 8f rank 3: repeated sampling of the SAME unmodified tensor is served from the longer sample's prefix;
-    any in-place modification (autograd version bump) or a different tensor object invalidates it."""
+    """inside a ``prefix_reuse()`` scope repeated sampling of the SAME unmodified tensor is served
+    from the longer sample's prefix; any in-place modification (autograd version bump) or a different tensor object
+    invalidates it; outside a scope nothing is cached; inference tensors are never cached (they have no version)."""
     fps = pointnet2_utils.furthest_point_sample
     xyz = synthetic.uniform(3, 1500, 77).to(dev)
     h0 = fps.prefix_hits
-    a256 = fps(xyz, 256)
-    a64 = fps(xyz, 64)
-    assert fps.prefix_hits == h0 + 1 and torch.equal(a64, a256[:, :64]) and a64.is_contiguous()
-    fps.reuse_prefix = False
-    try:
-        assert torch.equal(fps(xyz, 64), a64)  # identical to a fresh launch
-    finally:
+    assert fps.reuse_prefix is False
+    fps(xyz, 256)
+    fps(xyz, 64)
+    assert fps.prefix_hits == h0  # opt-in: no reuse outside a scope
+    with pointnet2_utils.prefix_reuse():
+        a256 = fps(xyz, 256)
+        a64 = fps(xyz, 64)
+        assert fps.prefix_hits == h0 + 1 and torch.equal(a64, a256[:, :64]) and a64.is_contiguous()
+        a64.zero_()  # a caller scribbling over a returned result must not corrupt later hits
+        a256.zero_()
+        again = fps(xyz, 64)
+        assert fps.prefix_hits == h0 + 2
+        fps.reuse_prefix = False
+        fresh = fps(xyz, 64)  # a fresh launch
         fps.reuse_prefix = True
-    b300 = fps(xyz, 300)  # longer than anything cached -> computed, and consistent with the prefix property
-    assert fps.prefix_hits == h0 + 1 and torch.equal(b300[:, :256], a256)
-    xyz[0, 0, 0] += 1.0  # in-place edit bumps the version: the cache must not be used
-    c64 = fps(xyz, 64)
-    assert fps.prefix_hits == h0 + 1
-    assert np.array_equal(c64.cpu().numpy(), oracle.fps(xyz.cpu().numpy(), 64, True))
-    clone = xyz.clone()
-    fps(clone, 32)
-    assert fps.prefix_hits == h0 + 1  # a different tensor object never hits
+        assert torch.equal(again, fresh)
+        b300 = fps(xyz, 300)  # longer than anything cached -> computed, and consistent with the prefix property
+        assert fps.prefix_hits == h0 + 2 and torch.equal(b300[:, :64], fresh)
+        xyz[0, 0, 0] += 1.0  # in-place edit bumps the version: the cache must not be used
+        c64 = fps(xyz, 64)
+        assert fps.prefix_hits == h0 + 2
+        assert np.array_equal(c64.cpu().numpy(), oracle.fps(xyz.cpu().numpy(), 64, True))
+        clone = xyz.clone()
+        fps(clone, 32)
+        assert fps.prefix_hits == h0 + 2  # a different tensor object never hits
+    assert fps.reuse_prefix is False
+    with pointnet2_utils.prefix_reuse():
+        with torch.inference_mode():
+            t = synthetic.uniform(2, 700, 78).to(dev)
+            i1 = fps(t, 128)
+            i2 = fps(t, 32)  # no crash (inference tensors do not track versions) and no stale reuse
+            assert fps.prefix_hits == h0 + 2 and torch.equal(i2, i1[:, :32])
 
 
 def test_snowflake_query_knn(dev):
