@@ -94,6 +94,20 @@ def fps(xyz, npoint: int, skip_near_origin: bool = True):
     return idx
 
 
+def fps_ex(xyz, npoint: int, skip_near_origin: bool = True, tie: str = "lowest"):
+    """FPS with the tie order as a parameter and tie statistics (see oracle.c: oracle_fps_ex).  ``tie`` = "lowest" (ours)
+    or "upstream" (smallest (k mod block, k), the published pointnet2_ops kernel's thread-strided scan + tree).
+    Returns (idx int32 [B,npoint], stats int64 [B,2] = rounds with a tie between DIFFERENT points / between exact
+    duplicates only)."""
+    xyz = _f32(xyz)
+    B, N, _ = xyz.shape
+    idx = np.zeros((B, npoint), np.int32)
+    stats = np.zeros((B, 2), np.int64)
+    lib().oracle_fps_ex(_p(xyz), B, N, int(npoint), int(bool(skip_near_origin)), {"lowest": 0, "upstream": 1}[tie],
+                        _p(idx), _p(stats))
+    return idx, stats
+
+
 def gather(features, idx):
     features, idx = _f32(features), _i32(idx)
     B, C, N = features.shape

@@ -253,6 +253,83 @@ void oracle_fps(const float *xyz, int B, int N, int npoint, int skip_near_origin
   parallel_for(B, fps_item, &c);
 }
 
+/* FPS with the tie order made a parameter, plus tie statistics - test infrastructure for the UNPINNED tie rule.
+ *   tie_mode 0: lowest index among equal maxima (ours, = oracle_fps);
+ *   tie_mode 1: upstream's order as published (pointnet2_ops furthest_point_sampling_kernel<block_size>): thread tid
+ *               scans k = tid, tid + block, ... with strict `>` (keeps its first maximum) and the shared-memory tree
+ *               keeps the LOWER thread on equal values (`v2 > v1 ? i2 : i1`), i.e. the winner among equal maxima is
+ *               the one with the smallest (k mod block, k); block = largest power of two <= N, at most 512.
+ * stats[b] = { rounds in which another point with DIFFERENT coordinates ties the maximum (the two tie orders can then
+ *              select different points), rounds in which only exact duplicates of the winner tie (either order selects
+ *              the same coordinates) }. */
+void oracle_fps_ex(const float *xyz, int B, int N, int npoint, int skip_near_origin, int tie_mode, int32_t *idx,
+                   int64_t *stats) {
+  int block = 1;
+  while (block * 2 <= N && block < 512) block *= 2;
+  for (int b = 0; b < B; ++b) {
+    const float *p = xyz + (size_t)b * N * 3;
+    int32_t *out = idx + (size_t)b * npoint;
+    int64_t t_distinct = 0, t_dup = 0;
+    if (npoint > 0) {
+      float *temp = (float *)malloc(sizeof(float) * (size_t)(N > 0 ? N : 1));
+      for (int k = 0; k < N; ++k) temp[k] = 1e10f;
+      int old = 0;
+      out[0] = 0;
+      for (int j = 1; j < npoint; ++j) {
+        int besti = 0, found = 0;
+        float best = -1.f;
+        for (int k = 0; k < N; ++k) {
+          const float *pk = p + 3 * (size_t)k;
+          if (skip_near_origin) {
+            float mag = fmaf(pk[2], pk[2], fmaf(pk[0], pk[0], pk[1] * pk[1]));
+            if ((double)mag <= 1e-3) continue;
+          }
+          float d = sqdist_f32(p + 3 * (size_t)old, pk);
+          float d2 = d < temp[k] ? d : temp[k];
+          temp[k] = d2;
+          int better = d2 > best;
+          if (!better && tie_mode == 1 && found && d2 == best) {
+            int ka = k % block, kb = besti % block;
+            better = ka < kb || (ka == kb && k < besti);
+          }
+          if (better) {
+            best = d2;
+            besti = k;
+            found = 1;
+          }
+        }
+        if (found) {  /* who else holds the maximum? */
+          int other_distinct = 0, other_dup = 0;
+          const float *pw = p + 3 * (size_t)besti;
+          for (int k = 0; k < N; ++k) {
+            const float *pk = p + 3 * (size_t)k;
+            if (k == besti || temp[k] != best) continue;
+            if (skip_near_origin) {
+              float mag = fmaf(pk[2], pk[2], fmaf(pk[0], pk[0], pk[1] * pk[1]));
+              if ((double)mag <= 1e-3) continue;
+            }
+            if (pk[0] == pw[0] && pk[1] == pw[1] && pk[2] == pw[2])
+              other_dup = 1;
+            else
+              other_distinct = 1;
+          }
+          if (other_distinct)
+            ++t_distinct;
+          else if (other_dup)
+            ++t_dup;
+        }
+        old = besti;
+        out[j] = old;
+      }
+      free(temp);
+    }
+    if (stats) {
+      stats[2 * b] = t_distinct;
+      stats[2 * b + 1] = t_dup;
+    }
+  }
+}
+
 /* gather_operation forward (pointnet2_ops gather_points_kernel): out[b,c,j] = features[b,c,idx[b,j]]. */
 void oracle_gather(const float *features, const int32_t *idx, int B, int C, int N, int npoint, float *out) {
   for (int b = 0; b < B; ++b)
