@@ -525,6 +525,349 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
   }
 }
 
+// =====================================================================================================================
+// Spatially pruned selection (k <= 16, 1024 <= R <= 4096): sort, bound, cull, select - still exact
+// =====================================================================================================================
+// The select kernel above evaluates every (query, reference) pair 1.5 times; this path evaluates only the pairs that
+// can matter.  (Default above 2048 references; at 2048 a k = 16 ball still touches a third of the tiles of a 3-D cloud
+// and the sort + per-tile latency eat the saved instructions - see knn_plan.)  Both clouds are sorted along a Morton curve (one CTA per cloud, bitonic sort of (code, index) keys in
+// shared memory), so the 32 queries of a warp and the 32 references of a tile are each spatially compact and have a
+// small bounding box.  Per warp:
+//   order : the tiles are visited nearest first (distance from the centre of the warp's query box to the farthest corner
+//           of the tile box - compact, close tiles first; a heuristic only);
+//   cull  : a tile farther from a query than that query's current tau cannot hold one of its neighbours (the
+//           point-to-box distance is a lower bound of every pair distance; compared with a 2^-18 margin, far above the
+//           rounding of either side) - a tile no query of the warp needs is never loaded;
+//   sweep : a visited tile is evaluated with the exact direct-form distance; d <= tau marks a candidate (tau = +inf
+//           until the first fold);
+//   fold  : when a lane's candidate list reaches fold_at entries its candidates are re-evaluated and inserted into a
+//           register-resident list ordered by the 64-bit key (distance bits, ORIGINAL index) - the same ascending
+//           (distance, index) order and lowest-index tie rule as every other path, although the sweep runs in Morton
+//           order - and the k-th key becomes the lane's new tau: the exact k-th nearest of everything swept so far.
+// The candidate list cannot overflow: a list with fewer than 32 free slots is folded into the running top-k before the
+// next tile, and the k-th key found so far becomes the new (exact, tighter) tau - so loose initial bounds, hundreds of
+// exact ties (zero padding: the points at the origin) or adversarial index layouts only cost extra folds, never a
+// fallback, and the result never depends on the cap.
+constexpr int kPrMaxN = 4096;        // points one CTA sorts in shared memory
+constexpr int kPrMinR = 1024;
+constexpr int kPrSortThreads = 1024;
+constexpr int kPrCap = 96;           // candidates per query
+constexpr int kPrSeeds = 6;          // tiles of the bound pass
+
+struct __align__(16) PrTileBox {
+  float4 lo, hi;
+};
+
+__device__ __forceinline__ unsigned morton_expand10(unsigned v) {  // 10 bits -> every third bit
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+// grid (B, 1 or 2): blockIdx.y == 0 sorts the references (and writes their tile boxes), 1 the queries.
+__global__ void __launch_bounds__(kPrSortThreads) knn_sort_kernel(const float* __restrict__ ref, int R, int Rp,
+                                                                  float4* __restrict__ sref,
+                                                                  PrTileBox* __restrict__ boxes,
+                                                                  const float* __restrict__ qry, int Q, int Qp,
+                                                                  float4* __restrict__ sqry) {
+  __shared__ u64 keys[kPrMaxN];
+  __shared__ float red[6][32];
+  const bool is_q = blockIdx.y == 1;
+  const int n = is_q ? Q : R, n_pad = is_q ? Qp : Rp;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* __restrict__ P = (is_q ? qry : ref) + (size_t)b * n * 3;
+  float4* __restrict__ out = (is_q ? sqry : sref) + (size_t)b * n_pad;
+  const float kInf = __int_as_float(0x7f800000);
+
+  // ---- bounding box of the cloud ------------------------------------------------------------------------------------
+  float lo[3] = {kInf, kInf, kInf}, hi[3] = {-kInf, -kInf, -kInf};
+  for (int i = tid; i < n; i += kPrSortThreads) {
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      const float v = __ldg(P + 3 * (size_t)i + e);
+      lo[e] = fminf(lo[e], v);
+      hi[e] = fmaxf(hi[e], v);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[e] = fminf(lo[e], __shfl_xor_sync(0xffffffffu, lo[e], o));
+      hi[e] = fmaxf(hi[e], __shfl_xor_sync(0xffffffffu, hi[e], o));
+    }
+    if (lane == 0) {
+      red[e][warp] = lo[e];
+      red[3 + e][warp] = hi[e];
+    }
+  }
+  __syncthreads();
+  float scale[3];
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    float l = kInf, h = -kInf;
+    for (int w = 0; w < kPrSortThreads / 32; ++w) {
+      l = fminf(l, red[e][w]);
+      h = fmaxf(h, red[3 + e][w]);
+    }
+    lo[e] = l;
+    scale[e] = (h > l) ? 1024.f / (h - l) : 0.f;
+  }
+
+  // ---- (Morton code, index) keys, bitonic sort --------------------------------------------------------------------------
+  int pow2 = 32;
+  while (pow2 < n) pow2 <<= 1;
+  for (int i = tid; i < pow2; i += kPrSortThreads) {
+    u64 key = ~0ull;
+    if (i < n) {
+      unsigned code = 0u;
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        const float v = (__ldg(P + 3 * (size_t)i + e) - lo[e]) * scale[e];
+        const int q = min(1023, max(0, (int)v));  // NaN -> 0: any order is a valid order
+        code |= morton_expand10((unsigned)q) << e;
+      }
+      key = ((u64)code << 16) | (u64)i;
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  for (int size = 2; size <= pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (pow2 >> 1); t += kPrSortThreads) {
+        const int i = 2 * t - (t & (stride - 1));
+        const int j = i + stride;
+        const u64 a = keys[i], c = keys[j];
+        if ((a > c) == ((i & size) == 0)) {
+          keys[i] = c;
+          keys[j] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- sorted points (x, y, z, original index) and the tile boxes ------------------------------------------------------
+  for (int t0 = warp * 32; t0 < n_pad; t0 += kPrSortThreads) {
+    const int i = t0 + lane;
+    float4 v = make_float4(kPadCoord(), kPadCoord(), kPadCoord(), __int_as_float(-1));
+    float bl[3] = {kInf, kInf, kInf}, bh[3] = {-kInf, -kInf, -kInf};
+    if (i < n) {
+      const int oi = (int)(keys[i] & 0xffffu);
+      v = make_float4(__ldg(P + 3 * (size_t)oi), __ldg(P + 3 * (size_t)oi + 1), __ldg(P + 3 * (size_t)oi + 2),
+                      __int_as_float(oi));
+      bl[0] = bh[0] = v.x;
+      bl[1] = bh[1] = v.y;
+      bl[2] = bh[2] = v.z;
+    }
+    out[i] = v;
+    if (!is_q) {
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          bl[e] = fminf(bl[e], __shfl_xor_sync(0xffffffffu, bl[e], o));
+          bh[e] = fmaxf(bh[e], __shfl_xor_sync(0xffffffffu, bh[e], o));
+        }
+      }
+      if (lane == 0) {
+        PrTileBox bx;
+        bx.lo = make_float4(bl[0], bl[1], bl[2], 0.f);
+        bx.hi = make_float4(bh[0], bh[1], bh[2], 0.f);
+        boxes[(size_t)b * (Rp / 32) + (t0 >> 5)] = bx;
+      }
+    }
+  }
+}
+
+template <int kK>
+__global__ void __launch_bounds__(32, 16) knn_pruned_kernel(const float4* __restrict__ sref,
+                                                            const PrTileBox* __restrict__ boxes,
+                                                            const float4* __restrict__ sqry, int R, int Rp, int Q, int Qp,
+                                                            int k, int q_blocks, int fold_at, int64_t* __restrict__ idx_out,
+                                                            float* __restrict__ dist_out) {
+  __shared__ float4 stage[32];
+  __shared__ unsigned short cand[kPrCap][32];
+  __shared__ unsigned order[kPrMaxN / 32];
+  const int lane = threadIdx.x;
+  const int b = blockIdx.x / q_blocks;
+  const int qb = blockIdx.x - b * q_blocks;
+  const float kInf = __int_as_float(0x7f800000);
+  const float4* __restrict__ Rb = sref + (size_t)b * Rp;
+  const float4 qv = __ldg(sqry + (size_t)b * Qp + qb * 32 + lane);
+  const int qi = __float_as_int(qv.w);
+  const bool live = qi >= 0;
+  const float qx = qv.x, qy = qv.y, qz = qv.z;
+  const PrTileBox* __restrict__ Bx = boxes + (size_t)b * (Rp / 32);
+  const int nt = Rp / 32;
+
+  // squared distance from this lane's query to a tile box: a lower bound of its distance to every reference inside
+  auto box_dist = [&](int t) {
+    const float4 bl = __ldg(&Bx[t].lo), bh = __ldg(&Bx[t].hi);  // warp-uniform addresses: one broadcast each
+    const float gx = fmaxf(0.f, fmaxf(bl.x - qx, qx - bh.x));
+    const float gy = fmaxf(0.f, fmaxf(bl.y - qy, qy - bh.y));
+    const float gz = fmaxf(0.f, fmaxf(bl.z - qz, qz - bh.z));
+    return gx * gx + gy * gy + gz * gz;
+  };
+
+  // ---- visiting order: tiles by the distance from the centre of the warp's query box to the FARTHEST corner of the tile
+  // box (compact, close tiles first; a Morton tile spanning a jump of the curve has a huge box that contains many queries
+  // without holding their neighbours).  A heuristic only - what is swept is decided by the exact cull test below.
+  {
+    float cl[3] = {live ? qx : kInf, live ? qy : kInf, live ? qz : kInf};
+    float ch[3] = {live ? qx : -kInf, live ? qy : -kInf, live ? qz : -kInf};
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        cl[e] = fminf(cl[e], __shfl_xor_sync(0xffffffffu, cl[e], o));
+        ch[e] = fmaxf(ch[e], __shfl_xor_sync(0xffffffffu, ch[e], o));
+      }
+      cl[e] = 0.5f * (cl[e] + ch[e]);
+    }
+#pragma unroll
+    for (int i = 0; i < kPrMaxN / 1024; ++i) {
+      const int t = lane + 32 * i;
+      unsigned key = 0xffffffffu;
+      if (t < nt) {
+        const float4 bl = Bx[t].lo, bh = Bx[t].hi;
+        const float fx = fmaxf(fabsf(cl[0] - bl.x), fabsf(cl[0] - bh.x));
+        const float fy = fmaxf(fabsf(cl[1] - bl.y), fabsf(cl[1] - bh.y));
+        const float fz = fmaxf(fabsf(cl[2] - bl.z), fabsf(cl[2] - bh.z));
+        key = (__float_as_uint(fx * fx + fy * fy + fz * fz) & 0xffffff00u) | (unsigned)t;  // >= +0: bits order like uints
+      }
+      order[t] = key;
+    }
+    __syncwarp();
+    for (int size = 2; size <= kPrMaxN / 32; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+        for (int h = 0; h < kPrMaxN / 2048; ++h) {
+          const int p = lane + 32 * h;
+          const int i = 2 * p - (p & (stride - 1));
+          const int j = i + stride;
+          const unsigned x = order[i], y = order[j];
+          if ((x > y) == ((i & size) == 0)) {
+            order[i] = y;
+            order[j] = x;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  // ---- bound: class minima over the kPrSeeds nearest tiles (class = position inside the tile; different tiles hold
+  // different references): the k-th smallest of the 32 minima bounds the k-th neighbour distance, like sweep 1 above ---------
+  float tau;
+  {
+    float mn[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mn[i] = kInf;
+    const int ns = min(nt, kPrSeeds);
+    float4 r = __ldg(Rb + (int)(order[0] & 0xffu) * 32 + lane);
+    for (int u = 0; u < ns; ++u) {
+      __syncwarp();
+      stage[lane] = r;
+      __syncwarp();
+      if (u + 1 < ns) r = __ldg(Rb + (int)(order[u + 1] & 0xffu) * 32 + lane);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float4 p = stage[c];
+        mn[c] = fminf(mn[c], sqdist(qx, qy, qz, p.x, p.y, p.z));
+      }
+    }
+    sort32(mn);
+    tau = mn[0];
+#pragma unroll
+    for (int i = 1; i < kK; ++i)
+      if (i < k) tau = mn[i];
+  }
+
+  // ---- sweep, nearest tiles first: candidates d <= tau go to a per-lane list; a list that fills up is folded into the
+  // running top-k, whose k-th key is the exact k-th nearest of everything swept so far = the new tau ------------------------
+  u64 tk[kK];  // ascending (distance bits, original index) keys of the best references seen so far
+#pragma unroll
+  for (int j = 0; j < kK; ++j) tk[j] = ~0ull;
+  int count = 0;
+  auto fold = [&]() {  // insert this lane's listed candidates into tk, empty the list, tighten tau
+    float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (count > 0) cp = __ldg(Rb + cand[0][lane]);
+    for (int c = 0; c < count; ++c) {
+      const u64 key = ((u64)__float_as_uint(sqdist(qx, qy, qz, cp.x, cp.y, cp.z)) << 32) | (unsigned)__float_as_int(cp.w);
+      if (c + 1 < count) cp = __ldg(Rb + cand[c + 1][lane]);  // the next candidate travels while this one is inserted
+#pragma unroll
+      for (int j = kK - 1; j >= 0; --j) {
+        const bool here = key < tk[j];
+        const bool up = j > 0 && key < tk[j > 0 ? j - 1 : 0];
+        tk[j] = up ? tk[j > 0 ? j - 1 : 0] : (here ? key : tk[j]);
+      }
+    }
+    count = 0;
+    u64 kth = tk[0];
+#pragma unroll
+    for (int j = 1; j < kK; ++j)
+      if (j < k) kth = tk[j];
+    if (kth != ~0ull) tau = fminf(tau, __uint_as_float((unsigned)(kth >> 32)));
+  };
+  // cull: a tile farther from a query than that query's tau holds none of its neighbours.  (1 - 2^-18): conservative
+  // against the rounding of both sides.  The next tile to sweep is looked up (and its load issued) one tile ahead, with
+  // the tau of that moment - tau only shrinks, so a stale test can only sweep a tile too many.
+  int u = 0;
+  auto next_needed = [&]() {
+    for (; u < nt; ++u) {
+      const int t = (int)(order[u] & 0xffu);
+      if (__any_sync(0xffffffffu, live && box_dist(t) * 0.99999619f <= tau)) {
+        ++u;
+        return t;
+      }
+    }
+    return -1;
+  };
+  int t_next = next_needed();
+  float4 r_next = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t_next >= 0) r_next = __ldg(Rb + t_next * 32 + lane);
+  while (t_next >= 0) {
+    const int t = t_next;
+    __syncwarp();  // every lane is done with the previous tile
+    stage[lane] = r_next;
+    __syncwarp();
+    t_next = next_needed();
+    if (t_next >= 0) r_next = __ldg(Rb + t_next * 32 + lane);
+    unsigned m = 0u;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const float4 p = stage[c];
+      if (sqdist(qx, qy, qz, p.x, p.y, p.z) <= tau) m |= 1u << c;
+    }
+    if (!live) m = 0u;
+    while (m) {
+      const int c = __ffs(m) - 1;
+      m &= m - 1u;
+      const int pos = t * 32 + c;
+      if (pos >= R) continue;  // padding sentinel of the last tile
+      cand[count][lane] = (unsigned short)pos;  // count < kPrCap: a list is folded before a tile could overfill it
+      ++count;
+    }
+    // fold_at <= kPrCap - 32 entries: the next tile may add 32.  Every lane folds when one has to: folds of different
+    // lanes at different tiles would serialise.
+    if (__any_sync(0xffffffffu, count >= fold_at)) fold();
+  }
+  if (!live) return;
+  fold();
+  const size_t o = ((size_t)b * Q + qi) * k;
+#pragma unroll
+  for (int j = 0; j < kK; ++j) {
+    if (j < k) {
+      // fewer than k entries only if distances were NaN (outside the contract): index 0 keeps consumers in range
+      idx_out[o + j] = tk[j] == ~0ull ? 0 : (int64_t)(unsigned)tk[j];
+      if (dist_out) dist_out[o + j] = tk[j] == ~0ull ? kInf : __uint_as_float((unsigned)(tk[j] >> 32));
+    }
+  }
+}
+
 // Reference-range splits for the list kernel: only when the query count cannot fill the machine on its own.
 static int knn_r_splits(int B, int R, int Q) {
   const long long ctas4 = (long long)B * ((Q + 31) / 32);
@@ -546,6 +889,7 @@ static int knn_r_splits(int B, int R, int Q) {
 struct KnnPlan {
   bool select;  // thread-per-query selection (k <= 16) vs warp-per-query list
   int splits;   // select: warps per 32 queries; list: reference slices merged by knn_merge_kernel
+  bool pruned;  // Morton-sorted, box-culled selection (k <= 16, kPrMinR <= R <= kPrMaxN, Q <= kPrMaxN)
 };
 
 static long long env_ll(const char* name, long long fallback) {
@@ -558,18 +902,29 @@ static KnnPlan knn_plan(int B, int R, int Q, int k) {
   static const long long min_warps = env_ll("IAPT_KNN_SELECT_MIN_WARPS", 256);
   static const long long want_warps = env_ll("IAPT_KNN_SELECT_WANT_WARPS", 2048);
   static const long long force_split = env_ll("IAPT_KNN_SELECT_SPLIT", 0);
+  // Pruned path: measured against the select kernel at B = 48, k = 16 (profiles/r02p_knn_pruned.txt): 2048 x 2048
+  // 0.19 ms vs 0.18 (uniform), 0.30 vs 0.18 (zero-padded partials: the points at the origin cost folds); 4096 x 4096
+  // 0.39 vs 0.52.  So it is the default only above 2048 references.  IAPT_KNN_PRUNED = 1 forces it wherever it applies,
+  // 2 disables it (read per call: the tests run both paths over the same cases).
+  const long long pruned_mode = env_ll("IAPT_KNN_PRUNED", 0);
   const long long warps = (long long)B * ((Q + 31) / 32);
+  const bool pruned_fits = k <= kSelMaxK && R >= kPrMinR && R <= kPrMaxN && Q >= 1 && Q <= kPrMaxN && B <= 65535;
+  if (!force_list && pruned_fits && pruned_mode != 2 && (pruned_mode == 1 || R > 2048)) return {false, 1, true};
   if (k <= kSelMaxK && R >= 64 && R <= 65536 && !force_list && warps >= min_warps) {
     int s = 1;
     while (s < 4 && warps * s < want_warps && R / (2 * s) >= 512) s *= 2;  // slices shorter than 512 do not pay
     if (force_split == 1 || force_split == 2 || force_split == 4) s = (int)force_split;
-    return {true, s};
+    return {true, s, false};
   }
-  return {false, knn_r_splits(B, R, Q)};
+  return {false, knn_r_splits(B, R, Q), false};
 }
 
 size_t knn_workspace_bytes(int B, int R, int Q, int k) {
   const KnnPlan plan = knn_plan(B, R, Q, k);
+  if (plan.pruned) {  // sorted references + their tile boxes + sorted queries
+    const size_t Rp = (size_t)(R + 31) / 32 * 32, Qp = (size_t)(Q + 31) / 32 * 32;
+    return (size_t)B * (Rp * sizeof(float4) + Rp / 32 * sizeof(PrTileBox) + Qp * sizeof(float4)) + 256;
+  }
   if (plan.select || plan.splits <= 1) return 0;
   return (sizeof(float) + sizeof(int)) * (size_t)B * Q * plan.splits * k;  // per-slice lists for knn_merge_kernel
 }
@@ -620,7 +975,29 @@ static void knn_select_dispatch(const float* ref, const float* qry, int B, int R
 int knn_launch(const float* ref, const float* qry, int B, int R, int Q, int k, int64_t* idx, float* dist,
                void* workspace, cudaStream_t stream) {
   const KnnPlan plan = knn_plan(B, R, Q, k);
-  if (plan.select) {
+  if (plan.pruned && workspace != nullptr) {
+    const int Rp = (R + 31) / 32 * 32, Qp = (Q + 31) / 32 * 32;
+    unsigned char* w = static_cast<unsigned char*>(workspace);
+    w += (256 - reinterpret_cast<uintptr_t>(w) % 256) % 256;
+    float4* sref = reinterpret_cast<float4*>(w);
+    PrTileBox* boxes = reinterpret_cast<PrTileBox*>(sref + (size_t)B * Rp);
+    float4* sqry = reinterpret_cast<float4*>(boxes + (size_t)B * (Rp / 32));
+    const bool self = ref == qry && R == Q;  // the self-query of DGCNN_Grouper: one sort serves both sides
+    knn_sort_kernel<<<dim3(B, self ? 1 : 2), kPrSortThreads, 0, stream>>>(ref, R, Rp, sref, boxes, qry, Q, Qp, sqry);
+    const int qb = Qp / 32;
+    int fold_at = (int)env_ll("IAPT_KNN_FOLD_AT", 32);  // development knob
+    if (fold_at > kPrCap - 32) fold_at = kPrCap - 32;
+    if (fold_at < 1) fold_at = 1;
+    if (k <= 8)
+      knn_pruned_kernel<8><<<(unsigned)((long long)B * qb), 32, 0, stream>>>(sref, boxes, self ? sref : sqry, R, Rp, Q, Qp,
+                                                                            k, qb, fold_at, idx, dist);
+    else
+      knn_pruned_kernel<16><<<(unsigned)((long long)B * qb), 32, 0, stream>>>(sref, boxes, self ? sref : sqry, R, Rp, Q, Qp,
+                                                                             k, qb, fold_at, idx, dist);
+    count_launch(2);
+    return (int)cudaGetLastError();
+  }
+  if (plan.select || plan.pruned) {
     if (k <= 8)
       knn_select_dispatch<8>(ref, qry, B, R, Q, k, plan.splits, idx, dist, stream);
     else

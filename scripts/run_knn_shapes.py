@@ -27,3 +27,9 @@ def t(fn, it=20):
 for k, r, q in shapes:
     print("k=%d R=%d Q=%d: %.4f ms" % (k, r.shape[1], q.shape[1], t(lambda: knn_point(k, r, q))))
 print("sequence: %.4f ms" % t(lambda: [knn_point(k, r, q) for k, r, q in shapes]))
+u = (torch.rand(48, 2048, 3, device=dev) - 0.5).contiguous()
+g2 = synthetic.pcn_gt(48, 2048, 5).to(dev)
+print("uniform self k=16 2048: %.4f ms" % t(lambda: knn_point(16, u, u)))
+print("pcn surface (no padding) self k=16 2048: %.4f ms" % t(lambda: knn_point(16, g2, g2)))
+g4 = synthetic.pcn_gt(48, 4096, 6).to(dev)
+print("pcn surface self k=16 4096: %.4f ms" % t(lambda: knn_point(16, g4, g4)))

@@ -114,7 +114,7 @@ def test_knn_matches_oracle_config3_shapes(dev, R, Q, k):
     (64, 2048, 1024, 16, "zeros"),    # one warp per 32 queries, sampled first sweep
     (300, 64, 32, 16, "uniform"),     # smallest reference count the select path takes
 ])
-def test_knn_select_path_slices_and_ties(dev, B, R, Q, k, kind):
+def test_knn_select_path_slices_and_ties(dev, knn_path, B, R, Q, k, kind):
     """Batches large enough (B*ceil(Q/32) >= 256 warps) for the thread-per-query select kernel, bit for bit against
     the oracle: every slice count, both k instantiations, unaligned clouds, zero padding and exact-tie grids."""
     if kind == "uniform":
@@ -132,7 +132,7 @@ def test_knn_select_path_slices_and_ties(dev, B, R, Q, k, kind):
     (16, 1000, 512, "few_classes"),   # full sweep: the cluster sits in 4 of the 32 classes, the other minima are far
     (8, 2048, 1024, "few_classes8"),  # 4 slices: 8 classes per slice hold 128 near references each
 ])
-def test_knn_select_overflow_falls_back_exactly(dev, B, R, Q, near):
+def test_knn_select_overflow_falls_back_exactly(dev, knn_path, B, R, Q, near):
     """Adversarial index layouts that leave the class-minima bound loose, so queries near the cluster collect more
     than the 112-entry candidate list holds and take the in-kernel exact fallback; the other queries of the same
     warps stay on the fast path.  Bit-exact against the oracle either way."""
@@ -156,7 +156,70 @@ def test_knn_select_overflow_falls_back_exactly(dev, B, R, Q, near):
     _knn_check(xyz, new_xyz, 7, dev)
 
 
-def test_knn_zero_padded_and_grid_ties(dev):
+@pytest.fixture(params=["pruned", "select"])
+def knn_path(request, monkeypatch):
+    """Shapes with 1024 <= R <= 4096 and k <= 16 can take the Morton-sorted, box-culled kernel (IAPT_KNN_PRUNED=1 forces
+    it; by default only above 2048 references) or the thread-per-query select kernel (IAPT_KNN_PRUNED=2) - the variable
+    is read per call and both must match the oracle bit for bit."""
+    monkeypatch.setenv("IAPT_KNN_PRUNED", "1" if request.param == "pruned" else "2")
+    return request.param
+
+
+@pytest.mark.parametrize("B,R,Q,k,kind", [
+    (3, 1024, 1024, 16, "self"),        # smallest reference count of the pruned path, self-query (one sort)
+    (2, 1025, 33, 9, "uniform"),        # ragged last tile and query block
+    (2, 2047, 700, 16, "pcn"),
+    (2, 4096, 4096, 16, "self"),        # largest cloud one CTA sorts
+    (3, 3000, 1, 1, "uniform"),         # a single query, k = 1
+    (2, 2048, 31, 5, "far"),            # queries outside the references' bounding box: no tile overlaps their box
+    (4, 2048, 2048, 16, "zeros_self"),  # zero-padded partial: hundreds of duplicates at the origin tie at tau = 0
+    (2, 1500, 400, 16, "grid"),         # quantised coordinates: exact ties between DIFFERENT positions
+    (2, 1200, 64, 8, "same"),           # every reference identical: all distances tie
+    (2, 2048, 512, 16, "fps"),          # queries = FPS centres of the cloud (the grouper's 2048 -> 512 call)
+    (48, 2048, 2048, 16, "self"),       # config 3's largest call at full batch
+])
+def test_knn_pruned_path_matches_oracle(dev, knn_path, B, R, Q, k, kind):
+    g = torch.Generator().manual_seed(1000 + R + Q + k)
+    if kind in ("self", "uniform", "far", "fps"):
+        xyz = torch.rand((B, R, 3), generator=g) - 0.5
+    elif kind == "pcn":
+        xyz = synthetic.pcn_gt(B, R, 11)
+    elif kind == "zeros_self":
+        xyz = synthetic.pcn_partial(synthetic.pcn_gt(B, 8192, 12), R, 13)
+        xyz[:, R // 2:] = 0.0
+    elif kind == "grid":
+        xyz = synthetic.grid(B, R, 14, bits=3, dup_frac=0.2)
+    else:
+        xyz = torch.full((B, R, 3), 0.25)
+    if kind in ("self", "zeros_self"):
+        new_xyz = xyz
+    elif kind == "far":
+        new_xyz = torch.rand((B, Q, 3), generator=g) * 0.1 + 3.0
+    elif kind == "fps":
+        idx = torch.from_numpy(oracle.fps(xyz.numpy(), Q, True)).long()
+        new_xyz = torch.gather(xyz, 1, idx[..., None].expand(-1, -1, 3)).contiguous()
+    elif kind == "grid":
+        new_xyz = xyz[:, :Q].contiguous()
+    else:
+        new_xyz = torch.rand((B, Q, 3), generator=g) - 0.5
+    if B > 8:  # the oracle is the slow side: check 4 clouds of the full batch
+        a, q = xyz.to(dev), (xyz.to(dev) if new_xyz is xyz else new_xyz.to(dev))
+        got, gd = knn_point(k, a, q, return_dist=True)
+        oi, od = oracle.knn(k, xyz[:4].numpy(), new_xyz[:4].numpy())
+        assert np.array_equal(got[:4].cpu().numpy(), oi) and np.array_equal(gd[:4].cpu().numpy(), od)
+        again, _ = knn_point(k, a, q, return_dist=True)
+        assert torch.equal(got, again)
+        return
+    if new_xyz is xyz:  # the same tensor object on the device: the self-query shortcut (one sort for both sides)
+        a = xyz.to(dev)
+        got, gd = knn_point(k, a, a, return_dist=True)
+        oi, od = oracle.knn(k, xyz.numpy(), xyz.numpy())
+        assert np.array_equal(got.cpu().numpy(), oi) and np.array_equal(gd.cpu().numpy(), od)
+    else:
+        _knn_check(xyz, new_xyz, k, dev)
+
+
+def test_knn_zero_padded_and_grid_ties(dev, knn_path):
     gt = synthetic.pcn_gt(2, 4096, 303)
     xyz = synthetic.pcn_partial(gt, 2048, 305)
     _knn_check(xyz, xyz, 16, dev)
