@@ -401,6 +401,49 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
   int count = 0, eq_taken = 0;
   float thr = tau;
   const float* tf = reinterpret_cast<const float*>(sm.tile);
+  // kSplit == 1: the running top-k lives in registers during the sweep.  A candidate list with fewer than 32 free slots
+  // is FOLDED into it (every lane of the warp at once) and the k-th entry becomes the new, exact threshold - so a loose
+  // class-minima bound (index layouts correlated with position: ordered surface samplings) or hundreds of exact ties
+  // cost extra folds instead of the exact-fallback sweeps below.  Candidates arrive in ascending index and the insert
+  // is stable, so equal distances keep the lowest indices.
+  float td[kK];
+  int ti[kK];
+#pragma unroll
+  for (int j = 0; j < kK; ++j) {
+    td[j] = kInf;
+    ti[j] = 0;
+  }
+  auto fold = [&]() {
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    int cr = 0;
+    if (count > 0) {
+      cr = sm.cand[0][lane];
+      const float* p = Rb + 3 * (size_t)cr;
+      cx = __ldg(p);
+      cy = __ldg(p + 1);
+      cz = __ldg(p + 2);
+    }
+    for (int c = 0; c < count; ++c) {
+      const int r = cr;
+      const float d = sqdist(qx, qy, qz, cx, cy, cz);
+      if (c + 1 < count) {  // the next candidate's coordinates travel while this one is inserted
+        cr = sm.cand[c + 1][lane];
+        const float* p = Rb + 3 * (size_t)cr;
+        cx = __ldg(p);
+        cy = __ldg(p + 1);
+        cz = __ldg(p + 2);
+      }
+      sorted_insert<kK>(d, r, td, ti);
+    }
+    count = 0;
+    float kth = td[0];
+#pragma unroll
+    for (int j = 1; j < kK; ++j)
+      if (j < k) kth = td[j];
+    // k references are in the list: the sweep runs in ascending index and ties keep the LOWEST indices, so from now on
+    // only a strictly smaller distance can enter (kth stays +inf while fewer than k references were folded)
+    if (kth < kInf) thr = fminf(thr, kth > 0.f ? __uint_as_float(__float_as_uint(kth) - 1u) : -1.f);
+  };
   if (n_tiles > 0) fetch(0, nx);
   for (int t = 0; t < n_tiles; ++t) {
     publish(t, nx);
@@ -417,11 +460,17 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
         if (sqdist(qx, qy, qz, Bv.z, Bv.w, C.x) <= thr) m |= 1u << (4 * j + 2);
         if (sqdist(qx, qy, qz, C.y, C.z, C.w) <= thr) m |= 1u << (4 * j + 3);
       }
+      if (kSplit == 1 && !live) m = 0u;  // a dead lane must not grow a list nobody folds
       while (m) {
         const int i = __ffs(m) - 1;
         m &= m - 1u;
         const int r = lo + t * kS2Tile + c * 32 + i;
         if (r >= hi) continue;  // sentinel (only reachable when tau itself is a sentinel distance or +inf)
+        if (kSplit == 1) {  // (the list is folded before a chunk could overfill it)
+          sm.cand[count][lane] = (unsigned short)r;
+          ++count;
+          continue;
+        }
         if (count >= kS2TieCheckFrom) {
           const float* p = tf + 3 * (c * 32 + i);
           if (sqdist(qx, qy, qz, p[0], p[1], p[2]) == tau) {
@@ -432,9 +481,10 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
         if (count < kS2Cap) sm.cand[count][lane] = (unsigned short)r;
         ++count;
       }
+      if (kSplit == 1 && __any_sync(0xffffffffu, live && count > kS2Cap - 32)) fold();
     }
   }
-  bool overflow = count > kS2Cap;
+  bool overflow = kSplit > 1 && count > kS2Cap;
   if (kSplit > 1) {  // warp 0 selects from every slice's candidates, in slice (= ascending index) order
     counts[w][lane] = count;
     __syncthreads();
@@ -482,15 +532,9 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
   if (!live || overflow) return;
 
   // ---- select: stable insert into a register-resident sorted list ---------------------------------------------------
-  float td[kK];
-  int ti[kK];
-#pragma unroll
-  for (int j = 0; j < kK; ++j) {
-    td[j] = kInf;
-    ti[j] = 0;
-  }
+  if (kSplit == 1) fold();
 #pragma unroll 1
-  for (int o = 0; o < kSplit; ++o) {
+  for (int o = 0; o < (kSplit == 1 ? 0 : kSplit); ++o) {
     const S2Smem& src = smem[o];
     const int n = kSplit > 1 ? counts[o][lane] : count;
     float cx = 0.f, cy = 0.f, cz = 0.f;
