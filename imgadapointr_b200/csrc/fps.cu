@@ -20,6 +20,16 @@ namespace iapt {
 
 constexpr int kFpsMaxSmemPoints = 14000;  // 16 B per point (float4) -> 224 KB
 
+// Tie order among equal maxima of the running minimum.  Default (lg < 0): the LOWEST index.  IAPT_FPS_TIE_UPSTREAM:
+// upstream's order as published (pointnet2_ops furthest_point_sampling_kernel<block>: thread k mod block scans its
+// points with strict `>`, the shared-memory tree keeps the lower thread) = the smallest (k mod block, k / block),
+// block = 2^lg = the largest power of two <= N, at most 512.  The reductions below minimise an integer among the
+// candidates holding the maximum; in upstream mode that integer is this key instead of the index.  The kernels get lg
+// in bits 8..15 of `flags` (as lg + 1; 0 = lowest index).
+__device__ __forceinline__ int fps_tie_key(int k, int lg) { return ((k & ((1 << lg) - 1)) << 16) | (k >> lg); }
+__device__ __forceinline__ int fps_tie_unkey(int key, int lg) { return ((key & 0xffff) << lg) | (key >> 16); }
+__device__ __forceinline__ int fps_tie_lg(int flags) { return ((flags >> 8) & 0xff) - 1; }
+
 struct FpsSlots {
   int val[2][32];
   int idx[2][32];
@@ -78,6 +88,7 @@ __global__ void __launch_bounds__(kT) fps_kernel(const float* __restrict__ xyz, 
 
   int old = 0;
   if (tid == 0) out[0] = 0;
+  const int lg = fps_tie_lg(flags);
 
   for (int j = 1; j < npoint; ++j) {
     const float4 o = sp[old];
@@ -100,9 +111,17 @@ __global__ void __launch_bounds__(kT) fps_kernel(const float* __restrict__ xyz, 
       const float d = sqdist(o.x, o.y, o.z, x, y, z);
       const float t = fminf(tmp[i], d);  // stays -1 for ineligible points (d >= 0)
       tmp[i] = t;
-      if (t > best) {  // ascending k inside a thread + strict '>' keeps the thread's lowest index
-        best = t;
-        besti = k;
+      if (lg < 0) {
+        if (t > best) {  // ascending k inside a thread + strict '>' keeps the thread's lowest index
+          best = t;
+          besti = k;
+        }
+      } else {
+        const int key = fps_tie_key(k, lg);
+        if (t > best || (t == best && key < besti)) {
+          best = t;
+          besti = key;
+        }
       }
     }
     // warp argmax: value bits order like signed ints (-1.f is negative, distances are >= +0)
@@ -116,6 +135,7 @@ __global__ void __launch_bounds__(kT) fps_kernel(const float* __restrict__ xyz, 
     if (lane < kNW) s = wslot[par + lane];
     const int gmax = redux_max_s32(s.x);
     old = redux_min_s32(s.x == gmax ? s.y : 0x7fffffff);
+    if (lg >= 0) old = fps_tie_unkey(old, lg);
     if (tid == 0) out[j] = old;
   }
 }
@@ -173,6 +193,7 @@ __global__ void __launch_bounds__(kT) fps_cluster_kernel(const float* __restrict
   }
   float ox = __ldg(P), oy = __ldg(P + 1), oz = __ldg(P + 2);  // round 0 selects index 0
   if (rank == 0 && tid == 0) out[0] = 0;
+  const int lg = fps_tie_lg(flags);
   cluster.sync();  // every CTA of the cluster is resident before the first remote store
 
   for (int j = 1; j < npoint; ++j) {
@@ -184,9 +205,10 @@ __global__ void __launch_bounds__(kT) fps_cluster_kernel(const float* __restrict
       const float d = sqdist(ox, oy, oz, px[i], py[i], pz[i]);
       const float t = fminf(tmp[i], d);
       tmp[i] = t;
-      if (t > best) {
+      const int kk = lg < 0 ? base + tid + i * kT : fps_tie_key(base + tid + i * kT, lg);
+      if (t > best || (lg >= 0 && t == best && kk < besti)) {
         best = t;
-        besti = base + tid + i * kT;
+        besti = kk;
         bx = px[i];
         by = py[i];
         bz = pz[i];
@@ -253,7 +275,7 @@ __global__ void __launch_bounds__(kT) fps_cluster_kernel(const float* __restrict
         oy = rec[src].y;
         oz = rec[src].z;
       }
-      if (rank == 0 && tid == 0) out[j] = gmax < 0 ? 0 : old;
+      if (rank == 0 && tid == 0) out[j] = gmax < 0 ? 0 : (lg < 0 ? old : fps_tie_unkey(old, lg));
     }
   }
   cluster.sync();  // no CTA exits while a peer may still write into its shared memory
@@ -279,6 +301,7 @@ __global__ void __launch_bounds__(1024) fps_generic_kernel(const float* __restri
   }
   int old = 0;
   if (tid == 0) out[0] = 0;
+  const int lg = fps_tie_lg(flags);
   __syncthreads();
   for (int j = 1; j < npoint; ++j) {
     const float ox = P[3 * (size_t)old], oy = P[3 * (size_t)old + 1], oz = P[3 * (size_t)old + 2];
@@ -288,9 +311,10 @@ __global__ void __launch_bounds__(1024) fps_generic_kernel(const float* __restri
       const float d = sqdist(ox, oy, oz, P[3 * (size_t)k], P[3 * (size_t)k + 1], P[3 * (size_t)k + 2]);
       const float t = fminf(temp[k], d);
       temp[k] = t;
-      if (t > best) {
+      const int kk = lg < 0 ? k : fps_tie_key(k, lg);
+      if (t > best || (lg >= 0 && t == best && kk < besti)) {
         best = t;
-        besti = k;
+        besti = kk;
       }
     }
     const int vb = __float_as_int(best);
@@ -306,6 +330,7 @@ __global__ void __launch_bounds__(1024) fps_generic_kernel(const float* __restri
     const int ii = slots.idx[par][lane];
     const int gmax = redux_max_s32(v);
     old = redux_min_s32(v == gmax ? ii : 0x7fffffff);
+    if (lg >= 0) old = fps_tie_unkey(old, lg);
     if (tid == 0) out[j] = old;
   }
 }
@@ -381,6 +406,14 @@ static int fps_cluster_width(int B, int N) {
 
 int fps_launch(const float* xyz, int B, int N, int npoint, int flags, int32_t* idx, void* workspace,
                cudaStream_t stream) {
+  {  // bit 1 (IAPT_FPS_TIE_UPSTREAM) -> lg + 1 in bits 8..15 for the kernels
+    int lg = -1;
+    if (flags & 2) {
+      lg = 0;
+      while ((2 << lg) <= N && lg < 9) ++lg;  // block = largest power of two <= N, at most 512
+    }
+    flags = (flags & 1) | ((lg + 1) << 8);
+  }
   const int cw = fps_cluster_width(B, N);
   if (cw > 1) {
     const int per = (N + cw - 1) / cw;  // points per CTA: registers hold up to 1024 x 8

@@ -7,8 +7,9 @@ Like upstream they are ``autograd.Function``s (``.apply`` aliases), require CUDA
 no CPU path.  Semantics of FPS: start at index 0, running minimum initialised to 1e10, upstream's near-origin skip
 (``|p|^2 <= 1e-3`` points are never selected; PCN partial clouds are zero padded) ON by default, and the LOWEST
 index on exact ties of the running minimum (upstream's tie order follows its thread layout; the selected
-coordinates are identical either way when the tie is between duplicated points).  Set
-``furthest_point_sample.skip_near_origin = False`` for plain FPS.
+coordinates are identical either way when the tie is between duplicated points; ``furthest_point_sample.tie_order =
+"upstream"`` selects the published kernel's order instead - exact ties between DIFFERENT points do occur on real
+clouds, see tests/test_oracle.py).  Set ``furthest_point_sample.skip_near_origin = False`` for plain FPS.
 
 The colder upstream functions the reference imports - three_nn, three_interpolate, grouping_operation, ball_query
 (Deformable* blocks, SnowFlakeNet; not reached by any shipped config, SURVEY.md note A) - are provided too, on the same
@@ -23,6 +24,14 @@ from .. import _lib
 SKIP_NEAR_ORIGIN_DEFAULT = True
 
 
+FPS_SKIP_NEAR_ORIGIN, FPS_TIE_UPSTREAM = 1, 2  # include/iapt_b200.h
+
+
+def _fps_flags(skip_near_origin: bool) -> int:
+    return (FPS_SKIP_NEAR_ORIGIN if skip_near_origin else 0) | \
+        (FPS_TIE_UPSTREAM if furthest_point_sample.tie_order == "upstream" else 0)
+
+
 def _fps(xyz: torch.Tensor, npoint: int, skip_near_origin: bool) -> torch.Tensor:
     _lib.require_cuda_f32(xyz, "xyz", 3)
     if xyz.size(2) != 3:
@@ -33,7 +42,7 @@ def _fps(xyz: torch.Tensor, npoint: int, skip_near_origin: bool) -> torch.Tensor
     npoint = int(npoint)
     ext = _lib.torch_ext()
     if ext is not None:
-        return ext.furthest_point_sampling(xyz, npoint, 1 if skip_near_origin else 0)
+        return ext.furthest_point_sampling(xyz, npoint, _fps_flags(skip_near_origin))
     dev = xyz.device
     L = _lib.lib()
     with _lib.on_device(dev):
@@ -41,7 +50,7 @@ def _fps(xyz: torch.Tensor, npoint: int, skip_near_origin: bool) -> torch.Tensor
         ws_bytes = int(L.iapt_fps_workspace_bytes(B, N, npoint))
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
         _lib.check(
-            L.iapt_fps(_lib.ptr(xyz), B, N, npoint, 1 if skip_near_origin else 0, _lib.ptr(idx), _lib.ptr(ws), ws_bytes,
+            L.iapt_fps(_lib.ptr(xyz), B, N, npoint, _fps_flags(skip_near_origin), _lib.ptr(idx), _lib.ptr(ws), ws_bytes,
                        _lib.stream_ptr(dev)), "iapt_fps")
     return idx
 
@@ -78,7 +87,7 @@ def _cacheable(xyz):
 
 def _prefix_lookup(xyz, npoint, skip):
     for ref, version, sk, idx in _prefix_cache:
-        if ref() is xyz and version == xyz._version and sk == skip and idx.size(1) >= npoint and idx.device == xyz.device:
+        if ref() is xyz and version == xyz._version and sk == skip and idx.size(1) >= npoint and idx.device == xyz.device:  # noqa: E501
             return idx
     return None
 
@@ -87,6 +96,7 @@ def furthest_point_sample(xyz, npoint):
     skip = SKIP_NEAR_ORIGIN_DEFAULT if furthest_point_sample.skip_near_origin is None \
         else furthest_point_sample.skip_near_origin
     reuse = furthest_point_sample.reuse_prefix and _cacheable(xyz)
+    skip = (skip, furthest_point_sample.tie_order)  # cache key: both settings change the sequence
     if reuse:
         hit = _prefix_lookup(xyz, int(npoint), skip)
         if hit is not None:
@@ -121,6 +131,7 @@ class prefix_reuse:
 
 
 furthest_point_sample.skip_near_origin = None  # None -> SKIP_NEAR_ORIGIN_DEFAULT
+furthest_point_sample.tie_order = "lowest"     # or "upstream": the published kernel's (k mod block, k) order on exact ties
 furthest_point_sample.reuse_prefix = False     # opt-in: see prefix_reuse
 furthest_point_sample.prefix_hits = 0
 

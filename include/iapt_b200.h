@@ -153,6 +153,12 @@ int iapt_fscore_counts(const float* dist1, const float* dist2, int B, int N, int
  * next = argmax with the LOWEST index on ties; flag IAPT_FPS_SKIP_NEAR_ORIGIN reproduces upstream's
  * `if (|p|^2 <= 1e-3) continue;` (points that are never updated nor selected - PCN zero padding). */
 #define IAPT_FPS_SKIP_NEAR_ORIGIN 1
+/* Tie order among equal maxima of the running minimum.  Default: the LOWEST index.  IAPT_FPS_TIE_UPSTREAM selects
+ * upstream's order as published (furthest_point_sampling_kernel<block>: thread-strided scan with strict `>`, shared-memory
+ * tree keeping the lower thread) = the smallest (k mod block, k), block = largest power of two <= N, at most 512.  The two
+ * differ only when points with DIFFERENT coordinates tie exactly - which happens on 4 of the reference's 8 demo clouds
+ * (tests/test_oracle.py); upstream's binary is absent from the image, so either order is unpinned against it. */
+#define IAPT_FPS_TIE_UPSTREAM 2
 size_t iapt_fps_workspace_bytes(int B, int N, int npoint);
 int iapt_fps(const float* xyz, int B, int N, int npoint, int flags, int32_t* idx, void* workspace,
              size_t workspace_bytes, iapt_stream_t stream);

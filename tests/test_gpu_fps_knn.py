@@ -53,6 +53,52 @@ def test_fps_ties_grid_and_degenerate(dev):
     assert int(pointnet2_utils.furthest_point_sample(zeros.to(dev), 16).abs().sum()) == 0  # nothing eligible -> 0
 
 
+@pytest.mark.parametrize("N,m", [(100, 40), (512, 256), (2048, 512), (4000, 300), (9000, 200), (16384, 256), (20000, 64)])
+def test_fps_upstream_tie_order_every_tier(dev, N, m):
+    """IAPT_FPS_TIE_UPSTREAM (the published kernel's (k mod block, k) order among equal maxima) against the oracle's
+    restatement of it, on tie-heavy grids, through every kernel tier (registers, shared memory, cluster, global); the
+    default order is unaffected.  On these inputs the two orders select different indices."""
+    fps = pointnet2_utils.furthest_point_sample
+    g = np.random.default_rng(N + m)
+    grid = (np.round(g.uniform(-0.5, 0.5, (2, N, 3)) * 8) / 8 + 2.0).astype(np.float32)
+    x = torch.from_numpy(grid).to(dev)
+    low = fps(x, m).cpu().numpy()
+    assert np.array_equal(low, oracle.fps(grid, m, True))
+    fps.tie_order = "upstream"
+    try:
+        up = fps(x, m).cpu().numpy()
+    finally:
+        fps.tie_order = "lowest"
+    want, stats = oracle.fps_ex(grid, m, True, "upstream")
+    assert np.array_equal(up, want)
+    assert stats[:, 0].sum() > 0
+    # a block at least as large as the cloud gives every thread one point: the tree then keeps the lowest index too
+    assert np.array_equal(up, low) == (N == 512)
+
+
+def test_fps_upstream_tie_order_on_the_demo_clouds(dev):
+    """The reference's demo clouds (zero-padded to 2048) at the grouper's sizes: both tie orders equal their oracles; on
+    the lamp (03636649) they differ in 41 of 512 indices (exact ties between different points of a symmetric mesh)."""
+    import glob
+    import os
+
+    fps = pointnet2_utils.furthest_point_sample
+    differing = 0
+    for f in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "sample_*.npz"))):
+        xyz = np.load(f)["xyz"][None]
+        x = torch.from_numpy(xyz).to(dev)
+        low = fps(x, 512).cpu().numpy()
+        fps.tie_order = "upstream"
+        try:
+            up = fps(x, 512).cpu().numpy()
+        finally:
+            fps.tie_order = "lowest"
+        assert np.array_equal(low, oracle.fps_ex(xyz, 512, True, "lowest")[0])
+        assert np.array_equal(up, oracle.fps_ex(xyz, 512, True, "upstream")[0])
+        differing += int((low != up).any())
+    assert differing >= 1
+
+
 def test_fps_input_checks(dev):
     xyz = synthetic.uniform(2, 64, 1)
     with pytest.raises(Exception):
