@@ -7,7 +7,7 @@ where the reference calls its pybind module ``chamfer`` (__init__.py:16,24).
 """
 import torch
 
-from ... import chamfer
+from ... import _lib, chamfer
 
 
 class ChamferFunction(torch.autograd.Function):
@@ -94,6 +94,12 @@ class _ChamferBase(torch.nn.Module):
         xyz1, xyz2 = _filter_zeros(xyz1, xyz2, self.ignore_zeros)
         if xyz1.size(0) == 0 or xyz1.size(1) == 0 or xyz2.size(1) == 0:
             return None  # degenerate: let the composed path reproduce the reference's NaN-from-empty-mean behaviour
+        ext = _lib.torch_ext()
+        if ext is not None and xyz1.is_cuda and xyz1.dtype == torch.float32 and xyz2.dtype == torch.float32:
+            # the same op as FusedChamferLoss below, as a C++ autograd node (csrc/torch_binding.cpp): no Python between
+            # the module call and the launch
+            out = ext.fused_chamfer_loss(xyz1, xyz2, kind)
+            return (out[0], out[1]) if kind == chamfer.LOSS_L2_SPLIT else out[0]
         return FusedChamferLoss.apply(xyz1, xyz2, kind)
 
 
