@@ -690,13 +690,29 @@ __device__ __noinline__ void prefix_item(const StepParams& p, TailSmem& ts, int 
   const int* cnt = p.cnt[side] + (size_t)b * n;
   int* off = p.off[side] + (size_t)b * (n + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // 16 counts per thread and iteration (4096 per CTA step): the loads of a step are independent, the steps are chained
+  // through `carry`, so fewer, fatter steps shorten the serial chain (65536 bins: 64 -> 16 steps)
+  constexpr int kPer = 16;
   int carry = 0;
-  for (int base = 0; base < n; base += kThreads * 4) {
-    int v[4];
-    const int i0 = base + tid * 4;
+  for (int base = 0; base < n; base += kThreads * kPer) {
+    int v[kPer];
+    const int i0 = base + tid * kPer;
+    if (i0 + kPer <= n && ((reinterpret_cast<uintptr_t>(cnt + i0) & 15) == 0)) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = (i0 + e < n) ? __ldcg(cnt + i0 + e) + 1 : 0;
-    const int mine = v[0] + v[1] + v[2] + v[3];
+      for (int e = 0; e < kPer; e += 4) {
+        const int4 q = __ldcg(reinterpret_cast<const int4*>(cnt + i0 + e));
+        v[e] = q.x + 1;
+        v[e + 1] = q.y + 1;
+        v[e + 2] = q.z + 1;
+        v[e + 3] = q.w + 1;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < kPer; ++e) v[e] = (i0 + e < n) ? __ldcg(cnt + i0 + e) + 1 : 0;
+    }
+    int mine = 0;
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) mine += v[e];
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -715,7 +731,7 @@ __device__ __noinline__ void prefix_item(const StepParams& p, TailSmem& ts, int 
     }
     int run = carry + wbase + incl - mine;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < kPer; ++e) {
       if (i0 + e < n) off[i0 + e] = run;
       run += v[e];
     }
