@@ -71,6 +71,15 @@ g = dist_utils.gather_tensor(torch.tensor([float(rank)]))
 assert g.tolist() == [0.0, 1.0]
 s = dist_utils.allreduce_sums(torch.tensor([1.0, float(e - b)]))
 assert s.tolist() == [2.0, 11.0]
+# the deferred form bench.py uses: issue now, consume one step later - same value as reduce_tensor
+pending = None
+seen = []
+for k in range(4):
+    if pending is not None:
+        seen.append(float(dist_utils.finish_reduce(*pending)))
+    pending = dist_utils.reduce_tensor_async(torch.tensor(float(rank + 1 + k)))
+seen.append(float(dist_utils.finish_reduce(*pending)))
+assert seen == [1.5, 2.5, 3.5, 4.5], seen
 dist.destroy_process_group()
 print('rank', rank, 'ok')
 """
@@ -84,6 +93,13 @@ def test_allreduce_world_size_2_gloo(tmp_path):
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_reduce_tensor_async_is_identity_without_a_process_group():
+    from imgadapointr_b200.utils import dist_utils
+
+    rt, work = dist_utils.reduce_tensor_async(torch.tensor(3.0))
+    assert float(dist_utils.finish_reduce(rt, work)) == 3.0
 
 
 def test_dropin_registers_reference_module_names():
