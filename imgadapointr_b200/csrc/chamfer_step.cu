@@ -111,6 +111,7 @@ struct __align__(16) PairSmem {
   uint4 col[kWarps][kSStage / 2];   // per warp, per streamed point pair: (min bits, ballot) x2
   float4 prev[QT / 4][kThreads];    // running minima at the last chunk boundary
   unsigned bestc[QT][kThreads];     // first chunk in which the running minimum strictly decreased
+  float sraw[kSStage * 3];          // the NEXT stage's [512,3] rows as they lie in global memory (cp.async landing zone)
 };
 template <>
 struct __align__(16) PairSmem<0> {
@@ -211,15 +212,38 @@ __device__ __forceinline__ int block_sum_i(int v, int* sh) {
 // =====================================================================================================================
 // PAIR
 // =====================================================================================================================
-__device__ __forceinline__ void stage_fill_load(const float* __restrict__ Sb, int NS, int base, int end, int tid,
-                                                bool mask, float (&v)[2][3]) {
+// The streamed cloud reaches shared memory by cp.async (LDGSTS): the 1536 floats of a stage are copied as they lie, 6
+// fully coalesced 4-byte copies per thread, while the previous stage is being evaluated - no register holds them during
+// the hot loop (the register-staged version kept 6 live across it).  At the stage boundary the raw rows are expanded
+// into the lane-duplicated layout the broadcast LDS.128 of the loop reads.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void stage_issue(const float* __restrict__ Sb, int base, int end, int tid, float* sraw) {
+  const float* src = Sb + 3 * (size_t)base;
+  const int nfl = 3 * (min(end - base, kSStage));  // floats of this stage that exist
+#pragma unroll
+  for (int i = 0; i < 3 * kSStage / kThreads; ++i) {
+    const int f = tid + i * kThreads;
+    if (f < nfl) cp_async4(sraw + f, src + f);
+  }
+  cp_async_commit();
+}
+
+// this thread's two points of the stage, from the landed rows (sentinels beyond the item's range / for masked points)
+__device__ __forceinline__ void stage_fill_load(const float* sraw, int base, int end, int tid, bool mask,
+                                                float (&v)[2][3]) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int s = base + 2 * tid + h;
     if (s < end) {
-      v[h][0] = __ldg(Sb + 3 * (size_t)s + 0);
-      v[h][1] = __ldg(Sb + 3 * (size_t)s + 1);
-      v[h][2] = __ldg(Sb + 3 * (size_t)s + 2);
+      v[h][0] = sraw[6 * tid + 3 * h + 0];
+      v[h][1] = sraw[6 * tid + 3 * h + 1];
+      v[h][2] = sraw[6 * tid + 3 * h + 2];
       if (mask && zero_sum(v[h][0], v[h][1], v[h][2])) v[h][0] = v[h][1] = v[h][2] = kPadCoord();
     } else {
       v[h][0] = v[h][1] = v[h][2] = kPadCoord();
@@ -319,9 +343,12 @@ __device__ __forceinline__ void pair_item(const StepParams& p, unsigned char* sm
 #pragma unroll
   for (int i = 0; i < QT / 4; ++i) sm.prev[i][tid] = make_float4(kInf, kInf, kInf, kInf);
 
-  {  // prologue: first stage -> buffer 0
+  {  // prologue: first stage -> landing zone -> buffer 0
+    stage_issue(Sb, s_begin, s_end, tid, sm.sraw);
+    cp_async_wait_all();
+    __syncthreads();
     float v[2][3];
-    stage_fill_load(Sb, NS, s_begin, s_end, tid, mask, v);
+    stage_fill_load(sm.sraw, s_begin, s_end, tid, mask, v);
     stage_fill_store<QT>(sm, 0, tid, v);
   }
   __syncthreads();
@@ -329,9 +356,8 @@ __device__ __forceinline__ void pair_item(const StepParams& p, unsigned char* sm
   for (int st = 0; st < n_stages; ++st) {
     const int buf = st & 1;
     const int s_base = s_begin + st * kSStage;
-    float nxt[2][3];
     const bool has_next = (st + 1 < n_stages);
-    if (has_next) stage_fill_load(Sb, NS, s_base + kSStage, s_end, tid, mask, nxt);
+    if (has_next) stage_issue(Sb, s_base + kSStage, s_end, tid, sm.sraw);  // lands while this stage is evaluated
 
     // number of 32-point chunks that hold at least one real point of this item
     const int n_valid = min(kSStage, s_end - s_base);
@@ -379,8 +405,13 @@ __device__ __forceinline__ void pair_item(const StepParams& p, unsigned char* sm
       }
     }
 
-    if (has_next) stage_fill_store<QT>(sm, buf ^ 1, tid, nxt);
-    __syncthreads();  // col[][] of this stage complete; next stage's points visible
+    cp_async_wait_all();
+    __syncthreads();  // col[][] of this stage complete; the next stage's rows have landed
+    if (has_next) {
+      float nxt[2][3];
+      stage_fill_load(sm.sraw, s_base + kSStage, s_end, tid, mask, nxt);
+      stage_fill_store<QT>(sm, buf ^ 1, tid, nxt);
+    }
 
     {
       // fold the 8 warps' column minima (lowest warp wins ties -> lowest A index) and publish
