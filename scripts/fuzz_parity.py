@@ -19,7 +19,7 @@ pointnet2_utils.furthest_point_sample.reuse_prefix = False
 
 
 def cloud(B, N):
-    kind = rng.integers(0, 4)
+    kind = rng.integers(0, 5)
     if kind == 0:
         x = rng.random((B, N, 3), dtype=np.float32) - 0.5
     elif kind == 1:  # coarse grid: exact ties everywhere
@@ -27,6 +27,10 @@ def cloud(B, N):
     elif kind == 2:  # zero-padded tail
         x = rng.random((B, N, 3), dtype=np.float32) - 0.5
         x[:, int(N * rng.uniform(0.3, 0.9)):] = 0.0
+    elif kind == 4:  # collapsed: every point is one of a handful of positions (fan-ins of thousands, exact-sum path)
+        centres = (rng.random((B, int(rng.integers(1, 6)), 3), dtype=np.float32) - 0.5)
+        x = np.take_along_axis(centres, rng.integers(0, centres.shape[1], size=(B, N, 1)).repeat(3, axis=2), axis=1)
+        x = np.ascontiguousarray(x.astype(np.float32))
     else:  # duplicates of a few points + wide dynamic range
         x = (rng.standard_normal((B, N, 3)) * 10 ** rng.uniform(-3, 2)).astype(np.float32)
         src = rng.integers(0, N, size=N // 3)
@@ -64,13 +68,29 @@ while time.time() < t_end:
             scale = max(float(np.abs(want).max()), 1e-30)
             err = np.abs(got.cpu().numpy() - want)
             assert bool((err <= 1e-5 * scale + 1e-6 * mag).all()), "chamfer grad"
+        # the one-launch step must agree bit for bit with the separate entry points (same kernel, other phase set)
+        up = torch.tensor([float(rng.uniform(0.1, 3.0))], device=dev)
+        kind_l = int(rng.choice([chamfer.LOSS_L1, chamfer.LOSS_L2, chamfer.LOSS_L1_PM]))
+        r = chamfer.step(ta, tb, kind_l, sums=True, grad1=True, grad2=(kind_l != chamfer.LOSS_L1_PM), grad_loss=up)
+        assert torch.equal(r.dist1, d1) and torch.equal(r.idx1, i1) and torch.equal(r.dist2, d2) and torch.equal(r.idx2, i2), "step search"
+        q1, q2 = chamfer.loss_backward(ta, tb, i1, i2, d1, d2, kind_l, up, True, kind_l != chamfer.LOSS_L1_PM)
+        same = lambda x, y: (x is None and y is None) or torch.equal(torch.nan_to_num(x, nan=7.0), torch.nan_to_num(y, nan=7.0))
+        assert same(r.grad1, q1) and same(r.grad2, q2), "step grad vs loss_backward"
+        s64 = [d1.double().sum(1), d2.double().sum(1), d1.double().sqrt().sum(1), d2.double().sqrt().sum(1)]
+        for c in range(4):
+            assert torch.allclose(r.sums[:, c].double(), s64[c], rtol=2e-5, atol=1e-30), "step sums"
         if N >= 2:
             m = int(rng.integers(1, min(N, 600) + 1))
             skip = bool(rng.integers(0, 2))
             pointnet2_utils.furthest_point_sample.skip_near_origin = skip
             fi = pointnet2_utils.furthest_point_sample(ta, m)
             assert np.array_equal(fi.cpu().numpy(), oracle.fps(a, m, skip)), "fps m=%d skip=%d" % (m, skip)
+            pointnet2_utils.furthest_point_sample.tie_order = "upstream"
+            fu = pointnet2_utils.furthest_point_sample(ta, m)
+            pointnet2_utils.furthest_point_sample.tie_order = "lowest"
+            assert np.array_equal(fu.cpu().numpy(), oracle.fps_ex(a, m, skip, "upstream")[0]), "fps upstream m=%d" % m
         k = int(rng.integers(1, min(N, 64) + 1))
+        os.environ["IAPT_KNN_PRUNED"] = str(int(rng.integers(0, 3)))  # default / forced pruned / forced select
         ki, kd = knn_point(k, ta, tb, return_dist=True)
         oi, od = oracle.knn(k, a, b)
         assert np.array_equal(ki.cpu().numpy(), oi) and np.array_equal(kd.cpu().numpy(), od), "knn k=%d" % k
