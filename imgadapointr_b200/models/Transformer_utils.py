@@ -174,37 +174,33 @@ def graph_feature_cl(q, v, idx):
     return _GraphFeatureCL.apply(q.contiguous(), v.contiguous(), idx.contiguous())
 
 
-def dynamic_graph_attention_forward(self, q, q_pos, v=None, v_pos=None, idx=None, denoise_length=None):
-    """DynamicGraphAttention.forward (Transformer_utils.py:796-860) with its geometry on the B200 kernels: fused kNN and
-    one fused gather / subtract / concat kernel per neighbourhood query; ``self.knn_map`` (the learned Linear + LeakyReLU)
-    and the max over k are the module's own.  ``dropin.patch_reference_modules()`` installs it on the reference class."""
+def _neighbour_indices(k, q_pos, v_pos, idx, denoise_length):
+    """[B, N, k] indices into v for every query token.  Plain mode: the given ``idx`` or one fused kNN.  Denoise mode
+    (self-attention only, Transformer_utils.py:826-849): the last ``denoise_length`` tokens look among ALL tokens, the
+    others only among themselves - both index v directly, so the two kNN results are simply stacked."""
     if denoise_length is None:
-        if v is None:
-            v = q
-        if v_pos is None:
-            v_pos = q_pos
-        assert len(v_pos.shape) == 3 and v_pos.size(-1) == 3, f'[ERROR] Got an unexpected shape for v_pos, expect it to be B N 3, but got {v_pos.shape}'
-        assert len(q_pos.shape) == 3 and q_pos.size(-1) == 3, f'[ERROR] Got an unexpected shape for q_pos, expect it to be B N 3, but got {q_pos.shape}'
-        assert q.size(-1) == v.size(-1) == self.dim
-        B, N, C = q.shape
-        if idx is None:
-            idx = knn_point(self.k, v_pos, q_pos)  # B N k
-        assert idx.size(-1) == self.k
-        feature = graph_feature_cl(q, v, idx)  # B N k 2C
-    else:
-        assert idx is None, f'we need online index calculation when denoise_length is set, denoise_length {denoise_length}'
-        assert v is None, f'mask for denoise_length is only consider in self-attention, but v is given'
-        assert v_pos is None, f'mask for denoise_length is only consider in self-attention, but v_pos is given'
-        v = q
-        v_pos = q_pos
-        assert len(v_pos.shape) == 3 and v_pos.size(-1) == 3, f'[ERROR] Got an unexpected shape for v_pos, expect it to be B N 3, but got {v_pos.shape}'
-        assert q.size(-1) == v.size(-1) == self.dim
-        B, N, C = q.shape
-        # reconstruction tokens look only among themselves, denoise tokens among all tokens (:838-849)
-        idx_r = knn_point(self.k, v_pos[:, :-denoise_length], q_pos[:, :-denoise_length])  # B N_r k
-        idx_n = knn_point(self.k, v_pos, q_pos[:, -denoise_length:])  # B N_n k
-        assert idx_n.size(1) == denoise_length
-        feature = graph_feature_cl(q, v, torch.cat([idx_r, idx_n], dim=1))  # indices of both parts address v directly
-    out = self.knn_map(feature).max(-2)[0]  # B N C
-    assert out.size(0) == B and out.size(1) == N and out.size(2) == C
-    return out
+        return knn_point(k, v_pos, q_pos) if idx is None else idx
+    head = knn_point(k, v_pos[:, :-denoise_length], q_pos[:, :-denoise_length])
+    tail = knn_point(k, v_pos, q_pos[:, -denoise_length:])
+    return torch.cat([head, tail], dim=1)
+
+
+def dynamic_graph_attention_forward(self, q, q_pos, v=None, v_pos=None, idx=None, denoise_length=None):
+    """Replacement for DynamicGraphAttention.forward (Transformer_utils.py:796-860), same signature and result: the
+    neighbourhood query runs on the fused kNN kernel and the gather / subtract / concat on one fused kernel
+    (``graph_feature_cl``: [B,N,k,2C] = cat(v[idx] - q, q)); ``self.knn_map`` (the learned Linear + LeakyReLU) and the
+    max over k are the module's own.  ``dropin.patch_reference_modules()`` installs it on the reference class."""
+    if denoise_length is not None and not (idx is None and v is None and v_pos is None):
+        raise ValueError("denoise_length applies to self-attention with on-line neighbour search: "
+                         "v, v_pos and idx must not be given")
+    v = q if v is None else v
+    v_pos = q_pos if v_pos is None else v_pos
+    for name, pos in (("q_pos", q_pos), ("v_pos", v_pos)):
+        if pos.dim() != 3 or pos.size(-1) != 3:
+            raise ValueError(f"{name} must be [B, N, 3], got {tuple(pos.shape)}")
+    if q.size(-1) != self.dim or v.size(-1) != self.dim:
+        raise ValueError(f"token width {q.size(-1)} / {v.size(-1)} does not match the module's dim {self.dim}")
+    idx = _neighbour_indices(self.k, q_pos, v_pos, idx, denoise_length)
+    if idx.size(-1) != self.k or idx.size(1) != q.size(1):
+        raise ValueError(f"neighbour indices must be [B, {q.size(1)}, {self.k}], got {tuple(idx.shape)}")
+    return self.knn_map(graph_feature_cl(q, v, idx)).max(-2)[0]  # [B, N, C]
