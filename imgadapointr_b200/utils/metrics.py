@@ -47,36 +47,23 @@ def _f_from_counts(counts, N, M):
     return f.mean().to(torch.float32)
 
 
-class Metrics(object):
-    ITEMS = [{
-        'name': 'F-Score',
-        'enabled': True,
-        'eval_func': 'cls._get_f_score',
-        'is_greater_better': True,
-        'init_value': 0
-    }, {
-        'name': 'CDL1',
-        'enabled': True,
-        'eval_func': 'cls._get_chamfer_distancel1',
-        'eval_object': ChamferDistanceL1(ignore_zeros=True),
-        'is_greater_better': False,
-        'init_value': 32767
-    }, {
-        'name': 'CDL2',
-        'enabled': True,
-        'eval_func': 'cls._get_chamfer_distancel2',
-        'eval_object': ChamferDistanceL2(ignore_zeros=True),
-        'is_greater_better': False,
-        'init_value': 32767
-    }, {
-        'name': 'EMDistance',
-        'enabled': True,
-        'eval_func': 'cls._get_emd_distance',
-        'eval_object': None,
-        'is_greater_better': False,
-        'init_value': 32767
-    }]
+def _item(name, func, greater_is_better, init, obj=None):
+    """One row of ``Metrics.ITEMS`` with the keys the reference's callers read (utils/metrics.py:16-43)."""
+    row = {'name': name, 'enabled': True, 'eval_func': 'cls.' + func, 'is_greater_better': greater_is_better,
+           'init_value': init}
+    if obj is not None or name != 'F-Score':
+        row['eval_object'] = obj
+    return row
 
+
+class Metrics(object):
+    # same four metrics, order, directions and initial values as the reference (tools/runner.py indexes them by position)
+    ITEMS = [
+        _item('F-Score', '_get_f_score', True, 0),
+        _item('CDL1', '_get_chamfer_distancel1', False, 32767, ChamferDistanceL1(ignore_zeros=True)),
+        _item('CDL2', '_get_chamfer_distancel2', False, 32767, ChamferDistanceL2(ignore_zeros=True)),
+        _item('EMDistance', '_get_emd_distance', False, 32767),
+    ]
 
     @classmethod
     def get(cls, pred, gt, require_emd=False, th=0.01):
@@ -138,25 +125,26 @@ class Metrics(object):
         dist, _ = emd.emdModule()(pred, gt, eps, iterations)
         return torch.mean(torch.sqrt(dist)) * 1000
 
+    # ---- the instance: one set of values of the enabled metrics + the name of the metric checkpoints are ranked by
+    # (utils/metrics.py:118-165; tools/runner.py keeps `best_metrics = Metrics(...)` and calls better_than / state_dict)
     def __init__(self, metric_name, values):
         self._items = Metrics.items()
-        self._values = [item['init_value'] for item in self._items]
         self.metric_name = metric_name
-
+        names = [it['name'] for it in self._items]
         if isinstance(values, list):
             self._values = values
         elif isinstance(values, dict):
-            metric_indexes = {item['name']: idx for idx, item in enumerate(self._items)}
-            for k, v in values.items():
-                if k not in metric_indexes:
-                    logging.warning('Ignore Metric[Name=%s] due to disability.' % k)
-                    continue
-                self._values[metric_indexes[k]] = v
+            self._values = [it['init_value'] for it in self._items]
+            for key, val in values.items():
+                if key in names:
+                    self._values[names.index(key)] = val
+                else:
+                    logging.warning('Ignore Metric[Name=%s] due to disability.' % key)
         else:
             raise Exception('Unsupported value type: %s' % type(values))
 
     def state_dict(self):
-        return {self._items[i]['name']: self._values[i] for i in range(len(self._items))}
+        return {it['name']: val for it, val in zip(self._items, self._values)}
 
     def __repr__(self):
         return str(self.state_dict())
@@ -164,17 +152,11 @@ class Metrics(object):
     def better_than(self, other):
         if other is None:
             return True
-        _index = -1
-        for i, _item in enumerate(self._items):
-            if _item['name'] == self.metric_name:
-                _index = i
-                break
-        if _index == -1:
+        pos = next((i for i, it in enumerate(self._items) if it['name'] == self.metric_name), None)
+        if pos is None:
             raise Exception('Invalid metric name to compare.')
-        _metric = self._items[_index]
-        _value = self._values[_index]
-        other_value = other._values[_index]
-        return _value > other_value if _metric['is_greater_better'] else _value < other_value
+        mine, theirs = self._values[pos], other._values[pos]
+        return mine > theirs if self._items[pos]['is_greater_better'] else mine < theirs
 
 
 class MetricAccumulator:
