@@ -33,3 +33,8 @@ print("uniform self k=16 2048: %.4f ms" % t(lambda: knn_point(16, u, u)))
 print("pcn surface (no padding) self k=16 2048: %.4f ms" % t(lambda: knn_point(16, g2, g2)))
 g4 = synthetic.pcn_gt(48, 4096, 6).to(dev)
 print("pcn surface self k=16 4096: %.4f ms" % t(lambda: knn_point(16, g4, g4)))
+gc512 = misc.fps(g2, 512)
+print("pcn surface (no padding) k=16 R=2048 Q=512: %.4f ms" % t(lambda: knn_point(16, g2, gc512)))
+print("pcn surface (no padding) k=16 R=512 Q=512: %.4f ms" % t(lambda: knn_point(16, gc512, gc512)))
+gq = g2[:, :256].contiguous()
+print("pcn surface (no padding) k=16 R=2048 Q=256 (first 256 points): %.4f ms" % t(lambda: knn_point(16, g2, gq)))
