@@ -65,7 +65,9 @@ int iapt_chamfer_forward(const float* xyz1, const float* xyz2, int B, int N, int
 /* Replaces chamfer.backward -> chamfer_cuda_backward (chamfer_cuda.cpp:27-34, chamfer.cu:203-229; kernel :173-201).
  *   grad_xyz1[b,j] = 2 g1[b,j] (x1_j - x2_idx1[j]) - sum_{k: idx2[k]==j} 2 g2[b,k] (x2_k - x1_j), and symmetrically
  *   for grad_xyz2.  Deterministic and free of floating-point atomics: the points that chose j as nearest neighbour are
- *   grouped per j (counting sort with integer atomics), ordered, and added in ascending source index by j's owner.
+ *   grouped per j (counting sort with integer atomics) and summed by j's owner - up to 8 of them in ascending source
+ *   index, more of them exactly (64-bit fixed point, scale from the segment's largest term), so the result depends
+ *   neither on scheduling nor on the launch geometry and a collapsed prediction is a parallel reduction.
  *   Outputs are fully written (no pre-zeroing needed); either gradient may be NULL (not wanted), a NULL grad_dist
  *   means zeros.  The workspace is REQUIRED (iapt_chamfer_backward_workspace_bytes: 12 bytes per point + O(B)).
  *   Indices outside [0, other side's size) are ignored (the reference would read out of bounds). */
