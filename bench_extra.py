@@ -260,7 +260,7 @@ def config2_get_loss(dev, B=48):
     return out
 
 
-def config4(dev, rank, world, n_per_cat=150, n_cat=8, chunk=25, emd=True):
+def config4(dev, rank, world, n_per_cat=150, n_cat=8, chunk=100, emd=True):
     total = n_per_cat * n_cat
     b, e = dist_utils.shard_range(total, rank, world)
     acc = MetricAccumulator(n_cat, dev)
@@ -355,6 +355,7 @@ def main():
     ap.add_argument("--configs", default="1,2,3,4,5")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "extra.json"))
     ap.add_argument("--c4-per-cat", type=int, default=150)
+    ap.add_argument("--c4-chunk", type=int, default=100)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -374,7 +375,7 @@ def main():
     if world > 1:
         dist.barrier()
     if 4 in want:
-        res["config4"] = config4(dev, rank, world, n_per_cat=args.c4_per_cat)
+        res["config4"] = config4(dev, rank, world, n_per_cat=args.c4_per_cat, chunk=args.c4_chunk)
     if 5 in want:
         res["config5"] = config5(dev, rank, world)
     if rank == 0:
