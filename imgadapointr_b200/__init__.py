@@ -18,4 +18,4 @@ without the built CUDA library every op raises.
 from . import _lib  # noqa: F401
 from ._lib import IaptError, launch_count  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
