@@ -2,15 +2,19 @@
 //
 // Replaces knn_point = square_distance + torch.topk(largest=False, sorted=False)
 // (reference models/Transformer_utils.py:19-51), which materialises the [B,Q,R] FP32 matrix (805 MB at
-// B=48, Q=R=2048) through a K=3 SGEMM and re-reads it in topk.  Here nothing is materialised.  Two kernels:
+// B=48, Q=R=2048) through a K=3 SGEMM and re-reads it in topk.  Here nothing is materialised.  Three paths:
 //  * knn_kernel (any k <= 64, any batch): reference points are staged once per CTA in shared memory (float4) and every
 //    warp owns one query, keeping the current k best as a sorted list spread over its lanes (lane i = i-th smallest).
 //    A 32-reference step costs one direct-form distance per lane, a compare against the current k-th distance and one
 //    ballot; the (rare) candidates are inserted with a ballot-computed position and one shuffle-up;
 //  * knn_select_kernel (k <= 16 and at least 256 warps of queries - the encoder's calls): one THREAD per query, two
-//    sweeps and a threshold (see below); 2.9x faster than the list kernel at 48 x 2048 x 2048, k = 16.
+//    sweeps and a threshold (see below); 2.9x faster than the list kernel at 48 x 2048 x 2048, k = 16;
+//  * knn_bin_kernel + knn_culled_kernel (k <= 16, 1024..4096 references, from 1024 warps of queries): both clouds binned
+//    along a Hilbert curve, one bound per query, and only the tiles of 32 references whose box can hold a neighbour are
+//    swept (a quarter of the pairs at 2048 points): another 1.4-1.8x at 2048 x 2048, 2.6x at 4096 x 4096.
 // Output is ascending by (distance, index); on exact distance ties the LOWEST index wins (references are scanned
 // in ascending index and only a strictly smaller distance displaces a list entry).
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -570,337 +574,651 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
 }
 
 // =====================================================================================================================
-// Spatially pruned selection (k <= 16, 1024 <= R <= 4096): sort, bound, cull, select - still exact
+// Spatially culled selection (k <= 16, 1024 <= R <= 4096): bin, bound, cull, select - still exact
 // =====================================================================================================================
 // The select kernel above evaluates every (query, reference) pair 1.5 times; this path evaluates only the pairs that
-// can matter.  (Default above 2048 references; at 2048 a k = 16 ball still touches a third of the tiles of a 3-D cloud
-// and the sort + per-tile latency eat the saved instructions - see knn_plan.)  Both clouds are sorted along a Morton curve (one CTA per cloud, bitonic sort of (code, index) keys in
-// shared memory), so the 32 queries of a warp and the 32 references of a tile are each spatially compact and have a
-// small bounding box.  Per warp:
-//   order : the tiles are visited nearest first (distance from the centre of the warp's query box to the farthest corner
-//           of the tile box - compact, close tiles first; a heuristic only);
-//   cull  : a tile farther from a query than that query's current tau cannot hold one of its neighbours (the
-//           point-to-box distance is a lower bound of every pair distance; compared with a 2^-18 margin, far above the
-//           rounding of either side) - a tile no query of the warp needs is never loaded;
-//   sweep : a visited tile is evaluated with the exact direct-form distance; d <= tau marks a candidate (tau = +inf
-//           until the first fold);
-//   fold  : when a lane's candidate list reaches fold_at entries its candidates are re-evaluated and inserted into a
-//           register-resident list ordered by the 64-bit key (distance bits, ORIGINAL index) - the same ascending
-//           (distance, index) order and lowest-index tie rule as every other path, although the sweep runs in Morton
-//           order - and the k-th key becomes the lane's new tau: the exact k-th nearest of everything swept so far.
-// The candidate list cannot overflow: a list with fewer than 32 free slots is folded into the running top-k before the
-// next tile, and the k-th key found so far becomes the new (exact, tighter) tau - so loose initial bounds, hundreds of
-// exact ties (zero padding: the points at the origin) or adversarial index layouts only cost extra folds, never a
-// fallback, and the result never depends on the cap.
-constexpr int kPrMaxN = 4096;        // points one CTA sorts in shared memory
-constexpr int kPrMinR = 1024;
-constexpr int kPrSortThreads = 1024;
-constexpr int kPrCap = 96;           // candidates per query
-constexpr int kPrSeeds = 6;          // tiles of the bound pass
-
+// can matter (a quarter of them at 2048 points) and keeps the selection machinery cheap.
+//  * knn_bin_kernel orders each cloud along a 3-D HILBERT curve over a 16^3 grid by ONE counting sort (shared-memory
+//    histogram, scan, scatter; the order inside a cell is whatever the atomics give - it only decides which tile a point
+//    lands in, never a result).  Consecutive Hilbert cells are face neighbours, so a tile of 32 consecutive points has a
+//    box about a third smaller than a Z-order tile: a warp of 32 consecutive queries needs 15-17 of the 64 tiles of a
+//    2048-point cloud (Z-order: 21-26; a k-d partition would need 12-15; simulated on the bench clouds).  Every tile
+//    gets its bounding box, its smallest original index and a flag "all 32 points coincide".
+//  * knn_culled_kernel computes ONE bound per query - the k-th smallest of 32 class minima over the n_seeds tiles
+//    nearest to the warp's queries - and then the list of tiles ANY of its queries needs (box distance <= bound) is
+//    fixed: the sweep over it has no data-dependent control flow between tiles and prefetches freely.  (The first cut
+//    of this path visited tiles nearest-first with a moving bound: a dependent chain cull test -> load -> stage -> sweep
+//    per tile that left the kernel latency-bound at 0.16 ms; it also used a Z-order bitonic sort of 28 us.)
+//  * the sweep's test is the sign of f = T - d evaluated as three FMAs onto T (T = the bound inflated by 2^-20, far
+//    above the rounding of either side: a prefilter that can only let too MANY through), collected with one funnel
+//    shift per reference: 7 instructions per pair instead of 9.  Candidates are re-evaluated with the exact direct-form
+//    distance when they are folded into the (distance bits, ORIGINAL index) ordered top-k, so values, order and the
+//    lowest-index tie rule are those of every other path although the sweep runs in curve order.
+//  * the fold takes 8 candidates at a time: sorted by a register network and merged into the sorted top-k by one
+//    bitonic split + merge (~45 instructions per candidate; an insertion costs ~100).
+//  * duplicates (the zero padding of a PCN partial: hundreds of references at the origin tie at every bound): a cell
+//    spanning several tiles is put in ascending original index by the bin kernel; once a query holds k references, a
+//    candidate is checked exactly against its k-th (distance, index) before it is listed, and a tile that is one point
+//    is skipped when that point ties or loses even with the tile's smallest index.
 struct __align__(16) PrTileBox {
-  float4 lo, hi;
+  float4 lo, hi;  // lo.w: smallest original index in the tile (int bits); hi.w: 1 when all its points coincide
 };
+constexpr int kPrMaxN = 4096;  // points per cloud on this path (4 per thread of the bin kernel; tile ids fit 7 bits)
+constexpr int kPrMinR = 1024;
 
-__device__ __forceinline__ unsigned morton_expand10(unsigned v) {  // 10 bits -> every third bit
-  v = (v | (v << 16)) & 0x030000FFu;
-  v = (v | (v << 8)) & 0x0300F00Fu;
-  v = (v | (v << 4)) & 0x030C30C3u;
-  v = (v | (v << 2)) & 0x09249249u;
-  return v;
+constexpr int kBinThreads = 1024;
+constexpr int kBinPer = kPrMaxN / kBinThreads;  // points per thread, kept in registers
+constexpr int kBinCells = 4096;                 // 16^3 Hilbert cells
+constexpr int kBinBig = 8;                      // cells of more than one tile that get re-ordered by index
+constexpr int kCuCap = 80;                      // candidates per query
+constexpr int kCuMaxTiles = kPrMaxN / 32;
+
+// float <-> unsigned whose order is the float order (for REDUX min / max over signed values)
+__device__ __forceinline__ unsigned f2ord(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// grid (B, 1 or 2): blockIdx.y == 0 sorts the references (and writes their tile boxes), 1 the queries.
-__global__ void __launch_bounds__(kPrSortThreads) knn_sort_kernel(const float* __restrict__ ref, int R, int Rp,
-                                                                  float4* __restrict__ sref,
-                                                                  PrTileBox* __restrict__ boxes,
-                                                                  const float* __restrict__ qry, int Q, int Qp,
-                                                                  float4* __restrict__ sqry) {
-  __shared__ u64 keys[kPrMaxN];
-  __shared__ float red[6][32];
+// Hilbert index of a cell (4 bits per axis -> 12 bits), Skilling's transposition algorithm.
+__device__ __forceinline__ unsigned hilbert12(unsigned X0, unsigned X1, unsigned X2) {
+#pragma unroll
+  for (unsigned Qb = 8; Qb > 1; Qb >>= 1) {
+    const unsigned P = Qb - 1;
+    if (X0 & Qb) X0 ^= P;
+    if (X1 & Qb) {
+      X0 ^= P;
+    } else {
+      const unsigned t = (X0 ^ X1) & P;
+      X0 ^= t;
+      X1 ^= t;
+    }
+    if (X2 & Qb) {
+      X0 ^= P;
+    } else {
+      const unsigned t = (X0 ^ X2) & P;
+      X0 ^= t;
+      X2 ^= t;
+    }
+  }
+  X1 ^= X0;
+  X2 ^= X1;
+  unsigned t = 0;
+#pragma unroll
+  for (unsigned Qb = 8; Qb > 1; Qb >>= 1)
+    if (X2 & Qb) t ^= Qb - 1;
+  X0 ^= t;
+  X1 ^= t;
+  X2 ^= t;
+  unsigned key = 0;
+#pragma unroll
+  for (int bit = 3; bit >= 0; --bit)
+    key = (key << 3) | (((X0 >> bit) & 1u) << 2) | (((X1 >> bit) & 1u) << 1) | ((X2 >> bit) & 1u);
+  return key;
+}
+
+// grid (B, 1 or 2): blockIdx.y == 0 bins the references (and writes their tile boxes), 1 the queries.
+__global__ void __launch_bounds__(kBinThreads) knn_bin_kernel(const float* __restrict__ ref, int R, int Rp,
+                                                              float4* sref, PrTileBox* __restrict__ boxes,
+                                                              const float* __restrict__ qry, int Q, int Qp, float4* sqry) {
+  __shared__ __align__(16) unsigned hist[kBinCells];
+  __shared__ unsigned red[6][32];
+  __shared__ unsigned wsum[32];
+  __shared__ unsigned big_n, big_start[kBinBig], big_count[kBinBig];
   const bool is_q = blockIdx.y == 1;
   const int n = is_q ? Q : R, n_pad = is_q ? Qp : Rp;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* __restrict__ P = (is_q ? qry : ref) + (size_t)b * n * 3;
-  float4* __restrict__ out = (is_q ? sqry : sref) + (size_t)b * n_pad;
+  float4* out = (is_q ? sqry : sref) + (size_t)b * n_pad;
   const float kInf = __int_as_float(0x7f800000);
 
-  // ---- bounding box of the cloud ------------------------------------------------------------------------------------
-  float lo[3] = {kInf, kInf, kInf}, hi[3] = {-kInf, -kInf, -kInf};
-  for (int i = tid; i < n; i += kPrSortThreads) {
+  // ---- the thread's points, the cloud's bounding box ------------------------------------------------------------------
+  float px[kBinPer], py[kBinPer], pz[kBinPer];
+  unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
 #pragma unroll
-    for (int e = 0; e < 3; ++e) {
-      const float v = __ldg(P + 3 * (size_t)i + e);
-      lo[e] = fminf(lo[e], v);
-      hi[e] = fmaxf(hi[e], v);
+  for (int j = 0; j < kBinPer; ++j) {
+    const int i = tid + j * kBinThreads;
+    px[j] = py[j] = pz[j] = 0.f;
+    if (i < n) {
+      px[j] = __ldg(P + 3 * (size_t)i);
+      py[j] = __ldg(P + 3 * (size_t)i + 1);
+      pz[j] = __ldg(P + 3 * (size_t)i + 2);
+      const unsigned ux = f2ord(px[j]), uy = f2ord(py[j]), uz = f2ord(pz[j]);
+      lo[0] = min(lo[0], ux), hi[0] = max(hi[0], ux);
+      lo[1] = min(lo[1], uy), hi[1] = max(hi[1], uy);
+      lo[2] = min(lo[2], uz), hi[2] = max(hi[2], uz);
     }
   }
 #pragma unroll
   for (int e = 0; e < 3; ++e) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo[e] = fminf(lo[e], __shfl_xor_sync(0xffffffffu, lo[e], o));
-      hi[e] = fmaxf(hi[e], __shfl_xor_sync(0xffffffffu, hi[e], o));
-    }
+    const unsigned l = redux_min_u32(lo[e]), h = redux_max_u32(hi[e]);
     if (lane == 0) {
-      red[e][warp] = lo[e];
-      red[3 + e][warp] = hi[e];
+      red[e][warp] = l;
+      red[3 + e][warp] = h;
     }
   }
+#pragma unroll
+  for (int j = 0; j < kBinCells / kBinThreads; ++j) hist[tid + j * kBinThreads] = 0u;
+  if (tid == 0) big_n = 0u;
   __syncthreads();
-  float scale[3];
+  float blo[3], scale[3];
 #pragma unroll
   for (int e = 0; e < 3; ++e) {
-    float l = kInf, h = -kInf;
-    for (int w = 0; w < kPrSortThreads / 32; ++w) {
-      l = fminf(l, red[e][w]);
-      h = fmaxf(h, red[3 + e][w]);
-    }
-    lo[e] = l;
-    scale[e] = (h > l) ? 1024.f / (h - l) : 0.f;
+    const float l = ord2f(redux_min_u32(red[e][lane])), h = ord2f(redux_max_u32(red[3 + e][lane]));
+    blo[e] = l;
+    scale[e] = (h > l) ? 16.f / (h - l) : 0.f;  // (NaN / Inf coordinates: any cell is a valid cell)
   }
 
-  // ---- (Morton code, index) keys, bitonic sort --------------------------------------------------------------------------
-  int pow2 = 32;
-  while (pow2 < n) pow2 <<= 1;
-  for (int i = tid; i < pow2; i += kPrSortThreads) {
-    u64 key = ~0ull;
-    if (i < n) {
-      unsigned code = 0u;
+  // ---- cell of every point, its rank inside the cell --------------------------------------------------------------------
+  unsigned cell[kBinPer], rank[kBinPer];
 #pragma unroll
-      for (int e = 0; e < 3; ++e) {
-        const float v = (__ldg(P + 3 * (size_t)i + e) - lo[e]) * scale[e];
-        const int q = min(1023, max(0, (int)v));  // NaN -> 0: any order is a valid order
-        code |= morton_expand10((unsigned)q) << e;
-      }
-      key = ((u64)code << 16) | (u64)i;
+  for (int j = 0; j < kBinPer; ++j) {
+    const int i = tid + j * kBinThreads;
+    cell[j] = 0u;
+    rank[j] = 0u;
+    if (i < n) {
+      const int cx = min(15, max(0, (int)((px[j] - blo[0]) * scale[0])));
+      const int cy = min(15, max(0, (int)((py[j] - blo[1]) * scale[1])));
+      const int cz = min(15, max(0, (int)((pz[j] - blo[2]) * scale[2])));
+      cell[j] = hilbert12((unsigned)cx, (unsigned)cy, (unsigned)cz);
+      rank[j] = atomicAdd(&hist[cell[j]], 1u);
     }
-    keys[i] = key;
   }
   __syncthreads();
-  for (int size = 2; size <= pow2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = tid; t < (pow2 >> 1); t += kPrSortThreads) {
-        const int i = 2 * t - (t & (stride - 1));
-        const int j = i + stride;
-        const u64 a = keys[i], c = keys[j];
-        if ((a > c) == ((i & size) == 0)) {
-          keys[i] = c;
-          keys[j] = a;
+
+  // ---- exclusive scan of the 4096 counts (4 consecutive cells per thread) ------------------------------------------------
+  {
+    constexpr int kPer = kBinCells / kBinThreads;
+    unsigned c[kPer], s = 0u;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      c[j] = hist[tid * kPer + j];
+      s += c[j];
+    }
+    unsigned inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    unsigned wv = wsum[lane], winc = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += v;
+    }
+    const unsigned wbase = __shfl_sync(0xffffffffu, winc - wv, warp);
+    unsigned base = wbase + inc - s;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      hist[tid * kPer + j] = base;
+      if (c[j] > 32u) {  // a cell spanning tiles: re-ordered by original index below
+        const unsigned slot = atomicAdd(&big_n, 1u);
+        if (slot < (unsigned)kBinBig) {
+          big_start[slot] = base;
+          big_count[slot] = c[j];
+        }
+      }
+      base += c[j];
+    }
+  }
+  __syncthreads();
+
+  // ---- binned points (x, y, z, original index); sentinels behind them ------------------------------------------------------
+#pragma unroll
+  for (int j = 0; j < kBinPer; ++j) {
+    const int i = tid + j * kBinThreads;
+    if (i < n) out[hist[cell[j]] + rank[j]] = make_float4(px[j], py[j], pz[j], __int_as_float(i));
+  }
+  for (int i = n + tid; i < n_pad; i += kBinThreads)
+    out[i] = make_float4(kPadCoord(), kPadCoord(), kPadCoord(), __int_as_float(-1));
+  if (is_q) return;
+
+  // ---- cells of more than one tile (duplicated points: the zero padding of a PCN partial, hundreds of references at the
+  // origin) are put in ascending ORIGINAL index: the first tiles of such a cell then hold its lowest indices, and once the
+  // top-k of a query is full of them the later tiles are skipped by their minimum index (knn_culled_kernel).  Rank by
+  // counting, the indices staged in hist[] (free now); only the order inside the cell changes - never a result. -----------
+  __syncthreads();
+  {
+    int* sidx = reinterpret_cast<int*>(hist);
+    const int nb = (int)min(big_n, (unsigned)kBinBig);
+    for (int g = 0; g < nb; ++g) {
+      const int start = (int)big_start[g], m = (int)big_count[g];
+      float4 v[kBinPer];
+#pragma unroll
+      for (int j = 0; j < kBinPer; ++j) {
+        const int e = tid + j * kBinThreads;
+        if (e < m) {
+          v[j] = __ldcg(out + start + e);
+          sidx[e] = __float_as_int(v[j].w);
+        }
+      }
+      if (tid < 3 && m + tid < kBinCells) sidx[m + tid] = 0x7fffffff;  // (the last int4 read runs up to 3 entries past m)
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < kBinPer; ++j) {
+        const int e = tid + j * kBinThreads;
+        if (e < m) {
+          const int mine = __float_as_int(v[j].w);
+          int rk = 0;
+          const int4* s4 = reinterpret_cast<const int4*>(sidx);
+          for (int f = 0; f < (m + 3) / 4; ++f) {
+            const int4 q4 = s4[f];
+            rk += (q4.x < mine ? 1 : 0) + (q4.y < mine ? 1 : 0) + (q4.z < mine ? 1 : 0) + (q4.w < mine ? 1 : 0);
+          }
+          out[start + rk] = v[j];
         }
       }
       __syncthreads();
     }
   }
 
-  // ---- sorted points (x, y, z, original index) and the tile boxes ------------------------------------------------------
-  for (int t0 = warp * 32; t0 < n_pad; t0 += kPrSortThreads) {
-    const int i = t0 + lane;
-    float4 v = make_float4(kPadCoord(), kPadCoord(), kPadCoord(), __int_as_float(-1));
-    float bl[3] = {kInf, kInf, kInf}, bh[3] = {-kInf, -kInf, -kInf};
-    if (i < n) {
-      const int oi = (int)(keys[i] & 0xffffu);
-      v = make_float4(__ldg(P + 3 * (size_t)oi), __ldg(P + 3 * (size_t)oi + 1), __ldg(P + 3 * (size_t)oi + 2),
-                      __int_as_float(oi));
-      bl[0] = bh[0] = v.x;
-      bl[1] = bh[1] = v.y;
-      bl[2] = bh[2] = v.z;
+  // ---- tile boxes (this CTA's own writes, visible after the barrier; read around L1).  lo.w = the smallest original
+  // index in the tile, hi.w = 1 when all its points coincide ---------------------------------------------------------------
+  for (int t = warp; t < n_pad / 32; t += kBinThreads / 32) {
+    const float4 v = __ldcg(out + t * 32 + lane);
+    const bool real = __float_as_int(v.w) >= 0;
+    const int min_idx = redux_min_s32(real ? __float_as_int(v.w) : 0x7fffffff);
+    const unsigned lx = redux_min_u32(real ? f2ord(v.x) : 0xffffffffu), hx = redux_max_u32(real ? f2ord(v.x) : 0u);
+    const unsigned ly = redux_min_u32(real ? f2ord(v.y) : 0xffffffffu), hy = redux_max_u32(real ? f2ord(v.y) : 0u);
+    const unsigned lz = redux_min_u32(real ? f2ord(v.z) : 0xffffffffu), hz = redux_max_u32(real ? f2ord(v.z) : 0u);
+    if (lane == 0) {
+      PrTileBox bx;
+      bx.lo = make_float4(ord2f(lx), ord2f(ly), ord2f(lz), __int_as_float(min_idx));
+      bx.hi = make_float4(ord2f(hx), ord2f(hy), ord2f(hz), __int_as_float((lx == hx && ly == hy && lz == hz) ? 1 : 0));
+      boxes[(size_t)b * (n_pad / 32) + t] = bx;
     }
-    out[i] = v;
-    if (!is_q) {
+  }
+  (void)kInf;
+}
+
+// ascending compare-exchange / bitonic networks on 64-bit keys held in registers (indices are compile-time after unrolling)
+__device__ __forceinline__ void cswap_u64(u64& a, u64& b) {
+  const bool s = b < a;
+  const u64 lo = s ? b : a, hi = s ? a : b;
+  a = lo;
+  b = hi;
+}
+template <int N>
+__device__ __forceinline__ void bitonic_merge_u64(u64 (&v)[N]) {  // bitonic sequence -> ascending
 #pragma unroll
-      for (int e = 0; e < 3; ++e) {
+  for (int stride = N / 2; stride > 0; stride >>= 1) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          bl[e] = fminf(bl[e], __shfl_xor_sync(0xffffffffu, bl[e], o));
-          bh[e] = fmaxf(bh[e], __shfl_xor_sync(0xffffffffu, bh[e], o));
+    for (int i = 0; i < N; ++i)
+      if ((i & stride) == 0) cswap_u64(v[i], v[i + stride]);
+  }
+}
+template <int N>
+__device__ __forceinline__ void bitonic_sort_u64(u64 (&v)[N]) {
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int j = i ^ stride;
+        if (j > i) {
+          if ((i & size) == 0)
+            cswap_u64(v[i], v[j]);
+          else
+            cswap_u64(v[j], v[i]);
         }
-      }
-      if (lane == 0) {
-        PrTileBox bx;
-        bx.lo = make_float4(bl[0], bl[1], bl[2], 0.f);
-        bx.hi = make_float4(bh[0], bh[1], bh[2], 0.f);
-        boxes[(size_t)b * (Rp / 32) + (t0 >> 5)] = bx;
       }
     }
   }
 }
 
-template <int kK>
-__global__ void __launch_bounds__(32, 16) knn_pruned_kernel(const float4* __restrict__ sref,
-                                                            const PrTileBox* __restrict__ boxes,
-                                                            const float4* __restrict__ sqry, int R, int Rp, int Q, int Qp,
-                                                            int k, int q_blocks, int fold_at, int64_t* __restrict__ idx_out,
-                                                            float* __restrict__ dist_out) {
-  __shared__ float4 stage[32];
-  __shared__ unsigned short cand[kPrCap][32];
-  __shared__ unsigned order[kPrMaxN / 32];
-  const int lane = threadIdx.x;
+constexpr int kCuBatch = 8;  // candidates folded at once
+
+// One CTA = kW warps on the SAME 32 queries: warp w takes the seed tiles and the listed tiles with index = w (mod kW),
+// keeps its own candidate list and top-k, and warp 0 merges the kW sorted lists at the end.  The per-tile work of a warp
+// of queries varies 3x with where the curve cuts the cloud; sharing a tile list between warps cuts the latency of the
+// heaviest tasks - which is what the kernel's duration is, all tasks being resident from the start.
+struct __align__(16) CuWarpSmem {
+  float stage[2][128];  // a tile as raw xyz rows (96 floats) + its 32 original indices, double-buffered
+  union {
+    unsigned short cand[kCuCap][32];  // sweep -> fold
+    float minima[32][32];             // this warp's class minima, exchanged after the bound pass
+    u64 keys[kSelMaxK][32];           // this warp's final top-k, for warp 0
+  };
+  unsigned char tlist[kCuMaxTiles];
+};
+
+template <int kK, int kW>
+__global__ void __launch_bounds__(32 * kW, kW == 1 ? 21 : kW == 2 ? 11 : 6) knn_culled_kernel(const float4* __restrict__ sref,
+                                                                     const PrTileBox* __restrict__ boxes,
+                                                                     const float4* __restrict__ sqry, int R, int Rp, int Q,
+                                                                     int Qp, int k, int q_blocks, int n_seeds, int probes,
+                                                                     int64_t* __restrict__ idx_out,
+                                                                     float* __restrict__ dist_out
+                                                                     ) {
+  extern __shared__ float4 sbox[];  // [2 * nt]: lo, hi of every tile of the cloud
+  __shared__ CuWarpSmem wsm[kW];
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  CuWarpSmem& sm = wsm[w];
   const int b = blockIdx.x / q_blocks;
   const int qb = blockIdx.x - b * q_blocks;
   const float kInf = __int_as_float(0x7f800000);
   const float4* __restrict__ Rb = sref + (size_t)b * Rp;
+  const int nt = Rp / 32;
   const float4 qv = __ldg(sqry + (size_t)b * Qp + qb * 32 + lane);
   const int qi = __float_as_int(qv.w);
   const bool live = qi >= 0;
   const float qx = qv.x, qy = qv.y, qz = qv.z;
-  const PrTileBox* __restrict__ Bx = boxes + (size_t)b * (Rp / 32);
-  const int nt = Rp / 32;
-
-  // squared distance from this lane's query to a tile box: a lower bound of its distance to every reference inside
-  auto box_dist = [&](int t) {
-    const float4 bl = __ldg(&Bx[t].lo), bh = __ldg(&Bx[t].hi);  // warp-uniform addresses: one broadcast each
-    const float gx = fmaxf(0.f, fmaxf(bl.x - qx, qx - bh.x));
-    const float gy = fmaxf(0.f, fmaxf(bl.y - qy, qy - bh.y));
-    const float gz = fmaxf(0.f, fmaxf(bl.z - qz, qz - bh.z));
-    return gx * gx + gy * gy + gz * gz;
-  };
-
-  // ---- visiting order: tiles by the distance from the centre of the warp's query box to the FARTHEST corner of the tile
-  // box (compact, close tiles first; a Morton tile spanning a jump of the curve has a huge box that contains many queries
-  // without holding their neighbours).  A heuristic only - what is swept is decided by the exact cull test below.
   {
-    float cl[3] = {live ? qx : kInf, live ? qy : kInf, live ? qz : kInf};
-    float ch[3] = {live ? qx : -kInf, live ? qy : -kInf, live ? qz : -kInf};
+    const float4* __restrict__ Bg = reinterpret_cast<const float4*>(boxes + (size_t)b * nt);
+    for (int i = threadIdx.x; i < 2 * nt; i += 32 * kW) sbox[i] = __ldg(Bg + i);
+  }
+  // box of the warp's queries
+  float cl[3], ch[3];
+  {
+    const float q3[3] = {qx, qy, qz};
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        cl[e] = fminf(cl[e], __shfl_xor_sync(0xffffffffu, cl[e], o));
-        ch[e] = fmaxf(ch[e], __shfl_xor_sync(0xffffffffu, ch[e], o));
-      }
-      cl[e] = 0.5f * (cl[e] + ch[e]);
-    }
-#pragma unroll
-    for (int i = 0; i < kPrMaxN / 1024; ++i) {
-      const int t = lane + 32 * i;
-      unsigned key = 0xffffffffu;
-      if (t < nt) {
-        const float4 bl = Bx[t].lo, bh = Bx[t].hi;
-        const float fx = fmaxf(fabsf(cl[0] - bl.x), fabsf(cl[0] - bh.x));
-        const float fy = fmaxf(fabsf(cl[1] - bl.y), fabsf(cl[1] - bh.y));
-        const float fz = fmaxf(fabsf(cl[2] - bl.z), fabsf(cl[2] - bh.z));
-        key = (__float_as_uint(fx * fx + fy * fy + fz * fz) & 0xffffff00u) | (unsigned)t;  // >= +0: bits order like uints
-      }
-      order[t] = key;
-    }
-    __syncwarp();
-    for (int size = 2; size <= kPrMaxN / 32; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-        for (int h = 0; h < kPrMaxN / 2048; ++h) {
-          const int p = lane + 32 * h;
-          const int i = 2 * p - (p & (stride - 1));
-          const int j = i + stride;
-          const unsigned x = order[i], y = order[j];
-          if ((x > y) == ((i & size) == 0)) {
-            order[i] = y;
-            order[j] = x;
-          }
-        }
-        __syncwarp();
-      }
+      cl[e] = ord2f(redux_min_u32(live ? f2ord(q3[e]) : 0xffffffffu));
+      ch[e] = ord2f(redux_max_u32(live ? f2ord(q3[e]) : 0u));
     }
   }
+  if (kW > 1)
+    __syncthreads();
+  else
+    __syncwarp();
 
-  // ---- bound: class minima over the kPrSeeds nearest tiles (class = position inside the tile; different tiles hold
-  // different references): the k-th smallest of the 32 minima bounds the k-th neighbour distance, like sweep 1 above ---------
+  auto stage_tile = [&](int buf, const float4& r) {
+    sm.stage[buf][3 * lane + 0] = r.x;
+    sm.stage[buf][3 * lane + 1] = r.y;
+    sm.stage[buf][3 * lane + 2] = r.z;
+    sm.stage[buf][96 + lane] = r.w;
+  };
+
+  // ---- bound: class minima over the n_seeds tiles nearest to the warp (distance from the centre of the query box to the
+  // FARTHEST corner of the tile box: compact close tiles first).  Class = position inside the tile; different tiles hold
+  // different references, so the k-th smallest of the 32 minima bounds the k-th neighbour distance. ---------------------
   float tau;
   {
+    unsigned key[kCuMaxTiles / 32];
+    unsigned deg = 0u;  // bit i: this lane's i-th tile is one point 32 times (duplicates)
+    const float cx = 0.5f * (cl[0] + ch[0]), cy = 0.5f * (cl[1] + ch[1]), cz = 0.5f * (cl[2] + ch[2]);
+#pragma unroll
+    for (int i = 0; i < kCuMaxTiles / 32; ++i) {
+      const int t = lane + 32 * i;
+      key[i] = 0xffffffffu;
+      if (t < nt) {
+        const float4 bl = sbox[2 * t], bh = sbox[2 * t + 1];
+        const float fx = fmaxf(fabsf(cx - bl.x), fabsf(cx - bh.x));
+        const float fy = fmaxf(fabsf(cy - bl.y), fabsf(cy - bh.y));
+        const float fz = fmaxf(fabsf(cz - bl.z), fabsf(cz - bh.z));
+        key[i] = (__float_as_uint(fx * fx + fy * fy + fz * fz) & 0xffffff80u) | (unsigned)t;  // >= +0: bits order like uints
+        if (__float_as_int(bh.w) == 1) deg |= 1u << i;
+      }
+    }
+    // Seeds alternate between the centre ranking and PROBES: the unused tile nearest to the query of one lane (0, the
+    // last live one, 16, 8, 24, ...).  A warp whose 32 consecutive queries straddle a jump of the curve (or the block of
+    // zero padding and the real points) has nothing near its centre; the probes give both ends their neighbourhood.
+    const int n_live = __popc(__ballot_sync(0xffffffffu, live));  // live lanes are a prefix
+    // a tile that is ONE point gives every class the same distance: a second one (the zero padding of a PCN partial
+    // fills dozens) would add nothing, so taking one retires them all
+    auto mark = [&](int id) {
+      bool was_deg = false;
+#pragma unroll
+      for (int i = 0; i < kCuMaxTiles / 32; ++i)
+        if (lane + 32 * i == id) {
+          key[i] = 0xffffffffu;
+          was_deg = (deg >> i) & 1u;
+        }
+      if (__any_sync(0xffffffffu, was_deg)) {
+#pragma unroll
+        for (int i = 0; i < kCuMaxTiles / 32; ++i)
+          if ((deg >> i) & 1u) key[i] = 0xffffffffu;
+      }
+    };
+    auto pick = [&](unsigned m) {  // -1: no tile left
+      const unsigned wk = redux_min_u32(m);
+      if (wk == 0xffffffffu) return -1;
+      const int id = (int)(wk & 0x7fu);
+      mark(id);
+      return id;
+    };
+    auto seed_centre = [&]() {
+      unsigned m = key[0];
+#pragma unroll
+      for (int i = 1; i < kCuMaxTiles / 32; ++i) m = min(m, key[i]);
+      return pick(m);
+    };
+    auto seed_probe = [&](int p) {
+      int L = p == 0 ? 0 : p == 1 ? 31 : (int)(__brev((unsigned)(p - 1)) >> 27);
+      L = min(L, max(n_live - 1, 0));
+      const float px = __shfl_sync(0xffffffffu, qx, L), py = __shfl_sync(0xffffffffu, qy, L),
+                  pz = __shfl_sync(0xffffffffu, qz, L);
+      unsigned m = 0xffffffffu;
+#pragma unroll
+      for (int i = 0; i < kCuMaxTiles / 32; ++i) {
+        const int t = lane + 32 * i;
+        if (key[i] != 0xffffffffu) {  // (unused, hence < nt)
+          const float4 bl = sbox[2 * t], bh = sbox[2 * t + 1];
+          const float fx = fmaxf(fabsf(px - bl.x), fabsf(px - bh.x));
+          const float fy = fmaxf(fabsf(py - bl.y), fabsf(py - bh.y));
+          const float fz = fmaxf(fabsf(pz - bl.z), fabsf(pz - bh.z));
+          m = min(m, (__float_as_uint(fx * fx + fy * fy + fz * fz) & 0xffffff80u) | (unsigned)t);
+        }
+      }
+      return pick(m);
+    };
+    int seed_no = 0;
+    auto next_seed = [&]() {
+      const int u = seed_no++;
+      return (probes && (u & 1)) ? seed_probe(u >> 1) : seed_centre();
+    };
+    auto my_next_seed = [&]() {  // every warp walks the same sequence and keeps every kW-th tile
+      int t = -1;
+#pragma unroll
+      for (int o = 0; o < kW; ++o) {
+        const int sd = next_seed();
+        if (o == w) t = sd;
+      }
+      return t;
+    };
     float mn[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) mn[i] = kInf;
-    const int ns = min(nt, kPrSeeds);
-    float4 r = __ldg(Rb + (int)(order[0] & 0xffu) * 32 + lane);
-    for (int u = 0; u < ns; ++u) {
+    const int ns = max(1, min(nt, n_seeds) / kW);  // seeds per warp
+    int t_seed = my_next_seed();
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t_seed >= 0) r = __ldg(Rb + t_seed * 32 + lane);
+    for (int u = 0; u < ns && t_seed >= 0; ++u) {
+      const int buf = u & 1;
+      stage_tile(buf, r);
       __syncwarp();
-      stage[lane] = r;
-      __syncwarp();
-      if (u + 1 < ns) r = __ldg(Rb + (int)(order[u + 1] & 0xffu) * 32 + lane);
+      t_seed = u + 1 < ns ? my_next_seed() : -1;
+      if (t_seed >= 0) r = __ldg(Rb + t_seed * 32 + lane);
+      const float4* G = reinterpret_cast<const float4*>(sm.stage[buf]);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float4 p = stage[c];
-        mn[c] = fminf(mn[c], sqdist(qx, qy, qz, p.x, p.y, p.z));
+      for (int j = 0; j < 8; ++j) {
+        const float4 A = G[3 * j], Bv = G[3 * j + 1], C = G[3 * j + 2];
+        mn[4 * j + 0] = fminf(mn[4 * j + 0], sqdist(qx, qy, qz, A.x, A.y, A.z));
+        mn[4 * j + 1] = fminf(mn[4 * j + 1], sqdist(qx, qy, qz, A.w, Bv.x, Bv.y));
+        mn[4 * j + 2] = fminf(mn[4 * j + 2], sqdist(qx, qy, qz, Bv.z, Bv.w, C.x));
+        mn[4 * j + 3] = fminf(mn[4 * j + 3], sqdist(qx, qy, qz, C.y, C.z, C.w));
       }
+    }
+    if (kW > 1) {  // the warps' tiles hold different references: the minimum over the warps is the class minimum
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sm.minima[i][lane] = mn[i];
+      __syncthreads();
+#pragma unroll
+      for (int o = 1; o < kW; ++o) {
+        const CuWarpSmem& other = wsm[(w + o) % kW];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mn[i] = fminf(mn[i], other.minima[i][lane]);
+      }
+      __syncthreads();  // minima[] aliases cand[]
     }
     sort32(mn);
     tau = mn[0];
 #pragma unroll
     for (int i = 1; i < kK; ++i)
       if (i < k) tau = mn[i];
+    __syncwarp();  // the stage buffers are reused by the sweep
+  }
+  // prefilter threshold: d <= tau (both in float) implies T - d >= 0 in the fused evaluation below - three roundings of at
+  // most 2^-24 relative to max(d, T) each against a margin of 2^-20 (+ an absolute one for the subnormal range)
+  auto inflate = [](float v) { return __fmaf_rn(v, 1.0f + 9.5367431640625e-7f, 1e-37f); };
+  float T = inflate(tau);
+
+  // ---- this warp's share (tile index = w mod kW) of the tiles any query needs: box-to-box prefilter (a lane per tile),
+  // then the exact per-query test -------------------------------------------------------------------------------------------
+  int n_list = 0;
+  {
+    const float tmax = __uint_as_float(redux_max_u32(live ? __float_as_uint(T) : 0u));  // T >= +0
+    for (int i = 0; i * 32 * kW < nt; ++i) {
+      const int t = (lane + 32 * i) * kW + w;
+      bool maybe = false;
+      if (t < nt) {
+        const float4 bl = sbox[2 * t], bh = sbox[2 * t + 1];
+        const float gx = fmaxf(0.f, fmaxf(bl.x - ch[0], cl[0] - bh.x));
+        const float gy = fmaxf(0.f, fmaxf(bl.y - ch[1], cl[1] - bh.y));
+        const float gz = fmaxf(0.f, fmaxf(bl.z - ch[2], cl[2] - bh.z));
+        maybe = (gx * gx + gy * gy + gz * gz) * 0.99999619f <= tmax;
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, maybe);
+      while (mask) {
+        const int t2 = (32 * i + __ffs(mask) - 1) * kW + w;
+        mask &= mask - 1u;
+        const float4 bl = sbox[2 * t2], bh = sbox[2 * t2 + 1];  // warp-uniform: broadcast
+        const float gx = fmaxf(0.f, fmaxf(bl.x - qx, qx - bh.x));
+        const float gy = fmaxf(0.f, fmaxf(bl.y - qy, qy - bh.y));
+        const float gz = fmaxf(0.f, fmaxf(bl.z - qz, qz - bh.z));
+        // (1 - 2^-18): conservative against the rounding of both sides
+        if (__any_sync(0xffffffffu, live && (gx * gx + gy * gy + gz * gz) * 0.99999619f <= T)) {
+          if (lane == 0) sm.tlist[n_list] = (unsigned char)t2;
+          ++n_list;
+        }
+      }
+    }
+    __syncwarp();
   }
 
-  // ---- sweep, nearest tiles first: candidates d <= tau go to a per-lane list; a list that fills up is folded into the
-  // running top-k, whose k-th key is the exact k-th nearest of everything swept so far = the new tau ------------------------
+  // ---- sweep the listed tiles; candidates go to a per-lane list, a list that fills up is folded into the running top-k ----
   u64 tk[kK];  // ascending (distance bits, original index) keys of the best references seen so far
 #pragma unroll
   for (int j = 0; j < kK; ++j) tk[j] = ~0ull;
   int count = 0;
-  auto fold = [&]() {  // insert this lane's listed candidates into tk, empty the list, tighten tau
-    float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (count > 0) cp = __ldg(Rb + cand[0][lane]);
-    for (int c = 0; c < count; ++c) {
-      const u64 key = ((u64)__float_as_uint(sqdist(qx, qy, qz, cp.x, cp.y, cp.z)) << 32) | (unsigned)__float_as_int(cp.w);
-      if (c + 1 < count) cp = __ldg(Rb + cand[c + 1][lane]);  // the next candidate travels while this one is inserted
+  bool folded = false;  // warp-uniform: a fold has happened (lanes that hold k references have an exact kth)
+  u64 kth = ~0ull;
+  // fold: kCuBatch candidates at a time are re-evaluated exactly (their loads in flight together), sorted by a register
+  // network and merged into the sorted top-k by one bitonic split + merge: ~45 instructions per candidate where an
+  // insertion costs ~100
+  auto fold = [&]() {
+    const int n_max = redux_max_s32(count);
+    for (int c0 = 0; c0 < n_max; c0 += kCuBatch) {
+      u64 nk[kCuBatch];
 #pragma unroll
-      for (int j = kK - 1; j >= 0; --j) {
-        const bool here = key < tk[j];
-        const bool up = j > 0 && key < tk[j > 0 ? j - 1 : 0];
-        tk[j] = up ? tk[j > 0 ? j - 1 : 0] : (here ? key : tk[j]);
+      for (int j = 0; j < kCuBatch; ++j) {
+        nk[j] = ~0ull;
+        if (c0 + j < count) {
+          const float4 cp = __ldg(Rb + sm.cand[c0 + j][lane]);
+          nk[j] = ((u64)__float_as_uint(sqdist(qx, qy, qz, cp.x, cp.y, cp.z)) << 32) | (unsigned)__float_as_int(cp.w);
+        }
       }
+      bitonic_sort_u64<kCuBatch>(nk);
+#pragma unroll
+      for (int j = 0; j < kK; ++j) {  // the kK smallest of (tk ascending, nk descending): a bitonic sequence
+        const int rj = kK - 1 - j;
+        if (rj < kCuBatch) tk[j] = nk[rj] < tk[j] ? nk[rj] : tk[j];
+      }
+      bitonic_merge_u64<kK>(tk);
     }
     count = 0;
-    u64 kth = tk[0];
+    kth = tk[0];
 #pragma unroll
     for (int j = 1; j < kK; ++j)
       if (j < k) kth = tk[j];
-    if (kth != ~0ull) tau = fminf(tau, __uint_as_float((unsigned)(kth >> 32)));
+    if (kth != ~0ull) T = fminf(T, inflate(__uint_as_float((unsigned)(kth >> 32))));
   };
-  // cull: a tile farther from a query than that query's tau holds none of its neighbours.  (1 - 2^-18): conservative
-  // against the rounding of both sides.  The next tile to sweep is looked up (and its load issued) one tile ahead, with
-  // the tau of that moment - tau only shrinks, so a stale test can only sweep a tile too many.
-  int u = 0;
-  auto next_needed = [&]() {
-    for (; u < nt; ++u) {
-      const int t = (int)(order[u] & 0xffu);
-      if (__any_sync(0xffffffffu, live && box_dist(t) * 0.99999619f <= tau)) {
-        ++u;
-        return t;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n_list > 0) r = __ldg(Rb + (int)sm.tlist[0] * 32 + lane);
+  int buf = 1;
+  for (int u = 0; u < n_list; ++u) {
+    const int t = sm.tlist[u];
+    if (folded) {
+      // bounds have moved since the list was made (a query that holds k references knows its exact k-th (distance,
+      // index)): a tile is skipped when no query can still gain from it - its box is farther than the query's bound, or
+      // it is ONE point (duplicates: zero padding) that ties or loses even with its smallest index
+      const float4 bl = sbox[2 * t], bh = sbox[2 * t + 1];
+      const float gx = fmaxf(0.f, fmaxf(bl.x - qx, qx - bh.x));
+      const float gy = fmaxf(0.f, fmaxf(bl.y - qy, qy - bh.y));
+      const float gz = fmaxf(0.f, fmaxf(bl.z - qz, qz - bh.z));
+      bool need = (gx * gx + gy * gy + gz * gz) * 0.99999619f <= T;  // (T >= the k-th distance, inflated)
+      if (__float_as_int(bh.w) == 1 && kth != ~0ull)
+        need = (((u64)__float_as_uint(sqdist(qx, qy, qz, bl.x, bl.y, bl.z)) << 32) | (unsigned)__float_as_int(bl.w)) < kth;
+      if (!__any_sync(0xffffffffu, live && need)) {
+        if (u + 1 < n_list) r = __ldg(Rb + (int)sm.tlist[u + 1] * 32 + lane);
+        continue;
       }
     }
-    return -1;
-  };
-  int t_next = next_needed();
-  float4 r_next = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (t_next >= 0) r_next = __ldg(Rb + t_next * 32 + lane);
-  while (t_next >= 0) {
-    const int t = t_next;
-    __syncwarp();  // every lane is done with the previous tile
-    stage[lane] = r_next;
+    buf ^= 1;  // (flips on swept tiles only: two tiles in a row never share a buffer)
+    stage_tile(buf, r);
     __syncwarp();
-    t_next = next_needed();
-    if (t_next >= 0) r_next = __ldg(Rb + t_next * 32 + lane);
-    unsigned m = 0u;
+    if (u + 1 < n_list) r = __ldg(Rb + (int)sm.tlist[u + 1] * 32 + lane);
+    const float4* G = reinterpret_cast<const float4*>(sm.stage[buf]);
+    unsigned rej = 0u;  // bit (31 - c): reference c of the tile is farther than T
+    auto test = [&](float x, float y, float z) {
+      const float dx = __fsub_rn(x, qx), dy = __fsub_rn(y, qy), dz = __fsub_rn(z, qz);
+      const float f = __fmaf_rn(-dz, dz, __fmaf_rn(-dx, dx, __fmaf_rn(-dy, dy, T)));
+      rej = __funnelshift_l(__float_as_uint(f), rej, 1);
+    };
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const float4 p = stage[c];
-      if (sqdist(qx, qy, qz, p.x, p.y, p.z) <= tau) m |= 1u << c;
+    for (int j = 0; j < 8; ++j) {
+      const float4 A = G[3 * j], Bv = G[3 * j + 1], C = G[3 * j + 2];
+      test(A.x, A.y, A.z);
+      test(A.w, Bv.x, Bv.y);
+      test(Bv.z, Bv.w, C.x);
+      test(C.y, C.z, C.w);
     }
-    if (!live) m = 0u;
+    unsigned m = live ? ~rej : 0u;
     while (m) {
-      const int c = __ffs(m) - 1;
-      m &= m - 1u;
+      const int c = __clz(m);
+      m &= ~(0x80000000u >> c);
       const int pos = t * 32 + c;
-      if (pos >= R) continue;  // padding sentinel of the last tile
-      cand[count][lane] = (unsigned short)pos;  // count < kPrCap: a list is folded before a tile could overfill it
+      if (pos >= R) continue;  // padding sentinel of the last tile (only reachable with a non-finite bound)
+      if (kth != ~0ull) {  // exact test against the current k-th (distance, index): ties at the bound do not flood the list
+        const float* p = &sm.stage[buf][3 * c];
+        const u64 key = ((u64)__float_as_uint(sqdist(qx, qy, qz, p[0], p[1], p[2])) << 32) |
+                        (unsigned)__float_as_int(sm.stage[buf][96 + c]);
+        if (key >= kth) continue;
+      }
+      sm.cand[count][lane] = (unsigned short)pos;  // count < kCuCap: a list is folded before a tile could overfill it
       ++count;
     }
-    // fold_at <= kPrCap - 32 entries: the next tile may add 32.  Every lane folds when one has to: folds of different
-    // lanes at different tiles would serialise.
-    if (__any_sync(0xffffffffu, count >= fold_at)) fold();
+    if (__any_sync(0xffffffffu, count > kCuCap - 32)) {
+      fold();
+      folded = true;
+    }
+  }
+  fold();
+  if (kW > 1) {  // warp 0 merges the other warps' sorted lists: one bitonic split + merge each
+    if (w != 0) {
+#pragma unroll
+      for (int j = 0; j < kK; ++j) sm.keys[j][lane] = tk[j];  // (own cand[] is done with)
+    }
+    __syncthreads();
+    if (w != 0) return;
+#pragma unroll
+    for (int o = 1; o < kW; ++o) {
+#pragma unroll
+      for (int j = 0; j < kK; ++j) {
+        const u64 ok = wsm[o].keys[kK - 1 - j][lane];
+        tk[j] = ok < tk[j] ? ok : tk[j];
+      }
+      bitonic_merge_u64<kK>(tk);
+    }
   }
   if (!live) return;
-  fold();
   const size_t o = ((size_t)b * Q + qi) * k;
 #pragma unroll
   for (int j = 0; j < kK; ++j) {
@@ -933,7 +1251,7 @@ static int knn_r_splits(int B, int R, int Q) {
 struct KnnPlan {
   bool select;  // thread-per-query selection (k <= 16) vs warp-per-query list
   int splits;   // select: warps per 32 queries; list: reference slices merged by knn_merge_kernel
-  bool pruned;  // Morton-sorted, box-culled selection (k <= 16, kPrMinR <= R <= kPrMaxN, Q <= kPrMaxN)
+  bool pruned;  // Hilbert-binned, box-culled selection (k <= 16, kPrMinR <= R <= kPrMaxN, Q <= kPrMaxN)
 };
 
 static long long env_ll(const char* name, long long fallback) {
@@ -946,14 +1264,15 @@ static KnnPlan knn_plan(int B, int R, int Q, int k) {
   static const long long min_warps = env_ll("IAPT_KNN_SELECT_MIN_WARPS", 256);
   static const long long want_warps = env_ll("IAPT_KNN_SELECT_WANT_WARPS", 2048);
   static const long long force_split = env_ll("IAPT_KNN_SELECT_SPLIT", 0);
-  // Pruned path: measured against the select kernel at B = 48, k = 16 (profiles/r02p_knn_pruned.txt): 2048 x 2048
-  // 0.19 ms vs 0.18 (uniform), 0.30 vs 0.18 (zero-padded partials: the points at the origin cost folds); 4096 x 4096
-  // 0.39 vs 0.52.  So it is the default only above 2048 references.  IAPT_KNN_PRUNED = 1 forces it wherever it applies,
-  // 2 disables it (read per call: the tests run both paths over the same cases).
+  // Culled path: measured against the select kernel at B = 48, k = 16 (profiles/r02y_knn_culled.txt): 2048 x 2048 0.10 -
+  // 0.13 ms vs 0.18, 4096 x 4096 0.20 vs 0.52, 1024 x 1024 0.058 vs 0.072; with 512 queries per cloud (768 warps of
+  // queries: a quarter of the machine) the select kernel's slices win, 0.064 vs 0.085.  So it is the default from 1024
+  // warps of queries.  IAPT_KNN_PRUNED = 1 forces it wherever it applies, 2 disables it (read per call: the tests run
+  // both paths over the same cases).
   const long long pruned_mode = env_ll("IAPT_KNN_PRUNED", 0);
   const long long warps = (long long)B * ((Q + 31) / 32);
   const bool pruned_fits = k <= kSelMaxK && R >= kPrMinR && R <= kPrMaxN && Q >= 1 && Q <= kPrMaxN && B <= 65535;
-  if (!force_list && pruned_fits && pruned_mode != 2 && (pruned_mode == 1 || R > 2048)) return {false, 1, true};
+  if (!force_list && pruned_fits && pruned_mode != 2 && (pruned_mode == 1 || warps >= 1024)) return {false, 1, true};
   if (k <= kSelMaxK && R >= 64 && R <= 65536 && !force_list && warps >= min_warps) {
     int s = 1;
     while (s < 4 && warps * s < want_warps && R / (2 * s) >= 512) s *= 2;  // slices shorter than 512 do not pay
@@ -1027,17 +1346,27 @@ int knn_launch(const float* ref, const float* qry, int B, int R, int Q, int k, i
     PrTileBox* boxes = reinterpret_cast<PrTileBox*>(sref + (size_t)B * Rp);
     float4* sqry = reinterpret_cast<float4*>(boxes + (size_t)B * (Rp / 32));
     const bool self = ref == qry && R == Q;  // the self-query of DGCNN_Grouper: one sort serves both sides
-    knn_sort_kernel<<<dim3(B, self ? 1 : 2), kPrSortThreads, 0, stream>>>(ref, R, Rp, sref, boxes, qry, Q, Qp, sqry);
+    knn_bin_kernel<<<dim3(B, self ? 1 : 2), kBinThreads, 0, stream>>>(ref, R, Rp, sref, boxes, qry, Q, Qp, sqry);
     const int qb = Qp / 32;
-    int fold_at = (int)env_ll("IAPT_KNN_FOLD_AT", 32);  // development knob
-    if (fold_at > kPrCap - 32) fold_at = kPrCap - 32;
-    if (fold_at < 1) fold_at = 1;
-    if (k <= 8)
-      knn_pruned_kernel<8><<<(unsigned)((long long)B * qb), 32, 0, stream>>>(sref, boxes, self ? sref : sqry, R, Rp, Q, Qp,
-                                                                            k, qb, fold_at, idx, dist);
-    else
-      knn_pruned_kernel<16><<<(unsigned)((long long)B * qb), 32, 0, stream>>>(sref, boxes, self ? sref : sqry, R, Rp, Q, Qp,
-                                                                             k, qb, fold_at, idx, dist);
+    const int nt = Rp / 32;
+    // development knobs (read per call); defaults from profiles/r02y_knn_culled.txt: one warp per 32 queries when those
+    // fill the machine, two below that; 12 seed tiles, every second one a probe
+    int n_seeds = (int)env_ll("IAPT_KNN_SEEDS", 12);
+    int warps = (int)env_ll("IAPT_KNN_CULL_WARPS", (long long)B * qb >= 2500 ? 1 : 2);
+    const int probes = env_ll("IAPT_KNN_PROBES", 1) == 1 ? 1 : 0;  // (2 = off)
+    if (warps != 1 && warps != 4) warps = 2;
+    n_seeds = std::max(warps, std::min(n_seeds, std::min(nt, 32)));
+    const size_t dyn = (size_t)2 * nt * sizeof(float4);
+    const float4* sq = self ? sref : sqry;
+    const unsigned grid = (unsigned)((long long)B * qb);
+#define KNN_CULLED(KK, W) \
+  knn_culled_kernel<KK, W><<<grid, 32 * W, dyn, stream>>>(sref, boxes, sq, R, Rp, Q, Qp, k, qb, n_seeds, probes, idx, dist)
+    if (k <= 8) {
+      if (warps == 1) KNN_CULLED(8, 1); else if (warps == 2) KNN_CULLED(8, 2); else KNN_CULLED(8, 4);
+    } else {
+      if (warps == 1) KNN_CULLED(16, 1); else if (warps == 2) KNN_CULLED(16, 2); else KNN_CULLED(16, 4);
+    }
+#undef KNN_CULLED
     count_launch(2);
     return (int)cudaGetLastError();
   }

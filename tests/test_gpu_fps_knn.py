@@ -202,12 +202,17 @@ def test_knn_select_overflow_falls_back_exactly(dev, knn_path, B, R, Q, near):
     _knn_check(xyz, new_xyz, 7, dev)
 
 
-@pytest.fixture(params=["pruned", "select"])
+@pytest.fixture(params=["culled-1", "culled-2", "culled-4", "select"])
 def knn_path(request, monkeypatch):
-    """Shapes with 1024 <= R <= 4096 and k <= 16 can take the Morton-sorted, box-culled kernel (IAPT_KNN_PRUNED=1 forces
-    it; by default only above 2048 references) or the thread-per-query select kernel (IAPT_KNN_PRUNED=2) - the variable
-    is read per call and both must match the oracle bit for bit."""
-    monkeypatch.setenv("IAPT_KNN_PRUNED", "1" if request.param == "pruned" else "2")
+    """Shapes with 1024 <= R <= 4096 and k <= 16 can take the Hilbert-binned, box-culled kernel (IAPT_KNN_PRUNED=1 forces
+    it; by default from 1024 warps of queries; IAPT_KNN_CULL_WARPS = warps sharing one tile of 32 queries) or the
+    thread-per-query select kernel (IAPT_KNN_PRUNED=2) - the variables are read per call and every variant must match
+    the oracle bit for bit."""
+    if request.param == "select":
+        monkeypatch.setenv("IAPT_KNN_PRUNED", "2")
+    else:
+        monkeypatch.setenv("IAPT_KNN_PRUNED", "1")
+        monkeypatch.setenv("IAPT_KNN_CULL_WARPS", request.param.split("-")[1])
     return request.param
 
 
@@ -223,11 +228,22 @@ def knn_path(request, monkeypatch):
     (2, 1200, 64, 8, "same"),           # every reference identical: all distances tie
     (2, 2048, 512, 16, "fps"),          # queries = FPS centres of the cloud (the grouper's 2048 -> 512 call)
     (48, 2048, 2048, 16, "self"),       # config 3's largest call at full batch
+    (2, 4096, 4096, 16, "zeros_self"),  # 2048 duplicates in ONE cell: the bin kernel's re-ordering of a multi-tile cell
+    (2, 2048, 300, 16, "dups"),         # 12 distinct points, each ~170 times: more multi-tile cells than get re-ordered
+    (2, 2048, 2048, 16, "scaled"),      # coordinates ~3e4 +- 1e4: the prefilter's margin against FP32 rounding
+    (2, 2048, 2048, 12, "tiny"),        # coordinates ~1e-19: squared distances in the subnormal range
 ])
 def test_knn_pruned_path_matches_oracle(dev, knn_path, B, R, Q, k, kind):
     g = torch.Generator().manual_seed(1000 + R + Q + k)
     if kind in ("self", "uniform", "far", "fps"):
         xyz = torch.rand((B, R, 3), generator=g) - 0.5
+    elif kind == "scaled":
+        xyz = (torch.rand((B, R, 3), generator=g) - 0.5) * 2e4 + 3e4
+    elif kind == "tiny":
+        xyz = (torch.rand((B, R, 3), generator=g) - 0.5) * 2e-19
+    elif kind == "dups":
+        base = torch.rand((B, 12, 3), generator=g) - 0.5
+        xyz = torch.gather(base, 1, torch.randint(0, 12, (B, R, 1), generator=g).expand(-1, -1, 3)).contiguous()
     elif kind == "pcn":
         xyz = synthetic.pcn_gt(B, R, 11)
     elif kind == "zeros_self":
@@ -237,7 +253,7 @@ def test_knn_pruned_path_matches_oracle(dev, knn_path, B, R, Q, k, kind):
         xyz = synthetic.grid(B, R, 14, bits=3, dup_frac=0.2)
     else:
         xyz = torch.full((B, R, 3), 0.25)
-    if kind in ("self", "zeros_self"):
+    if kind in ("self", "zeros_self", "scaled", "tiny"):
         new_xyz = xyz
     elif kind == "far":
         new_xyz = torch.rand((B, Q, 3), generator=g) * 0.1 + 3.0
