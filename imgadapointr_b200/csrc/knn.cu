@@ -1180,12 +1180,12 @@ __global__ void __launch_bounds__(32 * kW, kW == 1 ? 21 : kW == 2 ? 11 : 6) knn_
       test(Bv.z, Bv.w, C.x);
       test(C.y, C.z, C.w);
     }
-    unsigned m = live ? ~rej : 0u;
+    unsigned m = live ? __brev(~rej) : 0u;  // bit c: reference c is a candidate
+    if (t == nt - 1 && (R & 31)) m &= (1u << (R & 31)) - 1u;  // padding sentinels (only reachable with a non-finite bound)
     while (m) {
-      const int c = __clz(m);
-      m &= ~(0x80000000u >> c);
+      const int c = __ffs(m) - 1;
+      m &= m - 1u;
       const int pos = t * 32 + c;
-      if (pos >= R) continue;  // padding sentinel of the last tile (only reachable with a non-finite bound)
       if (kth != ~0ull) {  // exact test against the current k-th (distance, index): ties at the bound do not flood the list
         const float* p = &sm.stage[buf][3 * c];
         const u64 key = ((u64)__float_as_uint(sqdist(qx, qy, qz, p[0], p[1], p[2])) << 32) |

@@ -38,7 +38,8 @@ def t(fn, it=20):
     return e0.elapsed_time(e1) / it
 
 
-def mode(pruned, seeds=None, warps=2, probes=1):
+def mode(pruned, seeds=None, warps=2, probes=1, near=12):
+    os.environ["IAPT_KNN_NEAR"] = str(near)
     os.environ["IAPT_KNN_PROBES"] = str(probes)
     os.environ["IAPT_KNN_PRUNED"] = pruned
     os.environ["IAPT_KNN_CULL_WARPS"] = str(warps)
@@ -48,7 +49,9 @@ def mode(pruned, seeds=None, warps=2, probes=1):
         os.environ["IAPT_KNN_SEEDS"] = str(seeds)
 
 
-seed_list = [int(s) for s in os.environ.get("AB_SEEDS", "12").split(",")]
+seed_list = [int(s) for s in os.environ.get("AB_SEEDS", "4").split(",")]
+near_list = [int(s) for s in os.environ.get("AB_NEAR", "12").split(",")]
+probe_list = [int(s) for s in os.environ.get("AB_PROBES", "1").split(",")]
 warp_list = [int(s) for s in os.environ.get("AB_WARPS", "1,2,4").split(",")]
 for name, r, q in cases:
     mode("2")
@@ -56,8 +59,9 @@ for name, r, q in cases:
     line = "%-32s select %.4f" % (name, t(lambda: knn_point(16, r, q)))
     for s in seed_list:
         for w in warp_list:
-            for pr in (2, 1):
-                mode("1", s, w, pr)
-                same = bool((knn_point(16, r, q) == ref_idx).all())
-                line += "  culled(s=%d,w=%d,p=%d) %.4f%s" % (s, w, pr, t(lambda: knn_point(16, r, q)), "" if same else " MISMATCH")
+            for pr in probe_list:
+                for nr in near_list:
+                    mode("1", s, w, pr, nr)
+                    same = bool((knn_point(16, r, q) == ref_idx).all())
+                    line += "  s%d/n%d/w%d/p%d %.4f%s" % (s, nr, w, pr, t(lambda: knn_point(16, r, q)), "" if same else " MISMATCH")
     print(line, flush=True)
