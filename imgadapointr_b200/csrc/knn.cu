@@ -873,61 +873,68 @@ __device__ __forceinline__ void bitonic_sort_u64(u64 (&v)[N]) {
 }
 
 constexpr int kCuBatch = 8;  // candidates folded at once
+// every warp's last claim fails and still moves its end of the deque by one: the bias keeps the tail of a short list
+// from wrapping below zero (at most kG - 1 helpers, one failed claim each)
+constexpr int kCuDequeBias = 8;
 
-// One CTA = kW warps on the SAME 32 queries: warp w takes the seed tiles and the listed tiles with index = w (mod kW),
-// keeps its own candidate list and top-k, and warp 0 merges the kW sorted lists at the end.  The per-tile work of a warp
-// of queries varies 3x with where the curve cuts the cloud; sharing a tile list between warps cuts the latency of the
-// heaviest tasks - which is what the kernel's duration is, all tasks being resident from the start.
-struct __align__(16) CuWarpSmem {
+// One CTA = kG warps = kG TASKS (consecutive tiles of 32 queries of one cloud, sharing its tile boxes).  The work of a
+// task varies 3x with where the curve cuts the cloud (17 tiles on average, 35-50 for a warp whose queries straddle a jump),
+// all tasks are resident from the start, and a warp alone on its scheduler runs at a third of the shared rate - so the
+// kernel lasts as long as its heaviest task unless the others help.  Each task's tile list is a deque in shared memory
+// (head in the low half of one word, tail in the high half, one atomicAdd per claim: the owner takes tiles from the
+// front, a helper from the back, and whoever sees head >= tail in the value the atomic returns stops).  A warp that
+// finishes its own task un-helped writes its result, then helps the task of its CTA with the most tiles left: same
+// queries (from shared memory), the bound the owner last published, a top-k of its own - which the owner merges after the
+// CTA's final barrier (one bitonic split + merge per helper).
+struct __align__(16) CuTaskSmem {
   float stage[2][128];  // a tile as raw xyz rows (96 floats) + its 32 original indices, double-buffered
   union {
     unsigned short cand[kCuCap][32];  // sweep -> fold
-    float minima[32][32];             // this warp's class minima, exchanged after the bound pass
-    u64 keys[kSelMaxK][32];           // this warp's final top-k, for warp 0
+    u64 keys[kSelMaxK][32];           // a helper's top-k for the task it helped, read by that task's owner
   };
   unsigned char tlist[kCuMaxTiles];
+  float4 qv[32];        // the task's queries (x, y, z, original index)
+  float tpub[32];       // the bounds its owner last published
+  unsigned deque;       // tlist[head, tail): (head + bias) | (tail + bias) << 16; 0 = not open yet
+  unsigned helped_by;   // bit h: warp h took tiles of this task
 };
 
-template <int kK, int kW>
-__global__ void __launch_bounds__(32 * kW, kW == 1 ? 21 : kW == 2 ? 11 : 6) knn_culled_kernel(const float4* __restrict__ sref,
-                                                                     const PrTileBox* __restrict__ boxes,
-                                                                     const float4* __restrict__ sqry, int R, int Rp, int Q,
-                                                                     int Qp, int k, int q_blocks, int n_seeds, int probes,
-                                                                     int64_t* __restrict__ idx_out,
-                                                                     float* __restrict__ dist_out
-                                                                     ) {
+template <int kK, int kG>
+__global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_culled_kernel(const float4* __restrict__ sref,
+                                                                              const PrTileBox* __restrict__ boxes,
+                                                                              const float4* __restrict__ sqry, int R, int Rp,
+                                                                              int Q, int Qp, int k, int q_blocks,
+                                                                              int n_seeds, int probes,
+                                                                              int64_t* __restrict__ idx_out,
+                                                                              float* __restrict__ dist_out) {
   extern __shared__ float4 sbox[];  // [2 * nt]: lo, hi of every tile of the cloud
-  __shared__ CuWarpSmem wsm[kW];
+  __shared__ CuTaskSmem tsm[kG];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
-  CuWarpSmem& sm = wsm[w];
-  const int b = blockIdx.x / q_blocks;
-  const int qb = blockIdx.x - b * q_blocks;
+  CuTaskSmem& sm = tsm[w];
+  const int groups = (q_blocks + kG - 1) / kG;
+  const int b = blockIdx.x / groups;
+  const int qb = (blockIdx.x - b * groups) * kG + w;
+  const bool has_task = qb < q_blocks;  // (the last CTA of a cloud may hold fewer than kG tasks: those warps only help)
   const float kInf = __int_as_float(0x7f800000);
   const float4* __restrict__ Rb = sref + (size_t)b * Rp;
   const int nt = Rp / 32;
-  const float4 qv = __ldg(sqry + (size_t)b * Qp + qb * 32 + lane);
-  const int qi = __float_as_int(qv.w);
-  const bool live = qi >= 0;
-  const float qx = qv.x, qy = qv.y, qz = qv.z;
+  float4 qv = make_float4(kPadCoord(), kPadCoord(), kPadCoord(), __int_as_float(-1));
+  if (has_task) qv = __ldg(sqry + (size_t)b * Qp + qb * 32 + lane);
   {
     const float4* __restrict__ Bg = reinterpret_cast<const float4*>(boxes + (size_t)b * nt);
-    for (int i = threadIdx.x; i < 2 * nt; i += 32 * kW) sbox[i] = __ldg(Bg + i);
+    for (int i = threadIdx.x; i < 2 * nt; i += 32 * kG) sbox[i] = __ldg(Bg + i);
   }
-  // box of the warp's queries
-  float cl[3], ch[3];
-  {
-    const float q3[3] = {qx, qy, qz};
-#pragma unroll
-    for (int e = 0; e < 3; ++e) {
-      cl[e] = ord2f(redux_min_u32(live ? f2ord(q3[e]) : 0xffffffffu));
-      ch[e] = ord2f(redux_max_u32(live ? f2ord(q3[e]) : 0u));
+  if (kG > 1) {
+    sm.qv[lane] = qv;
+    if (lane == 0) {
+      sm.deque = 0u;
+      sm.helped_by = 0u;
     }
-  }
-  if (kW > 1)
     __syncthreads();
-  else
+  } else {
     __syncwarp();
+  }
 
   auto stage_tile = [&](int buf, const float4& r) {
     sm.stage[buf][3 * lane + 0] = r.x;
@@ -935,295 +942,359 @@ __global__ void __launch_bounds__(32 * kW, kW == 1 ? 21 : kW == 2 ? 11 : 6) knn_
     sm.stage[buf][3 * lane + 2] = r.z;
     sm.stage[buf][96 + lane] = r.w;
   };
+  // prefilter threshold: d <= tau (both in float) implies T - d >= 0 in the fused evaluation of the sweep - three roundings
+  // of at most 2^-24 relative to max(d, T) each against a margin of 2^-20 (+ an absolute one for the subnormal range)
+  auto inflate = [](float v) { return __fmaf_rn(v, 1.0f + 9.5367431640625e-7f, 1e-37f); };
 
-  // ---- bound: class minima over the n_seeds tiles nearest to the warp (distance from the centre of the query box to the
-  // FARTHEST corner of the tile box: compact close tiles first).  Class = position inside the tile; different tiles hold
-  // different references, so the k-th smallest of the 32 minima bounds the k-th neighbour distance. ---------------------
-  float tau;
-  {
-    unsigned key[kCuMaxTiles / 32];
-    unsigned deg = 0u;  // bit i: this lane's i-th tile is one point 32 times (duplicates)
-    const float cx = 0.5f * (cl[0] + ch[0]), cy = 0.5f * (cl[1] + ch[1]), cz = 0.5f * (cl[2] + ch[2]);
+  // state of the task being swept (the warp's own first, then possibly one it helps)
+  float qx = qv.x, qy = qv.y, qz = qv.z;
+  int qi = __float_as_int(qv.w);
+  bool live = qi >= 0;
+  float T = kInf;
+  int n_list = 0;
+
+  if (has_task) {
+    // box of the warp's queries
+    float cl[3], ch[3];
+    {
+      const float q3[3] = {qx, qy, qz};
 #pragma unroll
-    for (int i = 0; i < kCuMaxTiles / 32; ++i) {
-      const int t = lane + 32 * i;
-      key[i] = 0xffffffffu;
-      if (t < nt) {
-        const float4 bl = sbox[2 * t], bh = sbox[2 * t + 1];
-        const float fx = fmaxf(fabsf(cx - bl.x), fabsf(cx - bh.x));
-        const float fy = fmaxf(fabsf(cy - bl.y), fabsf(cy - bh.y));
-        const float fz = fmaxf(fabsf(cz - bl.z), fabsf(cz - bh.z));
-        key[i] = (__float_as_uint(fx * fx + fy * fy + fz * fz) & 0xffffff80u) | (unsigned)t;  // >= +0: bits order like uints
-        if (__float_as_int(bh.w) == 1) deg |= 1u << i;
+      for (int e = 0; e < 3; ++e) {
+        cl[e] = ord2f(redux_min_u32(live ? f2ord(q3[e]) : 0xffffffffu));
+        ch[e] = ord2f(redux_max_u32(live ? f2ord(q3[e]) : 0u));
       }
     }
-    // Seeds alternate between the centre ranking and PROBES: the unused tile nearest to the query of one lane (0, the
-    // last live one, 16, 8, 24, ...).  A warp whose 32 consecutive queries straddle a jump of the curve (or the block of
-    // zero padding and the real points) has nothing near its centre; the probes give both ends their neighbourhood.
-    const int n_live = __popc(__ballot_sync(0xffffffffu, live));  // live lanes are a prefix
-    // a tile that is ONE point gives every class the same distance: a second one (the zero padding of a PCN partial
-    // fills dozens) would add nothing, so taking one retires them all
-    auto mark = [&](int id) {
-      bool was_deg = false;
-#pragma unroll
-      for (int i = 0; i < kCuMaxTiles / 32; ++i)
-        if (lane + 32 * i == id) {
-          key[i] = 0xffffffffu;
-          was_deg = (deg >> i) & 1u;
-        }
-      if (__any_sync(0xffffffffu, was_deg)) {
-#pragma unroll
-        for (int i = 0; i < kCuMaxTiles / 32; ++i)
-          if ((deg >> i) & 1u) key[i] = 0xffffffffu;
-      }
-    };
-    auto pick = [&](unsigned m) {  // -1: no tile left
-      const unsigned wk = redux_min_u32(m);
-      if (wk == 0xffffffffu) return -1;
-      const int id = (int)(wk & 0x7fu);
-      mark(id);
-      return id;
-    };
-    auto seed_centre = [&]() {
-      unsigned m = key[0];
-#pragma unroll
-      for (int i = 1; i < kCuMaxTiles / 32; ++i) m = min(m, key[i]);
-      return pick(m);
-    };
-    auto seed_probe = [&](int p) {
-      int L = p == 0 ? 0 : p == 1 ? 31 : (int)(__brev((unsigned)(p - 1)) >> 27);
-      L = min(L, max(n_live - 1, 0));
-      const float px = __shfl_sync(0xffffffffu, qx, L), py = __shfl_sync(0xffffffffu, qy, L),
-                  pz = __shfl_sync(0xffffffffu, qz, L);
-      unsigned m = 0xffffffffu;
+    // ---- bound: class minima over the n_seeds tiles nearest to the warp (distance from the centre of the query box to
+    // the FARTHEST corner of the tile box: compact close tiles first).  Class = position inside the tile; different tiles
+    // hold different references, so the k-th smallest of the 32 minima bounds the k-th neighbour distance. -------------------
+    float tau;
+    {
+      unsigned key[kCuMaxTiles / 32];
+      unsigned deg = 0u;  // bit i: this lane's i-th tile is one point 32 times (duplicates)
+      const float cx = 0.5f * (cl[0] + ch[0]), cy = 0.5f * (cl[1] + ch[1]), cz = 0.5f * (cl[2] + ch[2]);
 #pragma unroll
       for (int i = 0; i < kCuMaxTiles / 32; ++i) {
         const int t = lane + 32 * i;
-        if (key[i] != 0xffffffffu) {  // (unused, hence < nt)
+        key[i] = 0xffffffffu;
+        if (t < nt) {
           const float4 bl = sbox[2 * t], bh = sbox[2 * t + 1];
-          const float fx = fmaxf(fabsf(px - bl.x), fabsf(px - bh.x));
-          const float fy = fmaxf(fabsf(py - bl.y), fabsf(py - bh.y));
-          const float fz = fmaxf(fabsf(pz - bl.z), fabsf(pz - bh.z));
-          m = min(m, (__float_as_uint(fx * fx + fy * fy + fz * fz) & 0xffffff80u) | (unsigned)t);
+          const float fx = fmaxf(fabsf(cx - bl.x), fabsf(cx - bh.x));
+          const float fy = fmaxf(fabsf(cy - bl.y), fabsf(cy - bh.y));
+          const float fz = fmaxf(fabsf(cz - bl.z), fabsf(cz - bh.z));
+          key[i] = (__float_as_uint(fx * fx + fy * fy + fz * fz) & 0xffffff80u) | (unsigned)t;  // >= +0: bits order like uints
+          if (__float_as_int(bh.w) == 1) deg |= 1u << i;
         }
       }
-      return pick(m);
-    };
-    int seed_no = 0;
-    auto next_seed = [&]() {
-      const int u = seed_no++;
-      return (probes && (u & 1)) ? seed_probe(u >> 1) : seed_centre();
-    };
-    auto my_next_seed = [&]() {  // every warp walks the same sequence and keeps every kW-th tile
-      int t = -1;
+      // Seeds alternate between the centre ranking and PROBES: the unused tile nearest to the query of one lane (0, the
+      // last live one, 16, 8, 24, ...).  A warp whose 32 consecutive queries straddle a jump of the curve (or the block of
+      // zero padding and the real points) has nothing near its centre; the probes give both ends their neighbourhood.
+      const int n_live = __popc(__ballot_sync(0xffffffffu, live));  // live lanes are a prefix
+      // a tile that is ONE point gives every class the same distance: a second one (the zero padding of a PCN partial
+      // fills dozens) would add nothing, so taking one retires them all
+      auto mark = [&](int id) {
+        bool was_deg = false;
 #pragma unroll
-      for (int o = 0; o < kW; ++o) {
-        const int sd = next_seed();
-        if (o == w) t = sd;
-      }
-      return t;
-    };
-    float mn[32];
+        for (int i = 0; i < kCuMaxTiles / 32; ++i)
+          if (lane + 32 * i == id) {
+            key[i] = 0xffffffffu;
+            was_deg = (deg >> i) & 1u;
+          }
+        if (__any_sync(0xffffffffu, was_deg)) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) mn[i] = kInf;
-    const int ns = max(1, min(nt, n_seeds) / kW);  // seeds per warp
-    int t_seed = my_next_seed();
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t_seed >= 0) r = __ldg(Rb + t_seed * 32 + lane);
-    for (int u = 0; u < ns && t_seed >= 0; ++u) {
-      const int buf = u & 1;
-      stage_tile(buf, r);
-      __syncwarp();
-      t_seed = u + 1 < ns ? my_next_seed() : -1;
+          for (int i = 0; i < kCuMaxTiles / 32; ++i)
+            if ((deg >> i) & 1u) key[i] = 0xffffffffu;
+        }
+      };
+      auto pick = [&](unsigned m) {  // -1: no tile left
+        const unsigned wk = redux_min_u32(m);
+        if (wk == 0xffffffffu) return -1;
+        const int id = (int)(wk & 0x7fu);
+        mark(id);
+        return id;
+      };
+      auto seed_centre = [&]() {
+        unsigned m = key[0];
+#pragma unroll
+        for (int i = 1; i < kCuMaxTiles / 32; ++i) m = min(m, key[i]);
+        return pick(m);
+      };
+      auto seed_probe = [&](int p) {
+        int L = p == 0 ? 0 : p == 1 ? 31 : (int)(__brev((unsigned)(p - 1)) >> 27);
+        L = min(L, max(n_live - 1, 0));
+        const float px = __shfl_sync(0xffffffffu, qx, L), py = __shfl_sync(0xffffffffu, qy, L),
+                    pz = __shfl_sync(0xffffffffu, qz, L);
+        unsigned m = 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < kCuMaxTiles / 32; ++i) {
+          const int t = lane + 32 * i;
+          if (key[i] != 0xffffffffu) {  // (unused, hence < nt)
+            const float4 bl = sbox[2 * t], bh = sbox[2 * t + 1];
+            const float fx = fmaxf(fabsf(px - bl.x), fabsf(px - bh.x));
+            const float fy = fmaxf(fabsf(py - bl.y), fabsf(py - bh.y));
+            const float fz = fmaxf(fabsf(pz - bl.z), fabsf(pz - bh.z));
+            m = min(m, (__float_as_uint(fx * fx + fy * fy + fz * fz) & 0xffffff80u) | (unsigned)t);
+          }
+        }
+        return pick(m);
+      };
+      int seed_no = 0;
+      auto next_seed = [&]() {
+        const int u = seed_no++;
+        return (probes && (u & 1)) ? seed_probe(u >> 1) : seed_centre();
+      };
+      float mn[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mn[i] = kInf;
+      int t_seed = next_seed();
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
       if (t_seed >= 0) r = __ldg(Rb + t_seed * 32 + lane);
-      const float4* G = reinterpret_cast<const float4*>(sm.stage[buf]);
+      for (int u = 0; u < n_seeds && t_seed >= 0; ++u) {
+        const int buf = u & 1;
+        stage_tile(buf, r);
+        __syncwarp();
+        t_seed = u + 1 < n_seeds ? next_seed() : -1;
+        if (t_seed >= 0) r = __ldg(Rb + t_seed * 32 + lane);
+        const float4* G = reinterpret_cast<const float4*>(sm.stage[buf]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 A = G[3 * j], Bv = G[3 * j + 1], C = G[3 * j + 2];
-        mn[4 * j + 0] = fminf(mn[4 * j + 0], sqdist(qx, qy, qz, A.x, A.y, A.z));
-        mn[4 * j + 1] = fminf(mn[4 * j + 1], sqdist(qx, qy, qz, A.w, Bv.x, Bv.y));
-        mn[4 * j + 2] = fminf(mn[4 * j + 2], sqdist(qx, qy, qz, Bv.z, Bv.w, C.x));
-        mn[4 * j + 3] = fminf(mn[4 * j + 3], sqdist(qx, qy, qz, C.y, C.z, C.w));
+        for (int j = 0; j < 8; ++j) {
+          const float4 A = G[3 * j], Bv = G[3 * j + 1], C = G[3 * j + 2];
+          mn[4 * j + 0] = fminf(mn[4 * j + 0], sqdist(qx, qy, qz, A.x, A.y, A.z));
+          mn[4 * j + 1] = fminf(mn[4 * j + 1], sqdist(qx, qy, qz, A.w, Bv.x, Bv.y));
+          mn[4 * j + 2] = fminf(mn[4 * j + 2], sqdist(qx, qy, qz, Bv.z, Bv.w, C.x));
+          mn[4 * j + 3] = fminf(mn[4 * j + 3], sqdist(qx, qy, qz, C.y, C.z, C.w));
+        }
       }
+      sort32(mn);
+      tau = mn[0];
+#pragma unroll
+      for (int i = 1; i < kK; ++i)
+        if (i < k) tau = mn[i];
+      __syncwarp();  // the stage buffers are reused by the sweep
     }
-    if (kW > 1) {  // the warps' tiles hold different references: the minimum over the warps is the class minimum
-#pragma unroll
-      for (int i = 0; i < 32; ++i) sm.minima[i][lane] = mn[i];
-      __syncthreads();
-#pragma unroll
-      for (int o = 1; o < kW; ++o) {
-        const CuWarpSmem& other = wsm[(w + o) % kW];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mn[i] = fminf(mn[i], other.minima[i][lane]);
-      }
-      __syncthreads();  // minima[] aliases cand[]
-    }
-    sort32(mn);
-    tau = mn[0];
-#pragma unroll
-    for (int i = 1; i < kK; ++i)
-      if (i < k) tau = mn[i];
-    __syncwarp();  // the stage buffers are reused by the sweep
-  }
-  // prefilter threshold: d <= tau (both in float) implies T - d >= 0 in the fused evaluation below - three roundings of at
-  // most 2^-24 relative to max(d, T) each against a margin of 2^-20 (+ an absolute one for the subnormal range)
-  auto inflate = [](float v) { return __fmaf_rn(v, 1.0f + 9.5367431640625e-7f, 1e-37f); };
-  float T = inflate(tau);
+    T = inflate(tau);
 
-  // ---- this warp's share (tile index = w mod kW) of the tiles any query needs: box-to-box prefilter (a lane per tile),
-  // then the exact per-query test -------------------------------------------------------------------------------------------
-  int n_list = 0;
-  {
-    const float tmax = __uint_as_float(redux_max_u32(live ? __float_as_uint(T) : 0u));  // T >= +0
-    for (int i = 0; i * 32 * kW < nt; ++i) {
-      const int t = (lane + 32 * i) * kW + w;
-      bool maybe = false;
-      if (t < nt) {
-        const float4 bl = sbox[2 * t], bh = sbox[2 * t + 1];
-        const float gx = fmaxf(0.f, fmaxf(bl.x - ch[0], cl[0] - bh.x));
-        const float gy = fmaxf(0.f, fmaxf(bl.y - ch[1], cl[1] - bh.y));
-        const float gz = fmaxf(0.f, fmaxf(bl.z - ch[2], cl[2] - bh.z));
-        maybe = (gx * gx + gy * gy + gz * gz) * 0.99999619f <= tmax;
+    // ---- the tiles any query of the warp needs: box-to-box prefilter (a lane per tile), then the exact per-query test ----
+    {
+      const float tmax = __uint_as_float(redux_max_u32(live ? __float_as_uint(T) : 0u));  // T >= +0
+      for (int i = 0; i < (nt + 31) / 32; ++i) {
+        const int t = lane + 32 * i;
+        bool maybe = false;
+        if (t < nt) {
+          const float4 bl = sbox[2 * t], bh = sbox[2 * t + 1];
+          const float gx = fmaxf(0.f, fmaxf(bl.x - ch[0], cl[0] - bh.x));
+          const float gy = fmaxf(0.f, fmaxf(bl.y - ch[1], cl[1] - bh.y));
+          const float gz = fmaxf(0.f, fmaxf(bl.z - ch[2], cl[2] - bh.z));
+          maybe = (gx * gx + gy * gy + gz * gz) * 0.99999619f <= tmax;
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, maybe);
+        while (mask) {
+          const int t2 = 32 * i + __ffs(mask) - 1;
+          mask &= mask - 1u;
+          const float4 bl = sbox[2 * t2], bh = sbox[2 * t2 + 1];  // warp-uniform: broadcast
+          const float gx = fmaxf(0.f, fmaxf(bl.x - qx, qx - bh.x));
+          const float gy = fmaxf(0.f, fmaxf(bl.y - qy, qy - bh.y));
+          const float gz = fmaxf(0.f, fmaxf(bl.z - qz, qz - bh.z));
+          // (1 - 2^-18): conservative against the rounding of both sides
+          if (__any_sync(0xffffffffu, live && (gx * gx + gy * gy + gz * gz) * 0.99999619f <= T)) {
+            if (lane == 0) sm.tlist[n_list] = (unsigned char)t2;
+            ++n_list;
+          }
+        }
       }
-      unsigned mask = __ballot_sync(0xffffffffu, maybe);
-      while (mask) {
-        const int t2 = (32 * i + __ffs(mask) - 1) * kW + w;
-        mask &= mask - 1u;
-        const float4 bl = sbox[2 * t2], bh = sbox[2 * t2 + 1];  // warp-uniform: broadcast
+    }
+    if (kG > 1) {  // publish the bounds and open the deque (after the list: release order for the helpers)
+      sm.tpub[lane] = T;
+      __syncwarp();
+      __threadfence_block();
+      if (lane == 0) atomicExch(&sm.deque, (unsigned)(n_list + kCuDequeBias) << 16 | (unsigned)kCuDequeBias);
+    }
+    __syncwarp();
+  }
+
+  // ---- sweep: role 0 = the warp's own task (tiles from the front of its deque), role 1 = the task it helps (from the back)
+  u64 tk[kK];  // ascending (distance bits, original index) keys of the best references seen so far
+  int victim = -1;
+  for (int role = 0; role < (kG > 1 ? 2 : 1); ++role) {
+    CuTaskSmem* task = &sm;  // whose tile list
+    if (role == 0) {
+      if (!has_task) continue;
+    } else {
+      // the task of this CTA with the most tiles left (at least 2); announce the help BEFORE the first claim
+      int best = 1;
+#pragma unroll
+      for (int o = 1; o < kG; ++o) {
+        const int v = (w + o) % kG;
+        const unsigned dq = *reinterpret_cast<volatile unsigned*>(&tsm[v].deque);
+        const int left = (int)(dq >> 16) - (int)(dq & 0xffffu);
+        if (left > best) {
+          best = left;
+          victim = v;
+        }
+      }
+      if (victim < 0) break;
+      task = &tsm[victim];
+      if (lane == 0) atomicOr(&task->helped_by, 1u << w);
+      __threadfence_block();
+      __syncwarp();
+      const float4 vq = task->qv[lane];
+      qx = vq.x, qy = vq.y, qz = vq.z;
+      qi = __float_as_int(vq.w);
+      live = qi >= 0;
+      T = *reinterpret_cast<volatile float*>(&task->tpub[lane]);  // (the owner may have tightened it since: any is valid)
+    }
+#pragma unroll
+    for (int j = 0; j < kK; ++j) tk[j] = ~0ull;
+    int count = 0;
+    bool folded = false;  // warp-uniform: a fold has happened (lanes that hold k references have an exact kth)
+    u64 kth = ~0ull;
+    // fold: kCuBatch candidates at a time are re-evaluated exactly (their loads in flight together), sorted by a register
+    // network and merged into the sorted top-k by one bitonic split + merge: ~45 instructions per candidate where an
+    // insertion costs ~100
+    auto fold = [&]() {
+      const int n_max = redux_max_s32(count);
+      for (int c0 = 0; c0 < n_max; c0 += kCuBatch) {
+        u64 nk[kCuBatch];
+#pragma unroll
+        for (int j = 0; j < kCuBatch; ++j) {
+          nk[j] = ~0ull;
+          if (c0 + j < count) {
+            const float4 cp = __ldg(Rb + sm.cand[c0 + j][lane]);
+            nk[j] = ((u64)__float_as_uint(sqdist(qx, qy, qz, cp.x, cp.y, cp.z)) << 32) | (unsigned)__float_as_int(cp.w);
+          }
+        }
+        bitonic_sort_u64<kCuBatch>(nk);
+#pragma unroll
+        for (int j = 0; j < kK; ++j) {  // the kK smallest of (tk ascending, nk descending): a bitonic sequence
+          const int rj = kK - 1 - j;
+          if (rj < kCuBatch) tk[j] = nk[rj] < tk[j] ? nk[rj] : tk[j];
+        }
+        bitonic_merge_u64<kK>(tk);
+      }
+      count = 0;
+      kth = tk[0];
+#pragma unroll
+      for (int j = 1; j < kK; ++j)
+        if (j < k) kth = tk[j];
+      if (kth != ~0ull) T = fminf(T, inflate(__uint_as_float((unsigned)(kth >> 32))));
+      if (kG > 1 && role == 0) sm.tpub[lane] = T;  // (helpers read it once, when they start)
+    };
+    // next tile of the task: the owner claims from the front, a helper from the back; -1 = the deque is empty
+    int next_own = 0;
+    auto claim = [&]() {
+      if (kG == 1) return next_own < n_list ? (int)sm.tlist[next_own++] : -1;  // (no deque)
+      unsigned old = 0u;
+      if (lane == 0) old = role == 0 ? atomicAdd(&task->deque, 1u) : atomicSub(&task->deque, 1u << 16);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      const int head = (int)(old & 0xffffu) - kCuDequeBias, tail = (int)(old >> 16) - kCuDequeBias;
+      if (head >= tail) return -1;
+      return (int)task->tlist[role == 0 ? head : tail - 1];
+    };
+    int buf = 1;
+    int t = claim();
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0) r = __ldg(Rb + t * 32 + lane);
+    while (t >= 0) {
+      const int t_next = claim();  // (claimed one tile ahead: its load travels during this tile's sweep)
+      const float4 rc = r;
+      if (t_next >= 0) r = __ldg(Rb + t_next * 32 + lane);
+      bool skip = false;
+      if (folded) {
+        // bounds have moved since the list was made (a query that holds k references knows its exact k-th (distance,
+        // index)): a tile is skipped when no query can still gain from it - its box is farther than the query's bound, or
+        // it is ONE point (duplicates: zero padding) that ties or loses even with its smallest index
+        const float4 bl = sbox[2 * t], bh = sbox[2 * t + 1];
         const float gx = fmaxf(0.f, fmaxf(bl.x - qx, qx - bh.x));
         const float gy = fmaxf(0.f, fmaxf(bl.y - qy, qy - bh.y));
         const float gz = fmaxf(0.f, fmaxf(bl.z - qz, qz - bh.z));
-        // (1 - 2^-18): conservative against the rounding of both sides
-        if (__any_sync(0xffffffffu, live && (gx * gx + gy * gy + gz * gz) * 0.99999619f <= T)) {
-          if (lane == 0) sm.tlist[n_list] = (unsigned char)t2;
-          ++n_list;
+        bool need = (gx * gx + gy * gy + gz * gz) * 0.99999619f <= T;  // (T >= the k-th distance, inflated)
+        if (__float_as_int(bh.w) == 1 && kth != ~0ull)
+          need = (((u64)__float_as_uint(sqdist(qx, qy, qz, bl.x, bl.y, bl.z)) << 32) | (unsigned)__float_as_int(bl.w)) < kth;
+        skip = !__any_sync(0xffffffffu, live && need);
+      }
+      if (!skip) {
+        buf ^= 1;  // (flips on swept tiles only: two tiles in a row never share a buffer)
+        stage_tile(buf, rc);
+        __syncwarp();
+        const float4* G = reinterpret_cast<const float4*>(sm.stage[buf]);
+        unsigned rej = 0u;  // bit (31 - c): reference c of the tile is farther than T
+        auto test = [&](float x, float y, float z) {
+          const float dx = __fsub_rn(x, qx), dy = __fsub_rn(y, qy), dz = __fsub_rn(z, qz);
+          const float f = __fmaf_rn(-dz, dz, __fmaf_rn(-dx, dx, __fmaf_rn(-dy, dy, T)));
+          rej = __funnelshift_l(__float_as_uint(f), rej, 1);
+        };
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 A = G[3 * j], Bv = G[3 * j + 1], C = G[3 * j + 2];
+          test(A.x, A.y, A.z);
+          test(A.w, Bv.x, Bv.y);
+          test(Bv.z, Bv.w, C.x);
+          test(C.y, C.z, C.w);
+        }
+        unsigned m = live ? __brev(~rej) : 0u;  // bit c: reference c is a candidate
+        if (t == nt - 1 && (R & 31)) m &= (1u << (R & 31)) - 1u;  // padding sentinels (only reachable with a non-finite bound)
+        while (m) {
+          const int c = __ffs(m) - 1;
+          m &= m - 1u;
+          if (kth != ~0ull) {  // exact test against the current k-th (distance, index): ties at the bound do not flood the list
+            const float* p = &sm.stage[buf][3 * c];
+            const u64 ck = ((u64)__float_as_uint(sqdist(qx, qy, qz, p[0], p[1], p[2])) << 32) |
+                           (unsigned)__float_as_int(sm.stage[buf][96 + c]);
+            if (ck >= kth) continue;
+          }
+          sm.cand[count][lane] = (unsigned short)(t * 32 + c);  // count < kCuCap: a list is folded before a tile could overfill it
+          ++count;
         }
       }
-    }
-    __syncwarp();
-  }
-
-  // ---- sweep the listed tiles; candidates go to a per-lane list, a list that fills up is folded into the running top-k ----
-  u64 tk[kK];  // ascending (distance bits, original index) keys of the best references seen so far
-#pragma unroll
-  for (int j = 0; j < kK; ++j) tk[j] = ~0ull;
-  int count = 0;
-  bool folded = false;  // warp-uniform: a fold has happened (lanes that hold k references have an exact kth)
-  u64 kth = ~0ull;
-  // fold: kCuBatch candidates at a time are re-evaluated exactly (their loads in flight together), sorted by a register
-  // network and merged into the sorted top-k by one bitonic split + merge: ~45 instructions per candidate where an
-  // insertion costs ~100
-  auto fold = [&]() {
-    const int n_max = redux_max_s32(count);
-    for (int c0 = 0; c0 < n_max; c0 += kCuBatch) {
-      u64 nk[kCuBatch];
-#pragma unroll
-      for (int j = 0; j < kCuBatch; ++j) {
-        nk[j] = ~0ull;
-        if (c0 + j < count) {
-          const float4 cp = __ldg(Rb + sm.cand[c0 + j][lane]);
-          nk[j] = ((u64)__float_as_uint(sqdist(qx, qy, qz, cp.x, cp.y, cp.z)) << 32) | (unsigned)__float_as_int(cp.w);
-        }
+      // the one fold site: a list with fewer than 32 free slots, and the end of the task
+      if (t_next < 0 || __any_sync(0xffffffffu, count > kCuCap - 32)) {
+        fold();
+        folded = true;
       }
-      bitonic_sort_u64<kCuBatch>(nk);
+      t = t_next;
+    }
+    if (role == 1) {  // leave the top-k for the owner (own cand[] is done with)
 #pragma unroll
-      for (int j = 0; j < kK; ++j) {  // the kK smallest of (tk ascending, nk descending): a bitonic sequence
-        const int rj = kK - 1 - j;
-        if (rj < kCuBatch) tk[j] = nk[rj] < tk[j] ? nk[rj] : tk[j];
-      }
-      bitonic_merge_u64<kK>(tk);
+      for (int j = 0; j < kK; ++j) sm.keys[j][lane] = tk[j];
+      break;
     }
-    count = 0;
-    kth = tk[0];
-#pragma unroll
-    for (int j = 1; j < kK; ++j)
-      if (j < k) kth = tk[j];
-    if (kth != ~0ull) T = fminf(T, inflate(__uint_as_float((unsigned)(kth >> 32))));
-  };
-  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (n_list > 0) r = __ldg(Rb + (int)sm.tlist[0] * 32 + lane);
-  int buf = 1;
-  for (int u = 0; u < n_list; ++u) {
-    const int t = sm.tlist[u];
-    if (folded) {
-      // bounds have moved since the list was made (a query that holds k references knows its exact k-th (distance,
-      // index)): a tile is skipped when no query can still gain from it - its box is farther than the query's bound, or
-      // it is ONE point (duplicates: zero padding) that ties or loses even with its smallest index
-      const float4 bl = sbox[2 * t], bh = sbox[2 * t + 1];
-      const float gx = fmaxf(0.f, fmaxf(bl.x - qx, qx - bh.x));
-      const float gy = fmaxf(0.f, fmaxf(bl.y - qy, qy - bh.y));
-      const float gz = fmaxf(0.f, fmaxf(bl.z - qz, qz - bh.z));
-      bool need = (gx * gx + gy * gy + gz * gz) * 0.99999619f <= T;  // (T >= the k-th distance, inflated)
-      if (__float_as_int(bh.w) == 1 && kth != ~0ull)
-        need = (((u64)__float_as_uint(sqdist(qx, qy, qz, bl.x, bl.y, bl.z)) << 32) | (unsigned)__float_as_int(bl.w)) < kth;
-      if (!__any_sync(0xffffffffu, live && need)) {
-        if (u + 1 < n_list) r = __ldg(Rb + (int)sm.tlist[u + 1] * 32 + lane);
-        continue;
-      }
+    // own task swept.  Nobody can take a tile any more; whoever did has set its bit before its first claim.
+    if (kG > 1) {
+      __threadfence_block();
+      const unsigned helped = *reinterpret_cast<volatile unsigned*>(&sm.helped_by);
+      if (helped != 0u) break;  // the helpers' lists are merged after the barrier
     }
-    buf ^= 1;  // (flips on swept tiles only: two tiles in a row never share a buffer)
-    stage_tile(buf, r);
-    __syncwarp();
-    if (u + 1 < n_list) r = __ldg(Rb + (int)sm.tlist[u + 1] * 32 + lane);
-    const float4* G = reinterpret_cast<const float4*>(sm.stage[buf]);
-    unsigned rej = 0u;  // bit (31 - c): reference c of the tile is farther than T
-    auto test = [&](float x, float y, float z) {
-      const float dx = __fsub_rn(x, qx), dy = __fsub_rn(y, qy), dz = __fsub_rn(z, qz);
-      const float f = __fmaf_rn(-dz, dz, __fmaf_rn(-dx, dx, __fmaf_rn(-dy, dy, T)));
-      rej = __funnelshift_l(__float_as_uint(f), rej, 1);
-    };
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 A = G[3 * j], Bv = G[3 * j + 1], C = G[3 * j + 2];
-      test(A.x, A.y, A.z);
-      test(A.w, Bv.x, Bv.y);
-      test(Bv.z, Bv.w, C.x);
-      test(C.y, C.z, C.w);
-    }
-    unsigned m = live ? __brev(~rej) : 0u;  // bit c: reference c is a candidate
-    if (t == nt - 1 && (R & 31)) m &= (1u << (R & 31)) - 1u;  // padding sentinels (only reachable with a non-finite bound)
-    while (m) {
-      const int c = __ffs(m) - 1;
-      m &= m - 1u;
-      const int pos = t * 32 + c;
-      if (kth != ~0ull) {  // exact test against the current k-th (distance, index): ties at the bound do not flood the list
-        const float* p = &sm.stage[buf][3 * c];
-        const u64 key = ((u64)__float_as_uint(sqdist(qx, qy, qz, p[0], p[1], p[2])) << 32) |
-                        (unsigned)__float_as_int(sm.stage[buf][96 + c]);
-        if (key >= kth) continue;
-      }
-      sm.cand[count][lane] = (unsigned short)pos;  // count < kCuCap: a list is folded before a tile could overfill it
-      ++count;
-    }
-    if (__any_sync(0xffffffffu, count > kCuCap - 32)) {
-      fold();
-      folded = true;
-    }
-  }
-  fold();
-  if (kW > 1) {  // warp 0 merges the other warps' sorted lists: one bitonic split + merge each
-    if (w != 0) {
-#pragma unroll
-      for (int j = 0; j < kK; ++j) sm.keys[j][lane] = tk[j];  // (own cand[] is done with)
-    }
-    __syncthreads();
-    if (w != 0) return;
-#pragma unroll
-    for (int o = 1; o < kW; ++o) {
+    if (live) {
+      const size_t o = ((size_t)b * Q + qi) * k;
 #pragma unroll
       for (int j = 0; j < kK; ++j) {
-        const u64 ok = wsm[o].keys[kK - 1 - j][lane];
-        tk[j] = ok < tk[j] ? ok : tk[j];
+        if (j < k) {
+          // fewer than k entries only if distances were NaN (outside the contract): index 0 keeps consumers in range
+          idx_out[o + j] = tk[j] == ~0ull ? 0 : (int64_t)(unsigned)tk[j];
+          if (dist_out) dist_out[o + j] = tk[j] == ~0ull ? kInf : __uint_as_float((unsigned)(tk[j] >> 32));
+        }
       }
-      bitonic_merge_u64<kK>(tk);
     }
   }
-  if (!live) return;
-  const size_t o = ((size_t)b * Q + qi) * k;
+  if (kG == 1) return;
+  __syncthreads();
+  const unsigned helped = has_task ? sm.helped_by : 0u;
+  if (helped == 0u) return;
+  // (tk still holds the own task's top-k: a helped owner left the loop before anything overwrote it)
+  for (int h = 0; h < kG; ++h) {
+    if (!((helped >> h) & 1u)) continue;
+#pragma unroll
+    for (int j = 0; j < kK; ++j) {
+      const u64 ok = tsm[h].keys[kK - 1 - j][lane];
+      tk[j] = ok < tk[j] ? ok : tk[j];
+    }
+    bitonic_merge_u64<kK>(tk);
+  }
+  const int own_qi = __float_as_int(qv.w);
+  if (own_qi < 0) return;
+  const size_t o = ((size_t)b * Q + own_qi) * k;
 #pragma unroll
   for (int j = 0; j < kK; ++j) {
     if (j < k) {
-      // fewer than k entries only if distances were NaN (outside the contract): index 0 keeps consumers in range
       idx_out[o + j] = tk[j] == ~0ull ? 0 : (int64_t)(unsigned)tk[j];
       if (dist_out) dist_out[o + j] = tk[j] == ~0ull ? kInf : __uint_as_float((unsigned)(tk[j] >> 32));
     }
@@ -1349,22 +1420,21 @@ int knn_launch(const float* ref, const float* qry, int B, int R, int Q, int k, i
     knn_bin_kernel<<<dim3(B, self ? 1 : 2), kBinThreads, 0, stream>>>(ref, R, Rp, sref, boxes, qry, Q, Qp, sqry);
     const int qb = Qp / 32;
     const int nt = Rp / 32;
-    // development knobs (read per call); defaults from profiles/r02y_knn_culled.txt: one warp per 32 queries when those
-    // fill the machine, two below that; 12 seed tiles, every second one a probe
+    // development knobs (read per call): 12 seed tiles, every second one a probe; 4 tasks per CTA helping each other
     int n_seeds = (int)env_ll("IAPT_KNN_SEEDS", 12);
-    int warps = (int)env_ll("IAPT_KNN_CULL_WARPS", (long long)B * qb >= 2500 ? 1 : 2);
+    int group = (int)env_ll("IAPT_KNN_CULL_GROUP", 4);
+    if (group != 1 && group != 2) group = 4;
     const int probes = env_ll("IAPT_KNN_PROBES", 1) == 1 ? 1 : 0;  // (2 = off)
-    if (warps != 1 && warps != 4) warps = 2;
-    n_seeds = std::max(warps, std::min(n_seeds, std::min(nt, 32)));
+    n_seeds = std::max(1, std::min(n_seeds, std::min(nt, 32)));
     const size_t dyn = (size_t)2 * nt * sizeof(float4);
     const float4* sq = self ? sref : sqry;
-    const unsigned grid = (unsigned)((long long)B * qb);
-#define KNN_CULLED(KK, W) \
-  knn_culled_kernel<KK, W><<<grid, 32 * W, dyn, stream>>>(sref, boxes, sq, R, Rp, Q, Qp, k, qb, n_seeds, probes, idx, dist)
+    const unsigned grid = (unsigned)((long long)B * ((qb + group - 1) / group));
+#define KNN_CULLED(KK, G) \
+  knn_culled_kernel<KK, G><<<grid, 32 * G, dyn, stream>>>(sref, boxes, sq, R, Rp, Q, Qp, k, qb, n_seeds, probes, idx, dist)
     if (k <= 8) {
-      if (warps == 1) KNN_CULLED(8, 1); else if (warps == 2) KNN_CULLED(8, 2); else KNN_CULLED(8, 4);
+      if (group == 1) KNN_CULLED(8, 1); else if (group == 2) KNN_CULLED(8, 2); else KNN_CULLED(8, 4);
     } else {
-      if (warps == 1) KNN_CULLED(16, 1); else if (warps == 2) KNN_CULLED(16, 2); else KNN_CULLED(16, 4);
+      if (group == 1) KNN_CULLED(16, 1); else if (group == 2) KNN_CULLED(16, 2); else KNN_CULLED(16, 4);
     }
 #undef KNN_CULLED
     count_launch(2);

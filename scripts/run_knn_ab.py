@@ -1,5 +1,5 @@
 """A/B timing of the kNN paths at B=48, k=16 (CUDA events): the select kernel against the Hilbert-binned culled kernel over
-its knobs (IAPT_KNN_SEEDS, IAPT_KNN_CULL_WARPS, IAPT_KNN_PROBES - read per call, so one process measures all of them);
+its knobs (IAPT_KNN_SEEDS, IAPT_KNN_CULL_GROUP, IAPT_KNN_PROBES - read per call, so one process measures all of them);
 every variant is also compared with the select kernel's indices."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -42,7 +42,7 @@ def mode(pruned, seeds=None, warps=2, probes=1, near=12):
     os.environ["IAPT_KNN_NEAR"] = str(near)
     os.environ["IAPT_KNN_PROBES"] = str(probes)
     os.environ["IAPT_KNN_PRUNED"] = pruned
-    os.environ["IAPT_KNN_CULL_WARPS"] = str(warps)
+    os.environ["IAPT_KNN_CULL_GROUP"] = str(warps)
     if seeds is None:
         os.environ.pop("IAPT_KNN_SEEDS", None)
     else:
@@ -52,7 +52,7 @@ def mode(pruned, seeds=None, warps=2, probes=1, near=12):
 seed_list = [int(s) for s in os.environ.get("AB_SEEDS", "4").split(",")]
 near_list = [int(s) for s in os.environ.get("AB_NEAR", "12").split(",")]
 probe_list = [int(s) for s in os.environ.get("AB_PROBES", "1").split(",")]
-warp_list = [int(s) for s in os.environ.get("AB_WARPS", "1,2,4").split(",")]
+warp_list = [int(s) for s in os.environ.get("AB_GROUP", "1,4").split(",")]
 for name, r, q in cases:
     mode("2")
     ref_idx = knn_point(16, r, q)
@@ -63,5 +63,5 @@ for name, r, q in cases:
                 for nr in near_list:
                     mode("1", s, w, pr, nr)
                     same = bool((knn_point(16, r, q) == ref_idx).all())
-                    line += "  s%d/n%d/w%d/p%d %.4f%s" % (s, nr, w, pr, t(lambda: knn_point(16, r, q)), "" if same else " MISMATCH")
+                    line += "  s%d/n%d/g%d/p%d %.4f%s" % (s, nr, w, pr, t(lambda: knn_point(16, r, q)), "" if same else " MISMATCH")
     print(line, flush=True)
