@@ -281,6 +281,22 @@ def test_knn_pruned_path_matches_oracle(dev, knn_path, B, R, Q, k, kind):
         _knn_check(xyz, new_xyz, k, dev)
 
 
+@pytest.mark.timeout(120)
+def test_knn_nan_inf_inputs_neither_hang_nor_leave_the_index_range(dev, knn_path):
+    """NaN / Inf coordinates are outside the contract (the reference's topk gives arbitrary neighbours for them), but
+    every path must finish and return indices a consumer can gather with."""
+    g = torch.Generator().manual_seed(77)
+    xyz = torch.rand((3, 2048, 3), generator=g) - 0.5
+    xyz[0, 5] = float("nan")
+    xyz[1, 7, 0] = float("inf")
+    xyz[1, 100:140] = float("nan")
+    xyz[2] = float("nan")
+    a = xyz.to(dev)
+    idx = knn_point(16, a, a)
+    torch.cuda.synchronize()
+    assert int(idx.min()) >= 0 and int(idx.max()) < 2048
+
+
 def test_knn_zero_padded_and_grid_ties(dev, knn_path):
     gt = synthetic.pcn_gt(2, 4096, 303)
     xyz = synthetic.pcn_partial(gt, 2048, 305)
