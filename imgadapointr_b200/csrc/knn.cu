@@ -887,7 +887,7 @@ constexpr int kCuDequeBias = 8;
 // queries (from shared memory), the bound the owner last published, a top-k of its own - which the owner merges after the
 // CTA's final barrier (one bitonic split + merge per helper).
 struct __align__(16) CuTaskSmem {
-  float stage[2][128];  // a tile as raw xyz rows (96 floats) + its 32 original indices, double-buffered
+  float4 stage[2][32];  // a tile of 32 references (x, y, z, original index), double-buffered: cp.async lands here
   union {
     unsigned short cand[kCuCap][32];  // sweep -> fold
     u64 keys[kSelMaxK][32];           // a helper's top-k for the task it helped, read by that task's owner
@@ -936,11 +936,17 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
     __syncwarp();
   }
 
-  auto stage_tile = [&](int buf, const float4& r) {
-    sm.stage[buf][3 * lane + 0] = r.x;
-    sm.stage[buf][3 * lane + 1] = r.y;
-    sm.stage[buf][3 * lane + 2] = r.z;
-    sm.stage[buf][96 + lane] = r.w;
+  // A tile travels from L2 to shared memory by cp.async (LDGSTS), 16 bytes per lane, issued one tile ahead: no register
+  // holds it during the sweep of the tile before (a register prefetch was spilled there, and the spill store waited for
+  // the load - ncu: the exposed L2 latency of every tile).
+  auto fetch_tile = [&](int buf, int t) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.stage[buf][lane]);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n cp.async.commit_group;" ::"r"(dst), "l"(Rb + t * 32 + lane)
+                 : "memory");
+  };
+  auto tile_landed = [&]() {  // every lane's part of the newest tile is in shared memory; every lane is done with the older one
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
   };
   // prefilter threshold: d <= tau (both in float) implies T - d >= 0 in the fused evaluation of the sweep - three roundings
   // of at most 2^-24 relative to max(d, T) each against a margin of 2^-20 (+ an absolute one for the subnormal range)
@@ -1046,22 +1052,16 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
 #pragma unroll
       for (int i = 0; i < 32; ++i) mn[i] = kInf;
       int t_seed = next_seed();
-      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t_seed >= 0) r = __ldg(Rb + t_seed * 32 + lane);
+      if (t_seed >= 0) fetch_tile(0, t_seed);
       for (int u = 0; u < n_seeds && t_seed >= 0; ++u) {
         const int buf = u & 1;
-        stage_tile(buf, r);
-        __syncwarp();
+        tile_landed();
         t_seed = u + 1 < n_seeds ? next_seed() : -1;
-        if (t_seed >= 0) r = __ldg(Rb + t_seed * 32 + lane);
-        const float4* G = reinterpret_cast<const float4*>(sm.stage[buf]);
+        if (t_seed >= 0) fetch_tile(buf ^ 1, t_seed);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 A = G[3 * j], Bv = G[3 * j + 1], C = G[3 * j + 2];
-          mn[4 * j + 0] = fminf(mn[4 * j + 0], sqdist(qx, qy, qz, A.x, A.y, A.z));
-          mn[4 * j + 1] = fminf(mn[4 * j + 1], sqdist(qx, qy, qz, A.w, Bv.x, Bv.y));
-          mn[4 * j + 2] = fminf(mn[4 * j + 2], sqdist(qx, qy, qz, Bv.z, Bv.w, C.x));
-          mn[4 * j + 3] = fminf(mn[4 * j + 3], sqdist(qx, qy, qz, C.y, C.z, C.w));
+        for (int c = 0; c < 32; ++c) {
+          const float4 p = sm.stage[buf][c];
+          mn[c] = fminf(mn[c], sqdist(qx, qy, qz, p.x, p.y, p.z));
         }
       }
       sort32(mn);
@@ -1189,14 +1189,13 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
       if (head >= tail) return -1;
       return (int)task->tlist[role == 0 ? head : tail - 1];
     };
-    int buf = 1;
+    int buf = 0;
     int t = claim();
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t >= 0) r = __ldg(Rb + t * 32 + lane);
+    if (t >= 0) fetch_tile(0, t);
     while (t >= 0) {
-      const int t_next = claim();  // (claimed one tile ahead: its load travels during this tile's sweep)
-      const float4 rc = r;
-      if (t_next >= 0) r = __ldg(Rb + t_next * 32 + lane);
+      const int t_next = claim();  // (claimed one tile ahead: its copy travels during this tile's sweep)
+      tile_landed();
+      if (t_next >= 0) fetch_tile(buf ^ 1, t_next);
       bool skip = false;
       if (folded) {
         // bounds have moved since the list was made (a query that holds k references knows its exact k-th (distance,
@@ -1212,23 +1211,13 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
         skip = !__any_sync(0xffffffffu, live && need);
       }
       if (!skip) {
-        buf ^= 1;  // (flips on swept tiles only: two tiles in a row never share a buffer)
-        stage_tile(buf, rc);
-        __syncwarp();
-        const float4* G = reinterpret_cast<const float4*>(sm.stage[buf]);
         unsigned rej = 0u;  // bit (31 - c): reference c of the tile is farther than T
-        auto test = [&](float x, float y, float z) {
-          const float dx = __fsub_rn(x, qx), dy = __fsub_rn(y, qy), dz = __fsub_rn(z, qz);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float4 p = sm.stage[buf][c];
+          const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy), dz = __fsub_rn(p.z, qz);
           const float f = __fmaf_rn(-dz, dz, __fmaf_rn(-dx, dx, __fmaf_rn(-dy, dy, T)));
           rej = __funnelshift_l(__float_as_uint(f), rej, 1);
-        };
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 A = G[3 * j], Bv = G[3 * j + 1], C = G[3 * j + 2];
-          test(A.x, A.y, A.z);
-          test(A.w, Bv.x, Bv.y);
-          test(Bv.z, Bv.w, C.x);
-          test(C.y, C.z, C.w);
         }
         unsigned m = live ? __brev(~rej) : 0u;  // bit c: reference c is a candidate
         if (t == nt - 1 && (R & 31)) m &= (1u << (R & 31)) - 1u;  // padding sentinels (only reachable with a non-finite bound)
@@ -1236,9 +1225,8 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
           const int c = __ffs(m) - 1;
           m &= m - 1u;
           if (kth != ~0ull) {  // exact test against the current k-th (distance, index): ties at the bound do not flood the list
-            const float* p = &sm.stage[buf][3 * c];
-            const u64 ck = ((u64)__float_as_uint(sqdist(qx, qy, qz, p[0], p[1], p[2])) << 32) |
-                           (unsigned)__float_as_int(sm.stage[buf][96 + c]);
+            const float4 p = sm.stage[buf][c];
+            const u64 ck = ((u64)__float_as_uint(sqdist(qx, qy, qz, p.x, p.y, p.z)) << 32) | (unsigned)__float_as_int(p.w);
             if (ck >= kth) continue;
           }
           sm.cand[count][lane] = (unsigned short)(t * 32 + c);  // count < kCuCap: a list is folded before a tile could overfill it
@@ -1251,6 +1239,7 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
         folded = true;
       }
       t = t_next;
+      buf ^= 1;
     }
     if (role == 1) {  // leave the top-k for the owner (own cand[] is done with)
 #pragma unroll
