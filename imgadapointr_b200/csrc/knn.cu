@@ -277,6 +277,44 @@ __device__ __forceinline__ void sort32(float (&v)[32]) {
   }
 }
 
+// ascending compare-exchange / bitonic networks on 64-bit keys held in registers (indices are compile-time after unrolling)
+__device__ __forceinline__ void cswap_u64(u64& a, u64& b) {
+  const bool s = b < a;
+  const u64 lo = s ? b : a, hi = s ? a : b;
+  a = lo;
+  b = hi;
+}
+template <int N>
+__device__ __forceinline__ void bitonic_merge_u64(u64 (&v)[N]) {  // bitonic sequence -> ascending
+#pragma unroll
+  for (int stride = N / 2; stride > 0; stride >>= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if ((i & stride) == 0) cswap_u64(v[i], v[i + stride]);
+  }
+}
+template <int N>
+__device__ __forceinline__ void bitonic_sort_u64(u64 (&v)[N]) {
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int j = i ^ stride;
+        if (j > i) {
+          if ((i & size) == 0)
+            cswap_u64(v[i], v[j]);
+          else
+            cswap_u64(v[j], v[i]);
+        }
+      }
+    }
+  }
+}
+
+constexpr int kCuBatch = 8;  // candidates folded at once (select and culled kernels)
+
 struct __align__(16) S2Smem {
   float4 tile[kS2Vec];
   union {
@@ -284,18 +322,6 @@ struct __align__(16) S2Smem {
     float minima[32][32];             // kSplit > 1: this slice's class minima, exchanged after sweep 1
   };
 };
-
-// new[j] = (d < old[j-1]) ? old[j-1] : (d < old[j]) ? d : old[j]; strict '<' puts d after equal, earlier entries
-template <int kK>
-__device__ __forceinline__ void sorted_insert(float d, int r, float (&td)[kK], int (&ti)[kK]) {
-#pragma unroll
-  for (int j = kK - 1; j >= 0; --j) {
-    const bool here = d < td[j];
-    const bool up = j > 0 && d < td[j > 0 ? j - 1 : 0];
-    td[j] = up ? td[j > 0 ? j - 1 : 0] : (here ? d : td[j]);
-    ti[j] = up ? ti[j > 0 ? j - 1 : 0] : (here ? r : ti[j]);
-  }
-}
 
 template <int kStride, int kK, int kSplit>
 __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
@@ -410,43 +436,47 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
   // class-minima bound (index layouts correlated with position: ordered surface samplings) or hundreds of exact ties
   // cost extra folds instead of the exact-fallback sweeps below.  Candidates arrive in ascending index and the insert
   // is stable, so equal distances keep the lowest indices.
-  float td[kK];
-  int ti[kK];
+  u64 tk[kK];  // ascending (distance bits, index) keys: the k nearest seen so far
 #pragma unroll
-  for (int j = 0; j < kK; ++j) {
-    td[j] = kInf;
-    ti[j] = 0;
-  }
-  auto fold = [&]() {
-    float cx = 0.f, cy = 0.f, cz = 0.f;
-    int cr = 0;
-    if (count > 0) {
-      cr = sm.cand[0][lane];
-      const float* p = Rb + 3 * (size_t)cr;
-      cx = __ldg(p);
-      cy = __ldg(p + 1);
-      cz = __ldg(p + 2);
-    }
-    for (int c = 0; c < count; ++c) {
-      const int r = cr;
-      const float d = sqdist(qx, qy, qz, cx, cy, cz);
-      if (c + 1 < count) {  // the next candidate's coordinates travel while this one is inserted
-        cr = sm.cand[c + 1][lane];
-        const float* p = Rb + 3 * (size_t)cr;
-        cx = __ldg(p);
-        cy = __ldg(p + 1);
-        cz = __ldg(p + 2);
+  for (int j = 0; j < kK; ++j) tk[j] = ~0ull;
+  // kCuBatch candidates of a list at a time are re-evaluated (their loads in flight together), sorted by a register
+  // network and merged into the sorted top-k by one bitonic split + merge: ~45 instructions per candidate where an
+  // insertion costs ~100.  Every lane of the warp takes part (n = 0 for a lane with nothing to fold).
+  auto fold_list = [&](const S2Smem& src, int n) {
+    const int n_max = redux_max_s32(n);
+    for (int c0 = 0; c0 < n_max; c0 += kCuBatch) {
+      u64 nk[kCuBatch];
+#pragma unroll
+      for (int j = 0; j < kCuBatch; ++j) {
+        nk[j] = ~0ull;
+        if (c0 + j < n) {
+          const unsigned cr = src.cand[c0 + j][lane];
+          const float* p = Rb + 3 * (size_t)cr;
+          nk[j] = ((u64)__float_as_uint(sqdist(qx, qy, qz, __ldg(p), __ldg(p + 1), __ldg(p + 2))) << 32) | cr;
+        }
       }
-      sorted_insert<kK>(d, r, td, ti);
+      bitonic_sort_u64<kCuBatch>(nk);
+#pragma unroll
+      for (int j = 0; j < kK; ++j) {  // the kK smallest of (tk ascending, nk descending): a bitonic sequence
+        const int rj = kK - 1 - j;
+        if (rj < kCuBatch) tk[j] = nk[rj] < tk[j] ? nk[rj] : tk[j];
+      }
+      bitonic_merge_u64<kK>(tk);
     }
+  };
+  auto fold = [&]() {
+    fold_list(sm, count);
     count = 0;
-    float kth = td[0];
+    u64 kth = tk[0];
 #pragma unroll
     for (int j = 1; j < kK; ++j)
-      if (j < k) kth = td[j];
+      if (j < k) kth = tk[j];
     // k references are in the list: the sweep runs in ascending index and ties keep the LOWEST indices, so from now on
-    // only a strictly smaller distance can enter (kth stays +inf while fewer than k references were folded)
-    if (kth < kInf) thr = fminf(thr, kth > 0.f ? __uint_as_float(__float_as_uint(kth) - 1u) : -1.f);
+    // only a strictly smaller distance can enter (kth stays empty while fewer than k references were folded)
+    if (kth != ~0ull) {
+      const float kd = __uint_as_float((unsigned)(kth >> 32));
+      thr = fminf(thr, kd > 0.f ? __uint_as_float(__float_as_uint(kd) - 1u) : -1.f);
+    }
   };
   if (n_tiles > 0) fetch(0, nx);
   for (int t = 0; t < n_tiles; ++t) {
@@ -533,42 +563,20 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
       pi = bi;
     }
   }
-  if (!live || overflow) return;
-
-  // ---- select: stable insert into a register-resident sorted list ---------------------------------------------------
-  if (kSplit == 1) fold();
+  // ---- select: the k nearest of the listed candidates (every lane of the warp folds; only live, non-overflowed ones list) ---
+  if (kSplit == 1) {
+    fold();
+  } else {
 #pragma unroll 1
-  for (int o = 0; o < (kSplit == 1 ? 0 : kSplit); ++o) {
-    const S2Smem& src = smem[o];
-    const int n = kSplit > 1 ? counts[o][lane] : count;
-    float cx = 0.f, cy = 0.f, cz = 0.f;
-    int cr = 0;
-    if (n > 0) {
-      cr = src.cand[0][lane];
-      const float* p = Rb + 3 * (size_t)cr;
-      cx = __ldg(p);
-      cy = __ldg(p + 1);
-      cz = __ldg(p + 2);
-    }
-    for (int c = 0; c < n; ++c) {
-      const int r = cr;
-      const float d = sqdist(qx, qy, qz, cx, cy, cz);
-      if (c + 1 < n) {  // the next candidate's coordinates travel while this one is inserted
-        cr = src.cand[c + 1][lane];
-        const float* p = Rb + 3 * (size_t)cr;
-        cx = __ldg(p);
-        cy = __ldg(p + 1);
-        cz = __ldg(p + 2);
-      }
-      sorted_insert<kK>(d, r, td, ti);
-    }
+    for (int sl = 0; sl < kSplit; ++sl) fold_list(smem[sl], (live && !overflow) ? counts[sl][lane] : 0);
   }
+  if (!live || overflow) return;
 #pragma unroll
   for (int j = 0; j < kK; ++j) {
     if (j < k) {
       // fewer than k entries only if distances were NaN (outside the contract): index 0 keeps consumers in range
-      idx_out[o + j] = (int64_t)ti[j];
-      if (dist_out) dist_out[o + j] = td[j];
+      idx_out[o + j] = tk[j] == ~0ull ? 0 : (int64_t)(unsigned)tk[j];
+      if (dist_out) dist_out[o + j] = tk[j] == ~0ull ? kInf : __uint_as_float((unsigned)(tk[j] >> 32));
     }
   }
 }
@@ -836,43 +844,6 @@ __global__ void __launch_bounds__(kBinThreads) knn_bin_kernel(const float* __res
   (void)kInf;
 }
 
-// ascending compare-exchange / bitonic networks on 64-bit keys held in registers (indices are compile-time after unrolling)
-__device__ __forceinline__ void cswap_u64(u64& a, u64& b) {
-  const bool s = b < a;
-  const u64 lo = s ? b : a, hi = s ? a : b;
-  a = lo;
-  b = hi;
-}
-template <int N>
-__device__ __forceinline__ void bitonic_merge_u64(u64 (&v)[N]) {  // bitonic sequence -> ascending
-#pragma unroll
-  for (int stride = N / 2; stride > 0; stride >>= 1) {
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-      if ((i & stride) == 0) cswap_u64(v[i], v[i + stride]);
-  }
-}
-template <int N>
-__device__ __forceinline__ void bitonic_sort_u64(u64 (&v)[N]) {
-#pragma unroll
-  for (int size = 2; size <= N; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        const int j = i ^ stride;
-        if (j > i) {
-          if ((i & size) == 0)
-            cswap_u64(v[i], v[j]);
-          else
-            cswap_u64(v[j], v[i]);
-        }
-      }
-    }
-  }
-}
-
-constexpr int kCuBatch = 8;  // candidates folded at once
 // every warp's last claim fails and still moves its end of the deque by one: the bias keeps the tail of a short list
 // from wrapping below zero (at most kG - 1 helpers, one failed claim each)
 constexpr int kCuDequeBias = 8;
