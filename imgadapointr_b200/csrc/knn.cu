@@ -1298,12 +1298,15 @@ static KnnPlan knn_plan(int B, int R, int Q, int k) {
   // Culled path: measured against the select kernel at B = 48, k = 16 (profiles/r02y_knn_culled.txt): 2048 x 2048 0.10 -
   // 0.13 ms vs 0.18, 4096 x 4096 0.20 vs 0.52, 1024 x 1024 0.058 vs 0.072; with 512 queries per cloud (768 warps of
   // queries: a quarter of the machine) the select kernel's slices win, 0.064 vs 0.085.  So it is the default from 1024
-  // warps of queries.  IAPT_KNN_PRUNED = 1 forces it wherever it applies, 2 disables it (read per call: the tests run
+  // warps of queries (1536 below 2048 references).  IAPT_KNN_PRUNED = 1 forces it wherever it applies, 2 disables it (read per call: the tests run
   // both paths over the same cases).
   const long long pruned_mode = env_ll("IAPT_KNN_PRUNED", 0);
   const long long warps = (long long)B * ((Q + 31) / 32);
   const bool pruned_fits = k <= kSelMaxK && R >= kPrMinR && R <= kPrMaxN && Q >= 1 && Q <= kPrMaxN && B <= 65535;
-  if (!force_list && pruned_fits && pruned_mode != 2 && (pruned_mode == 1 || warps >= 1024)) return {false, 1, true};
+  // (measured over B = 8 ... 48, profiles/r02y_knn_culled.txt: the select kernel's time grows with R, the culled path has
+  // a fixed part - at 1024 references it needs 1536 warps of queries to win, from 2048 references 1024)
+  const bool pruned_pays = warps >= (R >= 2048 ? 1024 : 1536);
+  if (!force_list && pruned_fits && pruned_mode != 2 && (pruned_mode == 1 || pruned_pays)) return {false, 1, true};
   if (k <= kSelMaxK && R >= 64 && R <= 65536 && !force_list && warps >= min_warps) {
     int s = 1;
     while (s < 4 && warps * s < want_warps && R / (2 * s) >= 512) s *= 2;  // slices shorter than 512 do not pay

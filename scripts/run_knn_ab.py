@@ -11,13 +11,14 @@ from imgadapointr_b200 import _lib
 
 dev = torch.device("cuda:0")
 pointnet2_utils.furthest_point_sample.reuse_prefix = False
-gt = synthetic.pcn_gt(48, 16384, 303)
+NB = int(os.environ.get("AB_B", "48"))
+gt = synthetic.pcn_gt(NB, 16384, 303)
 xyz = synthetic.pcn_partial(gt, 2048, 304).to(dev)
 c512 = misc.fps(xyz, 512)
-u = (torch.rand(48, 2048, 3, device=dev) - 0.5).contiguous()
-g2 = synthetic.pcn_gt(48, 2048, 5).to(dev)
-g4 = synthetic.pcn_gt(48, 4096, 6).to(dev)
-g1 = synthetic.pcn_gt(48, 1024, 7).to(dev)
+u = (torch.rand(NB, 2048, 3, device=dev) - 0.5).contiguous()
+g2 = synthetic.pcn_gt(NB, 2048, 5).to(dev)
+g4 = synthetic.pcn_gt(NB, 4096, 6).to(dev)
+g1 = synthetic.pcn_gt(NB, 1024, 7).to(dev)
 gc512 = misc.fps(g2, 512)
 z = xyz.clone()
 z[:, 1200:] = 0  # heavy zero padding: 848 of 2048 points at the origin in every cloud
