@@ -875,7 +875,7 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
                                                                               const PrTileBox* __restrict__ boxes,
                                                                               const float4* __restrict__ sqry, int R, int Rp,
                                                                               int Q, int Qp, int k, int q_blocks,
-                                                                              int n_seeds, int probes,
+                                                                              int n_seeds, int probes, int solo,
                                                                               int64_t* __restrict__ idx_out,
                                                                               float* __restrict__ dist_out) {
   extern __shared__ float4 sbox[];  // [2 * nt]: lo, hi of every tile of the cloud
@@ -883,10 +883,13 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
   CuTaskSmem& sm = tsm[w];
-  const int groups = (q_blocks + kG - 1) / kG;
+  // solo: ONE task per CTA (warp 0's), the other warps help from the moment its tile list is open - for calls whose tasks
+  // do not fill the machine (the grouper's 2048 x 512 call: 768 tasks for 592 schedulers x 5 warps)
+  const int groups = solo ? q_blocks : (q_blocks + kG - 1) / kG;
   const int b = blockIdx.x / groups;
-  const int qb = (blockIdx.x - b * groups) * kG + w;
-  const bool has_task = qb < q_blocks;  // (the last CTA of a cloud may hold fewer than kG tasks: those warps only help)
+  const int qb = solo ? blockIdx.x - b * groups : (blockIdx.x - b * groups) * kG + w;
+  // (without solo the last CTA of a cloud may hold fewer than kG tasks: those warps only help)
+  const bool has_task = solo ? w == 0 : qb < q_blocks;
   const float kInf = __int_as_float(0x7f800000);
   const float4* __restrict__ Rb = sref + (size_t)b * Rp;
   const int nt = Rp / 32;
@@ -1090,6 +1093,9 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
     if (role == 0) {
       if (!has_task) continue;
     } else {
+      if (solo) {  // wait for warp 0's list (it always opens its deque; bias > 0 makes an open deque non-zero)
+        while (*reinterpret_cast<volatile unsigned*>(&tsm[0].deque) == 0u) __nanosleep(100);
+      }
       // the task of this CTA with the most tiles left (at least 2); announce the help BEFORE the first claim
       int best = 1;
 #pragma unroll
@@ -1297,15 +1303,17 @@ static KnnPlan knn_plan(int B, int R, int Q, int k) {
   static const long long force_split = env_ll("IAPT_KNN_SELECT_SPLIT", 0);
   // Culled path: measured against the select kernel at B = 48, k = 16 (profiles/r02y_knn_culled.txt): 2048 x 2048 0.10 -
   // 0.13 ms vs 0.18, 4096 x 4096 0.20 vs 0.52, 1024 x 1024 0.058 vs 0.072; with 512 queries per cloud (768 warps of
-  // queries: a quarter of the machine) the select kernel's slices win, 0.064 vs 0.085.  So it is the default from 1024
-  // warps of queries (1536 below 2048 references).  IAPT_KNN_PRUNED = 1 forces it wherever it applies, 2 disables it (read per call: the tests run
-  // both paths over the same cases).
+  // queries: a quarter of the machine) the select kernel's slices win, 0.064 vs 0.072.  IAPT_KNN_PRUNED = 1 forces it
+  // wherever it applies, 2 disables it (read per call: the tests run both paths over the same cases).
   const long long pruned_mode = env_ll("IAPT_KNN_PRUNED", 0);
   const long long warps = (long long)B * ((Q + 31) / 32);
   const bool pruned_fits = k <= kSelMaxK && R >= kPrMinR && R <= kPrMaxN && Q >= 1 && Q <= kPrMaxN && B <= 65535;
-  // (measured over B = 8 ... 48, profiles/r02y_knn_culled.txt: the select kernel's time grows with R, the culled path has
-  // a fixed part - at 1024 references it needs 1536 warps of queries to win, from 2048 references 1024)
-  const bool pruned_pays = warps >= (R >= 2048 ? 1024 : 1536);
+  // (measured over B = 1 ... 48, profiles/r02y_knn_culled.txt: the select kernel's time grows with R, the culled path has
+  // a fixed part of ~37 us - bin kernel + one task's latency - so at 1024 references it needs 1536 warps of queries to
+  // win, at 2048 references 640, above that 128.  SPARSE queries - the grouper's 512 FPS centres against 2048 points -
+  // make every warp's query box, hence its tile list, 2-3x larger: there the select kernel's slices stay ahead.)
+  const bool dense = 2LL * Q >= R;
+  const bool pruned_pays = dense && warps >= (R > 2048 ? 128 : R >= 2048 ? 640 : 1536);
   if (!force_list && pruned_fits && pruned_mode != 2 && (pruned_mode == 1 || pruned_pays)) return {false, 1, true};
   if (k <= kSelMaxK && R >= 64 && R <= 65536 && !force_list && warps >= min_warps) {
     int s = 1;
@@ -1391,9 +1399,13 @@ int knn_launch(const float* ref, const float* qry, int B, int R, int Q, int k, i
     n_seeds = std::max(1, std::min(n_seeds, std::min(nt, 32)));
     const size_t dyn = (size_t)2 * nt * sizeof(float4);
     const float4* sq = self ? sref : sqry;
-    const unsigned grid = (unsigned)((long long)B * ((qb + group - 1) / group));
-#define KNN_CULLED(KK, G) \
-  knn_culled_kernel<KK, G><<<grid, 32 * G, dyn, stream>>>(sref, boxes, sq, R, Rp, Q, Qp, k, qb, n_seeds, probes, idx, dist)
+    // few tasks: one per CTA and its 4 warps share the tile list from the start
+    const long long solo_below = env_ll("IAPT_KNN_CULL_SOLO_BELOW", 900);  // (888 CTAs are resident at once)
+    const int solo = (group == 4 && (long long)B * qb < solo_below) ? 1 : 0;
+    const unsigned grid = (unsigned)((long long)B * (solo ? qb : (qb + group - 1) / group));
+#define KNN_CULLED(KK, G)                                                                                               \
+  knn_culled_kernel<KK, G><<<grid, 32 * G, dyn, stream>>>(sref, boxes, sq, R, Rp, Q, Qp, k, qb, n_seeds, probes, solo, idx, \
+                                                          dist)
     if (k <= 8) {
       if (group == 1) KNN_CULLED(8, 1); else if (group == 2) KNN_CULLED(8, 2); else KNN_CULLED(8, 4);
     } else {
