@@ -861,7 +861,8 @@ struct __align__(16) CuTaskSmem {
   float4 stage[2][32];  // a tile of 32 references (x, y, z, original index), double-buffered: cp.async lands here
   union {
     unsigned short cand[kCuCap][32];  // sweep -> fold
-    u64 keys[kSelMaxK][32];           // a helper's top-k for the task it helped, read by that task's owner
+    float minima[32][32];             // solo: this warp's class minima, exchanged after the bound pass
+    u64 keys[kSelMaxK][32];           // a warp's top-k for another warp to merge (a helper's; in solo mode every warp's)
   };
   unsigned char tlist[kCuMaxTiles];
   float4 qv[32];        // the task's queries (x, y, z, original index)
@@ -883,13 +884,17 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
   CuTaskSmem& sm = tsm[w];
-  // solo: ONE task per CTA (warp 0's), the other warps help from the moment its tile list is open - for calls whose tasks
-  // do not fill the machine (the grouper's 2048 x 512 call: 768 tasks for 592 schedulers x 5 warps)
+  // solo: ONE tile of 32 queries per CTA, shared by its kG warps - for calls whose tasks do not fill the machine (small
+  // batches).  Every warp holds the same queries, takes every kG-th seed tile of the common ranking (the class minima are
+  // exchanged through shared memory) and every kG-th tile of the cloud into a deque of its own; a warp that runs out takes
+  // tiles from the fullest deque and keeps folding into ITS OWN top-k (same queries: no hand-over), and warp 0 merges the kG
+  // sorted lists at the end.
   const int groups = solo ? q_blocks : (q_blocks + kG - 1) / kG;
   const int b = blockIdx.x / groups;
   const int qb = solo ? blockIdx.x - b * groups : (blockIdx.x - b * groups) * kG + w;
   // (without solo the last CTA of a cloud may hold fewer than kG tasks: those warps only help)
-  const bool has_task = solo ? w == 0 : qb < q_blocks;
+  const bool has_task = solo || qb < q_blocks;
+  const int tw = solo ? kG : 1, tr = solo ? w : 0;  // this warp takes the seeds / tiles with number = tr (mod tw)
   const float kInf = __int_as_float(0x7f800000);
   const float4* __restrict__ Rb = sref + (size_t)b * Rp;
   const int nt = Rp / 32;
@@ -1018,25 +1023,43 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
         return pick(m);
       };
       int seed_no = 0;
-      auto next_seed = [&]() {
-        const int u = seed_no++;
-        return (probes && (u & 1)) ? seed_probe(u >> 1) : seed_centre();
+      auto next_seed = [&]() {  // this warp's next tile of the common ranking (solo: every warp walks it, keeps every tw-th)
+        int t = -1;
+        for (int o = 0; o < tw; ++o) {
+          const int u = seed_no++;
+          const int id = (probes && (u & 1)) ? seed_probe(u >> 1) : seed_centre();
+          if (o == tr) t = id;
+        }
+        return t;
       };
       float mn[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) mn[i] = kInf;
       int t_seed = next_seed();
       if (t_seed >= 0) fetch_tile(0, t_seed);
-      for (int u = 0; u < n_seeds && t_seed >= 0; ++u) {
+      const int my_seeds = max(1, n_seeds / tw);
+      for (int u = 0; u < my_seeds && t_seed >= 0; ++u) {
         const int buf = u & 1;
         tile_landed();
-        t_seed = u + 1 < n_seeds ? next_seed() : -1;
+        t_seed = u + 1 < my_seeds ? next_seed() : -1;
         if (t_seed >= 0) fetch_tile(buf ^ 1, t_seed);
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const float4 p = sm.stage[buf][c];
           mn[c] = fminf(mn[c], sqdist(qx, qy, qz, p.x, p.y, p.z));
         }
+      }
+      if (kG > 1 && solo) {  // the warps' seed tiles hold different references: the minimum over the warps is the class minimum
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sm.minima[i][lane] = mn[i];
+        __syncthreads();
+#pragma unroll
+        for (int o = 1; o < kG; ++o) {
+          const CuTaskSmem& other = tsm[(w + o) % kG];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mn[i] = fminf(mn[i], other.minima[i][lane]);
+        }
+        __syncthreads();  // minima[] aliases cand[]
       }
       sort32(mn);
       tau = mn[0];
@@ -1050,8 +1073,8 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
     // ---- the tiles any query of the warp needs: box-to-box prefilter (a lane per tile), then the exact per-query test ----
     {
       const float tmax = __uint_as_float(redux_max_u32(live ? __float_as_uint(T) : 0u));  // T >= +0
-      for (int i = 0; i < (nt + 31) / 32; ++i) {
-        const int t = lane + 32 * i;
+      for (int i = 0; i * 32 * tw < nt; ++i) {
+        const int t = (lane + 32 * i) * tw + tr;
         bool maybe = false;
         if (t < nt) {
           const float4 bl = sbox[2 * t], bh = sbox[2 * t + 1];
@@ -1062,7 +1085,7 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
         }
         unsigned mask = __ballot_sync(0xffffffffu, maybe);
         while (mask) {
-          const int t2 = 32 * i + __ffs(mask) - 1;
+          const int t2 = (32 * i + __ffs(mask) - 1) * tw + tr;
           mask &= mask - 1u;
           const float4 bl = sbox[2 * t2], bh = sbox[2 * t2 + 1];  // warp-uniform: broadcast
           const float gx = fmaxf(0.f, fmaxf(bl.x - qx, qx - bh.x));
@@ -1087,16 +1110,17 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
 
   // ---- sweep: role 0 = the warp's own task (tiles from the front of its deque), role 1 = the task it helps (from the back)
   u64 tk[kK];  // ascending (distance bits, original index) keys of the best references seen so far
+  int count = 0;
+  bool folded = false;  // warp-uniform: a fold has happened (lanes that hold k references have an exact kth)
+  u64 kth = ~0ull;
   int victim = -1;
-  for (int role = 0; role < (kG > 1 ? 2 : 1); ++role) {
+  for (int role = 0; role < (kG > 1 ? (solo ? 1 + 2 * kG : 2) : 1); ++role) {  // (solo: a warp may help several times)
     CuTaskSmem* task = &sm;  // whose tile list
     if (role == 0) {
       if (!has_task) continue;
     } else {
-      if (solo) {  // wait for warp 0's list (it always opens its deque; bias > 0 makes an open deque non-zero)
-        while (*reinterpret_cast<volatile unsigned*>(&tsm[0].deque) == 0u) __nanosleep(100);
-      }
       // the task of this CTA with the most tiles left (at least 2); announce the help BEFORE the first claim
+      victim = -1;
       int best = 1;
 #pragma unroll
       for (int o = 1; o < kG; ++o) {
@@ -1110,20 +1134,24 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
       }
       if (victim < 0) break;
       task = &tsm[victim];
-      if (lane == 0) atomicOr(&task->helped_by, 1u << w);
-      __threadfence_block();
-      __syncwarp();
-      const float4 vq = task->qv[lane];
-      qx = vq.x, qy = vq.y, qz = vq.z;
-      qi = __float_as_int(vq.w);
-      live = qi >= 0;
-      T = *reinterpret_cast<volatile float*>(&task->tpub[lane]);  // (the owner may have tightened it since: any is valid)
+      if (!solo) {
+        if (lane == 0) atomicOr(&task->helped_by, 1u << w);
+        __threadfence_block();
+        __syncwarp();
+        const float4 vq = task->qv[lane];
+        qx = vq.x, qy = vq.y, qz = vq.z;
+        qi = __float_as_int(vq.w);
+        live = qi >= 0;
+        T = *reinterpret_cast<volatile float*>(&task->tpub[lane]);  // (the owner may have tightened it since: any is valid)
+      }
     }
+    if (!(solo && role >= 1)) {  // (solo: the same queries - the warp goes on with the top-k and the bound it has)
 #pragma unroll
-    for (int j = 0; j < kK; ++j) tk[j] = ~0ull;
-    int count = 0;
-    bool folded = false;  // warp-uniform: a fold has happened (lanes that hold k references have an exact kth)
-    u64 kth = ~0ull;
+      for (int j = 0; j < kK; ++j) tk[j] = ~0ull;
+      count = 0;
+      folded = false;
+      kth = ~0ull;
+    }
     // fold: kCuBatch candidates at a time are re-evaluated exactly (their loads in flight together), sorted by a register
     // network and merged into the sorted top-k by one bitonic split + merge: ~45 instructions per candidate where an
     // insertion costs ~100
@@ -1218,6 +1246,7 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
       t = t_next;
       buf ^= 1;
     }
+    if (solo) continue;  // (then helps once; the lists are merged below)
     if (role == 1) {  // leave the top-k for the owner (own cand[] is done with)
 #pragma unroll
       for (int j = 0; j < kK; ++j) sm.keys[j][lane] = tk[j];
@@ -1242,8 +1271,17 @@ __global__ void __launch_bounds__(32 * kG, kG == 1 ? 21 : kG == 2 ? 11 : 6) knn_
     }
   }
   if (kG == 1) return;
-  __syncthreads();
-  const unsigned helped = has_task ? sm.helped_by : 0u;
+  if (solo) {  // every warp's sorted list to warp 0
+    if (w != 0) {
+#pragma unroll
+      for (int j = 0; j < kK; ++j) sm.keys[j][lane] = tk[j];
+    }
+    __syncthreads();
+    if (w != 0) return;
+  } else {
+    __syncthreads();
+  }
+  const unsigned helped = solo ? ((1u << kG) - 2u) : has_task ? sm.helped_by : 0u;
   if (helped == 0u) return;
   // (tk still holds the own task's top-k: a helped owner left the loop before anything overwrote it)
   for (int h = 0; h < kG; ++h) {
@@ -1309,11 +1347,11 @@ static KnnPlan knn_plan(int B, int R, int Q, int k) {
   const long long warps = (long long)B * ((Q + 31) / 32);
   const bool pruned_fits = k <= kSelMaxK && R >= kPrMinR && R <= kPrMaxN && Q >= 1 && Q <= kPrMaxN && B <= 65535;
   // (measured over B = 1 ... 48, profiles/r02y_knn_culled.txt: the select kernel's time grows with R, the culled path has
-  // a fixed part of ~37 us - bin kernel + one task's latency - so at 1024 references it needs 1536 warps of queries to
-  // win, at 2048 references 640, above that 128.  SPARSE queries - the grouper's 512 FPS centres against 2048 points -
+  // a fixed part of ~35 us - bin kernel + one task's latency - so at 1024 references it needs 1536 warps of queries to
+  // win, at 2048 references 480, above that 128.  SPARSE queries - the grouper's 512 FPS centres against 2048 points -
   // make every warp's query box, hence its tile list, 2-3x larger: there the select kernel's slices stay ahead.)
   const bool dense = 2LL * Q >= R;
-  const bool pruned_pays = dense && warps >= (R > 2048 ? 128 : R >= 2048 ? 640 : 1536);
+  const bool pruned_pays = dense && warps >= (R > 2048 ? 128 : R >= 2048 ? 480 : 1536);
   if (!force_list && pruned_fits && pruned_mode != 2 && (pruned_mode == 1 || pruned_pays)) return {false, 1, true};
   if (k <= kSelMaxK && R >= 64 && R <= 65536 && !force_list && warps >= min_warps) {
     int s = 1;
