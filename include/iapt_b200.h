@@ -185,7 +185,7 @@ int iapt_gather_xyz(const float* xyz, const int32_t* idx, int B, int N, int npoi
  * 1 <= k <= 64 and k <= R. */
 #define IAPT_KNN_MAX_K 64
 /* Workspace: per-slice lists (few queries, many references: the loss kNN), or the curve-ordered copies of both clouds and
- * their tile boxes (k <= 16, 1024..4096 references, from 1024 warps of queries: the encoder's 2048 x 2048 call), else 0.
+ * their tile boxes (k <= 16, 1024..4096 references, dense queries in enough warps: the encoder's 2048 x 2048 call), else 0.
  * Ask for every call; the answer follows the same dispatch as iapt_knn. */
 size_t iapt_knn_workspace_bytes(int B, int R, int Q, int k);
 int iapt_knn(const float* ref, const float* query, int B, int R, int Q, int k, int64_t* idx, float* dist,

@@ -205,7 +205,7 @@ def test_knn_select_overflow_falls_back_exactly(dev, knn_path, B, R, Q, near):
 @pytest.fixture(params=["culled-4", "culled-2", "culled-1", "select"])
 def knn_path(request, monkeypatch):
     """Shapes with 1024 <= R <= 4096 and k <= 16 can take the Hilbert-binned, box-culled kernel (IAPT_KNN_PRUNED=1 forces
-    it; by default from 1024 warps of queries; IAPT_KNN_CULL_GROUP = tasks per CTA: 4 warps that help each other through
+    it; by default for dense queries in enough warps; IAPT_KNN_CULL_GROUP = tasks per CTA: 4 warps that help each other through
     shared-memory deques, or 1 = no helping) or the thread-per-query select kernel (IAPT_KNN_PRUNED=2) - the variables
     are read per call and every variant must match the oracle bit for bit."""
     if request.param == "select":
