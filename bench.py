@@ -220,17 +220,22 @@ def run_reference(args, rank, world):
     }))
 
 
-def _event_ms(fn, warm=3, iters=10):
+def _event_ms(fn, warm=3, iters=10, groups=5):
+    """ms per call: CUDA events around `iters` back-to-back calls, median of `groups` such measurements (sub-millisecond ops
+    are issued faster than they run, so one host hiccup inside a single group would otherwise show up as GPU time)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(iters):
-        fn()
-    b.record()
-    torch.cuda.synchronize()
-    return a.elapsed_time(b) / iters
+    times = []
+    for _ in range(groups):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b) / iters)
+    return sorted(times)[len(times) // 2]
 
 
 def secondary_gpu(dev, B=B_PER_GPU):
