@@ -320,6 +320,7 @@ struct __align__(16) S2Smem {
   union {
     unsigned short cand[kS2Cap][32];  // sweep 2 -> select
     float minima[32][32];             // kSplit > 1: this slice's class minima, exchanged after sweep 1
+    u64 keys[kSelMaxK][32];           // kSplit > 1: this slice's folded top-k, merged by warp 0
   };
 };
 
@@ -519,8 +520,13 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
     }
   }
   bool overflow = kSplit > 1 && count > kS2Cap;
-  if (kSplit > 1) {  // warp 0 selects from every slice's candidates, in slice (= ascending index) order
+  if (kSplit > 1) {  // every warp folds its own slice's list; warp 0 merges the sorted lists (keys carry the index: any order)
+    fold_list(sm, live ? min(count, kS2Cap) : 0);  // (an overflowed list's result is discarded below)
     counts[w][lane] = count;
+    if (w != 0) {
+#pragma unroll
+      for (int j = 0; j < kK; ++j) sm.keys[j][lane] = tk[j];  // (cand[] is done with)
+    }
     __syncthreads();
     if (w != 0) return;
 #pragma unroll
@@ -567,8 +573,15 @@ __global__ void __launch_bounds__(32 * kSplit, kSplit == 1 ? 21 : 24 / kSplit)
   if (kSplit == 1) {
     fold();
   } else {
-#pragma unroll 1
-    for (int sl = 0; sl < kSplit; ++sl) fold_list(smem[sl], (live && !overflow) ? counts[sl][lane] : 0);
+#pragma unroll
+    for (int sl = 1; sl < kSplit; ++sl) {  // one bitonic split + merge per slice
+#pragma unroll
+      for (int j = 0; j < kK; ++j) {
+        const u64 ok = smem[sl].keys[kK - 1 - j][lane];
+        tk[j] = ok < tk[j] ? ok : tk[j];
+      }
+      bitonic_merge_u64<kK>(tk);
+    }
   }
   if (!live || overflow) return;
 #pragma unroll
