@@ -1361,10 +1361,10 @@ static KnnPlan knn_plan(int B, int R, int Q, int k) {
   const bool pruned_fits = k <= kSelMaxK && R >= kPrMinR && R <= kPrMaxN && Q >= 1 && Q <= kPrMaxN && B <= 65535;
   // (measured over B = 1 ... 48, profiles/r02y_knn_culled.txt: the select kernel's time grows with R, the culled path has
   // a fixed part of ~35 us - bin kernel + one task's latency - so at 1024 references it needs 1536 warps of queries to
-  // win, at 2048 references 480, above that 128.  SPARSE queries - the grouper's 512 FPS centres against 2048 points -
+  // win, at 2048 references 640, above that 128.  SPARSE queries - the grouper's 512 FPS centres against 2048 points -
   // make every warp's query box, hence its tile list, 2-3x larger: there the select kernel's slices stay ahead.)
   const bool dense = 2LL * Q >= R;
-  const bool pruned_pays = dense && warps >= (R > 2048 ? 128 : R >= 2048 ? 480 : 1536);
+  const bool pruned_pays = dense && warps >= (R > 2048 ? 128 : R >= 2048 ? 640 : 1536);
   if (!force_list && pruned_fits && pruned_mode != 2 && (pruned_mode == 1 || pruned_pays)) return {false, 1, true};
   if (k <= kSelMaxK && R >= 64 && R <= 65536 && !force_list && warps >= min_warps) {
     int s = 1;

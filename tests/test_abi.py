@@ -83,7 +83,7 @@ def test_version_errors_and_workspace_arithmetic():
     assert L.iapt_knn(None, None, 1, 10, 10, 65, None, None, None, 0, None) == -3
     assert L.iapt_knn(None, None, 1, 10, 10, 11, None, None, None, 0, None) == -1
     assert L.iapt_knn_workspace_bytes(4, 2048, 2048, 16) == 0 and L.iapt_knn_workspace_bytes(48, 512, 2048, 32) == 0
-    # the culled path (dense queries, from 480 warps of them at 2048 references): curve-ordered copies of both clouds (16 B / point) + 32 B per tile of 32
+    # the culled path (dense queries, from 640 warps of them at 2048 references): curve-ordered copies of both clouds (16 B / point) + 32 B per tile of 32
     assert L.iapt_knn_workspace_bytes(48, 2048, 2048, 16) == 48 * (2048 * 16 + 64 * 32 + 2048 * 16) + 256
     assert L.iapt_knn_workspace_bytes(48, 16384, 64, 32) > 0  # few queries, many references: per-slice lists
     assert L.iapt_fps(None, 1, 0, 4, 0, None, None, 0, None) == -1
