@@ -1420,8 +1420,13 @@ static void knn_select_launch(const float* ref, const float* qry, int B, int R, 
 template <int kK>
 static void knn_select_dispatch(const float* ref, const float* qry, int B, int R, int Q, int k, int splits, int64_t* idx,
                                 float* dist, cudaStream_t stream) {
-  if (splits == 4)
+  static const bool sample_slices = env_ll("IAPT_KNN_SELECT_SAMPLE_SLICES", 1) == 1;  // (2 = off)
+  if (splits == 4 && sample_slices && R >= 2048)
+    knn_select_launch<2, kK, 4>(ref, qry, B, R, Q, k, idx, dist, stream);
+  else if (splits == 4)
     knn_select_launch<1, kK, 4>(ref, qry, B, R, Q, k, idx, dist, stream);
+  else if (splits == 2 && sample_slices && R >= 1024)
+    knn_select_launch<2, kK, 2>(ref, qry, B, R, Q, k, idx, dist, stream);
   else if (splits == 2)
     knn_select_launch<1, kK, 2>(ref, qry, B, R, Q, k, idx, dist, stream);
   else if (R >= 1024)  // sampled sweep 1 only where the slice is long enough to pay for the extra candidates
